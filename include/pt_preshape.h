@@ -1,0 +1,166 @@
+/*
+ * pt_preshape.h — C ABI of the B200 (sm_100a) implementation of the proxy-attention point-cloud
+ * preshaping hot path of pqh22/ProxyTransformation.
+ *
+ * The reference has no FFI for this path: it is a Python nn.Module
+ * (embodiedscan/models/necks/preshape_norm_reverse_drop.py, cited below as ":line") whose native
+ * kernels live in pytorch3d / ATen.  Every entry point here replaces one stage of that module's
+ * forward (:424-469) and is what the Python host module (proxytransformation_b200/necks/preshape.py,
+ * a drop-in for ProxyTransformationNormReverse) binds through ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *   - tensors are dense, row-major, fp32 unless stated; indices are int32 (the reference's int64
+ *     indices never leave the module); B scenes, N points/scene, M = grid_size^3 centres,
+ *     K = num_sub neighbours, n = kept clusters, c = embed_dim, l = proxy tokens;
+ *   - launches go to `stream` (a cudaStream_t passed as void*); nothing synchronises, nothing allocates;
+ *     scratch comes from the caller (`ws`, sized by the matching *_ws_bytes function);
+ *   - return value: 0 = ok, negative = error (PT_ERR_*); pt_last_error_string() describes the last one
+ *     on the calling thread.
+ */
+#ifndef PT_PRESHAPE_H_
+#define PT_PRESHAPE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PT_OK 0
+#define PT_ERR_INVALID (-1)   /* bad argument / unsupported shape */
+#define PT_ERR_CUDA (-2)      /* a CUDA runtime call or launch failed */
+#define PT_ERR_WORKSPACE (-3) /* workspace too small */
+
+#define PT_DTYPE_F32 0
+#define PT_DTYPE_BF16 1
+
+typedef void* pt_stream_t; /* cudaStream_t */
+
+int pt_abi_version(void);
+const char* pt_last_error_string(void);
+/* Number of kernels launched through this library by the calling process so far (bench.py's gpu_launches). */
+int64_t pt_launch_count(void);
+
+/* ---- S1 grid prior — DeformablePointCluster.init_uniform_cluster_center (:33-51) --------------------
+ * mn/mx (B,3) per-axis min/max over the scene; centres (B,M,3) = (mn + margin) + lin3[j] * ((mx - mn) - 2*margin),
+ * j = ix*gs^2 + iy*gs + iz ('ij' meshgrid).  `lin` is torch.linspace(0,1,gs) computed by the host (fp32).
+ * ws: pt_minmax_ws_bytes(B, N). */
+size_t pt_minmax_ws_bytes(int B, int N);
+int pt_minmax_centres(const float* points, int B, int N, int gs, const float* lin, float margin, float* mn, float* mx,
+                      float* centres, void* ws, size_t ws_bytes, pt_stream_t stream);
+
+/* ---- S2/S4 ball query — pytorch3d.ops.ball_query call sites (:56, :65) ------------------------------
+ * For every centre the first K point indices, in ascending index, with ((dx*dx)+(dy*dy))+(dz*dz) < radius^2
+ * (fp32, no FMA contraction); unfilled slots -1.  pad_counts (B,M) = number of -1 slots, may be NULL. */
+int pt_ball_query_firstk(const float* centres, const float* points, int B, int M, int N, int K, float radius,
+                         int32_t* idx, int32_t* pad_counts, pt_stream_t stream);
+
+/* ---- S3 offset network — OffsetNetwork.forward (:87-107) + tanh*margin, add, clamp (:58-62) ---------
+ * Gathers the K neighbours of `idx` from `points` (pad slot -> (0,0,0), masked_gather :627-672), builds the
+ * 6 features [rel (zeroed where the gathered point == (0,0,0)), abs], conv1x1 6->H + BatchNorm(eval, given as
+ * per-channel scale/shift) + ReLU, mean over K, H->3 map (no bias), tanh*margin, + centre, clamp to [mn,mx].
+ * conv_w (H,6), conv_b/bn_scale/bn_shift (H), map_w (3,H); H must be 256.  raw_offsets (B,M,3) may be NULL. */
+int pt_offset_net_fused(const float* points, const int32_t* idx, const float* centres0, const float* mn,
+                        const float* mx, const float* conv_w, const float* conv_b, const float* bn_scale,
+                        const float* bn_shift, const float* map_w, int B, int M, int N, int K, int H, float margin,
+                        float* centres_out, float* raw_offsets, pt_stream_t stream);
+
+/* ---- S5 cluster dropout — dynamic_cluster_dropout (:352-420) ----------------------------------------
+ * Per scene: pad count per cluster -> STABLE ascending order (pinned tie rule) -> first keep1 -> farthest point
+ * sampling of n_drop = keep1 - n_keep centres (start 0, first arg-max) = clusters to drop -> ascending
+ * complement truncated to n_keep.  Outputs: kept_src (B,n_keep) original cluster id of each kept slot,
+ * kept_centres (B,n_keep,3), kept_idx (B,n_keep,K), drop_idx (B,n_drop,K) (rows of the FPS-selected clusters,
+ * in FPS order), fps_sel (B,n_drop) FPS picks as positions in the keep1 list (may be NULL). */
+int pt_cluster_dropout(const float* centres, const int32_t* idx, int B, int M, int K, int keep1, int n_keep,
+                       int32_t* kept_src, float* kept_centres, int32_t* kept_idx, int32_t* drop_idx,
+                       int32_t* fps_sel, pt_stream_t stream);
+
+/* ---- S6 point proxies — SimplifiedPointNet.forward (:126-142) ----------------------------------------
+ * Same features/conv/BN/ReLU as S3 with the kept centres, max over K -> point_proxy (B,n,H), H = 256. */
+int pt_point_encoder_fused(const float* points, const int32_t* kept_idx, const float* kept_centres,
+                           const float* conv_w, const float* conv_b, const float* bn_scale, const float* bn_shift,
+                           int B, int n, int N, int K, int H, float* point_proxy, pt_stream_t stream);
+
+/* ---- S7 ProxyBlock (:273-276) + ProxyAttention (:206-257) + timm Mlp + trailing LayerNorm (:443/:452) ----
+ * out = LN_out( x1 + fc2(GELU_erf(fc1(LN2(x1)))) ),  x1 = x + proj(attn(LN1(x) + pos_bias, proxy, mask)).
+ * pos_bias (n,c) is the parameter-only table bilinear(pb 4x4 -> s x s) + pc + pr (:212-215), see pt_position_bias.
+ * mask (B,l) uint8, 1 = real token, NULL = no mask (image branch).  Dense layers run on tcgen05 tensor cores
+ * with fp32-accurate 3xBF16 operand splitting when the *_split weight pointers are set, else on fp32 CUDA cores. */
+typedef struct pt_proxy_block_params {
+    const float *ln1_w, *ln1_b;       /* (c) */
+    const float* pos_bias;            /* (n,c) */
+    const float* qkv_w;               /* (3c,c), no bias */
+    const float *pp_w, *pp_b;         /* proxy_proj (c,c),(c) */
+    const float *proj_w, *proj_b;     /* (c,c),(c) */
+    const float *ln2_w, *ln2_b;       /* (c) */
+    const float *fc1_w, *fc1_b;       /* (hid,c),(hid) */
+    const float *fc2_w, *fc2_b;       /* (c,hid),(c) */
+    const float *lno_w, *lno_b;       /* trailing text_norm[i] / img_norm[i] (c) */
+    /* optional bf16 hi/lo splits of the four big weights for the tensor-core path: each points at
+     * [2][rows][cols] bf16 (hi plane then lo plane), or NULL */
+    const void *qkv_w_split, *proj_w_split, *fc1_w_split, *fc2_w_split, *pp_w_split;
+} pt_proxy_block_params;
+
+size_t pt_proxy_block_ws_bytes(int B, int n, int l, int c, int hidden);
+int pt_proxy_block_fused(const float* x, const float* proxy, const uint8_t* mask, const pt_proxy_block_params* p,
+                         int B, int n, int l, int c, int heads, int hidden, float* out, void* ws, size_t ws_bytes,
+                         pt_stream_t stream);
+
+/* Position-bias table of one ProxyAttention: out (n, s*s) = bilinear_{4x4 -> s x s, align_corners=False}(pb[m])
+ * + pc[m,r] + pr[m,q]   (:212-215).  pb (n,4,4), pc (n,s), pr (n,s). */
+int pt_position_bias(const float* pb, const float* pc, const float* pr, int n, int s, float* out, pt_stream_t stream);
+
+/* ---- S8 heads — Linear + BatchNorm1d(eval) (:445-446, :454-455) ---------------------------------------
+ * out (rows,o) = (guide (rows,c) @ lin_w(o,c)^T + lin_b) * bn_scale + bn_shift, o <= 16. */
+int pt_heads(const float* guide, const float* lin_w, const float* lin_b, const float* bn_scale, const float* bn_shift,
+             int rows, int c, int o, float* out, pt_stream_t stream);
+
+/* ---- S9 image proxies — get_img_proxy (:335-342) + AttentionPool2d.forward (:154-177) -----------------
+ * Only token 0 of the 226-token attention is kept (:177), so the stage is evaluated in single-query form:
+ * one pass for the per-channel spatial mean, folded q/k projections, one pass for scores -> softmax ->
+ * attention-weighted feature sum, folded v/c projections, LayerNorm.  img_feat (BV, C, HW) fp32 or bf16.
+ * The folded weights are produced once per weight load by the host (see pt_img_pool_params). */
+typedef struct pt_img_pool_params {
+    const float* w_qc;   /* (c,C)   = Wq @ Wc                                             */
+    const float* q0;     /* (c)     = Wq @ (bc + pos[0]) + bq                              */
+    const float* w_kc;   /* (c,C)   = Wk @ Wc                                             */
+    const float* g_k;    /* (T,c)   = (pos + bc) @ Wk^T        (T = HW+1 tokens)           */
+    const float* w_vc;   /* (c,C)   = Wv @ Wc                                             */
+    const float* h_v;    /* (T,c)   = (pos + bc) @ Wv^T + bv                               */
+    const float *cproj_w, *cproj_b; /* (c,c),(c) */
+    const float *ln_w, *ln_b;       /* norm_img (c) */
+} pt_img_pool_params;
+
+size_t pt_img_attnpool_ws_bytes(int BV, int C, int HW, int c, int heads);
+int pt_img_attnpool(const void* img_feat, int img_dtype, const pt_img_pool_params* p, int BV, int C, int HW, int c,
+                    int heads, float* img_proxy, void* ws, size_t ws_bytes, pt_stream_t stream);
+
+/* ---- S10-S12 affine (:459-462) + pt_replace (:472-498) + remove_points_by_index (:501-525) ------------
+ * new = (T[m] @ (p - centre[m]) + centre[m]) + t[m] for every valid (m,k); duplicate destinations resolved by the
+ * pinned rule "largest flat m*K+k wins"; points listed in drop_idx (>= 0) are removed; survivors are written in
+ * ascending original order, packed per scene at out + b*N*3; counts (B) = survivors per scene.
+ * ws: pt_scatter_ws_bytes(B, N). */
+size_t pt_scatter_ws_bytes(int B, int N);
+int pt_affine_scatter_compact(const float* points, const int32_t* kept_idx, const int32_t* drop_idx,
+                              const float* kept_centres, const float* transform, const float* translate, int B, int N,
+                              int n, int K, int n_drop_entries, float* out, int32_t* counts, void* ws, size_t ws_bytes,
+                              pt_stream_t stream);
+
+/* ---- building blocks exposed for tests ------------------------------------------------------------------ */
+/* C (M,N) = act(A (M,K) @ W (N,K)^T + bias) + residual ; act: 0 none, 1 GELU(erf).  bias/residual may be NULL.
+ * w_split: optional [2][N][K] bf16 hi/lo planes of W -> tcgen05 path (A is split on the fly); NULL -> fp32 CUDA cores. */
+size_t pt_gemm_ws_bytes(int M, int N, int K);
+int pt_gemm_nt(const float* A, const float* W, const void* w_split, const float* bias, const float* residual, int act,
+               int M, int N, int K, float* C, void* ws, size_t ws_bytes, pt_stream_t stream);
+/* bf16 hi/lo split of an fp32 matrix: out [2][rows][cols] bf16, hi = bf16(x), lo = bf16(x - hi). */
+int pt_split_bf16(const float* x, int64_t count, void* out, pt_stream_t stream);
+/* out (rows,c) = LayerNorm(x) * w + b (+ add[row % add_rows]) ; eps 1e-5 ; c % 32 == 0, c <= 1024. */
+int pt_layernorm(const float* x, const float* w, const float* b, const float* add, int add_rows, int rows, int c,
+                 float* out, pt_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PT_PRESHAPE_H_ */

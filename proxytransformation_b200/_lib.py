@@ -1,0 +1,84 @@
+"""ctypes binding of csrc/libptpreshape.so (the C ABI declared in include/pt_preshape.h).
+
+There is no CPU fallback: if the library is missing or a call fails the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libptpreshape.so")
+
+PT_DTYPE_F32, PT_DTYPE_BF16 = 0, 1
+
+
+class PtError(RuntimeError):
+    pass
+
+
+class ProxyBlockParams(Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "ln1_w", "ln1_b", "pos_bias", "qkv_w", "pp_w", "pp_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b",
+        "fc2_w", "fc2_b", "lno_w", "lno_b", "qkv_w_split", "proj_w_split", "fc1_w_split", "fc2_w_split", "pp_w_split")]
+
+
+class ImgPoolParams(Structure):
+    _fields_ = [(n, c_void_p) for n in ("w_qc", "q0", "w_kc", "g_k", "w_vc", "h_v", "cproj_w", "cproj_b", "ln_w", "ln_b")]
+
+
+_P = c_void_p
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "pt_abi_version": (c_int, []),
+    "pt_last_error_string": (c_char_p, []),
+    "pt_launch_count": (c_int64, []),
+    "pt_minmax_ws_bytes": (c_size_t, [c_int, c_int]),
+    "pt_minmax_centres": (c_int, [_P, c_int, c_int, c_int, _P, c_float, _P, _P, _P, _P, c_size_t, _P]),
+    "pt_ball_query_firstk": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P]),
+    "pt_offset_net_fused": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P]),
+    "pt_cluster_dropout": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
+    "pt_point_encoder_fused": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "pt_proxy_block_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "pt_proxy_block_fused": (c_int, [_P, _P, _P, POINTER(ProxyBlockParams), c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "pt_position_bias": (c_int, [_P, _P, _P, c_int, c_int, _P, _P]),
+    "pt_heads": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "pt_img_attnpool_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "pt_img_attnpool": (c_int, [_P, c_int, POINTER(ImgPoolParams), c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "pt_scatter_ws_bytes": (c_size_t, [c_int, c_int]),
+    "pt_affine_scatter_compact": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "pt_gemm_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pt_gemm_nt": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "pt_split_bf16": (c_int, [_P, c_int64, _P, _P]),
+    "pt_layernorm": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    """dlopen the library and attach signatures.  Raises PtError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PtError(f"{LIB_PATH} is missing: build it with `python -m proxytransformation_b200.build_ext` "
+                      "(there is no CPU fallback for the preshape path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().pt_last_error_string()
+        raise PtError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+
+def launch_count() -> int:
+    return int(load().pt_launch_count())

@@ -1,0 +1,73 @@
+// Shared helpers for the sm_100a kernels behind include/pt_preshape.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pt_preshape.h"
+
+namespace pt {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define PT_REQUIRE(cond, ...)                 \
+    do {                                      \
+        if (!(cond)) {                        \
+            pt::set_error(__VA_ARGS__);       \
+            return PT_ERR_INVALID;            \
+        }                                     \
+    } while (0)
+
+#define PT_CUDA_OK(expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            pt::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return PT_ERR_CUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
+#define PT_LAUNCH_CHECK()                  \
+    do {                                   \
+        pt::count_launch();                \
+        PT_CUDA_OK(cudaGetLastError());    \
+    } while (0)
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long t = __shfl_xor_sync(FULL, v, o);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+
+// squared distance in the reference's evaluation order ((dx*dx)+(dy*dy))+(dz*dz), no FMA contraction
+__device__ __forceinline__ float dist2_rn(float ax, float ay, float az, float bx, float by, float bz) {
+    float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace pt

@@ -1,0 +1,426 @@
+// Geometric stages of the preshape path: grid prior (S1), first-K ball query (S2/S4), offset network (S3),
+// cluster dropout (S5) and the PointNet point encoder (S6).  HBM/latency-bound fp32 CUDA-core kernels.
+// Reference semantics: embodiedscan/models/necks/preshape_norm_reverse_drop.py (":line" below).
+#include "common.cuh"
+
+#include <math.h>
+
+namespace pt {
+
+// ------------------------------------------------------------------------------------------------ S1
+// :33-51.  Stage 1: per-block partial min/max of a slab of points; stage 2: finish the reduction and emit centres.
+constexpr int MM_THREADS = 256;
+constexpr int MM_POINTS_PER_BLOCK = 4096;
+
+__global__ void __launch_bounds__(MM_THREADS) minmax_partial_kernel(const float* __restrict__ points, int N,
+                                                                    float* __restrict__ partial) {
+    const int b = blockIdx.y, nblk = gridDim.x;
+    const float* P = points + (size_t)b * N * 3;
+    const int p0 = blockIdx.x * MM_POINTS_PER_BLOCK;
+    const int p1 = min(N, p0 + MM_POINTS_PER_BLOCK);
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int p = p0 + threadIdx.x; p < p1; p += MM_THREADS) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            float v = __ldg(P + (size_t)p * 3 + d);
+            mn[d] = fminf(mn[d], v);
+            mx[d] = fmaxf(mx[d], v);
+        }
+    }
+    __shared__ float s[MM_THREADS / 32][6];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        mn[d] = warp_min(mn[d]);
+        mx[d] = warp_max(mx[d]);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { s[w][d] = mn[d]; s[w][3 + d] = mx[d]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = s[0][threadIdx.x];
+        for (int i = 1; i < MM_THREADS / 32; ++i) v = threadIdx.x < 3 ? fminf(v, s[i][threadIdx.x]) : fmaxf(v, s[i][threadIdx.x]);
+        partial[((size_t)b * nblk + blockIdx.x) * 6 + threadIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) centres_kernel(const float* __restrict__ partial, int nblk, int gs, int M,
+                                                      const float* __restrict__ lin, float margin, float* __restrict__ mn_out,
+                                                      float* __restrict__ mx_out, float* __restrict__ centres) {
+    const int b = blockIdx.y;
+    __shared__ float s[6];
+    if (threadIdx.x < 6) {
+        const float* pp = partial + (size_t)b * nblk * 6 + threadIdx.x;
+        float v = pp[0];
+        for (int i = 1; i < nblk; ++i) v = threadIdx.x < 3 ? fminf(v, pp[(size_t)i * 6]) : fmaxf(v, pp[(size_t)i * 6]);
+        s[threadIdx.x] = v;
+        if (blockIdx.x == 0) {
+            if (threadIdx.x < 3) mn_out[b * 3 + threadIdx.x] = v;
+            else mx_out[b * 3 + threadIdx.x - 3] = v;
+        }
+    }
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    const int g[3] = {j / (gs * gs), (j / gs) % gs, j % gs};   // 'ij' meshgrid: x slowest (:44-45)
+    const float two_m = __fmul_rn(2.0f, margin);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        // ((mn + margin) + grid * ((mx - mn) - 2*margin)), no contraction (:48)
+        float ext = __fsub_rn(__fsub_rn(s[3 + d], s[d]), two_m);
+        centres[((size_t)b * M + j) * 3 + d] = __fadd_rn(__fadd_rn(s[d], margin), __fmul_rn(__ldg(lin + g[d]), ext));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ S2 / S4
+// pytorch3d ball_query semantics (:56,:65).  One warp per centre; the 8 centres of a block share point chunks
+// staged in shared memory (coalesced loads, 8x reuse); lanes test 32 consecutive points per step and append hits in
+// index order with ballot/popc; a warp stops at K hits, the block stops when all of its warps have.
+constexpr int BQ_WARPS = 8;
+constexpr int BQ_CHUNK = 2048;
+
+__global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_kernel(const float* __restrict__ centres,
+                                                                   const float* __restrict__ points, int M, int N, int K,
+                                                                   float r2, int32_t* __restrict__ idx,
+                                                                   int32_t* __restrict__ pad_counts) {
+    __shared__ float sp[BQ_CHUNK * 3];
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int m = blockIdx.x * BQ_WARPS + w;
+    const bool valid = m < M;
+    const float* P = points + (size_t)b * N * 3;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (valid) {
+        const float* c = centres + ((size_t)b * M + m) * 3;
+        cx = __ldg(c); cy = __ldg(c + 1); cz = __ldg(c + 2);
+    }
+    int32_t* out = idx + ((size_t)b * M + (valid ? m : 0)) * K;
+    int cnt = 0;
+    bool done = !valid;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = 0; base < N; base += BQ_CHUNK) {
+        const int npts = min(BQ_CHUNK, N - base);
+        const float* src = P + (size_t)base * 3;
+        for (int i = threadIdx.x; i < npts * 3; i += BQ_WARPS * 32) sp[i] = __ldg(src + i);
+        __syncthreads();
+        if (!done) {
+            for (int j0 = 0; j0 < npts && cnt < K; j0 += 32) {
+                const int j = j0 + lane;
+                bool hit = false;
+                if (j < npts) hit = dist2_rn(cx, cy, cz, sp[3 * j], sp[3 * j + 1], sp[3 * j + 2]) < r2;
+                const unsigned mask = __ballot_sync(FULL, hit);
+                if (hit) {
+                    const int slot = cnt + __popc(mask & lt);
+                    if (slot < K) out[slot] = base + j;
+                }
+                cnt += __popc(mask);
+            }
+            done = cnt >= K;
+        }
+        if (__syncthreads_and(done)) break;
+    }
+    if (valid) {
+        const int filled = min(cnt, K);
+        for (int k = filled + lane; k < K; k += 32) out[k] = -1;
+        if (pad_counts != nullptr && lane == 0) pad_counts[(size_t)b * M + m] = K - filled;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ S3 / S6
+// Shared body of OffsetNetwork (:87-107) and SimplifiedPointNet (:126-142): gather K neighbours, 6 features,
+// conv1x1 6->256 + BN(eval) + ReLU, then mean (offset net) or max (encoder) over K.  One warp per cluster; lane l owns
+// channels l, l+32, ..., l+224, so the 6x256 weights live in registers and features are broadcast by shuffle.
+constexpr int MLP_H = 256;
+constexpr int MLP_CPL = MLP_H / 32;   // channels per lane
+constexpr int MLP_WARPS = 8;
+
+template <bool ENCODER>
+__global__ void __launch_bounds__(MLP_WARPS * 32) cluster_mlp_kernel(
+    const float* __restrict__ points, const int32_t* __restrict__ idx, const float* __restrict__ centres,
+    const float* __restrict__ mn, const float* __restrict__ mx, const float* __restrict__ conv_w,
+    const float* __restrict__ conv_b, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
+    const float* __restrict__ map_w, int B, int M, int N, int K, float margin, float* __restrict__ out,
+    float* __restrict__ raw_offsets) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * MLP_WARPS + (threadIdx.x >> 5);
+    const int n_warps = gridDim.x * MLP_WARPS;
+    float w[MLP_CPL][6], bb[MLP_CPL], sc[MLP_CPL], sh[MLP_CPL];
+#pragma unroll
+    for (int i = 0; i < MLP_CPL; ++i) {
+        const int ch = lane + 32 * i;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) w[i][f] = __ldg(conv_w + ch * 6 + f);
+        bb[i] = __ldg(conv_b + ch);
+        sc[i] = __ldg(bn_scale + ch);
+        sh[i] = __ldg(bn_shift + ch);
+    }
+    for (int cm = warp_global; cm < B * M; cm += n_warps) {
+        const int b = cm / M;
+        const float* P = points + (size_t)b * N * 3;
+        const float cx = __ldg(centres + (size_t)cm * 3), cy = __ldg(centres + (size_t)cm * 3 + 1),
+                    cz = __ldg(centres + (size_t)cm * 3 + 2);
+        float red[MLP_CPL];
+#pragma unroll
+        for (int i = 0; i < MLP_CPL; ++i) red[i] = ENCODER ? -INFINITY : 0.0f;
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            const int kk = k0 + lane;
+            float px = 0.f, py = 0.f, pz = 0.f;
+            if (kk < K) {
+                const int id = __ldg(idx + (size_t)cm * K + kk);
+                if (id >= 0) { px = __ldg(P + (size_t)id * 3); py = __ldg(P + (size_t)id * 3 + 1); pz = __ldg(P + (size_t)id * 3 + 2); }
+            }
+            // padding is detected on the gathered COORDINATES, not on idx (:94, :132); -0.0 compares equal to 0
+            const bool pad = (px == 0.0f) && (py == 0.0f) && (pz == 0.0f);
+            const float rx = pad ? 0.0f : __fsub_rn(px, cx), ry = pad ? 0.0f : __fsub_rn(py, cy),
+                        rz = pad ? 0.0f : __fsub_rn(pz, cz);
+            const int kn = min(32, K - k0);
+            for (int t = 0; t < kn; ++t) {
+                const float f0 = __shfl_sync(FULL, rx, t), f1 = __shfl_sync(FULL, ry, t), f2 = __shfl_sync(FULL, rz, t);
+                const float f3 = __shfl_sync(FULL, px, t), f4 = __shfl_sync(FULL, py, t), f5 = __shfl_sync(FULL, pz, t);
+#pragma unroll
+                for (int i = 0; i < MLP_CPL; ++i) {
+                    float a = bb[i];
+                    a = fmaf(w[i][0], f0, a); a = fmaf(w[i][1], f1, a); a = fmaf(w[i][2], f2, a);
+                    a = fmaf(w[i][3], f3, a); a = fmaf(w[i][4], f4, a); a = fmaf(w[i][5], f5, a);
+                    const float y = fmaxf(fmaf(a, sc[i], sh[i]), 0.0f);
+                    red[i] = ENCODER ? fmaxf(red[i], y) : red[i] + y;
+                }
+            }
+        }
+        if (ENCODER) {
+#pragma unroll
+            for (int i = 0; i < MLP_CPL; ++i) out[(size_t)cm * MLP_H + lane + 32 * i] = red[i];
+        } else {
+            float o[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < MLP_CPL; ++i) {
+                const float z = __fdiv_rn(red[i], (float)K);   // torch.mean = sum / K (:102)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) o[d] = fmaf(__ldg(map_w + d * MLP_H + lane + 32 * i), z, o[d]);
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) o[d] = warp_sum(o[d]);
+            if (lane < 3) {
+                const float raw = lane == 0 ? o[0] : (lane == 1 ? o[1] : o[2]);
+                const float c0 = lane == 0 ? cx : (lane == 1 ? cy : cz);
+                if (raw_offsets != nullptr) raw_offsets[(size_t)cm * 3 + lane] = raw;
+                const float c1 = __fadd_rn(c0, __fmul_rn(tanhf(raw), margin));            // :59-61
+                out[(size_t)cm * 3 + lane] = fmaxf(fminf(c1, __ldg(mx + b * 3 + lane)), __ldg(mn + b * 3 + lane));  // :62
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ S5
+// dynamic_cluster_dropout (:352-420), one CTA per scene.  Everything is index work on <= a few thousand clusters:
+// pad counts -> stable counting sort (keys 0..K) -> FPS over the first keep1 centres (registers hold the running
+// minimum distances, one block-wide arg-max per round with a packed (dist,~index) key so the first maximum wins) ->
+// ordered complement -> gathers.
+constexpr int FPS_PER = 8;
+
+__global__ void cluster_dropout_kernel(const float* __restrict__ centres, const int32_t* __restrict__ idx, int M, int K,
+                                       int keep1, int n_keep, int32_t* __restrict__ kept_src,
+                                       float* __restrict__ kept_centres, int32_t* __restrict__ kept_idx,
+                                       int32_t* __restrict__ drop_idx, int32_t* __restrict__ fps_sel) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int b = blockIdx.x, T = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n_drop = keep1 - n_keep;
+    unsigned long long* red = reinterpret_cast<unsigned long long*>(smem_raw);          // [2][32]
+    float* ux = reinterpret_cast<float*>(red + 64);
+    float* uy = ux + keep1;
+    float* uz = uy + keep1;
+    int* order = reinterpret_cast<int*>(uz + keep1);                                     // [M]
+    int* start = order + M;                                                              // [K+2]
+    int* sel = start + (K + 2);                                                          // [n_drop]
+    int* kl = sel + n_drop;                                                              // [n_keep]
+    unsigned short* pcs = reinterpret_cast<unsigned short*>(kl + n_keep);                // [M]
+    unsigned char* flag = reinterpret_cast<unsigned char*>(pcs + M);                     // [keep1]
+
+    const int32_t* I = idx + (size_t)b * M * K;
+    const float* C = centres + (size_t)b * M * 3;
+    for (int i = tid; i < K + 2; i += T) start[i] = 0;
+    __syncthreads();
+    for (int m = tid; m < M; m += T) {                 // :372 padding_counts
+        int pc = 0;
+        for (int k = 0; k < K; ++k) pc += (__ldg(I + (size_t)m * K + k) == -1);
+        pcs[m] = (unsigned short)pc;
+        atomicAdd(&start[pc + 1], 1);
+    }
+    __syncthreads();
+    if (tid == 0) for (int k = 1; k <= K + 1; ++k) start[k] += start[k - 1];   // start[key] = first slot of key
+    __syncthreads();
+    if (wid == 0) {                                    // :378 argsort, pinned stable: ties keep ascending cluster id
+        const unsigned lt = (1u << lane) - 1u;
+        for (int m0 = 0; m0 < M; m0 += 32) {
+            const int m = m0 + lane;
+            const unsigned key = m < M ? pcs[m] : 0xffffu;
+            const unsigned grp = __match_any_sync(FULL, key);
+            const int rank = __popc(grp & lt);
+            if (m < M) order[start[key] + rank] = m;
+            __syncwarp();
+            if (m < M && rank == 0) start[key] += __popc(grp);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < keep1; i += T) {             // :379-385 keep the keep1 fullest clusters
+        const int m = order[i];
+        ux[i] = __ldg(C + m * 3); uy[i] = __ldg(C + m * 3 + 1); uz[i] = __ldg(C + m * 3 + 2);
+        flag[i] = 0;
+    }
+    __syncthreads();
+    // :393 farthest point sampling of n_drop centres (pytorch3d semantics; in-tree pin :577-614)
+    float px[FPS_PER], py[FPS_PER], pz[FPS_PER], dmin[FPS_PER];
+#pragma unroll
+    for (int r = 0; r < FPS_PER; ++r) {
+        const int p = tid + r * T;
+        px[r] = p < keep1 ? ux[p] : 0.f; py[r] = p < keep1 ? uy[p] : 0.f; pz[r] = p < keep1 ? uz[p] : 0.f;
+        dmin[r] = INFINITY;
+    }
+    int last = 0;
+    if (tid == 0) sel[0] = 0;
+    for (int k = 1; k < n_drop; ++k) {
+        const float lx = ux[last], ly = uy[last], lz = uz[last];
+        unsigned long long best = 0ull;
+#pragma unroll
+        for (int r = 0; r < FPS_PER; ++r) {
+            const int p = tid + r * T;
+            if (p < keep1) {
+                const float d = dist2_rn(lx, ly, lz, px[r], py[r], pz[r]);
+                dmin[r] = d < dmin[r] ? d : dmin[r];
+                const unsigned long long key = ((unsigned long long)__float_as_uint(dmin[r]) << 32) | (unsigned)(0xffffffffu - (unsigned)p);
+                best = key > best ? key : best;
+            }
+        }
+        best = warp_max_u64(best);
+        unsigned long long* slot = red + (k & 1) * 32;
+        if (lane == 0) slot[wid] = best;
+        __syncthreads();
+        unsigned long long v = lane < (T >> 5) ? slot[lane] : 0ull;
+        v = warp_max_u64(v);
+        last = (int)(0xffffffffu - (unsigned)(v & 0xffffffffull));
+        if (tid == 0) sel[k] = last;
+    }
+    __syncthreads();
+    for (int k = tid; k < n_drop; k += T) flag[sel[k]] = 1;
+    __syncthreads();
+    if (wid == 0) {                                    // :395-408 ascending complement, truncated to n_keep
+        const unsigned lt = (1u << lane) - 1u;
+        int cnt = 0;
+        for (int i0 = 0; i0 < keep1 && cnt < n_keep; i0 += 32) {
+            const int i = i0 + lane;
+            const bool kf = i < keep1 && !flag[i];
+            const unsigned mask = __ballot_sync(FULL, kf);
+            const int slot = cnt + __popc(mask & lt);
+            if (kf && slot < n_keep) kl[slot] = i;
+            cnt += __popc(mask);
+        }
+    }
+    __syncthreads();
+    for (int s = tid; s < n_keep; s += T) {            // :414-416
+        const int i = kl[s];
+        kept_src[(size_t)b * n_keep + s] = order[i];
+        float* kc = kept_centres + ((size_t)b * n_keep + s) * 3;
+        kc[0] = ux[i]; kc[1] = uy[i]; kc[2] = uz[i];
+    }
+    for (int e = tid; e < n_keep * K; e += T) {
+        const int s = e / K, k = e - s * K;
+        kept_idx[(size_t)b * n_keep * K + e] = __ldg(I + (size_t)order[kl[s]] * K + k);
+    }
+    for (int e = tid; e < n_drop * K; e += T) {        // :417-418
+        const int s = e / K, k = e - s * K;
+        drop_idx[(size_t)b * n_drop * K + e] = __ldg(I + (size_t)order[sel[s]] * K + k);
+    }
+    if (fps_sel != nullptr) for (int k = tid; k < n_drop; k += T) fps_sel[(size_t)b * n_drop + k] = sel[k];
+}
+
+}  // namespace pt
+
+using namespace pt;
+
+extern "C" size_t pt_minmax_ws_bytes(int B, int N) {
+    return (size_t)B * ceil_div(N, MM_POINTS_PER_BLOCK) * 6 * sizeof(float);
+}
+
+extern "C" int pt_minmax_centres(const float* points, int B, int N, int gs, const float* lin, float margin, float* mn,
+                                 float* mx, float* centres, void* ws, size_t ws_bytes, pt_stream_t stream) {
+    PT_REQUIRE(B > 0 && N > 0 && gs > 0, "pt_minmax_centres: B=%d N=%d gs=%d", B, N, gs);
+    PT_REQUIRE(points && lin && mn && mx && centres && ws, "pt_minmax_centres: null pointer");
+    if (ws_bytes < pt_minmax_ws_bytes(B, N)) { set_error("pt_minmax_centres: workspace %zu < %zu", ws_bytes, pt_minmax_ws_bytes(B, N)); return PT_ERR_WORKSPACE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nblk = ceil_div(N, MM_POINTS_PER_BLOCK), M = gs * gs * gs;
+    minmax_partial_kernel<<<dim3(nblk, B), MM_THREADS, 0, s>>>(points, N, (float*)ws);
+    PT_LAUNCH_CHECK();
+    centres_kernel<<<dim3(ceil_div(M, 256), B), 256, 0, s>>>((const float*)ws, nblk, gs, M, lin, margin, mn, mx, centres);
+    PT_LAUNCH_CHECK();
+    return PT_OK;
+}
+
+extern "C" int pt_ball_query_firstk(const float* centres, const float* points, int B, int M, int N, int K, float radius,
+                                    int32_t* idx, int32_t* pad_counts, pt_stream_t stream) {
+    PT_REQUIRE(B > 0 && M > 0 && N > 0 && K > 0, "pt_ball_query_firstk: B=%d M=%d N=%d K=%d", B, M, N, K);
+    PT_REQUIRE(centres && points && idx, "pt_ball_query_firstk: null pointer");
+    ball_query_kernel<<<dim3(ceil_div(M, BQ_WARPS), B), BQ_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        centres, points, M, N, K, radius * radius, idx, pad_counts);
+    PT_LAUNCH_CHECK();
+    return PT_OK;
+}
+
+static int mlp_grid(int clusters) {
+    // ~4 clusters per warp amortises the per-warp weight load; cap at a few waves of the 148 SMs
+    int blocks = ceil_div(ceil_div(clusters, 4), MLP_WARPS);
+    return blocks < 1 ? 1 : (blocks > 148 * 16 ? 148 * 16 : blocks);
+}
+
+extern "C" int pt_offset_net_fused(const float* points, const int32_t* idx, const float* centres0, const float* mn,
+                                   const float* mx, const float* conv_w, const float* conv_b, const float* bn_scale,
+                                   const float* bn_shift, const float* map_w, int B, int M, int N, int K, int H,
+                                   float margin, float* centres_out, float* raw_offsets, pt_stream_t stream) {
+    PT_REQUIRE(H == MLP_H, "pt_offset_net_fused: hidden width %d unsupported (reference hard-wires 256, :31)", H);
+    PT_REQUIRE(B > 0 && M > 0 && N > 0 && K > 0, "pt_offset_net_fused: bad shape");
+    PT_REQUIRE(points && idx && centres0 && mn && mx && conv_w && conv_b && bn_scale && bn_shift && map_w && centres_out,
+               "pt_offset_net_fused: null pointer");
+    cluster_mlp_kernel<false><<<mlp_grid(B * M), MLP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        points, idx, centres0, mn, mx, conv_w, conv_b, bn_scale, bn_shift, map_w, B, M, N, K, margin, centres_out, raw_offsets);
+    PT_LAUNCH_CHECK();
+    return PT_OK;
+}
+
+extern "C" int pt_point_encoder_fused(const float* points, const int32_t* kept_idx, const float* kept_centres,
+                                      const float* conv_w, const float* conv_b, const float* bn_scale,
+                                      const float* bn_shift, int B, int n, int N, int K, int H, float* point_proxy,
+                                      pt_stream_t stream) {
+    PT_REQUIRE(H == MLP_H, "pt_point_encoder_fused: width %d unsupported (reference hard-wires 256, :110,:302)", H);
+    PT_REQUIRE(B > 0 && n > 0 && N > 0 && K > 0, "pt_point_encoder_fused: bad shape");
+    PT_REQUIRE(points && kept_idx && kept_centres && conv_w && conv_b && bn_scale && bn_shift && point_proxy,
+               "pt_point_encoder_fused: null pointer");
+    cluster_mlp_kernel<true><<<mlp_grid(B * n), MLP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        points, kept_idx, kept_centres, nullptr, nullptr, conv_w, conv_b, bn_scale, bn_shift, nullptr, B, n, N, K, 0.f,
+        point_proxy, nullptr);
+    PT_LAUNCH_CHECK();
+    return PT_OK;
+}
+
+extern "C" int pt_cluster_dropout(const float* centres, const int32_t* idx, int B, int M, int K, int keep1, int n_keep,
+                                  int32_t* kept_src, float* kept_centres, int32_t* kept_idx, int32_t* drop_idx,
+                                  int32_t* fps_sel, pt_stream_t stream) {
+    PT_REQUIRE(B > 0 && M > 0 && K > 0 && K < 65535, "pt_cluster_dropout: bad shape");
+    PT_REQUIRE(keep1 <= M && n_keep >= 1 && keep1 - n_keep >= 1,
+               "pt_cluster_dropout: need 1 <= n_keep < keep1 <= M (got keep1=%d n_keep=%d M=%d); the reference's FPS needs n_drop >= 1 (:390-393)",
+               keep1, n_keep, M);
+    PT_REQUIRE(keep1 <= 1024 * FPS_PER, "pt_cluster_dropout: keep1=%d > %d unsupported", keep1, 1024 * FPS_PER);
+    PT_REQUIRE(centres && idx && kept_src && kept_centres && kept_idx && drop_idx, "pt_cluster_dropout: null pointer");
+    const int n_drop = keep1 - n_keep;
+    const int T = keep1 <= 256 * FPS_PER ? 256 : 1024;
+    size_t smem = 64 * sizeof(unsigned long long) + (size_t)3 * keep1 * sizeof(float) +
+                  ((size_t)M + (K + 2) + n_drop + n_keep) * sizeof(int) + (size_t)M * sizeof(unsigned short) + keep1;
+    smem = align_up(smem, 16);
+    PT_REQUIRE(smem <= 227 * 1024, "pt_cluster_dropout: M=%d needs %zu B shared memory", M, smem);
+    if (smem > 48 * 1024) PT_CUDA_OK(cudaFuncSetAttribute(cluster_dropout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cluster_dropout_kernel<<<B, T, smem, (cudaStream_t)stream>>>(centres, idx, M, K, keep1, n_keep, kept_src, kept_centres,
+                                                                 kept_idx, drop_idx, fps_sel);
+    PT_LAUNCH_CHECK();
+    return PT_OK;
+}

@@ -1,0 +1,113 @@
+// S10-S12: per-cluster affine (:459-462), duplicate-resolving scatter (pt_replace :472-498) and point removal
+// (remove_points_by_index :501-525) fused into one mark pass + one ordered compaction over the N points.
+// The transformed coordinates are never materialised per (m,k): the winning slot of a point is resolved with
+// atomicMax on the flat index m*K+k (the pinned "last writer wins" rule) and the affine is applied while compacting,
+// because a valid slot's source coordinate is the point itself.  HBM-bound: ~12N read + 12N' write + 8N scratch / scene.
+#include "common.cuh"
+
+namespace pt {
+
+constexpr int SC_DROP = 0x7fffffff;
+constexpr int SC_BLOCK = 1024;
+
+__global__ void mark_kernel(const int32_t* __restrict__ kept_idx, const int32_t* __restrict__ drop_idx, int B, int N, int nK,
+                            int n_drop_entries, int* __restrict__ winner) {
+    const long long total_keep = (long long)B * nK, total = total_keep + (long long)B * n_drop_entries;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        if (i < total_keep) {
+            const int b = (int)(i / nK), e = (int)(i - (long long)b * nK);
+            const int id = __ldg(kept_idx + i);
+            if (id >= 0) atomicMax(winner + (size_t)b * N + id, e);
+        } else {
+            const long long k = i - total_keep;
+            const int b = (int)(k / n_drop_entries);
+            const int id = __ldg(drop_idx + k);
+            if (id >= 0) atomicMax(winner + (size_t)b * N + id, SC_DROP);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SC_BLOCK) count_kernel(const int* __restrict__ winner, int N, int* __restrict__ blockcnt) {
+    const int b = blockIdx.y, i = blockIdx.x * SC_BLOCK + threadIdx.x;
+    const bool keep = i < N && winner[(size_t)b * N + i] != SC_DROP;
+    const int c = __syncthreads_count(keep);
+    if (threadIdx.x == 0) blockcnt[(size_t)b * gridDim.x + blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(SC_BLOCK) compact_kernel(const float* __restrict__ points, const int* __restrict__ winner,
+                                                           const int* __restrict__ blockcnt, const float* __restrict__ centres,
+                                                           const float* __restrict__ transform, const float* __restrict__ translate,
+                                                           int N, int n, int K, float* __restrict__ out, int32_t* __restrict__ counts) {
+    __shared__ int warp_tot[SC_BLOCK / 32];
+    __shared__ int base_s;
+    const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (wid == 0) {                                   // exclusive prefix over the preceding blocks of this scene
+        int s = 0;
+        for (int j = lane; j < blk; j += 32) s += blockcnt[(size_t)b * nblk + j];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        if (lane == 0) base_s = s;
+    }
+    const int i = blk * SC_BLOCK + tid;
+    int w = SC_DROP;
+    if (i < N) w = winner[(size_t)b * N + i];
+    const bool keep = w != SC_DROP;
+    const unsigned mask = __ballot_sync(FULL, keep);
+    if (lane == 0) warp_tot[wid] = __popc(mask);
+    __syncthreads();
+    int off = base_s;
+    for (int j = 0; j < wid; ++j) off += warp_tot[j];
+    if (keep) {
+        const float* p = points + ((size_t)b * N + i) * 3;
+        float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+        if (w >= 0) {
+            const int m = w / K;
+            const float* T = transform + ((size_t)b * n + m) * 9;
+            const float* c = centres + ((size_t)b * n + m) * 3;
+            const float* t = translate + ((size_t)b * n + m) * 3;
+            const float cx = __ldg(c), cy = __ldg(c + 1), cz = __ldg(c + 2);
+            const float rx = __fsub_rn(x, cx), ry = __fsub_rn(y, cy), rz = __fsub_rn(z, cz);
+            // ((T @ rel) + centre) + translate (:462)
+            x = __fadd_rn(__fadd_rn(fmaf(__ldg(T + 2), rz, fmaf(__ldg(T + 1), ry, __fmul_rn(__ldg(T + 0), rx))), cx), __ldg(t));
+            y = __fadd_rn(__fadd_rn(fmaf(__ldg(T + 5), rz, fmaf(__ldg(T + 4), ry, __fmul_rn(__ldg(T + 3), rx))), cy), __ldg(t + 1));
+            z = __fadd_rn(__fadd_rn(fmaf(__ldg(T + 8), rz, fmaf(__ldg(T + 7), ry, __fmul_rn(__ldg(T + 6), rx))), cz), __ldg(t + 2));
+        }
+        float* o = out + ((size_t)b * N + off + __popc(mask & ((1u << lane) - 1u))) * 3;
+        o[0] = x; o[1] = y; o[2] = z;
+    }
+    if (blk == nblk - 1 && tid == SC_BLOCK - 1) counts[b] = off + __popc(mask);
+}
+
+}  // namespace pt
+
+using namespace pt;
+
+extern "C" size_t pt_scatter_ws_bytes(int B, int N) {
+    return align_up((size_t)B * N * sizeof(int), 256) + align_up((size_t)B * ceil_div(N, SC_BLOCK) * sizeof(int), 256);
+}
+
+extern "C" int pt_affine_scatter_compact(const float* points, const int32_t* kept_idx, const int32_t* drop_idx,
+                                         const float* kept_centres, const float* transform, const float* translate, int B,
+                                         int N, int n, int K, int n_drop_entries, float* out, int32_t* counts, void* ws,
+                                         size_t ws_bytes, pt_stream_t stream) {
+    PT_REQUIRE(points && kept_idx && drop_idx && kept_centres && transform && translate && out && counts && ws,
+               "pt_affine_scatter_compact: null pointer");
+    PT_REQUIRE(B > 0 && N > 0 && n > 0 && K > 0 && n_drop_entries >= 0 && (long long)n * K < SC_DROP,
+               "pt_affine_scatter_compact: bad shape");
+    if (ws_bytes < pt_scatter_ws_bytes(B, N)) { set_error("pt_affine_scatter_compact: workspace %zu < %zu", ws_bytes, pt_scatter_ws_bytes(B, N)); return PT_ERR_WORKSPACE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int* winner = (int*)ws;
+    int* blockcnt = (int*)((char*)ws + align_up((size_t)B * N * sizeof(int), 256));
+    PT_CUDA_OK(cudaMemsetAsync(winner, 0xff, (size_t)B * N * sizeof(int), s));   // -1 = untouched
+    const long long total = (long long)B * ((long long)n * K + n_drop_entries);
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    mark_kernel<<<grid, 256, 0, s>>>(kept_idx, drop_idx, B, N, n * K, n_drop_entries, winner);
+    PT_LAUNCH_CHECK();
+    const int nblk = ceil_div(N, SC_BLOCK);
+    count_kernel<<<dim3(nblk, B), SC_BLOCK, 0, s>>>(winner, N, blockcnt);
+    PT_LAUNCH_CHECK();
+    compact_kernel<<<dim3(nblk, B), SC_BLOCK, 0, s>>>(points, winner, blockcnt, kept_centres, transform, translate, N, n, K, out, counts);
+    PT_LAUNCH_CHECK();
+    return PT_OK;
+}

@@ -1,0 +1,322 @@
+"""Drop-in for the reference's ``ProxyTransformationNormReverse``
+(embodiedscan/models/necks/preshape_norm_reverse_drop.py:280-469).
+
+Same registry name, constructor signature, ``forward(points, text_dict, img_feat)`` contract and ``state_dict`` keys
+(released checkpoints load with ``strict=True``); the forward pass itself runs entirely in the sm_100a kernels behind
+``include/pt_preshape.h`` — the sub-modules below are parameter containers that mirror the reference's key layout and
+are never called.  Eval/no-grad only: training mode (BN batch statistics, dropout, autograd through the gathers) is
+out of scope and raises.
+
+Algorithmic differences from the reference, all output-preserving:
+  * only the LAST block of ``textformer`` / ``imgformer`` is evaluated — every block is fed ``point_proxy`` and only the
+    last iteration's result is used (:441-443, :450-452);
+  * ``get_img_proxy`` is evaluated in single-query form (only token 0 of the attention pool survives, :177);
+  * ``argsort`` ties (:378) and duplicate scatter destinations (:495) follow the pinned rules of SURVEY.md §8c
+    (stable order; largest flat (m,k) wins) where the reference's own result depends on thread scheduling.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..registry import MODELS
+
+_BN_EPS = 1e-5
+
+
+# --------------------------------------------------------------------------- parameter containers (state_dict layout)
+class _ConvBnRelu(nn.Sequential):
+    def __init__(self, cin: int, cout: int):
+        super().__init__(nn.Conv2d(cin, cout, 1), nn.BatchNorm2d(cout), nn.ReLU())
+
+
+class _OffsetNetworkParams(nn.Module):                       # :69-77
+    def __init__(self, in_features: int = 6, hidden_features: int = 256):
+        super().__init__()
+        self.mlp = _ConvBnRelu(in_features, hidden_features)
+        self.channel_mapper = nn.Conv1d(hidden_features, 3, kernel_size=1, bias=False)
+
+
+class _DeformClusterParams(nn.Module):                       # :22-31 (radius=3, margin=4, hidden=256 are its defaults)
+    def __init__(self):
+        super().__init__()
+        self.get_offsets = _OffsetNetworkParams(6, 256)
+
+
+class _PointNetParams(nn.Module):                            # :109-116
+    def __init__(self):
+        super().__init__()
+        self.mlp = _ConvBnRelu(6, 256)
+
+
+class _AttnPoolParams(nn.Module):                            # :144-152
+    def __init__(self, spacial_dim: int, embed_dim: int):
+        super().__init__()
+        self.positional_embedding = nn.Parameter(torch.randn(spacial_dim ** 2 + 1, embed_dim) / embed_dim ** 0.5)
+        self.k_proj = nn.Linear(embed_dim, embed_dim)
+        self.q_proj = nn.Linear(embed_dim, embed_dim)
+        self.v_proj = nn.Linear(embed_dim, embed_dim)
+        self.c_proj = nn.Linear(embed_dim, embed_dim)
+
+
+class _ProxyAttentionParams(nn.Module):                      # :179-204
+    def __init__(self, dim: int, n_tokens: int, qkv_bias: bool):
+        super().__init__()
+        s = int(dim ** 0.5)
+        self.pb_bias = nn.Parameter(torch.zeros(1, n_tokens, 4, 4))
+        self.pc_bias = nn.Parameter(torch.zeros(1, n_tokens, s, 1))
+        self.pr_bias = nn.Parameter(torch.zeros(1, n_tokens, 1, s))
+        for p in (self.pb_bias, self.pc_bias, self.pr_bias):
+            nn.init.trunc_normal_(p, std=0.02)
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proxy_proj = nn.Linear(dim, dim)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _MlpParams(nn.Module):                                 # timm.models.layers.Mlp key layout (fc1 / fc2)
+    def __init__(self, dim: int, hidden: int):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class _ProxyBlockParams(nn.Module):                          # :259-271
+    def __init__(self, dim: int, n_tokens: int, mlp_ratio: float, qkv_bias: bool, norm_layer):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.attn = _ProxyAttentionParams(dim, n_tokens, qkv_bias)
+        self.norm2 = norm_layer(dim)
+        self.mlp = _MlpParams(dim, int(dim * mlp_ratio))
+
+
+def _bn_affine(bn: nn.modules.batchnorm._BatchNorm):
+    """Eval-mode BatchNorm as y = x*scale + shift, computed like ATen's CPU kernel (invstd*weight; bias - mean*alpha)."""
+    invstd = 1.0 / torch.sqrt(bn.running_var.float() + bn.eps)
+    scale = invstd * bn.weight.float()
+    shift = bn.bias.float() - bn.running_mean.float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+@MODELS.register_module()
+class ProxyTransformationNormReverse(nn.Module):
+    """See module docstring.  Constructor mirrors :282-285 (including the reference's spelling of ``*_radio``)."""
+
+    def __init__(self, embed_dim=256, num_heads=8, n_points=100000, grid_size=4, text_blocks=1, img_blocks=1,
+                 dynamic_drop_radio=0.8, mlp_radio=4, qkv_bias=False, drop_rate=0.2, attn_drop_rate=0.2,
+                 drop_path_rate=0.2, act_layer=nn.GELU, norm_layer=nn.LayerNorm, num_sub=30, drop_radio=0.2,
+                 input_dim=512, img_spacial_dim=15):
+        super().__init__()
+        if act_layer is not nn.GELU or norm_layer is not nn.LayerNorm:
+            raise NotImplementedError("the CUDA path implements the shipped configuration: GELU(erf) + LayerNorm")
+        if qkv_bias:
+            raise NotImplementedError("qkv_bias=True is not used by any shipped config and is not implemented")
+        if embed_dim != 256:
+            # the reference hard-wires 256 in SimplifiedPointNet()/OffsetNetwork (:31,:110,:302): any other embed_dim
+            # fails at norm1 there as well
+            raise ValueError("embed_dim must be 256 (reference :302 hard-wires the point encoder width)")
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.grid_size = grid_size
+        self.num_cluster = grid_size ** 3
+        self.num_sub = num_sub or n_points // self.num_cluster      # :291
+        self.input_dim = input_dim
+        self.img_spacial_dim = img_spacial_dim
+        self.drop_radio = drop_radio
+        self.text_blocks = text_blocks
+        self.img_blocks = img_blocks
+        self.dynamic_drop_radio = dynamic_drop_radio
+        self.mlp_radio = mlp_radio
+        # rates only matter in training mode, which this implementation does not run
+        self.drop_rate, self.attn_drop_rate, self.drop_path_rate = drop_rate, attn_drop_rate, drop_path_rate
+        self.real_cluster_num = int(self.num_cluster * (1 - dynamic_drop_radio))      # :195, :389
+        self.keep1 = self.num_cluster - int(self.num_cluster * 0.3)                    # :374-376, empty_drop=0.3
+        if text_blocks < 1 or img_blocks < 1:
+            raise ValueError("text_blocks and img_blocks must be >= 1 (the reference's forward needs one iteration)")
+
+        self.get_deformable_cluster = _DeformClusterParams()
+        self.simple_encoder = _PointNetParams()
+        self.channel_mapper = nn.Conv2d(input_dim, embed_dim, kernel_size=1)
+        self.attn_pool2d = _AttnPoolParams(img_spacial_dim, embed_dim)
+        self.norm_img = nn.LayerNorm(embed_dim)
+        n = self.real_cluster_num
+        self.textformer = nn.ModuleList([_ProxyBlockParams(embed_dim, n, mlp_radio, qkv_bias, norm_layer) for _ in range(text_blocks)])
+        self.text_norm = nn.ModuleList([norm_layer(embed_dim) for _ in range(text_blocks)])
+        self.imgformer = nn.ModuleList([_ProxyBlockParams(embed_dim, n, mlp_radio, qkv_bias, norm_layer) for _ in range(img_blocks)])
+        self.img_norm = nn.ModuleList([norm_layer(embed_dim) for _ in range(img_blocks)])
+        self.text_trans = nn.Linear(embed_dim, 3)
+        self.img_trans = nn.Linear(embed_dim, 9)
+        self.text_trans_norm = nn.BatchNorm1d(3)
+        self.img_trans_norm = nn.BatchNorm1d(9)
+
+        self._packed: Optional[dict] = None
+        self._packed_key = None
+        self._ws: Dict[str, torch.Tensor] = {}
+        self.use_tensor_cores = True     # 3xBF16 tcgen05 GEMMs for the dense layers (falls back per shape inside the C side)
+
+    # ------------------------------------------------------------------ reference helper API (same names, :332-350)
+    def get_text_proxy(self, text_dict):
+        return text_dict.values()
+
+    def get_img_proxy(self, img_feat: torch.Tensor) -> torch.Tensor:
+        w = self._weights(img_feat.device)
+        return ops.img_attnpool(img_feat.contiguous(), w["img"], self.num_heads, params=w["img_struct"])
+
+    def get_point_proxy(self, center, cluster_idx, points):
+        w = self._weights(points.device)
+        return ops.point_encoder(points, cluster_idx, center, w["encoder"])
+
+    # ------------------------------------------------------------------ weight packing
+    def _weight_key(self, device):
+        return (str(device), self.use_tensor_cores) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def refresh_weights(self):
+        """Force re-packing (folded BN, position-bias tables, folded image-pool projections) on the next forward."""
+        self._packed = None
+
+    def _weights(self, device) -> dict:
+        key = self._weight_key(device)
+        if self._packed is not None and self._packed_key == key:
+            return self._packed
+        f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+        with torch.no_grad():
+            def conv_bn(seq):
+                sc, sh = _bn_affine(seq[1])
+                return dict(conv_w=f32(seq[0].weight.reshape(seq[0].weight.shape[0], -1)), conv_b=f32(seq[0].bias),
+                            bn_scale=f32(sc), bn_shift=f32(sh))
+
+            off = conv_bn(self.get_deformable_cluster.get_offsets.mlp)
+            off["map_w"] = f32(self.get_deformable_cluster.get_offsets.channel_mapper.weight.reshape(3, -1))
+            enc = conv_bn(self.simple_encoder.mlp)
+
+            def block(blk: _ProxyBlockParams, out_norm: nn.LayerNorm):
+                a = blk.attn
+                d = dict(ln1_w=f32(blk.norm1.weight), ln1_b=f32(blk.norm1.bias),
+                         pos_bias=ops.position_bias(f32(a.pb_bias), f32(a.pc_bias), f32(a.pr_bias)),
+                         qkv_w=f32(a.qkv.weight), pp_w=f32(a.proxy_proj.weight), pp_b=f32(a.proxy_proj.bias),
+                         proj_w=f32(a.proj.weight), proj_b=f32(a.proj.bias), ln2_w=f32(blk.norm2.weight),
+                         ln2_b=f32(blk.norm2.bias), fc1_w=f32(blk.mlp.fc1.weight), fc1_b=f32(blk.mlp.fc1.bias),
+                         fc2_w=f32(blk.mlp.fc2.weight), fc2_b=f32(blk.mlp.fc2.bias), lno_w=f32(out_norm.weight),
+                         lno_b=f32(out_norm.bias))
+                if self.use_tensor_cores:
+                    for k in ("qkv_w", "proj_w", "fc1_w", "fc2_w", "pp_w"):
+                        d[k + "_split"] = ops.split_bf16(d[k])
+                return d
+
+            tb = block(self.textformer[-1], self.text_norm[-1])      # only the last block of each stack is live
+            ib = block(self.imgformer[-1], self.img_norm[-1])
+
+            def head(lin: nn.Linear, bn: nn.BatchNorm1d):
+                sc, sh = _bn_affine(bn)
+                return dict(lin_w=f32(lin.weight), lin_b=f32(lin.bias), bn_scale=f32(sc), bn_shift=f32(sh))
+
+            img = self._fold_img_pool(device)
+        self._packed = dict(offset=off, encoder=enc, text=tb, text_struct=ops.make_block_params(tb), imgb=ib,
+                            imgb_struct=ops.make_block_params(ib), text_head=head(self.text_trans, self.text_trans_norm),
+                            img_head=head(self.img_trans, self.img_trans_norm), img=img, img_struct=ops.make_img_params(img),
+                            lin=ops.linspace01(self.grid_size, device))
+        self._packed_key = key
+        return self._packed
+
+    def _fold_img_pool(self, device) -> dict:
+        """Single-query folding of channel_mapper + AttentionPool2d (:154-177, :338-340); fp64 on the device, once per
+        weight load.  See csrc/imgpool.cu for the algebra."""
+        d64 = lambda t: t.detach().to(device=device, dtype=torch.float64)
+        c, C, heads = self.embed_dim, self.input_dim, self.num_heads
+        hd = c // heads
+        ap = self.attn_pool2d
+        Wc, bc = d64(self.channel_mapper.weight).reshape(c, C), d64(self.channel_mapper.bias)
+        pos = d64(ap.positional_embedding)
+        Wq, bq, Wk, Wv, bv = d64(ap.q_proj.weight), d64(ap.q_proj.bias), d64(ap.k_proj.weight), d64(ap.v_proj.weight), d64(ap.v_proj.bias)
+        T = pos.shape[0]
+        Tp = (T + 3) // 4 * 4
+        posb = pos + bc
+        g_k = torch.zeros(Tp, c, dtype=torch.float64, device=device)
+        g_k[:T] = posb @ Wk.T                                              # k-bias dropped: constant over tokens
+        h_v = torch.zeros(heads, hd, Tp, dtype=torch.float64, device=device)
+        h_v[:, :, :T] = (posb @ Wv.T + bv).T.reshape(heads, hd, T)
+        w_kc = (Wk @ Wc).reshape(heads, hd, C).transpose(1, 2)             # (heads, C, hd): NT operand per head
+        f = lambda t: t.to(torch.float32).contiguous()
+        return dict(w_qc=f(Wq @ Wc), q0=f(Wq @ posb[0] + bq), w_kc=f(w_kc), g_k=f(g_k), w_vc=f(Wv @ Wc), h_v=f(h_v),
+                    cproj_w=f(d64(ap.c_proj.weight)), cproj_b=f(d64(ap.c_proj.bias)), ln_w=f(d64(self.norm_img.weight)),
+                    ln_b=f(d64(self.norm_img.bias)))
+
+    # ------------------------------------------------------------------ forward (:424-469)
+    @torch.no_grad()
+    def forward(self, points: Sequence[torch.Tensor], text_dict, img_feat: torch.Tensor, *, img_proxy: Optional[torch.Tensor] = None,
+                trace: Optional[dict] = None) -> List[torch.Tensor]:
+        """points: list of B (N,3) fp32 tensors (equal N); text_dict: values() = (text_feats (B,L,c), mask (B,L) bool);
+        img_feat: (B,V,input_dim,H,W) fp32 or bf16.  Returns the list of (N'_b,3) tensors on the inputs' device.
+        Host tensors are accepted (pinned memory makes the copies asynchronous); results then come back on the host.
+        ``img_proxy`` (B,V,c) may replace ``img_feat`` (core region of the benchmark); ``trace`` collects intermediates."""
+        if self.training:
+            raise NotImplementedError("ProxyTransformationNormReverse (B200): eval() only — training mode is out of scope")
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("ProxyTransformationNormReverse (B200) has no CPU path: move the module to a CUDA device")
+        in_dev = points[0].device
+        P = self._stack_points(points, dev)                                                     # :426-427
+        text, mask = tuple(self.get_text_proxy(text_dict))                                      # :440
+        text = text.to(dev, torch.float32, non_blocking=True).contiguous()
+        mask = mask.to(dev, non_blocking=True).to(torch.uint8).contiguous() if mask is not None else None
+        if img_proxy is None:
+            img_feat = img_feat.to(dev, non_blocking=True)
+            if img_feat.dtype not in (torch.float32, torch.bfloat16):
+                img_feat = img_feat.float()
+            img_feat = img_feat.contiguous()
+        else:
+            img_proxy = img_proxy.to(dev, torch.float32, non_blocking=True).contiguous()
+        out, counts = self.forward_packed(P, text, mask, img_feat, img_proxy=img_proxy, trace=trace)
+        cnt = counts.cpu().tolist()                                                             # the one D2H sync
+        res = [out[b, :cnt[b]] for b in range(len(cnt))]
+        if in_dev.type != "cuda":
+            res = [r.to(in_dev) for r in res]
+        return res
+
+    @staticmethod
+    def _stack_points(points, dev) -> torch.Tensor:
+        if isinstance(points, torch.Tensor):          # already (B,N,3)
+            P = points
+        else:
+            n0 = points[0].shape
+            for p in points:
+                if p.shape != n0:
+                    raise RuntimeError(f"all scenes must have the same number of points (got {tuple(p.shape)} vs {tuple(n0)})")
+            P = torch.stack([p.to(dev, non_blocking=True) for p in points], 0)
+        if P.dim() != 3 or P.shape[-1] != 3:
+            raise ValueError(f"points must be (N,3) xyz per scene, got {tuple(P.shape)}")
+        return P.to(dev, torch.float32, non_blocking=True).contiguous()
+
+    def forward_packed(self, P, text, mask, img_feat, *, img_proxy=None, trace=None):
+        """Device-resident form: P (B,N,3), text (B,L,c), mask (B,L) uint8|None, img_feat (B,V,C,H,W) ->
+        (out (B,N,3) packed per scene, counts (B,) int32), no host synchronisation."""
+        w = self._weights(P.device)
+        K, n = self.num_sub, self.real_cluster_num
+        # S1-S4 deformable clustering (:53-67)
+        mn, mx, c0 = ops.minmax_centres(P, self.grid_size, w["lin"])
+        idx1, _ = ops.ball_query(c0, P, K)
+        centres = ops.offset_net(P, idx1, c0, mn, mx, w["offset"])
+        idx2, _ = ops.ball_query(centres, P, K)
+        # S5 dropout (:352-420)
+        kept_src, kc, kidx, drop_idx, fps = ops.cluster_dropout(centres, idx2, self.keep1, n)
+        # S6 point proxies (:437)
+        pp = ops.point_encoder(P, kidx, kc, w["encoder"])
+        # S7/S8 text branch -> translate (:440-446)
+        tg = ops.proxy_block(pp, text, mask, w["text"], self.num_heads, params=w["text_struct"])
+        th = w["text_head"]
+        translate = ops.heads(tg, th["lin_w"], th["lin_b"], th["bn_scale"], th["bn_shift"])
+        # S9 image proxies (:449) and image branch -> transform (:450-455)
+        if img_proxy is None:
+            img_proxy = ops.img_attnpool(img_feat, w["img"], self.num_heads, params=w["img_struct"])
+        ig = ops.proxy_block(pp, img_proxy, None, w["imgb"], self.num_heads, params=w["imgb_struct"])
+        ih = w["img_head"]
+        transform = ops.heads(ig, ih["lin_w"], ih["lin_b"], ih["bn_scale"], ih["bn_shift"])
+        # S10-S12 (:459-467)
+        out, counts = ops.affine_scatter_compact(P, kidx, drop_idx, kc, transform, translate)
+        if trace is not None:
+            trace.update(mn=mn, mx=mx, c0=c0, idx1=idx1, centres=centres, idx2=idx2, kept_src=kept_src, kept_centres=kc,
+                         kept_idx=kidx, drop_idx=drop_idx, fps=fps, point_proxy=pp, text_guide=tg, translate=translate,
+                         img_proxy=img_proxy, img_guide=ig, transform=transform, counts=counts, out=out)
+        return out, counts

@@ -1,0 +1,267 @@
+"""Stage-level Python entry points over the C ABI (include/pt_preshape.h).
+
+Each function takes CUDA torch tensors (torch is used for device memory and the current stream only), checks
+dtype/contiguity, and launches the corresponding sm_100a kernels.  No function here has a CPU path.
+Reference stages: embodiedscan/models/necks/preshape_norm_reverse_drop.py (":line" in the C header).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ImgPoolParams, ProxyBlockParams, check
+
+RADIUS = 3.0   # DeformablePointCluster(radius=3)  (:23)
+MARGIN = 4.0   # DeformablePointCluster(margin=4)  (:23)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: Optional[torch.Tensor], dtype, name: str, optional: bool = False):
+    if t is None:
+        if optional:
+            return None
+        raise ValueError(f"{name} is required")
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (the preshape path has no CPU implementation)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t.data_ptr()
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def linspace01(gs: int, device) -> torch.Tensor:
+    """torch.linspace(0, 1, gs) exactly as the reference builds it (:41), fp32."""
+    return torch.linspace(0, 1, gs, dtype=torch.float32).to(device)
+
+
+def minmax_centres(points: torch.Tensor, gs: int, lin: Optional[torch.Tensor] = None, margin: float = MARGIN):
+    """S1 (:33-51).  points (B,N,3) -> (mn (B,3), mx (B,3), centres (B,gs^3,3))."""
+    L = _lib.load()
+    B, N, _ = points.shape
+    dev = points.device
+    lin = linspace01(gs, dev) if lin is None else lin
+    mn = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    mx = torch.empty_like(mn)
+    centres = torch.empty(B, gs ** 3, 3, dtype=torch.float32, device=dev)
+    ws = _ws(L.pt_minmax_ws_bytes(B, N), dev)
+    check(L.pt_minmax_centres(_chk(points, torch.float32, "points"), B, N, gs, _chk(lin, torch.float32, "lin"), margin,
+                              mn.data_ptr(), mx.data_ptr(), centres.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+          "pt_minmax_centres")
+    return mn, mx, centres
+
+
+def ball_query(centres: torch.Tensor, points: torch.Tensor, K: int, radius: float = RADIUS):
+    """S2/S4 (:56,:65).  -> idx (B,M,K) int32 (-1 padded), pad_counts (B,M) int32."""
+    L = _lib.load()
+    B, M, _ = centres.shape
+    N = points.shape[1]
+    idx = torch.empty(B, M, K, dtype=torch.int32, device=points.device)
+    pc = torch.empty(B, M, dtype=torch.int32, device=points.device)
+    check(L.pt_ball_query_firstk(_chk(centres, torch.float32, "centres"), _chk(points, torch.float32, "points"), B, M, N, K,
+                                 radius, idx.data_ptr(), pc.data_ptr(), _stream()), "pt_ball_query_firstk")
+    return idx, pc
+
+
+def offset_net(points, idx, centres0, mn, mx, w: Dict[str, torch.Tensor], margin: float = MARGIN, want_raw: bool = False):
+    """S3 (:87-107, :58-62).  w: conv_w (256,6), conv_b, bn_scale, bn_shift (256), map_w (3,256)."""
+    L = _lib.load()
+    B, M, K = idx.shape
+    N = points.shape[1]
+    out = torch.empty(B, M, 3, dtype=torch.float32, device=points.device)
+    raw = torch.empty_like(out) if want_raw else None
+    f = torch.float32
+    check(L.pt_offset_net_fused(_chk(points, f, "points"), _chk(idx, torch.int32, "idx"), _chk(centres0, f, "centres0"),
+                                _chk(mn, f, "mn"), _chk(mx, f, "mx"), _chk(w["conv_w"], f, "conv_w"), _chk(w["conv_b"], f, "conv_b"),
+                                _chk(w["bn_scale"], f, "bn_scale"), _chk(w["bn_shift"], f, "bn_shift"), _chk(w["map_w"], f, "map_w"),
+                                B, M, N, K, w["conv_w"].shape[0], margin, out.data_ptr(), raw.data_ptr() if want_raw else None,
+                                _stream()), "pt_offset_net_fused")
+    return (out, raw) if want_raw else out
+
+
+def cluster_dropout(centres, idx, keep1: int, n_keep: int):
+    """S5 (:352-420).  -> kept_src (B,n), kept_centres (B,n,3), kept_idx (B,n,K), drop_idx (B,n_drop*K), fps_sel (B,n_drop)."""
+    L = _lib.load()
+    B, M, K = idx.shape
+    dev = idx.device
+    n_drop = keep1 - n_keep
+    kept_src = torch.empty(B, n_keep, dtype=torch.int32, device=dev)
+    kept_centres = torch.empty(B, n_keep, 3, dtype=torch.float32, device=dev)
+    kept_idx = torch.empty(B, n_keep, K, dtype=torch.int32, device=dev)
+    drop_idx = torch.empty(B, max(n_drop, 0) * K, dtype=torch.int32, device=dev)
+    fps_sel = torch.empty(B, max(n_drop, 0), dtype=torch.int32, device=dev)
+    check(L.pt_cluster_dropout(_chk(centres, torch.float32, "centres"), _chk(idx, torch.int32, "idx"), B, M, K, keep1, n_keep,
+                               kept_src.data_ptr(), kept_centres.data_ptr(), kept_idx.data_ptr(), drop_idx.data_ptr(),
+                               fps_sel.data_ptr(), _stream()), "pt_cluster_dropout")
+    return kept_src, kept_centres, kept_idx, drop_idx, fps_sel
+
+
+def point_encoder(points, kept_idx, kept_centres, w: Dict[str, torch.Tensor]):
+    """S6 (:126-142) -> point_proxy (B,n,256)."""
+    L = _lib.load()
+    B, n, K = kept_idx.shape
+    N = points.shape[1]
+    H = w["conv_w"].shape[0]
+    out = torch.empty(B, n, H, dtype=torch.float32, device=points.device)
+    f = torch.float32
+    check(L.pt_point_encoder_fused(_chk(points, f, "points"), _chk(kept_idx, torch.int32, "kept_idx"),
+                                   _chk(kept_centres, f, "kept_centres"), _chk(w["conv_w"], f, "conv_w"),
+                                   _chk(w["conv_b"], f, "conv_b"), _chk(w["bn_scale"], f, "bn_scale"),
+                                   _chk(w["bn_shift"], f, "bn_shift"), B, n, N, K, H, out.data_ptr(), _stream()),
+          "pt_point_encoder_fused")
+    return out
+
+
+_BLOCK_F32 = ("ln1_w", "ln1_b", "pos_bias", "qkv_w", "pp_w", "pp_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b",
+              "fc2_w", "fc2_b", "lno_w", "lno_b")
+_BLOCK_SPLIT = ("qkv_w_split", "proj_w_split", "fc1_w_split", "fc2_w_split", "pp_w_split")
+
+
+def make_block_params(w: Dict[str, torch.Tensor]) -> ProxyBlockParams:
+    p = ProxyBlockParams()
+    for k in _BLOCK_F32:
+        setattr(p, k, _chk(w[k], torch.float32, k))
+    for k in _BLOCK_SPLIT:
+        t = w.get(k)
+        setattr(p, k, _chk(t, torch.bfloat16, k) if t is not None else None)
+    return p
+
+
+def proxy_block(x, proxy, mask, w: Dict[str, torch.Tensor], heads: int, ws: Optional[torch.Tensor] = None,
+                params: Optional[ProxyBlockParams] = None, out: Optional[torch.Tensor] = None):
+    """S7 (:206-276 + trailing norm :443/:452).  x (B,n,c), proxy (B,l,c), mask (B,l) bool/uint8 or None."""
+    L = _lib.load()
+    B, n, c = x.shape
+    l = proxy.shape[1]
+    hidden = w["fc1_w"].shape[0]
+    p = params if params is not None else make_block_params(w)
+    if mask is not None and mask.dtype == torch.bool:
+        mask = mask.to(torch.uint8)
+    need = L.pt_proxy_block_ws_bytes(B, n, l, c, hidden)
+    if ws is None or ws.numel() < need:
+        ws = _ws(need, x.device)
+    out = torch.empty_like(x) if out is None else out
+    check(L.pt_proxy_block_fused(_chk(x, torch.float32, "x"), _chk(proxy, torch.float32, "proxy"),
+                                 _chk(mask, torch.uint8, "mask", optional=True), ctypes.byref(p), B, n, l, c, heads, hidden,
+                                 out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "pt_proxy_block_fused")
+    return out
+
+
+def position_bias(pb, pc, pr):
+    """:212-215.  pb (1,n,4,4), pc (1,n,s,1), pr (1,n,1,s) -> (n, s*s)."""
+    L = _lib.load()
+    n, s = pb.shape[1], pc.shape[2]
+    out = torch.empty(n, s * s, dtype=torch.float32, device=pb.device)
+    f = torch.float32
+    check(L.pt_position_bias(_chk(pb.contiguous(), f, "pb"), _chk(pc.contiguous(), f, "pc"), _chk(pr.contiguous(), f, "pr"),
+                             n, s, out.data_ptr(), _stream()), "pt_position_bias")
+    return out
+
+
+def heads(guide, lin_w, lin_b, bn_scale, bn_shift):
+    """S8 (:445-446, :454-455).  guide (..., c) -> (..., o)."""
+    L = _lib.load()
+    c = guide.shape[-1]
+    rows = guide.numel() // c
+    o = lin_w.shape[0]
+    out = torch.empty(*guide.shape[:-1], o, dtype=torch.float32, device=guide.device)
+    f = torch.float32
+    check(L.pt_heads(_chk(guide, f, "guide"), _chk(lin_w, f, "lin_w"), _chk(lin_b, f, "lin_b"), _chk(bn_scale, f, "bn_scale"),
+                     _chk(bn_shift, f, "bn_shift"), rows, c, o, out.data_ptr(), _stream()), "pt_heads")
+    return out
+
+
+_IMG_KEYS = ("w_qc", "q0", "w_kc", "g_k", "w_vc", "h_v", "cproj_w", "cproj_b", "ln_w", "ln_b")
+
+
+def make_img_params(w: Dict[str, torch.Tensor]) -> ImgPoolParams:
+    p = ImgPoolParams()
+    for k in _IMG_KEYS:
+        setattr(p, k, _chk(w[k], torch.float32, k))
+    return p
+
+
+def img_attnpool(img_feat, w: Dict[str, torch.Tensor], heads: int, ws: Optional[torch.Tensor] = None,
+                 params: Optional[ImgPoolParams] = None):
+    """S9 (:335-342, :154-177).  img_feat (B,V,C,H,W) fp32/bf16 -> (B,V,c)."""
+    L = _lib.load()
+    B, V, C, H, W = img_feat.shape
+    c = w["cproj_w"].shape[0]
+    if img_feat.dtype == torch.float32:
+        dt = _lib.PT_DTYPE_F32
+    elif img_feat.dtype == torch.bfloat16:
+        dt = _lib.PT_DTYPE_BF16
+    else:
+        raise ValueError(f"img_feat must be fp32 or bf16, got {img_feat.dtype}")
+    p = params if params is not None else make_img_params(w)
+    need = L.pt_img_attnpool_ws_bytes(B * V, C, H * W, c, heads)
+    if ws is None or ws.numel() < need:
+        ws = _ws(need, img_feat.device)
+    out = torch.empty(B, V, c, dtype=torch.float32, device=img_feat.device)
+    check(L.pt_img_attnpool(_chk(img_feat, img_feat.dtype, "img_feat"), dt, ctypes.byref(p), B * V, C, H * W, c, heads,
+                            out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "pt_img_attnpool")
+    return out
+
+
+def affine_scatter_compact(points, kept_idx, drop_idx, kept_centres, transform, translate, ws: Optional[torch.Tensor] = None):
+    """S10-S12 (:459-525).  -> out (B,N,3) packed per scene, counts (B,) int32 (device)."""
+    L = _lib.load()
+    B, N, _ = points.shape
+    n, K = kept_idx.shape[1], kept_idx.shape[2]
+    nde = drop_idx.shape[1]
+    dev = points.device
+    out = torch.empty(B, N, 3, dtype=torch.float32, device=dev)
+    counts = torch.empty(B, dtype=torch.int32, device=dev)
+    need = L.pt_scatter_ws_bytes(B, N)
+    if ws is None or ws.numel() < need:
+        ws = _ws(need, dev)
+    f = torch.float32
+    check(L.pt_affine_scatter_compact(_chk(points, f, "points"), _chk(kept_idx, torch.int32, "kept_idx"),
+                                      _chk(drop_idx, torch.int32, "drop_idx"), _chk(kept_centres, f, "kept_centres"),
+                                      _chk(transform, f, "transform"), _chk(translate, f, "translate"), B, N, n, K, nde,
+                                      out.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+          "pt_affine_scatter_compact")
+    return out, counts
+
+
+def gemm_nt(A, W, bias=None, residual=None, act: int = 0, w_split=None):
+    """C = act(A @ W^T + bias) + residual.  w_split: (2,N,K) bf16 hi/lo planes -> tcgen05 3xBF16 path."""
+    L = _lib.load()
+    M, K = A.shape
+    N = W.shape[0] if W is not None else w_split.shape[1]
+    C = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    ws = _ws(L.pt_gemm_ws_bytes(M, N, K), A.device)
+    f = torch.float32
+    check(L.pt_gemm_nt(_chk(A, f, "A"), _chk(W, f, "W", optional=True), _chk(w_split, torch.bfloat16, "w_split", optional=True),
+                       _chk(bias, f, "bias", optional=True), _chk(residual, f, "residual", optional=True), act, M, N, K,
+                       C.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "pt_gemm_nt")
+    return C
+
+
+def split_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 (...) -> bf16 (2, ...) hi/lo planes, hi = bf16(x), lo = bf16(x - hi)."""
+    L = _lib.load()
+    out = torch.empty((2,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+    check(L.pt_split_bf16(_chk(x, torch.float32, "x"), x.numel(), out.data_ptr(), _stream()), "pt_split_bf16")
+    return out
+
+
+def layernorm(x, w, b, add=None):
+    L = _lib.load()
+    c = x.shape[-1]
+    rows = x.numel() // c
+    out = torch.empty_like(x)
+    f = torch.float32
+    check(L.pt_layernorm(_chk(x, f, "x"), _chk(w, f, "w"), _chk(b, f, "b"), _chk(add, f, "add", optional=True),
+                         add.shape[0] if add is not None else 1, rows, c, out.data_ptr(), _stream()), "pt_layernorm")
+    return out

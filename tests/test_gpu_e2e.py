@@ -1,0 +1,146 @@
+"""-m gpu: the drop-in module end to end (through the C ABI) against the oracle and the reference's golden outputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import preshape_oracle as po
+from proxytransformation_b200 import ops
+from proxytransformation_b200 import synthetic as syn
+from tests.golden_cases import CASES, LARGE_CASES, SMALL_CASES, load_case
+from tests.gpu_util import DEV, build_module, cu, np_, oracle_forward
+
+pytestmark = pytest.mark.gpu
+
+# scenes whose geometry is non-degenerate: the CUDA path must reproduce the reference's cluster indices exactly.
+# The others (collapsed grid / duplicated centres / room-sized box) have zero-margin FPS ties where a 1e-6 difference in
+# the offset network flips the arg-max even between two CPU thread counts; there every stage is
+# checked on its own inputs (chained check) and flips are tolerated.
+EXACT = {"c1_b2", "c1_origin", "c1_sparse", "c1_very_sparse", "c1_blocks3", "gs5_ragged", "c2_wide_b1", "c3_wide_b1"}
+
+
+def _chain_check(cfg, sd, P, tr):
+    """Every index-producing stage re-run by the oracle on the CUDA path's OWN inputs must agree bit for bit."""
+    centres = tr["centres"].cpu()
+    idx2, cl2 = po.ball_query(centres, P, cfg.num_sub)
+    assert np.array_equal(np_(tr["idx2"]), idx2.numpy()), "ball query #2 differs from the oracle on identical centres"
+    t2 = {}
+    po.cluster_dropout(cl2, centres, idx2, cfg.dynamic_drop_radio, t2)
+    assert np.array_equal(np_(tr["kept_idx"]), t2["kept_idx"].numpy())
+    assert np.array_equal(np_(tr["drop_idx"]), t2["drop_idx"].numpy())
+    assert np.array_equal(np_(tr["kept_centres"]), t2["kept_centres"].numpy())
+
+
+@pytest.mark.parametrize("name", SMALL_CASES + LARGE_CASES)
+@pytest.mark.parametrize("tc", [True], ids=["default"])
+def test_forward_matches_reference(name, tc):
+    cfg, sd, pts, text_dict, img, g = load_case(name)
+    m = build_module(cfg, sd, tensor_cores=tc)
+    tr = {}
+    out = m([p.to(DEV) for p in pts], {k: v.to(DEV) for k, v in text_dict.items()}, img.to(DEV), trace=tr)
+    P = torch.stack(pts, 0)
+    assert all(o.is_cuda and o.dtype == torch.float32 and o.shape[1] == 3 for o in out)
+    np.testing.assert_allclose(np_(tr["centres"]), g["centres"], rtol=0, atol=1e-5)
+    _chain_check(cfg, sd, P, tr)
+    same_idx = np.array_equal(np_(tr["kept_idx"]), g["kept_idx"]) and np.array_equal(np_(tr["drop_idx"]), g["drop_idx"])
+    if name in EXACT:
+        assert np.array_equal(np_(tr["idx2"]), g["idx2"]), "cluster indices differ from the reference"
+        assert same_idx, "kept/drop indices differ from the reference"
+    if same_idx:
+        # coordinates within 1e-4 of the reference (north_star tolerance)
+        assert [o.shape[0] for o in out] == g["out_counts"].tolist()
+        np.testing.assert_allclose(np_(tr["translate"]), g["translate"], rtol=0, atol=5e-5)
+        np.testing.assert_allclose(np_(tr["transform"]), g["transform"], rtol=0, atol=5e-5)
+        for b, o in enumerate(out):
+            o = np_(o)
+            if f"out_{b}" in g:
+                np.testing.assert_allclose(o, g[f"out_{b}"], rtol=0, atol=1e-4)
+            else:
+                np.testing.assert_allclose(o[:2048], g[f"out_head_{b}"], rtol=0, atol=1e-4)
+                np.testing.assert_allclose(o[::97], g[f"out_stride_{b}"], rtol=0, atol=1e-4)
+    else:
+        # degenerate geometry with flipped ties: the rest of the path is checked by the oracle on the CUDA path's clusters
+        kc, kidx = tr["kept_centres"].cpu(), tr["kept_idx"].cpu().long()
+        cl = po.masked_gather(P, kidx)
+        pp = po.point_encoder(sd, kc, cl)
+        np.testing.assert_allclose(np_(tr["point_proxy"]), pp.numpy(), rtol=0, atol=1e-5 + 2e-6 * pp.abs().max().item())
+        new = po.affine(tr["transform"].cpu(), tr["translate"].cpu(), kc, cl)
+        want = po.remove_points(po.scatter_last_writer_wins(P, kidx, new), tr["drop_idx"].cpu().long())
+        for o, w in zip(out, want):
+            assert o.shape == w.shape
+            np.testing.assert_allclose(np_(o), w.numpy(), rtol=0, atol=1e-4)
+
+
+def test_forward_accepts_host_tensors_and_returns_host_results():
+    cfg, sd, pts, text_dict, img, g = load_case("c1_b2")
+    m = build_module(cfg, sd)
+    out = m([p.pin_memory() for p in pts], text_dict, img.pin_memory())
+    assert all(not o.is_cuda for o in out)
+    for b, o in enumerate(out):
+        np.testing.assert_allclose(o.numpy(), g[f"out_{b}"], rtol=0, atol=1e-4)
+
+
+def test_forward_does_not_mutate_inputs_and_is_deterministic():
+    cfg, sd, pts, text_dict, img, g = load_case("gs5_ragged")
+    m = build_module(cfg, sd)
+    dpts = [p.to(DEV) for p in pts]
+    keep = [p.clone() for p in dpts]
+    td = {k: v.to(DEV) for k, v in text_dict.items()}
+    a = m(dpts, td, img.to(DEV))
+    b = m(dpts, td, img.to(DEV))
+    for p, q in zip(dpts, keep):
+        assert torch.equal(p, q)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
+def test_ragged_scene_sizes_raise_like_torch_cat():
+    cfg, sd, pts, text_dict, img, g = load_case("c1_b2")
+    m = build_module(cfg, sd)
+    with pytest.raises(RuntimeError):
+        m([pts[0].to(DEV), pts[1][:-5].to(DEV)], {k: v.to(DEV) for k, v in text_dict.items()}, img.to(DEV))
+
+
+def test_bf16_config_against_oracle_on_identically_rounded_inputs():
+    """BASELINE config 2 ("bf16"): weights and image features rounded to bf16 once and fed to both sides."""
+    cfg = syn.C2_WIDE.replace(n_views=12)
+    sd = syn.make_state_dict(cfg, 21, bf16_round=True)
+    pts, text_dict, img = syn.make_inputs(cfg, 1, first_scene=40, img_dtype=torch.bfloat16)
+    text_dict["text_feats"] = text_dict["text_feats"].to(torch.bfloat16).float()
+    want, wtr = oracle_forward(cfg, sd, pts, text_dict, img.float())
+    m = build_module(cfg, sd)
+    tr = {}
+    out = m([p.to(DEV) for p in pts], {k: v.to(DEV) for k, v in text_dict.items()}, img.to(DEV), trace=tr)
+    np.testing.assert_allclose(np_(tr["centres"]), wtr["centres"].numpy(), rtol=0, atol=1e-5)
+    assert np.array_equal(np_(tr["kept_idx"]), wtr["kept_idx"].numpy())
+    assert np.array_equal(np_(tr["drop_idx"]), wtr["drop_idx"].numpy())
+    for o, w in zip(out, want):
+        assert o.shape == w.shape
+        np.testing.assert_allclose(np_(o), w.numpy(), rtol=0, atol=1e-4)
+
+
+def test_full_size_batch_properties():
+    """C2 at full size, B=4 (no stored outputs): size-independent properties — untouched survivors are bit-identical to
+    the input in ascending order, counts = N - |unique dropped|, changed rows = points owned by kept clusters."""
+    cfg = syn.C2_WIDE.replace(n_views=4)
+    sd = syn.make_state_dict(cfg, 5)
+    B = 4
+    pts, text_dict, img = syn.make_inputs(cfg, B, first_scene=100)
+    m = build_module(cfg, sd)
+    tr = {}
+    out = m([p.to(DEV) for p in pts], {k: v.to(DEV) for k, v in text_dict.items()}, img.to(DEV), trace=tr)
+    for b in range(B):
+        P = pts[b]
+        drop = tr["drop_idx"][b].cpu().long()
+        drop = torch.unique(drop[drop >= 0])
+        kidx = tr["kept_idx"][b].cpu().long().reshape(-1)
+        touched = torch.unique(kidx[kidx >= 0])
+        assert out[b].shape[0] == cfg.n_points - drop.numel()
+        keep = torch.ones(cfg.n_points, dtype=torch.bool)
+        keep[drop] = False
+        surv = keep.nonzero(as_tuple=True)[0]
+        o = out[b].cpu()
+        is_touched = torch.zeros(cfg.n_points, dtype=torch.bool)
+        is_touched[touched] = True
+        untouched = ~is_touched[surv]
+        assert torch.equal(o[untouched], P[surv][untouched]), "untouched survivors must be copied bit-exactly, in order"
+        assert (o[~untouched] != P[surv][~untouched]).any(-1).float().mean() > 0.99

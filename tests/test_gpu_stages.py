@@ -1,0 +1,211 @@
+"""-m gpu: every CUDA stage behind the C ABI against the oracle / golden fixtures ON IDENTICAL INPUTS.
+Bars: bit-exact for indices, mins/maxes and the grid prior; stated absolute tolerances for floating point."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import preshape_oracle as po
+from proxytransformation_b200 import ops
+from proxytransformation_b200 import synthetic as syn
+from tests.golden_cases import CASES, LARGE_CASES, SMALL_CASES, load_case
+from tests.gpu_util import DEV, build_module, conv_bn_weights, cu, np_
+
+pytestmark = pytest.mark.gpu
+ALL = SMALL_CASES + LARGE_CASES
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_grid_prior_bit_exact(name):
+    cfg, sd, pts, *_ = load_case(name)
+    P = torch.stack(pts, 0)
+    c0, mn, mx = po.grid_prior(P, cfg.grid_size)
+    gmn, gmx, gc = ops.minmax_centres(cu(P), cfg.grid_size)
+    assert np.array_equal(np_(gmn), mn[:, 0].numpy()) and np.array_equal(np_(gmx), mx[:, 0].numpy())
+    assert np.array_equal(np_(gc), c0.numpy())
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_ball_query_bit_exact_on_golden_centres(name):
+    cfg, sd, pts, _, _, g = load_case(name)
+    P = torch.stack(pts, 0)
+    idx, pc = ops.ball_query(cu(g["centres"]), cu(P), cfg.num_sub)
+    assert np.array_equal(np_(idx), g["idx2"])
+    assert np.array_equal(np_(pc), (g["idx2"] == -1).sum(-1))
+
+
+@pytest.mark.parametrize("N,M,K,r,box", [(100000, 512, 30, 3.0, 24.0), (4097, 33, 30, 3.0, 6.0), (31, 5, 30, 3.0, 2.0),
+                                         (2048, 64, 7, 1.5, 10.0), (65536, 100, 64, 2.0, 16.0), (1, 3, 30, 3.0, 1.0)])
+def test_ball_query_random_vs_oracle(N, M, K, r, box):
+    g = torch.Generator().manual_seed(N + M)
+    p2 = torch.rand(2, N, 3, generator=g) * box
+    p1 = torch.rand(2, M, 3, generator=g) * box * 1.2 - 0.1 * box      # some centres outside the cloud: zero hits
+    want, _ = po.ball_query(p1, p2, K, r)
+    got, pc = ops.ball_query(cu(p1), cu(p2), K, r)
+    assert np.array_equal(np_(got), want.numpy())
+    assert np.array_equal(np_(pc), (want == -1).sum(-1).numpy())
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_offset_network_on_oracle_inputs(name):
+    """tolerance 1e-5 on the clamped centres (|offset| <= 4 m)."""
+    cfg, sd, pts, *_ = load_case(name)
+    P = torch.stack(pts, 0)
+    c0, mn, mx = po.grid_prior(P, cfg.grid_size)
+    idx1, knn1 = po.ball_query(c0, P, cfg.num_sub)
+    raw = po.offset_network(sd, c0, knn1)
+    want = torch.max(torch.min(c0 + raw.tanh() * 4.0, mx), mn)
+    w = conv_bn_weights(sd, "get_deformable_cluster.get_offsets.mlp")
+    w["map_w"] = cu(sd["get_deformable_cluster.get_offsets.channel_mapper.weight"].reshape(3, 256))
+    got, graw = ops.offset_net(cu(P), cu(idx1, torch.int32), cu(c0), cu(mn[:, 0]), cu(mx[:, 0]), w, want_raw=True)
+    scale = max(1.0, raw.abs().max().item())
+    np.testing.assert_allclose(np_(graw), raw.numpy(), rtol=0, atol=2e-6 * scale * 10)
+    np.testing.assert_allclose(np_(got), want.numpy(), rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_cluster_dropout_bit_exact_on_golden_inputs(name):
+    cfg, sd, pts, _, _, g = load_case(name)
+    ks, kc, kidx, didx, fps = ops.cluster_dropout(cu(g["centres"]), cu(g["idx2"]), cfg.keep1, cfg.real_cluster_num)
+    assert np.array_equal(np_(kidx), g["kept_idx"])
+    assert np.array_equal(np_(didx), g["drop_idx"])
+    assert np.array_equal(np_(kc), g["kept_centres"])
+    # kept_src really indexes the original clusters
+    assert np.array_equal(np.take_along_axis(g["centres"], np_(ks).astype(np.int64)[..., None], 1), g["kept_centres"])
+
+
+def test_cluster_dropout_stable_ties_and_fps_vs_oracle_random():
+    g = torch.Generator().manual_seed(11)
+    B, M, K = 3, 343, 30
+    centres = torch.rand(B, M, 3, generator=g) * 20
+    centres[1, 100:] = centres[1, 5]                   # heavy duplication -> FPS repeats index 0, truncation path
+    idx = torch.randint(0, 5000, (B, M, K), generator=g)
+    npad = torch.randint(0, 4, (B, M), generator=g) * 10     # massive key ties: 0/10/20/30 pads
+    idx[torch.arange(K)[None, None, :] >= (K - npad)[..., None]] = -1
+    cl = po.masked_gather(torch.rand(B, 5000, 3, generator=g), idx)
+    for ddr in (0.5, 0.6):
+        tr = {}
+        po.cluster_dropout(cl, centres, idx, ddr, tr)
+        keep1, n = M - int(M * 0.3), int(M * (1 - ddr))
+        ks, kc, kidx, didx, fps = ops.cluster_dropout(cu(centres), cu(idx, torch.int32), keep1, n)
+        assert np.array_equal(np_(fps), tr["fps"].numpy())
+        assert np.array_equal(np_(ks), tr["kept_src"].numpy())
+        assert np.array_equal(np_(kidx), tr["kept_idx"].numpy())
+        assert np.array_equal(np_(didx), tr["drop_idx"].numpy())
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_point_encoder_on_golden_inputs(name):
+    """rtol 2e-6 of the largest activation + atol 1e-5 (activations scale with the absolute coordinates)."""
+    cfg, sd, pts, _, _, g = load_case(name)
+    P = torch.stack(pts, 0)
+    got = ops.point_encoder(cu(P), cu(g["kept_idx"]), cu(g["kept_centres"]), conv_bn_weights(sd, "simple_encoder.mlp"))
+    want = g["point_proxy"]
+    np.testing.assert_allclose(np_(got), want, rtol=0, atol=1e-5 + 2e-6 * np.abs(want).max())
+
+
+def _block_weights(sd, stack, norm, i):
+    p = f"{stack}.{i}"
+    a = f"{p}.attn"
+    w = dict(ln1_w=cu(sd[f"{p}.norm1.weight"]), ln1_b=cu(sd[f"{p}.norm1.bias"]),
+             pos_bias=ops.position_bias(cu(sd[f"{a}.pb_bias"]), cu(sd[f"{a}.pc_bias"]), cu(sd[f"{a}.pr_bias"])),
+             qkv_w=cu(sd[f"{a}.qkv.weight"]), pp_w=cu(sd[f"{a}.proxy_proj.weight"]), pp_b=cu(sd[f"{a}.proxy_proj.bias"]),
+             proj_w=cu(sd[f"{a}.proj.weight"]), proj_b=cu(sd[f"{a}.proj.bias"]), ln2_w=cu(sd[f"{p}.norm2.weight"]),
+             ln2_b=cu(sd[f"{p}.norm2.bias"]), fc1_w=cu(sd[f"{p}.mlp.fc1.weight"]), fc1_b=cu(sd[f"{p}.mlp.fc1.bias"]),
+             fc2_w=cu(sd[f"{p}.mlp.fc2.weight"]), fc2_b=cu(sd[f"{p}.mlp.fc2.bias"]), lno_w=cu(sd[f"{norm}.{i}.weight"]),
+             lno_b=cu(sd[f"{norm}.{i}.bias"]))
+    return w
+
+
+@pytest.mark.parametrize("name", ["c1_b2", "c1_blocks3", "gs5_ragged", "c2_wide_b1", "c3_wide_b1"])
+@pytest.mark.parametrize("tc", [False, True], ids=["fp32", "tc3xbf16"])
+def test_proxy_block_on_golden_point_proxies(name, tc):
+    """LayerNorm-ed outputs are O(1); tolerance 3e-5 absolute (fp32 CUDA cores) / 1e-4 (3xBF16 tensor cores)."""
+    cfg, sd, pts, text_dict, img, g = load_case(name)
+    pp = torch.from_numpy(g["point_proxy"])
+    text, mask = text_dict["text_feats"], text_dict["text_token_mask"]
+    for stack, norm, nblk, proxy, m in (("textformer", "text_norm", cfg.text_blocks, text, mask),
+                                        ("imgformer", "img_norm", cfg.img_blocks, torch.from_numpy(g["img_proxy"]), None)):
+        i = nblk - 1
+        want = po.branch(sd, stack, norm, nblk, pp, proxy, m, cfg.num_heads)
+        w = _block_weights(sd, stack, norm, i)
+        if tc:
+            for k in ("qkv_w", "proj_w", "fc1_w", "fc2_w", "pp_w"):
+                w[k + "_split"] = ops.split_bf16(w[k])
+        got = ops.proxy_block(cu(pp), cu(proxy), cu(m) if m is not None else None, w, cfg.num_heads)
+        np.testing.assert_allclose(np_(got), want.numpy(), rtol=0, atol=1e-4 if tc else 3e-5)
+
+
+def test_position_bias_table():
+    cfg = syn.C1
+    sd = syn.make_state_dict(cfg, 1)
+    a = "textformer.0.attn"
+    want = po.position_bias(sd, a, 16)
+    got = ops.position_bias(cu(sd[f"{a}.pb_bias"]), cu(sd[f"{a}.pc_bias"]), cu(sd[f"{a}.pr_bias"]))
+    np.testing.assert_allclose(np_(got), want.numpy(), rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["c1_b2", "c2_wide_b1"])
+def test_heads_on_oracle_inputs(name):
+    cfg, sd, *_ , g = load_case(name)
+    guide = torch.randn(2, cfg.real_cluster_num, 256, generator=torch.Generator().manual_seed(1))
+    for lin, bn in (("text_trans", "text_trans_norm"), ("img_trans", "img_trans_norm")):
+        want = po.head(sd, lin, bn, guide)
+        inv = 1.0 / torch.sqrt(sd[f"{bn}.running_var"] + 1e-5)
+        sc = inv * sd[f"{bn}.weight"]
+        sh = sd[f"{bn}.bias"] - sd[f"{bn}.running_mean"] * sc
+        got = ops.heads(cu(guide), cu(sd[f"{lin}.weight"]), cu(sd[f"{lin}.bias"]), cu(sc), cu(sh))
+        np.testing.assert_allclose(np_(got), want.numpy(), rtol=0, atol=5e-6)
+
+
+@pytest.mark.parametrize("name", ["c1_b2", "gs5_ragged", "c2_wide_b1"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_image_proxies_single_query_form(name, dtype):
+    """vs the reference formulation (conv + 226-token MHA, token 0): LayerNorm-ed outputs, tolerance 3e-5.  The bf16
+    case feeds the SAME bf16-rounded features to both sides."""
+    cfg, sd, pts, text_dict, img, g = load_case(name)
+    m = build_module(cfg, sd)
+    x = img.to(dtype)
+    want = torch.from_numpy(g["img_proxy"]) if dtype == torch.float32 else po.image_proxies(sd, x.float(), cfg.num_heads)
+    got = m.get_img_proxy(x.to(DEV))
+    np.testing.assert_allclose(np_(got), want.numpy(), rtol=0, atol=3e-5)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_affine_scatter_compact_on_golden_inputs(name):
+    """duplicates resolved by the pinned rule (largest flat (m,k) wins); coords within 2e-5 of the reference; survivor
+    order and counts exact."""
+    cfg, sd, pts, _, _, g = load_case(name)
+    P = torch.stack(pts, 0)
+    out, counts = ops.affine_scatter_compact(cu(P), cu(g["kept_idx"]), cu(g["drop_idx"]), cu(g["kept_centres"]),
+                                             cu(g["transform"]), cu(g["translate"]))
+    assert np.array_equal(np_(counts), g["out_counts"])
+    out = np_(out)
+    for b, nb in enumerate(g["out_counts"]):
+        o = out[b, :nb]
+        if f"out_{b}" in g:
+            np.testing.assert_allclose(o, g[f"out_{b}"], rtol=0, atol=2e-5)
+        else:
+            np.testing.assert_allclose(o[:2048], g[f"out_head_{b}"], rtol=0, atol=2e-5)
+            np.testing.assert_allclose(o[::97], g[f"out_stride_{b}"], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(o.astype(np.float64).sum(0), g["out_sum"][b], rtol=1e-7, atol=1e-2)
+
+
+@pytest.mark.parametrize("M,N,K,act", [(300, 768, 256, 0), (1000, 256, 1024, 0), (129, 130, 36, 1), (16384, 1024, 256, 1), (64, 3, 8, 0)])
+def test_gemm_fp32_cuda_cores(M, N, K, act):
+    g = torch.Generator().manual_seed(M)
+    A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    bias, res = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    y = A.double() @ W.double().T + bias.double()
+    if act:
+        y = torch.nn.functional.gelu(y)
+    want = (y + res.double()).float()
+    got = ops.gemm_nt(cu(A), cu(W), cu(bias), cu(res), act)
+    np.testing.assert_allclose(np_(got), want.numpy(), rtol=0, atol=2e-5)
+
+
+def test_layernorm_with_row_bias():
+    g = torch.Generator().manual_seed(2)
+    x, w, b, add = torch.randn(77, 256, generator=g) * 3 + 1, torch.randn(256, generator=g), torch.randn(256, generator=g), torch.randn(11, 256, generator=g)
+    want = torch.nn.functional.layer_norm(x, (256,), w, b, 1e-5) + add[torch.arange(77) % 11]
+    got = ops.layernorm(cu(x), cu(w), cu(b), cu(add))
+    np.testing.assert_allclose(np_(got), want.numpy(), rtol=0, atol=5e-6)
