@@ -43,6 +43,14 @@ const char* pt_last_error_string(void);
 /* Number of kernels launched through this library by the calling process so far (bench.py's gpu_launches). */
 int64_t pt_launch_count(void);
 
+/* Per-kernel device timing for the benchmark: while enabled every kernel launched through this library is bracketed
+ * by CUDA events on its stream.  pt_profile_enable(on) also clears the records; pt_profile_read synchronises on the
+ * recorded events and returns the summed duration and the number of launches of one kernel kind. */
+int pt_profile_enable(int on);
+int pt_profile_num_tags(void);
+const char* pt_profile_tag_name(int tag);
+int pt_profile_read(int tag, double* total_ms, int64_t* launches);
+
 /* ---- S1 grid prior — DeformablePointCluster.init_uniform_cluster_center (:33-51) --------------------
  * mn/mx (B,3) per-axis min/max over the scene; centres (B,M,3) = (mn + margin) + lin3[j] * ((mx - mn) - 2*margin),
  * j = ix*gs^2 + iy*gs + iz ('ij' meshgrid).  `lin` is torch.linspace(0,1,gs) computed by the host (fp32).

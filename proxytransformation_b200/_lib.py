@@ -34,6 +34,10 @@ _SIGNATURES = {
     "pt_abi_version": (c_int, []),
     "pt_last_error_string": (c_char_p, []),
     "pt_launch_count": (c_int64, []),
+    "pt_profile_enable": (c_int, [c_int]),
+    "pt_profile_num_tags": (c_int, []),
+    "pt_profile_tag_name": (c_char_p, [c_int]),
+    "pt_profile_read": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(c_int64)]),
     "pt_minmax_ws_bytes": (c_size_t, [c_int, c_int]),
     "pt_minmax_centres": (c_int, [_P, c_int, c_int, c_int, _P, c_float, _P, _P, _P, _P, c_size_t, _P]),
     "pt_ball_query_firstk": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P]),
@@ -82,3 +86,19 @@ def check(rc: int, what: str):
 
 def launch_count() -> int:
     return int(load().pt_launch_count())
+
+
+def profile_enable(on: bool):
+    check(load().pt_profile_enable(1 if on else 0), "pt_profile_enable")
+
+
+def profile_read() -> dict:
+    """-> {kernel kind: (total ms, launches)} for everything launched since profile_enable(True)."""
+    L = load()
+    out = {}
+    for t in range(L.pt_profile_num_tags()):
+        ms, n = ctypes.c_double(0.0), c_int64(0)
+        check(L.pt_profile_read(t, ctypes.byref(ms), ctypes.byref(n)), "pt_profile_read")
+        if n.value:
+            out[L.pt_profile_tag_name(t).decode()] = (ms.value, n.value)
+    return out

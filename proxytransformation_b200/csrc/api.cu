@@ -2,6 +2,8 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <mutex>
+#include <vector>
 #include <stdarg.h>
 #include <string.h>
 
@@ -17,6 +19,34 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- profiling: (tag, start, stop) event records, filled only while enabled
+static const char* const g_prof_names[PROF_NTAGS] = {
+    "minmax_partial", "centres", "ball_query", "offset_net", "cluster_dropout", "point_encoder", "layernorm", "gemm_f32",
+    "gemm_tc_3xbf16", "split_bf16", "proxy_attention", "heads", "img_mean", "img_pool", "scatter_mark", "scatter_count",
+    "scatter_compact", "misc"};
+struct ProfRec { int tag; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+constexpr size_t PROF_MAX = 1 << 17;
+
+ProfScope::ProfScope(int tag, cudaStream_t s) : slot(-1), stream(s) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (g_prof.size() >= PROF_MAX) return;
+    ProfRec r;
+    r.tag = tag;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, s);
+    g_prof.push_back(r);
+    slot = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_prof[slot].b, stream);
+}
 
 int launch_layernorm(const float* x, const float* w, const float* b, const float* add, int add_rows, int rows, int c,
                      float* out, cudaStream_t s);
@@ -71,6 +101,33 @@ using namespace pt;
 extern "C" int pt_abi_version(void) { return 1; }
 extern "C" const char* pt_last_error_string(void) { return g_err; }
 extern "C" int64_t pt_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" int pt_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = on != 0;
+    return PT_OK;
+}
+extern "C" int pt_profile_num_tags(void) { return PROF_NTAGS; }
+extern "C" const char* pt_profile_tag_name(int tag) { return tag >= 0 && tag < PROF_NTAGS ? g_prof_names[tag] : ""; }
+extern "C" int pt_profile_read(int tag, double* total_ms, int64_t* launches) {
+    PT_REQUIRE(tag >= 0 && tag < PROF_NTAGS && total_ms && launches, "pt_profile_read: bad argument");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    double tot = 0.0;
+    int64_t n = 0;
+    for (auto& r : g_prof) {
+        if (r.tag != tag) continue;
+        PT_CUDA_OK(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        PT_CUDA_OK(cudaEventElapsedTime(&ms, r.a, r.b));
+        tot += ms;
+        ++n;
+    }
+    *total_ms = tot;
+    *launches = n;
+    return PT_OK;
+}
 
 extern "C" size_t pt_proxy_block_ws_bytes(int B, int n, int l, int c, int hidden) {
     return carve_block(nullptr, B, n, l, c, hidden).total;

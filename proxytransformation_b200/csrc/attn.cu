@@ -133,7 +133,7 @@ int launch_proxy_attention(const float* qkv, const float* pt_tok, const uint8_t*
 #define PT_AT_CASE(HD)                                                                                                   \
     case HD:                                                                                                             \
         if (smem > 48 * 1024) PT_CUDA_OK(cudaFuncSetAttribute(proxy_attention_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        proxy_attention_kernel<HD><<<grid, AT_THREADS, smem, s>>>(qkv, pt_tok, mask, n, l, c, scale, o);                 \
+        { ProfScope prof_(PROF_ATTENTION, s); proxy_attention_kernel<HD><<<grid, AT_THREADS, smem, s>>>(qkv, pt_tok, mask, n, l, c, scale, o); }                 \
         break;
     switch (hd) {
         PT_AT_CASE(8) PT_AT_CASE(16) PT_AT_CASE(32) PT_AT_CASE(64)

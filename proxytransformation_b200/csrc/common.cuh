@@ -12,6 +12,19 @@ namespace pt {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline figures).
+enum ProfTag {
+    PROF_MINMAX = 0, PROF_CENTRES, PROF_BALL_QUERY, PROF_OFFSET_NET, PROF_DROPOUT, PROF_ENCODER, PROF_LAYERNORM,
+    PROF_GEMM_F32, PROF_GEMM_TC, PROF_SPLIT, PROF_ATTENTION, PROF_HEADS, PROF_IMG_MEAN, PROF_IMG_POOL, PROF_MARK,
+    PROF_COUNT, PROF_COMPACT, PROF_MISC, PROF_NTAGS
+};
+struct ProfScope {
+    int slot;
+    cudaStream_t stream;
+    ProfScope(int tag, cudaStream_t s);
+    ~ProfScope();
+};
+
 #define PT_REQUIRE(cond, ...)                 \
     do {                                      \
         if (!(cond)) {                        \

@@ -194,7 +194,7 @@ int launch_layernorm(const float* x, const float* w, const float* b, const float
     PT_REQUIRE(c % 32 == 0 && c >= 32 && c <= 1024, "layernorm: c=%d unsupported", c);
     const int wpb = 8, grid = ceil_div(rows, wpb);
     switch (c / 32) {
-#define PT_LN_CASE(CPL) case CPL: layernorm_kernel<CPL><<<grid, wpb * 32, 0, s>>>(x, w, b, add, add_rows, rows, out); break;
+#define PT_LN_CASE(CPL) case CPL: { ProfScope prof_(PROF_LAYERNORM, s); layernorm_kernel<CPL><<<grid, wpb * 32, 0, s>>>(x, w, b, add, add_rows, rows, out); } break;
         PT_LN_CASE(1) PT_LN_CASE(2) PT_LN_CASE(4) PT_LN_CASE(8) PT_LN_CASE(16) PT_LN_CASE(32)
 #undef PT_LN_CASE
         default: PT_REQUIRE(false, "layernorm: c=%d unsupported (c/32 must be a power of two)", c);
@@ -208,8 +208,8 @@ int launch_gemm_f32_strided(const float* A, const float* W, const float* bias, c
                             long long bsC, long long bsBias, cudaStream_t s) {
     PT_REQUIRE(M > 0 && N > 0 && K > 0 && (K % 4) == 0 && (lda % 4) == 0 && (ldw % 4) == 0 && (bsA % 4) == 0 && (bsW % 4) == 0,
                "gemm: M=%d N=%d K=%d lda=%d ldw=%d (K, strides must be multiples of 4)", M, N, K, lda, ldw);
-    gemm_nt_f32_kernel<<<dim3(ceil_div(N, G_BN), ceil_div(M, G_BM), batch), G_THREADS, 0, s>>>(
-        A, W, bias, residual, act, M, N, K, C, lda, ldw, ldc, bsA, bsW, bsC, bsBias);
+    { ProfScope prof_(PROF_GEMM_F32, s); gemm_nt_f32_kernel<<<dim3(ceil_div(N, G_BN), ceil_div(M, G_BM), batch), G_THREADS, 0, s>>>(
+        A, W, bias, residual, act, M, N, K, C, lda, ldw, ldc, bsA, bsW, bsC, bsBias); }
     PT_LAUNCH_CHECK();
     return PT_OK;
 }
@@ -235,7 +235,7 @@ extern "C" int pt_split_bf16(const float* x, int64_t count, void* out, pt_stream
     __nv_bfloat16* hi = (__nv_bfloat16*)out;
     int grid = (int)((count + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
-    split_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, count, hi, hi + count);
+    { ProfScope prof_(PROF_SPLIT, (cudaStream_t)stream); split_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, count, hi, hi + count); }
     PT_LAUNCH_CHECK();
     return PT_OK;
 }
@@ -243,7 +243,7 @@ extern "C" int pt_split_bf16(const float* x, int64_t count, void* out, pt_stream
 extern "C" int pt_position_bias(const float* pb, const float* pc, const float* pr, int n, int s, float* out,
                                 pt_stream_t stream) {
     PT_REQUIRE(pb && pc && pr && out && n > 0 && s > 0, "pt_position_bias: bad argument");
-    position_bias_kernel<<<ceil_div(n * s * s, 256), 256, 0, (cudaStream_t)stream>>>(pb, pc, pr, n, s, out);
+    { ProfScope prof_(PROF_MISC, (cudaStream_t)stream); position_bias_kernel<<<ceil_div(n * s * s, 256), 256, 0, (cudaStream_t)stream>>>(pb, pc, pr, n, s, out); }
     PT_LAUNCH_CHECK();
     return PT_OK;
 }
@@ -252,7 +252,7 @@ extern "C" int pt_heads(const float* guide, const float* lin_w, const float* lin
                         const float* bn_shift, int rows, int c, int o, float* out, pt_stream_t stream) {
     PT_REQUIRE(guide && lin_w && lin_b && bn_scale && bn_shift && out && rows > 0 && c > 0 && o > 0 && o <= 16,
                "pt_heads: bad argument");
-    heads_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(guide, lin_w, lin_b, bn_scale, bn_shift, rows, c, o, out);
+    { ProfScope prof_(PROF_HEADS, (cudaStream_t)stream); heads_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(guide, lin_w, lin_b, bn_scale, bn_shift, rows, c, o, out); }
     PT_LAUNCH_CHECK();
     return PT_OK;
 }

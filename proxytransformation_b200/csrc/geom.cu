@@ -351,9 +351,9 @@ extern "C" int pt_minmax_centres(const float* points, int B, int N, int gs, cons
     if (ws_bytes < pt_minmax_ws_bytes(B, N)) { set_error("pt_minmax_centres: workspace %zu < %zu", ws_bytes, pt_minmax_ws_bytes(B, N)); return PT_ERR_WORKSPACE; }
     cudaStream_t s = (cudaStream_t)stream;
     const int nblk = ceil_div(N, MM_POINTS_PER_BLOCK), M = gs * gs * gs;
-    minmax_partial_kernel<<<dim3(nblk, B), MM_THREADS, 0, s>>>(points, N, (float*)ws);
+    { ProfScope prof_(PROF_MINMAX, s); minmax_partial_kernel<<<dim3(nblk, B), MM_THREADS, 0, s>>>(points, N, (float*)ws); }
     PT_LAUNCH_CHECK();
-    centres_kernel<<<dim3(ceil_div(M, 256), B), 256, 0, s>>>((const float*)ws, nblk, gs, M, lin, margin, mn, mx, centres);
+    { ProfScope prof_(PROF_CENTRES, s); centres_kernel<<<dim3(ceil_div(M, 256), B), 256, 0, s>>>((const float*)ws, nblk, gs, M, lin, margin, mn, mx, centres); }
     PT_LAUNCH_CHECK();
     return PT_OK;
 }
@@ -362,8 +362,8 @@ extern "C" int pt_ball_query_firstk(const float* centres, const float* points, i
                                     int32_t* idx, int32_t* pad_counts, pt_stream_t stream) {
     PT_REQUIRE(B > 0 && M > 0 && N > 0 && K > 0, "pt_ball_query_firstk: B=%d M=%d N=%d K=%d", B, M, N, K);
     PT_REQUIRE(centres && points && idx, "pt_ball_query_firstk: null pointer");
-    ball_query_kernel<<<dim3(ceil_div(M, BQ_WARPS), B), BQ_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        centres, points, M, N, K, radius * radius, idx, pad_counts);
+    { ProfScope prof_(PROF_BALL_QUERY, (cudaStream_t)stream); ball_query_kernel<<<dim3(ceil_div(M, BQ_WARPS), B), BQ_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        centres, points, M, N, K, radius * radius, idx, pad_counts); }
     PT_LAUNCH_CHECK();
     return PT_OK;
 }
@@ -382,8 +382,8 @@ extern "C" int pt_offset_net_fused(const float* points, const int32_t* idx, cons
     PT_REQUIRE(B > 0 && M > 0 && N > 0 && K > 0, "pt_offset_net_fused: bad shape");
     PT_REQUIRE(points && idx && centres0 && mn && mx && conv_w && conv_b && bn_scale && bn_shift && map_w && centres_out,
                "pt_offset_net_fused: null pointer");
-    cluster_mlp_kernel<false><<<mlp_grid(B * M), MLP_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        points, idx, centres0, mn, mx, conv_w, conv_b, bn_scale, bn_shift, map_w, B, M, N, K, margin, centres_out, raw_offsets);
+    { ProfScope prof_(PROF_OFFSET_NET, (cudaStream_t)stream); cluster_mlp_kernel<false><<<mlp_grid(B * M), MLP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        points, idx, centres0, mn, mx, conv_w, conv_b, bn_scale, bn_shift, map_w, B, M, N, K, margin, centres_out, raw_offsets); }
     PT_LAUNCH_CHECK();
     return PT_OK;
 }
@@ -396,9 +396,9 @@ extern "C" int pt_point_encoder_fused(const float* points, const int32_t* kept_i
     PT_REQUIRE(B > 0 && n > 0 && N > 0 && K > 0, "pt_point_encoder_fused: bad shape");
     PT_REQUIRE(points && kept_idx && kept_centres && conv_w && conv_b && bn_scale && bn_shift && point_proxy,
                "pt_point_encoder_fused: null pointer");
-    cluster_mlp_kernel<true><<<mlp_grid(B * n), MLP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    { ProfScope prof_(PROF_ENCODER, (cudaStream_t)stream); cluster_mlp_kernel<true><<<mlp_grid(B * n), MLP_WARPS * 32, 0, (cudaStream_t)stream>>>(
         points, kept_idx, kept_centres, nullptr, nullptr, conv_w, conv_b, bn_scale, bn_shift, nullptr, B, n, N, K, 0.f,
-        point_proxy, nullptr);
+        point_proxy, nullptr); }
     PT_LAUNCH_CHECK();
     return PT_OK;
 }
@@ -419,8 +419,8 @@ extern "C" int pt_cluster_dropout(const float* centres, const int32_t* idx, int 
     smem = align_up(smem, 16);
     PT_REQUIRE(smem <= 227 * 1024, "pt_cluster_dropout: M=%d needs %zu B shared memory", M, smem);
     if (smem > 48 * 1024) PT_CUDA_OK(cudaFuncSetAttribute(cluster_dropout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cluster_dropout_kernel<<<B, T, smem, (cudaStream_t)stream>>>(centres, idx, M, K, keep1, n_keep, kept_src, kept_centres,
-                                                                 kept_idx, drop_idx, fps_sel);
+    { ProfScope prof_(PROF_DROPOUT, (cudaStream_t)stream); cluster_dropout_kernel<<<B, T, smem, (cudaStream_t)stream>>>(centres, idx, M, K, keep1, n_keep, kept_src, kept_centres,
+                                                                 kept_idx, drop_idx, fps_sel); }
     PT_LAUNCH_CHECK();
     return PT_OK;
 }

@@ -250,8 +250,8 @@ extern "C" int pt_img_attnpool(const void* img_feat, int img_dtype, const pt_img
     {   // pass A
         const long long units = bf ? rows / 2 : rows;
         int grid = (int)((units + 7) / 8 < 148 * 8 ? (units + 7) / 8 : 148 * 8);
-        if (bf) img_mean_kernel<true><<<grid, 256, 0, s>>>(img_feat, C, HW, rows, w.xbar);
-        else img_mean_kernel<false><<<grid, 256, 0, s>>>(img_feat, C, HW, rows, w.xbar);
+        if (bf) { ProfScope prof_(PROF_IMG_MEAN, s); img_mean_kernel<true><<<grid, 256, 0, s>>>(img_feat, C, HW, rows, w.xbar); }
+        else { ProfScope prof_(PROF_IMG_MEAN, s); img_mean_kernel<false><<<grid, 256, 0, s>>>(img_feat, C, HW, rows, w.xbar); }
         PT_LAUNCH_CHECK();
     }
     int rc;
@@ -268,10 +268,10 @@ extern "C" int pt_img_attnpool(const void* img_feat, int img_dtype, const pt_img
         const float scale = (float)(1.0 / sqrt((double)hd));
         if (bf) {
             PT_CUDA_OK(cudaFuncSetAttribute(img_pool_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            img_pool_kernel<true><<<BV, PB_THREADS, smem, s>>>(img_feat, w.xbar, w.w_eff, w.cterm, C, HW, Tp, scale, w.y, w.attn);
+            { ProfScope prof_(PROF_IMG_POOL, s); img_pool_kernel<true><<<BV, PB_THREADS, smem, s>>>(img_feat, w.xbar, w.w_eff, w.cterm, C, HW, Tp, scale, w.y, w.attn); }
         } else {
             PT_CUDA_OK(cudaFuncSetAttribute(img_pool_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            img_pool_kernel<false><<<BV, PB_THREADS, smem, s>>>(img_feat, w.xbar, w.w_eff, w.cterm, C, HW, Tp, scale, w.y, w.attn);
+            { ProfScope prof_(PROF_IMG_POOL, s); img_pool_kernel<false><<<BV, PB_THREADS, smem, s>>>(img_feat, w.xbar, w.w_eff, w.cterm, C, HW, Tp, scale, w.y, w.attn); }
         }
         PT_LAUNCH_CHECK();
     }

@@ -102,12 +102,12 @@ extern "C" int pt_affine_scatter_compact(const float* points, const int32_t* kep
     const long long total = (long long)B * ((long long)n * K + n_drop_entries);
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    mark_kernel<<<grid, 256, 0, s>>>(kept_idx, drop_idx, B, N, n * K, n_drop_entries, winner);
+    { ProfScope prof_(PROF_MARK, s); mark_kernel<<<grid, 256, 0, s>>>(kept_idx, drop_idx, B, N, n * K, n_drop_entries, winner); }
     PT_LAUNCH_CHECK();
     const int nblk = ceil_div(N, SC_BLOCK);
-    count_kernel<<<dim3(nblk, B), SC_BLOCK, 0, s>>>(winner, N, blockcnt);
+    { ProfScope prof_(PROF_COUNT, s); count_kernel<<<dim3(nblk, B), SC_BLOCK, 0, s>>>(winner, N, blockcnt); }
     PT_LAUNCH_CHECK();
-    compact_kernel<<<dim3(nblk, B), SC_BLOCK, 0, s>>>(points, winner, blockcnt, kept_centres, transform, translate, N, n, K, out, counts);
+    { ProfScope prof_(PROF_COMPACT, s); compact_kernel<<<dim3(nblk, B), SC_BLOCK, 0, s>>>(points, winner, blockcnt, kept_centres, transform, translate, N, n, K, out, counts); }
     PT_LAUNCH_CHECK();
     return PT_OK;
 }

@@ -15,6 +15,14 @@ pytestmark = pytest.mark.gpu
 # The others (collapsed grid / duplicated centres / room-sized box) have zero-margin FPS ties where a 1e-6 difference in
 # the offset network flips the arg-max even between two CPU thread counts; there every stage is
 # checked on its own inputs (chained check) and flips are tolerated.
+
+
+def CENTRE_TOL(c):
+    """clamped centres: 1e-5 m + 2e-6 relative to the scene extent (fp32 accumulation-order noise of the offset
+    network scales with the absolute coordinates it is fed, :99) — well inside the 1e-4 coordinate tolerance."""
+    return 1e-5 + 2e-6 * float(np.abs(c).max())
+
+
 EXACT = {"c1_b2", "c1_origin", "c1_sparse", "c1_very_sparse", "c1_blocks3", "gs5_ragged", "c2_wide_b1", "c3_wide_b1"}
 
 
@@ -39,7 +47,7 @@ def test_forward_matches_reference(name, tc):
     out = m([p.to(DEV) for p in pts], {k: v.to(DEV) for k, v in text_dict.items()}, img.to(DEV), trace=tr)
     P = torch.stack(pts, 0)
     assert all(o.is_cuda and o.dtype == torch.float32 and o.shape[1] == 3 for o in out)
-    np.testing.assert_allclose(np_(tr["centres"]), g["centres"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(np_(tr["centres"]), g["centres"], rtol=0, atol=CENTRE_TOL(g["centres"]))
     _chain_check(cfg, sd, P, tr)
     same_idx = np.array_equal(np_(tr["kept_idx"]), g["kept_idx"]) and np.array_equal(np_(tr["drop_idx"]), g["drop_idx"])
     if name in EXACT:
@@ -110,7 +118,7 @@ def test_bf16_config_against_oracle_on_identically_rounded_inputs():
     m = build_module(cfg, sd)
     tr = {}
     out = m([p.to(DEV) for p in pts], {k: v.to(DEV) for k, v in text_dict.items()}, img.to(DEV), trace=tr)
-    np.testing.assert_allclose(np_(tr["centres"]), wtr["centres"].numpy(), rtol=0, atol=1e-5)
+    np.testing.assert_allclose(np_(tr["centres"]), wtr["centres"].numpy(), rtol=0, atol=CENTRE_TOL(wtr["centres"].numpy()))
     assert np.array_equal(np_(tr["kept_idx"]), wtr["kept_idx"].numpy())
     assert np.array_equal(np_(tr["drop_idx"]), wtr["drop_idx"].numpy())
     for o, w in zip(out, want):
