@@ -162,6 +162,24 @@ int pt_affine_scatter_compact(const float* points, const int32_t* kept_idx, cons
 size_t pt_gemm_ws_bytes(int M, int N, int K);
 int pt_gemm_nt(const float* A, const float* W, const void* w_split, const float* bias, const float* residual, int act,
                int M, int N, int K, float* C, void* ws, size_t ws_bytes, pt_stream_t stream);
+/* General (batched, pre-split operands, optional split output) form of the tensor-core GEMM:
+ *   C_z[M,N] = act(A[:, z*a_koff_z : +K] W_z[N,K]^T + bias_z) + residual_z,  z in [0,batch)
+ * A: bf16 planes [2][a_rows][lda] (hi then lo), a_cols readable columns (reads past a_cols are zero);
+ * W: bf16 planes [2][w_rows][ldw], batch z uses rows [z*w_row_z, z*w_row_z+N);
+ * C (fp32, optional): element (row,n) of batch z at C + z*c_off_z + row*ldc + n; residual is laid out like C;
+ * c_split (optional): bf16 hi plane of the result with pitch ldcs, lo plane cs_plane elements later.
+ * K % 64 == 0, N % 4 == 0; bn = tile width (32/64/128/256) or 0 = automatic. */
+typedef struct pt_gemm_tc_desc {
+    int M, N, K, batch;
+    const void* a_split; int a_rows, a_cols, lda, a_koff_z;
+    const void* w_split; int w_rows, ldw, w_row_z;
+    const float* bias; long long bias_off_z;
+    const float* residual; int act;
+    float* C; int ldc; long long c_off_z;
+    void* c_split; long long cs_plane; int ldcs; long long cs_off_z;
+    int bn;
+} pt_gemm_tc_desc;
+int pt_gemm_tc(const pt_gemm_tc_desc* desc, pt_stream_t stream);
 /* bf16 hi/lo split of an fp32 matrix: out [2][rows][cols] bf16, hi = bf16(x), lo = bf16(x - hi). */
 int pt_split_bf16(const float* x, int64_t count, void* out, pt_stream_t stream);
 /* out (rows,c) = LayerNorm(x) * w + b (+ add[row % add_rows]) ; eps 1e-5 ; c % 32 == 0, c <= 1024. */

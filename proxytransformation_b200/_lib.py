@@ -24,6 +24,16 @@ class ProxyBlockParams(Structure):
         "fc2_w", "fc2_b", "lno_w", "lno_b", "qkv_w_split", "proj_w_split", "fc1_w_split", "fc2_w_split", "pp_w_split")]
 
 
+class GemmTcDesc(Structure):
+    _fields_ = [("M", c_int), ("N", c_int), ("K", c_int), ("batch", c_int),
+                ("a_split", c_void_p), ("a_rows", c_int), ("a_cols", c_int), ("lda", c_int), ("a_koff_z", c_int),
+                ("w_split", c_void_p), ("w_rows", c_int), ("ldw", c_int), ("w_row_z", c_int),
+                ("bias", c_void_p), ("bias_off_z", ctypes.c_longlong), ("residual", c_void_p), ("act", c_int),
+                ("C", c_void_p), ("ldc", c_int), ("c_off_z", ctypes.c_longlong),
+                ("c_split", c_void_p), ("cs_plane", ctypes.c_longlong), ("ldcs", c_int), ("cs_off_z", ctypes.c_longlong),
+                ("bn", c_int)]
+
+
 class ImgPoolParams(Structure):
     _fields_ = [(n, c_void_p) for n in ("w_qc", "q0", "w_kc", "g_k", "w_vc", "h_v", "cproj_w", "cproj_b", "ln_w", "ln_b")]
 
@@ -54,6 +64,7 @@ _SIGNATURES = {
     "pt_affine_scatter_compact": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "pt_gemm_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pt_gemm_nt": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "pt_gemm_tc": (c_int, [POINTER(GemmTcDesc), _P]),
     "pt_split_bf16": (c_int, [_P, c_int64, _P, _P]),
     "pt_layernorm": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
 }

@@ -1,5 +1,6 @@
 // C-ABI glue: error reporting, launch accounting and the multi-kernel ProxyBlock stage (S7).
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 #include <atomic>
 #include <mutex>
@@ -54,11 +55,6 @@ int launch_gemm_f32(const float* A, const float* W, const float* bias, const flo
                     float* C, cudaStream_t s);
 int launch_proxy_attention(const float* qkv, const float* pt_tok, const uint8_t* mask, int B, int n, int l, int c,
                            int heads, float* o, cudaStream_t s);
-// tensor-core path (gemm_tc.cu)
-bool gemm_tc_supported(int M, int N, int K);
-size_t gemm_tc_ws_bytes(int M, int N, int K);
-int launch_gemm_tc(const float* A, const void* w_split, const float* bias, const float* residual, int act, int M, int N,
-                   int K, float* C, void* ws, size_t ws_bytes, cudaStream_t s);
 
 static int gemm_any(const float* A, const float* W, const void* w_split, const float* bias, const float* residual, int act,
                     int M, int N, int K, float* C, void* ws, size_t ws_bytes, cudaStream_t s) {
@@ -172,4 +168,16 @@ extern "C" int pt_gemm_nt(const float* A, const float* W, const void* w_split, c
         return launch_gemm_tc(A, w_split, bias, residual, act, M, N, K, C, ws, ws_bytes, (cudaStream_t)stream);
     }
     return launch_gemm_f32(A, W, bias, residual, act, M, N, K, C, (cudaStream_t)stream);
+}
+
+extern "C" int pt_gemm_tc(const pt_gemm_tc_desc* d, pt_stream_t stream) {
+    PT_REQUIRE(d != nullptr, "pt_gemm_tc: null descriptor");
+    GemmTc p;
+    p.M = d->M; p.N = d->N; p.K = d->K; p.batch = d->batch;
+    p.a_split = d->a_split; p.a_rows = d->a_rows; p.a_cols = d->a_cols; p.lda = d->lda; p.a_koff_z = d->a_koff_z;
+    p.w_split = d->w_split; p.w_rows = d->w_rows; p.ldw = d->ldw; p.w_row_z = d->w_row_z;
+    p.bias = d->bias; p.bias_off_z = d->bias_off_z; p.residual = d->residual; p.act = d->act;
+    p.C = d->C; p.ldc = d->ldc; p.c_off_z = d->c_off_z;
+    p.c_split = d->c_split; p.cs_plane = d->cs_plane; p.ldcs = d->ldcs; p.cs_off_z = d->cs_off_z; p.bn = d->bn;
+    return launch_gemm_tc_ex(p, (cudaStream_t)stream);
 }

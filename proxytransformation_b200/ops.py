@@ -248,6 +248,23 @@ def gemm_nt(A, W, bias=None, residual=None, act: int = 0, w_split=None):
     return C
 
 
+def gemm_tc(a_split, w_split, M, N, K, *, batch=1, a_koff_z=0, w_row_z=0, bias=None, bias_off_z=0, residual=None, act=0,
+            C=None, ldc=0, c_off_z=0, c_split=None, ldcs=0, cs_off_z=0, bn=0):
+    """General tensor-core GEMM (pt_gemm_tc): a_split (2,a_rows,lda) bf16, w_split (2,w_rows,ldw) bf16."""
+    L = _lib.load()
+    d = _lib.GemmTcDesc()
+    d.M, d.N, d.K, d.batch = M, N, K, batch
+    d.a_split, d.a_rows, d.a_cols, d.lda, d.a_koff_z = _chk(a_split, torch.bfloat16, "a_split"), a_split.shape[1], a_split.shape[2], a_split.shape[2], a_koff_z
+    d.w_split, d.w_rows, d.ldw, d.w_row_z = _chk(w_split, torch.bfloat16, "w_split"), w_split.shape[1], w_split.shape[2], w_row_z
+    d.bias, d.bias_off_z = _chk(bias, torch.float32, "bias", optional=True), bias_off_z
+    d.residual, d.act = _chk(residual, torch.float32, "residual", optional=True), act
+    d.C, d.ldc, d.c_off_z = _chk(C, torch.float32, "C", optional=True), ldc, c_off_z
+    if c_split is not None:
+        d.c_split, d.cs_plane, d.ldcs, d.cs_off_z = _chk(c_split, torch.bfloat16, "c_split"), c_split[0].numel(), ldcs, cs_off_z
+    d.bn = bn
+    check(L.pt_gemm_tc(ctypes.byref(d), _stream()), "pt_gemm_tc")
+
+
 def split_bf16(x: torch.Tensor) -> torch.Tensor:
     """fp32 (...) -> bf16 (2, ...) hi/lo planes, hi = bf16(x), lo = bf16(x - hi)."""
     L = _lib.load()

@@ -229,3 +229,34 @@ def test_gemm_tensor_core_3xbf16(M, N, K, act):
     plain = (A.bfloat16().double() @ W.bfloat16().double().T + bias.double())
     if not act:
         assert (np_(got) - want.numpy()).std() * 20 < ((plain + res.double()).float() - want).std().item()
+
+
+@pytest.mark.parametrize("bn", [32, 64, 128, 256])
+def test_gemm_tensor_core_tile_widths_and_split_output(bn):
+    """every tile width of the persistent tcgen05 kernel, ragged M/N, fp32 + bf16 hi/lo outputs (hi+lo == fp32 result to 2^-16)."""
+    M, N, K = 1000, 320, 192
+    g = torch.Generator().manual_seed(bn)
+    A, W = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    want = (A.double() @ W.double().T + bias.double()).float()
+    C = torch.zeros(M, N, device=DEV)
+    Cs = torch.zeros(2, M, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm_tc(ops.split_bf16(cu(A)), ops.split_bf16(cu(W)), M, N, K, bias=cu(bias), C=C, ldc=N, c_split=Cs, ldcs=N, bn=bn)
+    np.testing.assert_allclose(np_(C), want.numpy(), rtol=0, atol=6e-5)
+    np.testing.assert_allclose(np_(Cs[0].float() + Cs[1].float()), np_(C), rtol=2e-5, atol=1e-6)
+
+
+def test_gemm_tensor_core_batched_head_slices():
+    """batched form used by the image-pool projections: per-head column slices of A (K=32 zero-padded to 64 in W),
+    per-head W rows, per-head output column blocks."""
+    BV, heads, hd, C = 777, 8, 32, 512
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(BV, heads * hd, generator=g)
+    wk = torch.randn(heads, C, hd, generator=g) / hd ** 0.5            # per head (C, hd): w_eff_h = q_h @ wk_h^T
+    want = torch.einsum("bhe,hce->bhc", q.view(BV, heads, hd).double(), wk.double()).float()
+    wpad = torch.zeros(heads * C, 64)
+    wpad[:, :hd] = wk.reshape(heads * C, hd)
+    out = torch.zeros(BV, heads, C, device=DEV)
+    ops.gemm_tc(ops.split_bf16(cu(q)), ops.split_bf16(cu(wpad)), BV, C, 64, batch=heads, a_koff_z=hd, w_row_z=C, C=out,
+                ldc=heads * C, c_off_z=C)
+    np.testing.assert_allclose(np_(out), want.numpy(), rtol=0, atol=6e-5)
