@@ -139,6 +139,14 @@ typedef struct pt_img_pool_params {
     const float* h_v;    /* (T,c)   = (pos + bc) @ Wv^T + bv                               */
     const float *cproj_w, *cproj_b; /* (c,c),(c) */
     const float *ln_w, *ln_b;       /* norm_img (c) */
+    /* Optional bf16 hi/lo planes ([2][rows][cols], see pt_split_bf16) for the tensor-core fast path taken when img_feat
+     * is bf16 and (C, HW, c, heads) = (512, 225, 256, 8); all five or none:
+     *   w_qc_split   (c, C)            W_qc
+     *   wk_pad_split (heads*C, 64)     row h*C + ch, col e < hd: (Wk Wc)[h*hd+e][ch]; cols >= hd zero
+     *   gk_pad_split (heads*228, 64)   row h*228 + t, col e < hd: g_k[t][h*hd+e]; rows t >= T and cols >= hd zero
+     *   wv_cat_split (c, 768)          cols [0,C): Wv Wc ; cols C + t: h_v[t][row] (t < T), rest zero
+     *   cproj_split  (c, c)            c_proj weight */
+    const void *w_qc_split, *wk_pad_split, *gk_pad_split, *wv_cat_split, *cproj_split;
 } pt_img_pool_params;
 
 size_t pt_img_attnpool_ws_bytes(int BV, int C, int HW, int c, int heads);

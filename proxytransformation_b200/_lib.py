@@ -35,7 +35,8 @@ class GemmTcDesc(Structure):
 
 
 class ImgPoolParams(Structure):
-    _fields_ = [(n, c_void_p) for n in ("w_qc", "q0", "w_kc", "g_k", "w_vc", "h_v", "cproj_w", "cproj_b", "ln_w", "ln_b")]
+    _fields_ = [(n, c_void_p) for n in ("w_qc", "q0", "w_kc", "g_k", "w_vc", "h_v", "cproj_w", "cproj_b", "ln_w", "ln_b",
+                                        "w_qc_split", "wk_pad_split", "gk_pad_split", "wv_cat_split", "cproj_split")]
 
 
 _P = c_void_p

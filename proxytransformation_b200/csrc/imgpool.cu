@@ -195,6 +195,11 @@ __global__ void __launch_bounds__(PB_THREADS) img_pool_kernel(const void* __rest
     }
 }
 
+size_t img_attnpool_tc_ws_bytes(int BV);
+bool img_attnpool_tc_supported(int img_dtype, const pt_img_pool_params* p, int C, int HW, int c, int heads);
+int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, int BV, float* img_proxy, void* ws, size_t ws_bytes,
+                           cudaStream_t s);
+
 static size_t pool_smem_bytes(int HW, int Tp) {
     return ((size_t)PB_CH * (HW | 1) + PB_CH * PB_HEADS + (size_t)Tp * PB_HEADS + 4 * PB_HEADS * PB_CH) * sizeof(float);
 }
@@ -226,7 +231,8 @@ static ImgWs carve(void* ws, int BV, int C, int HW, int c, int heads) {
 using namespace pt;
 
 extern "C" size_t pt_img_attnpool_ws_bytes(int BV, int C, int HW, int c, int heads) {
-    return carve(nullptr, BV, C, HW, c, heads).total;
+    const size_t a = carve(nullptr, BV, C, HW, c, heads).total, b = img_attnpool_tc_ws_bytes(BV);
+    return a > b ? a : b;
 }
 
 // Host-prepared folded weights (see pt_img_pool_params): w_qc (c,C); q0 (c); w_kc is consumed TRANSPOSED PER HEAD as
@@ -236,6 +242,8 @@ extern "C" int pt_img_attnpool(const void* img_feat, int img_dtype, const pt_img
                                int c, int heads, float* img_proxy, void* ws, size_t ws_bytes, pt_stream_t stream) {
     PT_REQUIRE(img_feat && p && img_proxy && ws, "pt_img_attnpool: null pointer");
     PT_REQUIRE(img_dtype == PT_DTYPE_F32 || img_dtype == PT_DTYPE_BF16, "pt_img_attnpool: dtype %d", img_dtype);
+    if (BV > 0 && img_attnpool_tc_supported(img_dtype, p, C, HW, c, heads))      // bf16 tensor-core fast path (imgpool_tc.cu)
+        return launch_img_attnpool_tc(img_feat, p, BV, img_proxy, ws, ws_bytes, (cudaStream_t)stream);
     PT_REQUIRE(heads == PB_HEADS, "pt_img_attnpool: heads=%d unsupported (8)", heads);
     PT_REQUIRE(BV > 0 && C % PB_CH == 0 && c % heads == 0 && HW >= 1 && HW <= PB_THREADS,
                "pt_img_attnpool: BV=%d C=%d HW=%d c=%d unsupported", BV, C, HW, c);

@@ -1,0 +1,510 @@
+// S9 image proxies, bf16 fast path: get_img_proxy (:335-342) + AttentionPool2d.forward (:154-177) in single-query form
+// (algebra in imgpool.cu) for the shipped geometry C=512 channels, 15x15=225 positions, 8 heads of 32.
+//
+//   pass A  img_mean_bf16_kernel   per-channel spatial mean (HBM-bound stream, one warp per 8 channels = 3600 B)
+//   G1-G3   tcgen05 3xBF16 GEMMs   q = W_qc xbar + q0 ; w_eff_h = q_h W_kc_h ; cterm_h = q_h . g_k     (gemm_tc.cu)
+//   pass B  img_pool_mma_kernel    scores -> softmax -> attention-weighted feature sums, one persistent CTA per SM:
+//             * a producer warp streams the view as eight 64-channel slabs (28.8 KB, cp.async.bulk + mbarrier) through a
+//               6-deep shared-memory ring; 6 of the 8 slabs stay resident between the score and the weighted-sum phase,
+//               2 are fetched again (L2 hits), so HBM sees every byte once;
+//             * scores S[8 heads][225] = W_eff X and sums Y[8][512] = P X^T run on the tensor cores (mma.sync m16n8k16
+//               bf16, fp32 accumulate): the fp32 operand (w_eff / probabilities) is split into bf16 hi + lo halves that
+//               occupy rows 0-7 / 8-15 of the 16-row A tile, X is already bf16, so the products are exact to ~2^-17;
+//             * the k index of every MMA is permuted so that the B fragments can be read straight from the raw
+//               [channel][225] bf16 rows (450-byte pitch, not 16-byte aligned: no ldmatrix / UMMA layout possible)
+//               without shared-memory bank conflicts.
+//   G4-G5   z_h = [y_h | a_h] [W_vc_h | h_v_h]^T ; o = W_c z + b_c ; LayerNorm                      (gemm_tc.cu, dense.cu)
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+#include <math.h>
+
+namespace pt {
+
+int launch_layernorm(const float* x, const float* w, const float* b, const float* add, int add_rows, int rows, int c,
+                     float* out, cudaStream_t s);
+
+namespace ip {
+constexpr int C = 512, HW = 225, HEADS = 8, HD = 32, EMB = 256;
+constexpr int T = HW + 1;                  // attention tokens (mean token first)
+constexpr int TP = 228;                    // cterm row pitch
+constexpr int YA = 768;                    // per (view, head) row of the value GEMM: 512 weighted sums + 256 probabilities
+constexpr int SLAB_CH = 64, NSLAB = C / SLAB_CH;
+constexpr int SLAB_BYTES = SLAB_CH * HW * 2;          // 28800
+constexpr int RING = 6, REFETCH = NSLAB - RING;       // 2 slabs are streamed a second time per view
+constexpr int LOADS_PER_VIEW = NSLAB + REFETCH;
+constexpr int NT_SCORE = 29;               // 8-token score tiles (232 >= 225)
+constexpr int CONSUMER_WARPS = 8, THREADS = 32 * (CONSUMER_WARPS + 1);
+// shared memory carve-up (bytes)
+constexpr int OFF_RING = 0;
+constexpr int OFF_PAD = OFF_RING + RING * SLAB_BYTES;                 // 128 B of zeros behind the ring (fragment over-reads)
+constexpr int OFF_WFRAG = OFF_PAD + 128;                              // [32 k-blocks][32 lanes][4 x u32]
+constexpr int OFF_PFRAG = OFF_WFRAG + 32 * 32 * 16;                   // [16 k-blocks][32 lanes][4 x u32]
+constexpr int OFF_S = OFF_PFRAG + 16 * 32 * 16;                       // fp32 scores [8][232]
+constexpr int OFF_XBAR = OFF_S + HEADS * 232 * 4;                     // fp32 [512]
+constexpr int OFF_MISC = OFF_XBAR + C * 4;                            // s0 partials [8 warps][8], p0 [8]
+constexpr int OFF_BAR = OFF_MISC + (64 + 8) * 4;                      // full[RING], empty[RING]
+constexpr int SMEM_BYTES = OFF_BAR + 2 * RING * 8 + 32;
+static_assert(OFF_WFRAG % 16 == 0 && OFF_PFRAG % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
+}  // namespace ip
+
+__device__ __forceinline__ uint32_t ip_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ip_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ip_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void ip_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ip_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ip_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ip_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ip_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(ip_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void ip_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ip_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(ip_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void ip_consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// fp32 -> (bf16 hi, bf16 lo) with hi + lo == x to ~2^-17
+__device__ __forceinline__ void split_hi_lo(float x, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    hi = (uint32_t)__bfloat16_as_ushort(h);
+    lo = (uint32_t)__bfloat16_as_ushort(l);
+}
+
+// ------------------------------------------------------------------------------------------------ pass A
+// One warp per group of 8 channels (1800 bf16 = 225 uint4, 16-byte aligned).  Iteration i of a lane reads uint4
+// lane + 32 i, whose 8 elements belong to channel i or i+1 of the group only, so the 8 running sums are static registers.
+__global__ void __launch_bounds__(256) img_mean_bf16_kernel(const uint4* __restrict__ img, long long groups,
+                                                            float* __restrict__ xbar, __nv_bfloat16* __restrict__ xb_hi,
+                                                            __nv_bfloat16* __restrict__ xb_lo) {
+    const int lane = threadIdx.x & 31;
+    const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long grp = wg; grp < groups; grp += nw) {
+        const uint4* src = img + grp * 225;
+        uint4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int j = lane + 32 * i;
+            v[i] = j < 225 ? __ldg(src + j) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        float acc[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int j = lane + 32 * i;
+            const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { f[2 * e] = __uint_as_float(w[e] << 16); f[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
+            const float s_all = ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
+            const int nlo = min(max(225 * (i + 1) - 8 * j, 0), 8);       // elements of this uint4 that belong to channel i
+            if (nlo == 8) acc[i] += s_all;
+            else if (nlo == 0) acc[i + 1] += s_all;
+            else {
+                float s_lo = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s_lo += e < nlo ? f[e] : 0.f;
+                float s_hi = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s_hi += e < nlo ? 0.f : f[e];
+                acc[i] += s_lo;
+                acc[i + 1] += s_hi;
+            }
+        }
+        // transposed butterfly: after three exchange steps lane l holds the partial of channel (l & 7) summed over the
+        // lanes congruent to l mod 4... (8 values x 32 lanes -> 8 totals with 3 + 2 shuffle rounds instead of 40 shuffles)
+        float r4[4], r2[2], r1;
+        {
+            const bool up = lane & 16;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float keep = up ? acc[k + 4] : acc[k], give = up ? acc[k] : acc[k + 4];
+                r4[k] = keep + __shfl_xor_sync(FULL, give, 16);
+            }
+        }
+        {
+            const bool up = lane & 8;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float keep = up ? r4[k + 2] : r4[k], give = up ? r4[k] : r4[k + 2];
+                r2[k] = keep + __shfl_xor_sync(FULL, give, 8);
+            }
+        }
+        {
+            const bool up = lane & 4;
+            const float keep = up ? r2[1] : r2[0], give = up ? r2[0] : r2[1];
+            r1 = keep + __shfl_xor_sync(FULL, give, 4);
+        }
+        r1 += __shfl_xor_sync(FULL, r1, 2);
+        r1 += __shfl_xor_sync(FULL, r1, 1);
+        // lane bits: 16 -> +4, 8 -> +2, 4 -> +1 of the channel index
+        if ((lane & 3) == 0) {
+            const int ch = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            const float m = r1 / 225.0f;
+            const long long o = grp * 8 + ch;
+            xbar[o] = m;
+            const __nv_bfloat16 h = __float2bfloat16_rn(m);
+            xb_hi[o] = h;
+            xb_lo[o] = __float2bfloat16_rn(m - __bfloat162float(h));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ pass B
+struct PoolArgs {
+    const uint8_t* img;          // (BV, 512, 225) bf16
+    const float* w_eff;          // (BV, 8, 512) fp32
+    const float* cterm;          // (BV, 8, TP) fp32: q_h . g_k[t,h]
+    const float* xbar;           // (BV, 512) fp32
+    __nv_bfloat16* ya_hi;        // (BV, 8, 768) bf16 hi plane: [0,512) weighted sums, [512,768) probabilities (zero padded)
+    long long ya_plane;          // elements between the hi and lo planes
+    int BV;
+    float scale;
+};
+
+__global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const PoolArgs a) {
+    using namespace ip;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* empty = full + RING;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int b = 0; b < RING; ++b) { ip_mbar_init(full + b, 1); ip_mbar_init(empty + b, CONSUMER_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 32) reinterpret_cast<uint32_t*>(smem + OFF_PAD)[tid] = 0u;
+    __syncthreads();
+
+    if (warp == CONSUMER_WARPS) {
+        // ===== producer: slabs 0..7 of the view, then slabs 0..REFETCH-1 again (FIFO ring, see header) =====
+        if (lane == 0) {
+            unsigned cnt = 0;
+            for (int bv = blockIdx.x; bv < a.BV; bv += gridDim.x) {
+                const uint8_t* view = a.img + (size_t)bv * C * HW * 2;
+                for (int k = 0; k < LOADS_PER_VIEW; ++k, ++cnt) {
+                    const int slab = k < NSLAB ? k : k - NSLAB;
+                    const unsigned b = cnt % RING, ph = (cnt / RING) & 1u;
+                    ip_mbar_wait(empty + b, ph ^ 1u);
+                    ip_mbar_expect_tx(full + b, SLAB_BYTES);
+                    ip_bulk_load(smem + OFF_RING + b * SLAB_BYTES, view + (size_t)slab * SLAB_BYTES, SLAB_BYTES, full + b);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const int g = lane >> 2, q = lane & 3;
+    uint4* wfrag = reinterpret_cast<uint4*>(smem + OFF_WFRAG);
+    uint32_t* pfrag32 = reinterpret_cast<uint32_t*>(smem + OFF_PFRAG);
+    float* S = reinterpret_cast<float*>(smem + OFF_S);
+    float* sxbar = reinterpret_cast<float*>(smem + OFF_XBAR);
+    float* s0part = reinterpret_cast<float*>(smem + OFF_MISC);
+    float* p0 = s0part + 64;
+    // score tiles of this warp: i = warp, warp+8, warp+16, warp+24 (< 29)
+    const int ntile = warp < NT_SCORE - 24 ? 4 : 3;
+    unsigned cnt = 0;              // loads consumed so far (ring position / parity)
+
+    for (int bv = blockIdx.x; bv < a.BV; bv += gridDim.x) {
+        // ---- (0) per-view operands: xbar -> smem, w_eff -> bf16 hi/lo A fragments, s0 = w_eff . xbar
+        ip_consumer_sync();                                   // every warp is done with the previous view's smem operands
+        const float* we = a.w_eff + (size_t)bv * HEADS * C;
+        const float* xb = a.xbar + (size_t)bv * C;
+        for (int i = tid; i < C / 4; i += 256) reinterpret_cast<float4*>(sxbar)[i] = __ldg(reinterpret_cast<const float4*>(xb) + i);
+        float dotp = 0.f;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int id = tid + 256 * r, kb = id >> 5;        // fragment entry (k-block kb, lane id & 31 == lane)
+            const int ch = 64 * (kb >> 2) + 16 * q + 4 * (kb & 3);
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(we + g * C + ch));
+            const float4 x4 = __ldg(reinterpret_cast<const float4*>(xb + ch));
+            dotp = fmaf(w4.x, x4.x, fmaf(w4.y, x4.y, fmaf(w4.z, x4.z, fmaf(w4.w, x4.w, dotp))));
+            uint32_t h0, l0, h1, l1, h2, l2, h3, l3;
+            split_hi_lo(w4.x, h0, l0); split_hi_lo(w4.y, h1, l1); split_hi_lo(w4.z, h2, l2); split_hi_lo(w4.w, h3, l3);
+            // a0 = (row g: hi, k-slots 2q,2q+1), a1 = (row g+8: lo), a2 = (row g: hi, slots 2q+8,2q+9), a3 = lo
+            wfrag[id] = make_uint4(h0 | (h1 << 16), l0 | (l1 << 16), h2 | (h3 << 16), l2 | (l3 << 16));
+        }
+        dotp += __shfl_xor_sync(FULL, dotp, 1);
+        dotp += __shfl_xor_sync(FULL, dotp, 2);
+        if (q == 0) s0part[warp * 8 + g] = dotp;
+        // cterm of the score columns this thread will own (attention token = spatial token + 1)
+        const float* ct = a.cterm + ((size_t)bv * HEADS + g) * TP;
+        float ctv[4][2];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int tok = 8 * (warp + 8 * t) + 2 * q;
+            ctv[t][0] = (t < ntile && tok < HW) ? __ldg(ct + 1 + tok) : 0.f;
+            ctv[t][1] = (t < ntile && tok + 1 < HW) ? __ldg(ct + 2 + tok) : 0.f;
+        }
+        ip_consumer_sync();
+
+        // ---- (1) scores: S[h][tok] = sum_ch w_eff[h][ch] X[ch][tok]
+        float acc[4][4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
+        for (int sl = 0; sl < NSLAB; ++sl) {
+            const unsigned k = cnt + sl, b = k % RING, ph = (k / RING) & 1u;
+            ip_mbar_wait(full + b, ph);
+            const unsigned short* X = reinterpret_cast<const unsigned short*>(smem + OFF_RING + b * SLAB_BYTES) + (16 * q) * HW + g + 8 * warp;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint4 af = wfrag[(sl * 4 + j) * 32 + lane];
+                const uint32_t A[4] = {af.x, af.y, af.z, af.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (t < ntile) {
+                        const unsigned short* x = X + (4 * j) * HW + 64 * t;
+                        const uint32_t b0 = (uint32_t)x[0] | ((uint32_t)x[HW] << 16);
+                        const uint32_t b1 = (uint32_t)x[2 * HW] | ((uint32_t)x[3 * HW] << 16);
+                        mma_bf16_16816(acc[t], A, b0, b1);
+                    }
+                }
+            }
+            if (sl < REFETCH) {                                // this slab is not kept: hand the buffer back
+                __syncwarp();
+                if (lane == 0) ip_mbar_arrive(empty + b);
+            }
+        }
+        // write the scores (hi + lo rows of the accumulator) ; token 0 = mean token
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (t < ntile) {
+                const int tok = 8 * (warp + 8 * t) + 2 * q;
+                if (tok < HW) S[g * 232 + 1 + tok] = a.scale * ((acc[t][0] + acc[t][2]) + ctv[t][0]);
+                if (tok + 1 < HW) S[g * 232 + 2 + tok] = a.scale * ((acc[t][1] + acc[t][3]) + ctv[t][1]);
+            }
+        }
+        ip_consumer_sync();
+
+        // ---- (2) softmax over the 226 tokens, warp <-> head ; probabilities -> bf16 hi/lo A fragments + global
+        {
+            const int h = warp;
+            if (lane == 0) {
+                float s0 = 0.f;
+#pragma unroll
+                for (int w = 0; w < CONSUMER_WARPS; ++w) s0 += s0part[w * 8 + h];
+                S[h * 232] = a.scale * (s0 + __ldg(a.cterm + ((size_t)bv * HEADS + h) * TP));
+            }
+            __syncwarp();
+            float sv[8];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int t = lane + 32 * i;
+                sv[i] = t < T ? S[h * 232 + t] : -INFINITY;
+                mx = fmaxf(mx, sv[i]);
+            }
+            mx = warp_max(mx);
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { sv[i] = (lane + 32 * i) < T ? expf(sv[i] - mx) : 0.f; sum += sv[i]; }
+            sum = warp_sum(sum);
+            const float inv = 1.0f / sum;
+            __nv_bfloat16* ya = a.ya_hi + ((size_t)bv * HEADS + h) * YA + C;
+            unsigned short* pf16 = reinterpret_cast<unsigned short*>(pfrag32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int t = lane + 32 * i;                   // attention token 0..255 (>= 226: zero padding)
+                const float p = sv[i] * inv;
+                uint32_t hi, lo;
+                split_hi_lo(p, hi, lo);
+                ya[t] = __ushort_as_bfloat16((unsigned short)hi);
+                ya[a.ya_plane + t] = __ushort_as_bfloat16((unsigned short)lo);
+                if (t == 0) p0[h] = p;
+                // spatial token tau = t - 1 -> fragment slot (tokens 225..255 of the k range are written as zeros below)
+                const int tau = t - 1;
+                if (tau >= 0) {
+                    const int kb = 2 * (tau >> 5) + ((tau >> 2) & 1), fl = 4 * h + ((tau >> 3) & 3), reg = (tau & 2);
+                    const int o16 = ((kb * 32 + fl) * 4 + reg) * 2 + (tau & 1);
+                    pf16[o16] = (unsigned short)hi;
+                    pf16[o16 + 2] = (unsigned short)lo;       // reg + 1
+                }
+            }
+            if (lane == 0) {                                   // tau = 255 (t = 256) is not covered by the loop above
+                const int tau = 255;
+                const int kb = 2 * (tau >> 5) + ((tau >> 2) & 1), fl = 4 * h + ((tau >> 3) & 3), reg = (tau & 2);
+                const int o16 = ((kb * 32 + fl) * 4 + reg) * 2 + (tau & 1);
+                pf16[o16] = 0; pf16[o16 + 2] = 0;
+            }
+        }
+        ip_consumer_sync();
+
+        // ---- (3) weighted sums: Y[h][ch] = sum_tok P[h][tok] X[ch][tok]  (+ p0[h] xbar[ch]) ; warp <-> 8 channels of a slab
+        uint32_t PA[16][4];
+#pragma unroll
+        for (int kb = 0; kb < 16; ++kb) {
+            const uint4 pf = reinterpret_cast<const uint4*>(pfrag32)[kb * 32 + lane];
+            PA[kb][0] = pf.x; PA[kb][1] = pf.y; PA[kb][2] = pf.z; PA[kb][3] = pf.w;
+        }
+        const float p0g = p0[g];
+        const uint32_t shift = (g & 1) * 16;                   // rows of odd channels start on an odd bf16 (225 is odd)
+        __nv_bfloat16* yrow = a.ya_hi + ((size_t)bv * HEADS + g) * YA;
+        for (int s2 = 0; s2 < NSLAB; ++s2) {
+            // resident slabs REFETCH..7 first (FIFO release order), then the re-fetched slabs 0..REFETCH-1
+            const int sl = s2 < NSLAB - REFETCH ? s2 + REFETCH : s2 - (NSLAB - REFETCH);
+            const unsigned k = s2 < NSLAB - REFETCH ? cnt + sl : cnt + NSLAB + sl;
+            const unsigned b = k % RING;
+            if (s2 >= NSLAB - REFETCH) ip_mbar_wait(full + b, (k / RING) & 1u);
+            const int cl = 8 * warp + g;                        // channel within the slab
+            const uint32_t* Xw = reinterpret_cast<const uint32_t*>(smem + OFF_RING + b * SLAB_BYTES) + ((cl * HW + 8 * q) >> 1);
+            float y[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                uint32_t w[5];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) w[i] = Xw[16 * p + i];
+                uint32_t r[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) r[i] = __funnelshift_r(w[i], w[i + 1], shift);
+                if (p == 7) {                                  // tokens 224..255: only 224 is real, the rest must not leak NaNs
+                    r[0] = q == 0 ? (r[0] & 0xffffu) : 0u;
+                    r[1] = 0u; r[2] = 0u; r[3] = 0u;
+                }
+                mma_bf16_16816(y, PA[2 * p], r[0], r[1]);
+                mma_bf16_16816(y, PA[2 * p + 1], r[2], r[3]);
+            }
+            __syncwarp();
+            if (lane == 0) ip_mbar_arrive(empty + b);
+            // accumulator rows g (hi part) / g+8 (lo part), columns = channels 8*warp + 2q, +1 of slab sl
+            const int ch = sl * SLAB_CH + 8 * warp + 2 * q;
+            const float y0 = (y[0] + y[2]) + p0g * sxbar[ch], y1 = (y[1] + y[3]) + p0g * sxbar[ch + 1];
+            uint32_t h0, l0, h1, l1;
+            split_hi_lo(y0, h0, l0);
+            split_hi_lo(y1, h1, l1);
+            *reinterpret_cast<uint32_t*>(yrow + ch) = h0 | (h1 << 16);
+            *reinterpret_cast<uint32_t*>(yrow + a.ya_plane + ch) = l0 | (l1 << 16);
+        }
+        cnt += LOADS_PER_VIEW;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+struct ImgTcWs {
+    float *xbar, *w_eff, *cterm, *o;
+    __nv_bfloat16 *xbar_split, *q_split, *ya_split, *z_split;
+    size_t total;
+};
+
+static ImgTcWs carve_tc(void* ws, int BV) {
+    using namespace ip;
+    ImgTcWs r;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* p = ws ? (void*)((char*)ws + off) : nullptr; off += align_up(bytes, 256); return p; };
+    r.xbar = (float*)take((size_t)BV * C * 4);
+    r.xbar_split = (__nv_bfloat16*)take((size_t)2 * BV * C * 2);
+    r.q_split = (__nv_bfloat16*)take((size_t)2 * BV * EMB * 2);
+    r.w_eff = (float*)take((size_t)BV * HEADS * C * 4);
+    r.cterm = (float*)take((size_t)BV * HEADS * TP * 4);
+    r.ya_split = (__nv_bfloat16*)take((size_t)2 * BV * HEADS * YA * 2);
+    r.z_split = (__nv_bfloat16*)take((size_t)2 * BV * EMB * 2);
+    r.o = (float*)take((size_t)BV * EMB * 4);
+    r.total = off;
+    return r;
+}
+
+size_t img_attnpool_tc_ws_bytes(int BV) { return carve_tc(nullptr, BV).total; }
+
+bool img_attnpool_tc_supported(int img_dtype, const pt_img_pool_params* p, int C, int HW, int c, int heads) {
+    return img_dtype == PT_DTYPE_BF16 && C == ip::C && HW == ip::HW && c == ip::EMB && heads == ip::HEADS && p->w_qc_split &&
+           p->wk_pad_split && p->gk_pad_split && p->wv_cat_split && p->cproj_split;
+}
+
+int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, int BV, float* img_proxy, void* ws, size_t ws_bytes,
+                           cudaStream_t s) {
+    using namespace ip;
+    PT_REQUIRE(((uintptr_t)img_feat & 15) == 0, "pt_img_attnpool: img_feat must be 16-byte aligned");
+    ImgTcWs w = carve_tc(ws, BV);
+    if (ws_bytes < w.total) { set_error("pt_img_attnpool: workspace %zu < %zu", ws_bytes, w.total); return PT_ERR_WORKSPACE; }
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    {   // pass A
+        const long long groups = (long long)BV * (C / 8);
+        const long long blocks = (groups + 7) / 8;
+        const int grid = (int)(blocks < (long long)sms * 8 ? blocks : (long long)sms * 8);
+        ProfScope prof_(PROF_IMG_MEAN, s);
+        img_mean_bf16_kernel<<<grid, 256, 0, s>>>((const uint4*)img_feat, groups, w.xbar, w.xbar_split, w.xbar_split + (size_t)BV * C);
+    }
+    PT_LAUNCH_CHECK();
+    int rc;
+    {   // G1: q = xbar W_qc^T + q0  -> split planes only
+        GemmTc gp;
+        gp.M = BV; gp.N = EMB; gp.K = C;
+        gp.a_split = w.xbar_split; gp.a_rows = BV; gp.a_cols = C; gp.lda = C;
+        gp.w_split = p->w_qc_split; gp.w_rows = EMB; gp.ldw = C;
+        gp.bias = p->q0;
+        gp.c_split = w.q_split; gp.cs_plane = (long long)BV * EMB; gp.ldcs = EMB;
+        if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
+    }
+    {   // G2: w_eff[:, h, :] = q[:, 32h:32h+32] W_kc_h   (K = 32 real + 32 columns that hit zero weights)
+        GemmTc gp;
+        gp.M = BV; gp.N = C; gp.K = 64; gp.batch = HEADS;
+        gp.a_split = w.q_split; gp.a_rows = BV; gp.a_cols = EMB; gp.lda = EMB; gp.a_koff_z = HD;
+        gp.w_split = p->wk_pad_split; gp.w_rows = HEADS * C; gp.ldw = 64; gp.w_row_z = C;
+        gp.C = w.w_eff; gp.ldc = HEADS * C; gp.c_off_z = C;
+        if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
+    }
+    {   // G3: cterm[:, h, t] = q[:, 32h:32h+32] . g_k[t, 32h:32h+32]
+        GemmTc gp;
+        gp.M = BV; gp.N = TP; gp.K = 64; gp.batch = HEADS;
+        gp.a_split = w.q_split; gp.a_rows = BV; gp.a_cols = EMB; gp.lda = EMB; gp.a_koff_z = HD;
+        gp.w_split = p->gk_pad_split; gp.w_rows = HEADS * TP; gp.ldw = 64; gp.w_row_z = TP;
+        gp.C = w.cterm; gp.ldc = HEADS * TP; gp.c_off_z = TP;
+        if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
+    }
+    {   // pass B
+        static bool attr_set = false;
+        if (!attr_set) {
+            PT_CUDA_OK(cudaFuncSetAttribute(img_pool_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            attr_set = true;
+        }
+        PoolArgs a;
+        a.img = (const uint8_t*)img_feat; a.w_eff = w.w_eff; a.cterm = w.cterm; a.xbar = w.xbar;
+        a.ya_hi = w.ya_split; a.ya_plane = (long long)BV * HEADS * YA; a.BV = BV;
+        a.scale = (float)(1.0 / sqrt((double)HD));
+        const int grid = BV < sms ? BV : sms;
+        { ProfScope prof_(PROF_IMG_POOL, s); img_pool_mma_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(a); }
+        PT_LAUNCH_CHECK();
+    }
+    {   // G4: z[:, 32h:32h+32] = [y_h | a_h] [W_vc_h | h_v_h]^T   -> split planes only
+        GemmTc gp;
+        gp.M = BV; gp.N = HD; gp.K = YA; gp.batch = HEADS;
+        gp.a_split = w.ya_split; gp.a_rows = BV; gp.a_cols = HEADS * YA; gp.lda = HEADS * YA; gp.a_koff_z = YA;
+        gp.w_split = p->wv_cat_split; gp.w_rows = EMB; gp.ldw = YA; gp.w_row_z = HD;
+        gp.c_split = w.z_split; gp.cs_plane = (long long)BV * EMB; gp.ldcs = EMB; gp.cs_off_z = HD;
+        if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
+    }
+    {   // G5: o = z W_c^T + b_c
+        GemmTc gp;
+        gp.M = BV; gp.N = EMB; gp.K = EMB;
+        gp.a_split = w.z_split; gp.a_rows = BV; gp.a_cols = EMB; gp.lda = EMB;
+        gp.w_split = p->cproj_split; gp.w_rows = EMB; gp.ldw = EMB;
+        gp.bias = p->cproj_b;
+        gp.C = w.o; gp.ldc = EMB;
+        if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
+    }
+    return launch_layernorm(w.o, p->ln_w, p->ln_b, nullptr, 1, BV, EMB, img_proxy, s);
+}
+
+}  // namespace pt

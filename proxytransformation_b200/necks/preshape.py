@@ -239,9 +239,23 @@ class ProxyTransformationNormReverse(nn.Module):
         h_v[:, :, :T] = (posb @ Wv.T + bv).T.reshape(heads, hd, T)
         w_kc = (Wk @ Wc).reshape(heads, hd, C).transpose(1, 2)             # (heads, C, hd): NT operand per head
         f = lambda t: t.to(torch.float32).contiguous()
-        return dict(w_qc=f(Wq @ Wc), q0=f(Wq @ posb[0] + bq), w_kc=f(w_kc), g_k=f(g_k), w_vc=f(Wv @ Wc), h_v=f(h_v),
-                    cproj_w=f(d64(ap.c_proj.weight)), cproj_b=f(d64(ap.c_proj.bias)), ln_w=f(d64(self.norm_img.weight)),
-                    ln_b=f(d64(self.norm_img.bias)))
+        out = dict(w_qc=f(Wq @ Wc), q0=f(Wq @ posb[0] + bq), w_kc=f(w_kc), g_k=f(g_k), w_vc=f(Wv @ Wc), h_v=f(h_v),
+                   cproj_w=f(d64(ap.c_proj.weight)), cproj_b=f(d64(ap.c_proj.bias)), ln_w=f(d64(self.norm_img.weight)),
+                   ln_b=f(d64(self.norm_img.bias)))
+        if self.use_tensor_cores and (C, self.img_spacial_dim, c, heads) == (512, 15, 256, 8):
+            # operands of the bf16 tensor-core fast path (csrc/imgpool_tc.cu), layouts in include/pt_preshape.h
+            TPc = 228
+            wk_pad = torch.zeros(heads * C, 64, dtype=torch.float64, device=device)
+            wk_pad[:, :hd] = w_kc.reshape(heads * C, hd)
+            gk_pad = torch.zeros(heads, TPc, 64, dtype=torch.float64, device=device)
+            gk_pad[:, :T, :hd] = (posb @ Wk.T).reshape(T, heads, hd).transpose(0, 1)
+            wv_cat = torch.zeros(c, 768, dtype=torch.float64, device=device)
+            wv_cat[:, :C] = Wv @ Wc
+            wv_cat[:, C:C + T] = (posb @ Wv.T + bv).T
+            out.update(w_qc_split=ops.split_bf16(out["w_qc"]), wk_pad_split=ops.split_bf16(f(wk_pad)),
+                       gk_pad_split=ops.split_bf16(f(gk_pad.reshape(heads * TPc, 64))), wv_cat_split=ops.split_bf16(f(wv_cat)),
+                       cproj_split=ops.split_bf16(out["cproj_w"]))
+        return out
 
     # ------------------------------------------------------------------ forward (:424-469)
     @torch.no_grad()

@@ -181,6 +181,7 @@ def heads(guide, lin_w, lin_b, bn_scale, bn_shift):
     return out
 
 
+_IMG_SPLIT_KEYS = ("w_qc_split", "wk_pad_split", "gk_pad_split", "wv_cat_split", "cproj_split")
 _IMG_KEYS = ("w_qc", "q0", "w_kc", "g_k", "w_vc", "h_v", "cproj_w", "cproj_b", "ln_w", "ln_b")
 
 
@@ -188,6 +189,9 @@ def make_img_params(w: Dict[str, torch.Tensor]) -> ImgPoolParams:
     p = ImgPoolParams()
     for k in _IMG_KEYS:
         setattr(p, k, _chk(w[k], torch.float32, k))
+    for k in _IMG_SPLIT_KEYS:      # tensor-core fast path operands (all or none)
+        t = w.get(k)
+        setattr(p, k, _chk(t, torch.bfloat16, k) if t is not None else None)
     return p
 
 
