@@ -51,6 +51,11 @@ ProfScope::~ProfScope() {
 
 int launch_layernorm(const float* x, const float* w, const float* b, const float* add, int add_rows, int rows, int c,
                      float* out, cudaStream_t s);
+int launch_layernorm_split(const float* x, const float* w, const float* b, const float* add, int add_rows, int rows, int c,
+                           float* out, __nv_bfloat16* out_hi, long long out_plane, cudaStream_t s);
+bool proxy_attention_mma_supported(int n, int l, int c, int heads);
+int launch_proxy_attention_mma(const float* qkv, const float* pt_tok, const uint8_t* mask, int B, int n, int l, int c, int heads,
+                               float* o, void* o_split, long long o_plane, cudaStream_t s);
 int launch_gemm_f32(const float* A, const float* W, const float* bias, const float* residual, int act, int M, int N, int K,
                     float* C, cudaStream_t s);
 int launch_proxy_attention(const float* qkv, const float* pt_tok, const uint8_t* mask, int B, int n, int l, int c,
@@ -66,6 +71,8 @@ struct BlockWs {
     float *u, *qkv, *pt, *o, *x1, *h2, *hid, *x2;
     void* gemm;
     size_t gemm_bytes, total;
+    // tensor-core pipeline: bf16 hi/lo planes alias the fp32 buffers of the same stage (2 planes x 2 B == 4 B per element)
+    __nv_bfloat16 *u_s, *o_s, *h2_s, *hid_s, *proxy_s;
 };
 
 static BlockWs carve_block(void* ws, int B, int n, int l, int c, int hidden) {
@@ -87,6 +94,8 @@ static BlockWs carve_block(void* ws, int B, int n, int l, int c, int hidden) {
     r.gemm_bytes = g > g2 ? (g > g3 ? g : g3) : (g2 > g3 ? g2 : g3);
     r.gemm = take(r.gemm_bytes);
     r.total = off;
+    r.u_s = (__nv_bfloat16*)r.u; r.o_s = (__nv_bfloat16*)r.o; r.h2_s = (__nv_bfloat16*)r.h2; r.hid_s = (__nv_bfloat16*)r.hid;
+    r.proxy_s = (__nv_bfloat16*)r.gemm;          // (B*l, c) split planes fit: gemm_bytes >= gemm_tc_ws_bytes(B*l, c, c)
     return r;
 }
 
@@ -139,6 +148,40 @@ extern "C" int pt_proxy_block_fused(const float* x, const float* proxy, const ui
     cudaStream_t s = (cudaStream_t)stream;
     const int rows = B * n;
     int rc;
+    const bool tc = p->qkv_w_split && p->pp_w_split && p->proj_w_split && p->fc1_w_split && p->fc2_w_split && c % 64 == 0 &&
+                    hidden % 64 == 0 && proxy_attention_mma_supported(n, l, c, heads);
+    if (tc) {
+        // Tensor-core pipeline: every GEMM operand is produced directly as bf16 hi/lo planes by the kernel before it
+        // (LayerNorm, attention, fc1 epilogue), so no separate splitting passes and no fp32 copies of u / o / h2 / hid.
+        auto gemm = [&](const __nv_bfloat16* a, int M, int K, const void* w, int N, const float* bias, const float* res, int act,
+                        float* C, __nv_bfloat16* Cs) {
+            GemmTc gp;
+            gp.M = M; gp.N = N; gp.K = K;
+            gp.a_split = a; gp.a_rows = M; gp.a_cols = K; gp.lda = K;
+            gp.w_split = w; gp.w_rows = N; gp.ldw = K;
+            gp.bias = bias; gp.residual = res; gp.act = act;
+            gp.C = C; gp.ldc = N;
+            gp.c_split = Cs; gp.cs_plane = (long long)M * N; gp.ldcs = N;
+            return launch_gemm_tc_ex(gp, s);
+        };
+        // u = LN1(x) + bias[m]                                        (:274, :212-217)
+        if ((rc = launch_layernorm_split(x, p->ln1_w, p->ln1_b, p->pos_bias, n, rows, c, nullptr, w.u_s, (long long)rows * c, s))) return rc;
+        // [Q|K|V] = u Wqkv^T                                          (:221)
+        if ((rc = gemm(w.u_s, rows, c, p->qkv_w_split, 3 * c, nullptr, nullptr, 0, w.qkv, nullptr))) return rc;
+        // Pt = proxy Wp^T + bp                                        (:223)
+        if ((rc = split_rows_bf16(proxy, (long long)B * l * c, w.proxy_s, w.proxy_s + (size_t)B * l * c, s))) return rc;
+        if ((rc = gemm(w.proxy_s, B * l, c, p->pp_w_split, c, p->pp_b, nullptr, 0, w.pt, nullptr))) return rc;
+        // two-stage proxy attention                                   (:225-252)
+        if ((rc = launch_proxy_attention_mma(w.qkv, w.pt, mask, B, n, l, c, heads, nullptr, w.o_s, (long long)rows * c, s))) return rc;
+        // x1 = x + (o Wo^T + bo)                                      (:255, :274)
+        if ((rc = gemm(w.o_s, rows, c, p->proj_w_split, c, p->proj_b, x, 0, w.x1, nullptr))) return rc;
+        // x2 = x1 + fc2(GELU(fc1(LN2(x1))))                           (:275)
+        if ((rc = launch_layernorm_split(w.x1, p->ln2_w, p->ln2_b, nullptr, 1, rows, c, nullptr, w.h2_s, (long long)rows * c, s))) return rc;
+        if ((rc = gemm(w.h2_s, rows, c, p->fc1_w_split, hidden, p->fc1_b, nullptr, 1, nullptr, w.hid_s))) return rc;
+        if ((rc = gemm(w.hid_s, rows, hidden, p->fc2_w_split, c, p->fc2_b, w.x1, 0, w.x2, nullptr))) return rc;
+        return launch_layernorm(w.x2, p->lno_w, p->lno_b, nullptr, 1, rows, c, out, s);
+    }
+    // fp32 CUDA-core pipeline (no split weights supplied, or a shape the tensor-core kernels do not cover)
     // u = LN1(x) + bias[m]                                           (:274, :212-217)
     if ((rc = launch_layernorm(x, p->ln1_w, p->ln1_b, p->pos_bias, n, rows, c, w.u, s))) return rc;
     // [Q|K|V] = u Wqkv^T                                             (:221)

@@ -12,7 +12,8 @@ namespace pt {
 template <int CPL>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ b, const float* __restrict__ add,
-                                                        int add_rows, int rows, float* __restrict__ out) {
+                                                        int add_rows, int rows, float* __restrict__ out,
+                                                        __nv_bfloat16* __restrict__ out_hi, long long out_plane) {
     constexpr int C = CPL * 32;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -32,7 +33,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         const int ch = lane + 32 * i;
         float y = fmaf((v[i] - mean) * rstd, __ldg(w + ch), __ldg(b + ch));
         if (ad) y += __ldg(ad + ch);
-        out[(size_t)row * C + ch] = y;
+        if (out != nullptr) out[(size_t)row * C + ch] = y;
+        if (out_hi != nullptr) {                  // bf16 hi/lo planes: operand of the following tensor-core GEMM
+            const __nv_bfloat16 h = __float2bfloat16_rn(y);
+            out_hi[(size_t)row * C + ch] = h;
+            out_hi[out_plane + (size_t)row * C + ch] = __float2bfloat16_rn(y - __bfloat162float(h));
+        }
     }
 }
 
@@ -189,12 +195,19 @@ __global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ g,
     }
 }
 
+int launch_layernorm_split(const float* x, const float* w, const float* b, const float* add, int add_rows, int rows, int c,
+                           float* out, __nv_bfloat16* out_hi, long long out_plane, cudaStream_t s);
 int launch_layernorm(const float* x, const float* w, const float* b, const float* add, int add_rows, int rows, int c,
                      float* out, cudaStream_t s) {
+    return launch_layernorm_split(x, w, b, add, add_rows, rows, c, out, nullptr, 0, s);
+}
+
+int launch_layernorm_split(const float* x, const float* w, const float* b, const float* add, int add_rows, int rows, int c,
+                           float* out, __nv_bfloat16* out_hi, long long out_plane, cudaStream_t s) {
     PT_REQUIRE(c % 32 == 0 && c >= 32 && c <= 1024, "layernorm: c=%d unsupported", c);
     const int wpb = 8, grid = ceil_div(rows, wpb);
     switch (c / 32) {
-#define PT_LN_CASE(CPL) case CPL: { ProfScope prof_(PROF_LAYERNORM, s); layernorm_kernel<CPL><<<grid, wpb * 32, 0, s>>>(x, w, b, add, add_rows, rows, out); } break;
+#define PT_LN_CASE(CPL) case CPL: { ProfScope prof_(PROF_LAYERNORM, s); layernorm_kernel<CPL><<<grid, wpb * 32, 0, s>>>(x, w, b, add, add_rows, rows, out, out_hi, out_plane); } break;
         PT_LN_CASE(1) PT_LN_CASE(2) PT_LN_CASE(4) PT_LN_CASE(8) PT_LN_CASE(16) PT_LN_CASE(32)
 #undef PT_LN_CASE
         default: PT_REQUIRE(false, "layernorm: c=%d unsupported (c/32 must be a power of two)", c);
