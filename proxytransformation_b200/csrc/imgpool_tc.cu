@@ -18,6 +18,7 @@
 #include "gemm_tc.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace pt {
 
@@ -33,19 +34,22 @@ constexpr int SLAB_CH = 64, NSLAB = C / SLAB_CH;
 constexpr int SLAB_BYTES = SLAB_CH * HW * 2;          // 28800
 constexpr int RING = 6, REFETCH = NSLAB - RING;       // 2 slabs are streamed a second time per view
 constexpr int LOADS_PER_VIEW = NSLAB + REFETCH;
+constexpr int PF_DIST = 4;                 // L2 prefetch distance of the producer, in ring loads
 constexpr int NT_SCORE = 29;               // 8-token score tiles (232 >= 225)
-constexpr int CONSUMER_WARPS = 8, THREADS = 32 * (CONSUMER_WARPS + 1);
+constexpr int CONSUMER_WARPS = 16, THREADS = 32 * (CONSUMER_WARPS + 1);
 // shared memory carve-up (bytes)
 constexpr int OFF_RING = 0;
 constexpr int OFF_PAD = OFF_RING + RING * SLAB_BYTES;                 // 128 B of zeros behind the ring (fragment over-reads)
 constexpr int OFF_WFRAG = OFF_PAD + 128;                              // [32 k-blocks][32 lanes][4 x u32]
 constexpr int OFF_PFRAG = OFF_WFRAG + 32 * 32 * 16;                   // [16 k-blocks][32 lanes][4 x u32]
 constexpr int OFF_S = OFF_PFRAG + 16 * 32 * 16;                       // fp32 scores [8][232]
-constexpr int OFF_XBAR = OFF_S + HEADS * 232 * 4;                     // fp32 [512]
-constexpr int OFF_MISC = OFF_XBAR + C * 4;                            // s0 partials [8 warps][8], p0 [8]
-constexpr int OFF_BAR = OFF_MISC + (64 + 8) * 4;                      // full[RING], empty[RING]
-constexpr int SMEM_BYTES = OFF_BAR + 2 * RING * 8 + 32;
-static_assert(OFF_WFRAG % 16 == 0 && OFF_PFRAG % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
+constexpr int OFF_XBAR = OFF_S + HEADS * 232 * 4;                     // fp32 [2][512]  (double-buffered by view parity)
+constexpr int OFF_WSTAGE = OFF_XBAR + 2 * C * 4;                      // fp32 [8][512]  next view's w_eff (bulk-copied)
+constexpr int OFF_MISC = OFF_WSTAGE + HEADS * C * 4;                  // s0 partials [16 warps][8], p0 [8], softmax exchange [32]
+constexpr int OFF_BAR = OFF_MISC + (128 + 8 + 32) * 4;                      // full[RING], empty[RING], wfull, wempty
+constexpr int SMEM_BYTES = OFF_BAR + (2 * RING + 2) * 8 + 16;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(OFF_WFRAG % 16 == 0 && OFF_PFRAG % 16 == 0 && OFF_BAR % 8 == 0 && OFF_WSTAGE % 16 == 0 && OFF_XBAR % 16 == 0, "alignment");
 }  // namespace ip
 
 __device__ __forceinline__ uint32_t ip_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -74,7 +78,10 @@ __device__ __forceinline__ void ip_bulk_load(void* dst, const void* src, uint32_
                  "l"(src), "r"(bytes), "r"(ip_smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void ip_consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void ip_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ip_consumer_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -179,6 +186,8 @@ struct PoolArgs {
     long long ya_plane;          // elements between the hi and lo planes
     int BV;
     float scale;
+    int pf_dist;                 // L2 prefetch distance of the producer in ring loads (0 = off)
+    int debug_skip;              // PT_POOL_DEBUG=1: consumers only wait/release (load-pipeline ceiling), results are garbage
 };
 
 __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const PoolArgs a) {
@@ -186,10 +195,14 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* empty = full + RING;
+    uint64_t* wfull = empty + RING;
+    uint64_t* wempty = wfull + 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
         for (int b = 0; b < RING; ++b) { ip_mbar_init(full + b, 1); ip_mbar_init(empty + b, CONSUMER_WARPS); }
+        ip_mbar_init(wfull, 1);
+        ip_mbar_init(wempty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 32) reinterpret_cast<uint32_t*>(smem + OFF_PAD)[tid] = 0u;
@@ -198,12 +211,26 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
     if (warp == CONSUMER_WARPS) {
         // ===== producer: slabs 0..7 of the view, then slabs 0..REFETCH-1 again (FIFO ring, see header) =====
         if (lane == 0) {
-            unsigned cnt = 0;
-            for (int bv = blockIdx.x; bv < a.BV; bv += gridDim.x) {
+            unsigned cnt = 0, vi = 0;
+            for (int bv = blockIdx.x; bv < a.BV; bv += gridDim.x, ++vi) {
+                // per-view operands (w_eff 16 KB -> staging, xbar 2 KB -> buffer vi & 1); they are requested as soon as the
+                // previous view's slab loads are all in flight, i.e. while the consumers are still in its weighted-sum phase
+                ip_mbar_wait(wempty, (vi & 1u) ^ 1u);
+                ip_mbar_expect_tx(wfull, HEADS * C * 4 + C * 4);
+                ip_bulk_load(smem + OFF_WSTAGE, a.w_eff + (size_t)bv * HEADS * C, HEADS * C * 4, wfull);
+                ip_bulk_load(smem + OFF_XBAR + (vi & 1u) * C * 4, a.xbar + (size_t)bv * C, C * 4, wfull);
                 const uint8_t* view = a.img + (size_t)bv * C * HW * 2;
                 for (int k = 0; k < LOADS_PER_VIEW; ++k, ++cnt) {
                     const int slab = k < NSLAB ? k : k - NSLAB;
                     const unsigned b = cnt % RING, ph = (cnt / RING) & 1u;
+                    // The ring holds barely one view, so a slab can only be requested when the consumers let go of a
+                    // buffer: too late to hide HBM latency.  Pull the slab that will be requested PF_DIST loads from now
+                    // into L2 already (re-fetched slabs are L2-resident anyway).
+                    {
+                        int k2 = k + a.pf_dist, bv2 = bv;
+                        if (k2 >= LOADS_PER_VIEW) { k2 -= LOADS_PER_VIEW; bv2 += gridDim.x; }
+                        if (a.pf_dist > 0 && k2 < NSLAB && bv2 < a.BV) ip_prefetch_l2(a.img + (size_t)bv2 * C * HW * 2 + (size_t)k2 * SLAB_BYTES, SLAB_BYTES);
+                    }
                     ip_mbar_wait(empty + b, ph ^ 1u);
                     ip_mbar_expect_tx(full + b, SLAB_BYTES);
                     ip_bulk_load(smem + OFF_RING + b * SLAB_BYTES, view + (size_t)slab * SLAB_BYTES, SLAB_BYTES, full + b);
@@ -213,72 +240,89 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
         return;
     }
 
-    // ===== consumers =====
+    // ===== consumers: 16 warps =====
     const int g = lane >> 2, q = lane & 3;
     uint4* wfrag = reinterpret_cast<uint4*>(smem + OFF_WFRAG);
     uint32_t* pfrag32 = reinterpret_cast<uint32_t*>(smem + OFF_PFRAG);
     float* S = reinterpret_cast<float*>(smem + OFF_S);
-    float* sxbar = reinterpret_cast<float*>(smem + OFF_XBAR);
-    float* s0part = reinterpret_cast<float*>(smem + OFF_MISC);
-    float* p0 = s0part + 64;
-    // score tiles of this warp: i = warp, warp+8, warp+16, warp+24 (< 29)
-    const int ntile = warp < NT_SCORE - 24 ? 4 : 3;
-    unsigned cnt = 0;              // loads consumed so far (ring position / parity)
+    const float* wstage = reinterpret_cast<const float*>(smem + OFF_WSTAGE);
+    float* s0part = reinterpret_cast<float*>(smem + OFF_MISC);          // [16 warps][8 heads]
+    float* p0 = s0part + 128;                                           // [8]
+    float* red = p0 + 8;                                                // [2][16] softmax max / sum exchange
+    float4* ypart = reinterpret_cast<float4*>(smem + OFF_WFRAG);        // [2][8 n-tiles][32 lanes], aliases Wfrag (dead in phase 3)
+    // scores: warp <-> (pair of 16-token groups gp, gp + 8 ; channel parity)
+    const int gp = warp & 7, par = warp >> 3;
+    const int ngrp = gp + 8 < 15 ? 2 : 1;                               // 15 groups = 240 tokens >= 225
+    // sums: warp <-> (8-channel tile nt of the slab ; token half kh: tokens [128 kh, 128 kh + 128))
+    const int nt = warp & 7, kh = warp >> 3;
+    unsigned cnt = 0, vi = 0;      // loads consumed so far (ring position / parity), views done
 
-    for (int bv = blockIdx.x; bv < a.BV; bv += gridDim.x) {
-        // ---- (0) per-view operands: xbar -> smem, w_eff -> bf16 hi/lo A fragments, s0 = w_eff . xbar
-        ip_consumer_sync();                                   // every warp is done with the previous view's smem operands
-        const float* we = a.w_eff + (size_t)bv * HEADS * C;
-        const float* xb = a.xbar + (size_t)bv * C;
-        for (int i = tid; i < C / 4; i += 256) reinterpret_cast<float4*>(sxbar)[i] = __ldg(reinterpret_cast<const float4*>(xb) + i);
-        float dotp = 0.f;
+    for (int bv = blockIdx.x; bv < a.BV; bv += gridDim.x, ++vi) {
+        // ---- (0) per-view operands (staged by the producer): w_eff -> bf16 hi/lo A fragments, s0 = w_eff . xbar
+        ip_consumer_sync();                                   // every warp is done with the previous view's Wfrag / ypart / scores
+        const float* sxbar = reinterpret_cast<const float*>(smem + OFF_XBAR + (vi & 1u) * C * 4);
+        ip_mbar_wait(wfull, vi & 1u);
+        {
+            // 8 consecutive channels ch..ch+7 of head g -> two fragment entries: k-block 4*sl+jj takes the even channels,
+            // k-block 4*sl+2+jj the odd ones (k-slot s <-> channel ch + 2s + parity), see the score loop
+            const int sl = warp >> 1, jj = warp & 1;
+            const int ch = 64 * sl + 16 * q + 8 * jj;
+            float f[8], x[8];
+            *reinterpret_cast<float4*>(f) = *reinterpret_cast<const float4*>(wstage + g * C + ch);
+            *reinterpret_cast<float4*>(f + 4) = *reinterpret_cast<const float4*>(wstage + g * C + ch + 4);
+            *reinterpret_cast<float4*>(x) = *reinterpret_cast<const float4*>(sxbar + ch);
+            *reinterpret_cast<float4*>(x + 4) = *reinterpret_cast<const float4*>(sxbar + ch + 4);
+            uint32_t hi[8], lo[8];
+            float dotp = 0.f;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int id = tid + 256 * r, kb = id >> 5;        // fragment entry (k-block kb, lane id & 31 == lane)
-            const int ch = 64 * (kb >> 2) + 16 * q + 4 * (kb & 3);
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(we + g * C + ch));
-            const float4 x4 = __ldg(reinterpret_cast<const float4*>(xb + ch));
-            dotp = fmaf(w4.x, x4.x, fmaf(w4.y, x4.y, fmaf(w4.z, x4.z, fmaf(w4.w, x4.w, dotp))));
-            uint32_t h0, l0, h1, l1, h2, l2, h3, l3;
-            split_hi_lo(w4.x, h0, l0); split_hi_lo(w4.y, h1, l1); split_hi_lo(w4.z, h2, l2); split_hi_lo(w4.w, h3, l3);
+            for (int e = 0; e < 8; ++e) { dotp = fmaf(f[e], x[e], dotp); split_hi_lo(f[e], hi[e], lo[e]); }
             // a0 = (row g: hi, k-slots 2q,2q+1), a1 = (row g+8: lo), a2 = (row g: hi, slots 2q+8,2q+9), a3 = lo
-            wfrag[id] = make_uint4(h0 | (h1 << 16), l0 | (l1 << 16), h2 | (h3 << 16), l2 | (l3 << 16));
+            wfrag[(4 * sl + jj) * 32 + lane] = make_uint4(hi[0] | (hi[2] << 16), lo[0] | (lo[2] << 16), hi[4] | (hi[6] << 16), lo[4] | (lo[6] << 16));
+            wfrag[(4 * sl + 2 + jj) * 32 + lane] = make_uint4(hi[1] | (hi[3] << 16), lo[1] | (lo[3] << 16), hi[5] | (hi[7] << 16), lo[5] | (lo[7] << 16));
+            dotp += __shfl_xor_sync(FULL, dotp, 1);
+            dotp += __shfl_xor_sync(FULL, dotp, 2);
+            if (q == 0) s0part[warp * 8 + g] = dotp;
         }
-        dotp += __shfl_xor_sync(FULL, dotp, 1);
-        dotp += __shfl_xor_sync(FULL, dotp, 2);
-        if (q == 0) s0part[warp * 8 + g] = dotp;
-        // cterm of the score columns this thread will own (attention token = spatial token + 1)
-        const float* ct = a.cterm + ((size_t)bv * HEADS + g) * TP;
-        float ctv[4][2];
+        // cterm of the score columns the even-parity warps own: tokens 16 i + 4 q + {0,1,2,3} (attention token = spatial + 1)
+        float ctv[2][4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int tok = 8 * (warp + 8 * t) + 2 * q;
-            ctv[t][0] = (t < ntile && tok < HW) ? __ldg(ct + 1 + tok) : 0.f;
-            ctv[t][1] = (t < ntile && tok + 1 < HW) ? __ldg(ct + 2 + tok) : 0.f;
-        }
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int tok = 16 * (gp + 8 * t) + 4 * q + e;
+                ctv[t][e] = (par == 0 && t < ngrp && tok < HW) ? __ldg(a.cterm + ((size_t)bv * HEADS + g) * TP + 1 + tok) : 0.f;
+            }
         ip_consumer_sync();
+        if (tid == 0) ip_mbar_arrive(wempty);                 // staging may be refilled with the next view's w_eff
 
-        // ---- (1) scores: S[h][tok] = sum_ch w_eff[h][ch] X[ch][tok]
-        float acc[4][4];
+        // ---- (1) scores: S[h][tok] = sum_ch w_eff[h][ch] X[ch][tok].
+        // A B register packs two k-consecutive bf16, i.e. the same token of two channels (two rows of the slab), so every
+        // aligned 32-bit word read from a row carries TWO tokens: one k-block (16 channels of one parity, chosen so that the
+        // words are aligned and the 32 lanes hit 32 different banks) feeds two 8-token tiles at once.  Even channels see
+        // tokens (16i+2g, +1) -> tiles E_i, O_i; odd channels (rows start on an odd bf16) see (16i+2g-1, 16i+2g) -> O'_i, E_i;
+        // O' is O shifted by one token (its first column, token -1, is the previous row's tail and is dropped).
+        // Warps 0-7 take the even channels, warps 8-15 the odd ones; the partial scores meet in shared memory.
+        float accA[2][4], accB[2][4];            // first / second token of the words
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
+        for (int t = 0; t < 2; ++t)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
+            for (int e = 0; e < 4; ++e) { accA[t][e] = 0.f; accB[t][e] = 0.f; }
         for (int sl = 0; sl < NSLAB; ++sl) {
             const unsigned k = cnt + sl, b = k % RING, ph = (k / RING) & 1u;
             ip_mbar_wait(full + b, ph);
-            const unsigned short* X = reinterpret_cast<const unsigned short*>(smem + OFF_RING + b * SLAB_BYTES) + (16 * q) * HW + g + 8 * warp;
+            const uint32_t* X0 = reinterpret_cast<const uint32_t*>(smem + OFF_RING + b * SLAB_BYTES) + 1800 * q + g + 8 * gp + (par ? 112 : 0);
+            if (!a.debug_skip)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint4 af = wfrag[(sl * 4 + j) * 32 + lane];
+            for (int jj = 0; jj < 2; ++jj) {
+                const uint4 af = wfrag[(sl * 4 + 2 * par + jj) * 32 + lane];
                 const uint32_t A[4] = {af.x, af.y, af.z, af.w};
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    if (t < ntile) {
-                        const unsigned short* x = X + (4 * j) * HW + 64 * t;
-                        const uint32_t b0 = (uint32_t)x[0] | ((uint32_t)x[HW] << 16);
-                        const uint32_t b1 = (uint32_t)x[2 * HW] | ((uint32_t)x[3 * HW] << 16);
-                        mma_bf16_16816(acc[t], A, b0, b1);
+                for (int t = 0; t < 2; ++t) {
+                    if (t < ngrp) {
+                        const uint32_t* x = X0 + (4 * jj) * HW + 64 * t;
+                        const uint32_t wa = x[0], wb = x[HW], wc = x[2 * HW], wd = x[3 * HW];
+                        mma_bf16_16816(accA[t], A, __byte_perm(wa, wb, 0x5410), __byte_perm(wc, wd, 0x5410));
+                        mma_bf16_16816(accB[t], A, __byte_perm(wa, wb, 0x7632), __byte_perm(wc, wd, 0x7632));
                     }
                 }
             }
@@ -287,53 +331,79 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
                 if (lane == 0) ip_mbar_arrive(empty + b);
             }
         }
-        // write the scores (hi + lo rows of the accumulator) ; token 0 = mean token
+        // unscaled scores (hi + lo rows of the accumulators): even-parity warps store E, O (+ cterm), then odd-parity warps
+        // add their E and O' contributions
+        if (par == 0) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            if (t < ntile) {
-                const int tok = 8 * (warp + 8 * t) + 2 * q;
-                if (tok < HW) S[g * 232 + 1 + tok] = a.scale * ((acc[t][0] + acc[t][2]) + ctv[t][0]);
-                if (tok + 1 < HW) S[g * 232 + 2 + tok] = a.scale * ((acc[t][1] + acc[t][3]) + ctv[t][1]);
+            for (int t = 0; t < 2; ++t) {
+                if (t < ngrp) {
+                    const int tok = 16 * (gp + 8 * t) + 4 * q;
+                    float* Sr = S + g * 232 + 1 + tok;
+                    if (tok < HW) Sr[0] = (accA[t][0] + accA[t][2]) + ctv[t][0];
+                    if (tok + 1 < HW) Sr[1] = (accB[t][0] + accB[t][2]) + ctv[t][1];
+                    if (tok + 2 < HW) Sr[2] = (accA[t][1] + accA[t][3]) + ctv[t][2];
+                    if (tok + 3 < HW) Sr[3] = (accB[t][1] + accB[t][3]) + ctv[t][3];
+                }
             }
         }
         ip_consumer_sync();
-
-        // ---- (2) softmax over the 226 tokens, warp <-> head ; probabilities -> bf16 hi/lo A fragments + global
-        {
-            const int h = warp;
-            if (lane == 0) {
-                float s0 = 0.f;
+        if (par == 1) {
 #pragma unroll
-                for (int w = 0; w < CONSUMER_WARPS; ++w) s0 += s0part[w * 8 + h];
-                S[h * 232] = a.scale * (s0 + __ldg(a.cterm + ((size_t)bv * HEADS + h) * TP));
+            for (int t = 0; t < 2; ++t) {
+                if (t < ngrp) {
+                    const int tok = 16 * (gp + 8 * t) + 4 * q;
+                    float* Sr = S + g * 232 + 1 + tok;
+                    // each (head, token) below is touched by exactly one thread: O' columns are tokens tok-1, tok+1
+                    float o_prev = accA[t][0] + accA[t][2], o_next = accA[t][1] + accA[t][3];
+                    if (tok < HW) Sr[0] += accB[t][0] + accB[t][2];
+                    if (tok + 2 < HW) Sr[2] += accB[t][1] + accB[t][3];
+                    if (tok >= 1 && tok - 1 < HW) Sr[-1] += o_prev;
+                    if (tok + 1 < HW) Sr[1] += o_next;
+                }
             }
-            __syncwarp();
-            float sv[8];
+        }
+        if (warp < HEADS && lane == 0) {                        // token 0 = mean token
+            float s0 = 0.f;
+#pragma unroll
+            for (int w = 0; w < CONSUMER_WARPS; ++w) s0 += s0part[w * 8 + warp];
+            S[warp * 232] = s0 + __ldg(a.cterm + ((size_t)bv * HEADS + warp) * TP);
+        }
+        ip_consumer_sync();
+
+        // ---- (2) softmax over the 226 tokens, two warps per head ; probabilities -> bf16 hi/lo A fragments + global
+        {
+            const int h = warp & 7, half = warp >> 3;
+            float sv[4];
             float mx = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int t = lane + 32 * i;
-                sv[i] = t < T ? S[h * 232 + t] : -INFINITY;
+            for (int i = 0; i < 4; ++i) {
+                const int t = 128 * half + lane + 32 * i;
+                sv[i] = t < T ? a.scale * S[h * 232 + t] : -INFINITY;
                 mx = fmaxf(mx, sv[i]);
             }
             mx = warp_max(mx);
+            if (lane == 0) red[warp] = mx;
+            ip_consumer_sync();
+            mx = fmaxf(red[h], red[h + 8]);
             float sum = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { sv[i] = (lane + 32 * i) < T ? expf(sv[i] - mx) : 0.f; sum += sv[i]; }
+            for (int i = 0; i < 4; ++i) { sv[i] = (128 * half + lane + 32 * i) < T ? expf(sv[i] - mx) : 0.f; sum += sv[i]; }
             sum = warp_sum(sum);
-            const float inv = 1.0f / sum;
+            if (lane == 0) red[16 + warp] = sum;
+            ip_consumer_sync();
+            const float inv = 1.0f / (red[16 + h] + red[16 + h + 8]);
             __nv_bfloat16* ya = a.ya_hi + ((size_t)bv * HEADS + h) * YA + C;
             unsigned short* pf16 = reinterpret_cast<unsigned short*>(pfrag32);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int t = lane + 32 * i;                   // attention token 0..255 (>= 226: zero padding)
+            for (int i = 0; i < 4; ++i) {
+                const int t = 128 * half + lane + 32 * i;      // attention token 0..255 (>= 226: zero padding)
                 const float p = sv[i] * inv;
                 uint32_t hi, lo;
                 split_hi_lo(p, hi, lo);
                 ya[t] = __ushort_as_bfloat16((unsigned short)hi);
                 ya[a.ya_plane + t] = __ushort_as_bfloat16((unsigned short)lo);
                 if (t == 0) p0[h] = p;
-                // spatial token tau = t - 1 -> fragment slot (tokens 225..255 of the k range are written as zeros below)
+                // spatial token tau = t - 1 -> fragment slot
                 const int tau = t - 1;
                 if (tau >= 0) {
                     const int kb = 2 * (tau >> 5) + ((tau >> 2) & 1), fl = 4 * h + ((tau >> 3) & 3), reg = (tau & 2);
@@ -342,7 +412,7 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
                     pf16[o16 + 2] = (unsigned short)lo;       // reg + 1
                 }
             }
-            if (lane == 0) {                                   // tau = 255 (t = 256) is not covered by the loop above
+            if (half == 1 && lane == 0) {                       // tau = 255 (t = 256) is not covered by the loop above
                 const int tau = 255;
                 const int kb = 2 * (tau >> 5) + ((tau >> 2) & 1), fl = 4 * h + ((tau >> 3) & 3), reg = (tau & 2);
                 const int o16 = ((kb * 32 + fl) * 4 + reg) * 2 + (tau & 1);
@@ -351,11 +421,12 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
         }
         ip_consumer_sync();
 
-        // ---- (3) weighted sums: Y[h][ch] = sum_tok P[h][tok] X[ch][tok]  (+ p0[h] xbar[ch]) ; warp <-> 8 channels of a slab
-        uint32_t PA[16][4];
+        // ---- (3) weighted sums: Y[h][ch] = sum_tok P[h][tok] X[ch][tok]  (+ p0[h] xbar[ch]).
+        // warp <-> (8 channels of the slab, half of the tokens); the two halves meet through ypart + a 64-thread barrier
+        uint32_t PA[8][4];
 #pragma unroll
-        for (int kb = 0; kb < 16; ++kb) {
-            const uint4 pf = reinterpret_cast<const uint4*>(pfrag32)[kb * 32 + lane];
+        for (int kb = 0; kb < 8; ++kb) {
+            const uint4 pf = reinterpret_cast<const uint4*>(pfrag32)[(8 * kh + kb) * 32 + lane];
             PA[kb][0] = pf.x; PA[kb][1] = pf.y; PA[kb][2] = pf.z; PA[kb][3] = pf.w;
         }
         const float p0g = p0[g];
@@ -367,34 +438,43 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
             const unsigned k = s2 < NSLAB - REFETCH ? cnt + sl : cnt + NSLAB + sl;
             const unsigned b = k % RING;
             if (s2 >= NSLAB - REFETCH) ip_mbar_wait(full + b, (k / RING) & 1u);
-            const int cl = 8 * warp + g;                        // channel within the slab
-            const uint32_t* Xw = reinterpret_cast<const uint32_t*>(smem + OFF_RING + b * SLAB_BYTES) + ((cl * HW + 8 * q) >> 1);
-            float y[4] = {0.f, 0.f, 0.f, 0.f};
+            const int cl = 8 * nt + g;                          // channel within the slab
+            const uint32_t* Xw = reinterpret_cast<const uint32_t*>(smem + OFF_RING + b * SLAB_BYTES) + ((cl * HW + 8 * q) >> 1) + 64 * kh;
+            float y[4] = {0.f, 0.f, 0.f, 0.f}, y2[4] = {0.f, 0.f, 0.f, 0.f};     // two independent MMA chains
+            if (!a.debug_skip)
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
+            for (int p = 0; p < 4; ++p) {
                 uint32_t w[5];
 #pragma unroll
                 for (int i = 0; i < 5; ++i) w[i] = Xw[16 * p + i];
                 uint32_t r[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) r[i] = __funnelshift_r(w[i], w[i + 1], shift);
-                if (p == 7) {                                  // tokens 224..255: only 224 is real, the rest must not leak NaNs
+                if (p == 3 && kh == 1) {                       // tokens 224..255: only 224 is real, the rest must not leak NaNs
                     r[0] = q == 0 ? (r[0] & 0xffffu) : 0u;
                     r[1] = 0u; r[2] = 0u; r[3] = 0u;
                 }
                 mma_bf16_16816(y, PA[2 * p], r[0], r[1]);
-                mma_bf16_16816(y, PA[2 * p + 1], r[2], r[3]);
+                mma_bf16_16816(y2, PA[2 * p + 1], r[2], r[3]);
             }
             __syncwarp();
             if (lane == 0) ip_mbar_arrive(empty + b);
-            // accumulator rows g (hi part) / g+8 (lo part), columns = channels 8*warp + 2q, +1 of slab sl
-            const int ch = sl * SLAB_CH + 8 * warp + 2 * q;
-            const float y0 = (y[0] + y[2]) + p0g * sxbar[ch], y1 = (y[1] + y[3]) + p0g * sxbar[ch + 1];
-            uint32_t h0, l0, h1, l1;
-            split_hi_lo(y0, h0, l0);
-            split_hi_lo(y1, h1, l1);
-            *reinterpret_cast<uint32_t*>(yrow + ch) = h0 | (h1 << 16);
-            *reinterpret_cast<uint32_t*>(yrow + a.ya_plane + ch) = l0 | (l1 << 16);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) y[e] += y2[e];
+            float4* yp = ypart + ((s2 & 1) * 8 + nt) * 32 + lane;
+            if (kh == 1) *yp = make_float4(y[0], y[1], y[2], y[3]);
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + nt) : "memory");
+            if (kh == 0) {
+                const float4 o4 = *yp;
+                // accumulator rows g (hi part) / g+8 (lo part), columns = channels 8*nt + 2q, +1 of slab sl
+                const int ch = sl * SLAB_CH + 8 * nt + 2 * q;
+                const float y0 = ((y[0] + o4.x) + (y[2] + o4.z)) + p0g * sxbar[ch], y1 = ((y[1] + o4.y) + (y[3] + o4.w)) + p0g * sxbar[ch + 1];
+                uint32_t h0, l0, h1, l1;
+                split_hi_lo(y0, h0, l0);
+                split_hi_lo(y1, h1, l1);
+                *reinterpret_cast<uint32_t*>(yrow + ch) = h0 | (h1 << 16);
+                *reinterpret_cast<uint32_t*>(yrow + a.ya_plane + ch) = l0 | (l1 << 16);
+            }
         }
         cnt += LOADS_PER_VIEW;
     }
@@ -483,6 +563,10 @@ int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, in
         a.img = (const uint8_t*)img_feat; a.w_eff = w.w_eff; a.cterm = w.cterm; a.xbar = w.xbar;
         a.ya_hi = w.ya_split; a.ya_plane = (long long)BV * HEADS * YA; a.BV = BV;
         a.scale = (float)(1.0 / sqrt((double)HD));
+        const char* dbg = getenv("PT_POOL_DEBUG");
+        a.debug_skip = dbg ? atoi(dbg) : 0;
+        const char* pf = getenv("PT_POOL_PF");
+        a.pf_dist = pf ? atoi(pf) : PF_DIST;
         const int grid = BV < sms ? BV : sms;
         { ProfScope prof_(PROF_IMG_POOL, s); img_pool_mma_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(a); }
         PT_LAUNCH_CHECK();
