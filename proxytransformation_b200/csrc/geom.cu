@@ -75,57 +75,87 @@ __global__ void __launch_bounds__(256) centres_kernel(const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------ S2 / S4
-// pytorch3d ball_query semantics (:56,:65).  One warp per centre; the 8 centres of a block share point chunks
-// staged in shared memory (coalesced loads, 8x reuse); lanes test 32 consecutive points per step and append hits in
-// index order with ballot/popc; a warp stops at K hits, the block stops when all of its warps have.
+// pytorch3d ball_query semantics (:56,:65): first K point indices in ascending index with d2 < r2, -1 padding.
+// One warp per centre, no shared memory and no block barriers: every centre scans the same point stream from index 0,
+// so the stream is L1/L2-resident and each warp stops exactly when ITS centre has K hits.  A lane tests 4 consecutive
+// points per step (3 x LDG.128 = 48 contiguous bytes, next step prefetched while the current one is tested); hits are
+// appended in index order from 4 ballots: slot = count + (hits of lower lanes) + (earlier hits of this lane).
 constexpr int BQ_WARPS = 8;
-constexpr int BQ_CHUNK = 2048;
+
+__device__ __forceinline__ void bq_unpack(const float4& a, const float4& b, const float4& c, float (&x)[4], float (&y)[4], float (&z)[4]) {
+    x[0] = a.x; y[0] = a.y; z[0] = a.z;
+    x[1] = a.w; y[1] = b.x; z[1] = b.y;
+    x[2] = b.z; y[2] = b.w; z[2] = c.x;
+    x[3] = c.y; y[3] = c.z; z[3] = c.w;
+}
 
 __global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_kernel(const float* __restrict__ centres,
                                                                    const float* __restrict__ points, int M, int N, int K,
                                                                    float r2, int32_t* __restrict__ idx,
-                                                                   int32_t* __restrict__ pad_counts) {
-    __shared__ float sp[BQ_CHUNK * 3];
-    const int b = blockIdx.y;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int m = blockIdx.x * BQ_WARPS + w;
-    const bool valid = m < M;
+                                                                   int32_t* __restrict__ pad_counts, long long total) {
+    const int lane = threadIdx.x & 31;
+    const long long cm = (long long)blockIdx.x * BQ_WARPS + (threadIdx.x >> 5);      // flat (scene, centre)
+    if (cm >= total) return;
+    const int b = (int)(cm / M);
     const float* P = points + (size_t)b * N * 3;
-    float cx = 0.f, cy = 0.f, cz = 0.f;
-    if (valid) {
-        const float* c = centres + ((size_t)b * M + m) * 3;
-        cx = __ldg(c); cy = __ldg(c + 1); cz = __ldg(c + 2);
-    }
-    int32_t* out = idx + ((size_t)b * M + (valid ? m : 0)) * K;
-    int cnt = 0;
-    bool done = !valid;
+    const float cx = __ldg(centres + cm * 3), cy = __ldg(centres + cm * 3 + 1), cz = __ldg(centres + cm * 3 + 2);
+    int32_t* out = idx + cm * K;
     const unsigned lt = (1u << lane) - 1u;
-    for (int base = 0; base < N; base += BQ_CHUNK) {
-        const int npts = min(BQ_CHUNK, N - base);
-        const float* src = P + (size_t)base * 3;
-        for (int i = threadIdx.x; i < npts * 3; i += BQ_WARPS * 32) sp[i] = __ldg(src + i);
-        __syncthreads();
-        if (!done) {
-            for (int j0 = 0; j0 < npts && cnt < K; j0 += 32) {
-                const int j = j0 + lane;
-                bool hit = false;
-                if (j < npts) hit = dist2_rn(cx, cy, cz, sp[3 * j], sp[3 * j + 1], sp[3 * j + 2]) < r2;
-                const unsigned mask = __ballot_sync(FULL, hit);
-                if (hit) {
-                    const int slot = cnt + __popc(mask & lt);
-                    if (slot < K) out[slot] = base + j;
-                }
-                cnt += __popc(mask);
+    int cnt = 0;
+    const int nfull = N / 128;                        // full 128-point steps (vector loads need 4 whole points per lane)
+    const bool vec_ok = (((uintptr_t)P) & 15) == 0;   // scene base 16-byte aligned (N*12 bytes per scene)
+    int step = 0;
+    if (vec_ok && nfull > 0) {
+        const float4* P4 = reinterpret_cast<const float4*>(P) + 3 * lane;
+        float4 a = __ldg(P4), bq = __ldg(P4 + 1), c = __ldg(P4 + 2);
+        for (; step < nfull; ++step) {
+            float4 na = a, nb = bq, nc = c;
+            if (step + 1 < nfull) {                   // prefetch the next 128 points
+                const float4* q4 = P4 + (size_t)(step + 1) * 96;
+                na = __ldg(q4); nb = __ldg(q4 + 1); nc = __ldg(q4 + 2);
             }
-            done = cnt >= K;
+            float x[4], y[4], z[4];
+            bq_unpack(a, bq, c, x, y, z);
+            unsigned m[4];
+            bool h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                h[i] = dist2_rn(cx, cy, cz, x[i], y[i], z[i]) < r2;
+                m[i] = __ballot_sync(FULL, h[i]);
+            }
+            if ((m[0] | m[1] | m[2] | m[3]) != 0u) {
+                int slot = cnt + __popc(m[0] & lt) + __popc(m[1] & lt) + __popc(m[2] & lt) + __popc(m[3] & lt);
+                const int j0 = step * 128 + 4 * lane;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (h[i]) {
+                        if (slot < K) out[slot] = j0 + i;
+                        ++slot;
+                    }
+                }
+                cnt += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
+                if (cnt >= K) break;
+            }
+            a = na; bq = nb; c = nc;
         }
-        if (__syncthreads_and(done)) break;
+        step = cnt >= K ? nfull : step;               // (unused after a break)
     }
-    if (valid) {
-        const int filled = min(cnt, K);
-        for (int k = filled + lane; k < K; k += 32) out[k] = -1;
-        if (pad_counts != nullptr && lane == 0) pad_counts[(size_t)b * M + m] = K - filled;
+    if (cnt < K) {                                     // scalar tail (and the unaligned / tiny-N case): 32 points per step
+        for (int j0 = (vec_ok ? nfull * 128 : 0); j0 < N && cnt < K; j0 += 32) {
+            const int j = j0 + lane;
+            bool hit = false;
+            if (j < N) hit = dist2_rn(cx, cy, cz, __ldg(P + (size_t)j * 3), __ldg(P + (size_t)j * 3 + 1), __ldg(P + (size_t)j * 3 + 2)) < r2;
+            const unsigned mask = __ballot_sync(FULL, hit);
+            if (hit) {
+                const int slot = cnt + __popc(mask & lt);
+                if (slot < K) out[slot] = j;
+            }
+            cnt += __popc(mask);
+        }
     }
+    const int filled = min(cnt, K);
+    for (int k = filled + lane; k < K; k += 32) out[k] = -1;
+    if (pad_counts != nullptr && lane == 0) pad_counts[cm] = K - filled;
 }
 
 // ------------------------------------------------------------------------------------------------ S3 / S6
@@ -362,8 +392,9 @@ extern "C" int pt_ball_query_firstk(const float* centres, const float* points, i
                                     int32_t* idx, int32_t* pad_counts, pt_stream_t stream) {
     PT_REQUIRE(B > 0 && M > 0 && N > 0 && K > 0, "pt_ball_query_firstk: B=%d M=%d N=%d K=%d", B, M, N, K);
     PT_REQUIRE(centres && points && idx, "pt_ball_query_firstk: null pointer");
-    { ProfScope prof_(PROF_BALL_QUERY, (cudaStream_t)stream); ball_query_kernel<<<dim3(ceil_div(M, BQ_WARPS), B), BQ_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        centres, points, M, N, K, radius * radius, idx, pad_counts); }
+    const long long total = (long long)B * M;
+    { ProfScope prof_(PROF_BALL_QUERY, (cudaStream_t)stream); ball_query_kernel<<<(unsigned)((total + BQ_WARPS - 1) / BQ_WARPS), BQ_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        centres, points, M, N, K, radius * radius, idx, pad_counts, total); }
     PT_LAUNCH_CHECK();
     return PT_OK;
 }
