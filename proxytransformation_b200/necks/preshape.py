@@ -155,6 +155,9 @@ class ProxyTransformationNormReverse(nn.Module):
         self._packed_key = None
         self._ws: Dict[str, torch.Tensor] = {}
         self.use_tensor_cores = True     # 3xBF16 tcgen05 GEMMs for the dense layers (falls back per shape inside the C side)
+        self.overlap_image_stage = False  # option: image proxies on a side CUDA stream; measured SLOWER on B200 (3.04 vs 2.86 ms/step)
+        # because the persistent pool kernel owns every SM's shared memory and the small kernels queue behind it
+        self._streams: Dict[str, torch.cuda.Stream] = {}
 
     # ------------------------------------------------------------------ reference helper API (same names, :332-350)
     def get_text_proxy(self, text_dict):
@@ -303,11 +306,28 @@ class ProxyTransformationNormReverse(nn.Module):
             raise ValueError(f"points must be (N,3) xyz per scene, got {tuple(P.shape)}")
         return P.to(dev, torch.float32, non_blocking=True).contiguous()
 
+    def _side_stream(self, device) -> "torch.cuda.Stream":
+        key = str(device)
+        if key not in self._streams:
+            self._streams[key] = torch.cuda.Stream(device=device)
+        return self._streams[key]
+
     def forward_packed(self, P, text, mask, img_feat, *, img_proxy=None, trace=None):
         """Device-resident form: P (B,N,3), text (B,L,c), mask (B,L) uint8|None, img_feat (B,V,C,H,W) ->
         (out (B,N,3) packed per scene, counts (B,) int32), no host synchronisation."""
         w = self._weights(P.device)
         K, n = self.num_sub, self.real_cluster_num
+        # S9 image proxies (:449) depend on nothing but img_feat and are HBM-bound, the geometric stages are latency/ALU
+        # bound: run them concurrently on a side stream and join before the image ProxyBlock.
+        side = None
+        if img_proxy is None and self.overlap_image_stage:
+            cur = torch.cuda.current_stream(P.device)
+            side = self._side_stream(P.device)
+            side.wait_stream(cur)
+            img_feat.record_stream(side)
+            with torch.cuda.stream(side):
+                img_proxy = ops.img_attnpool(img_feat, w["img"], self.num_heads, params=w["img_struct"])
+            img_proxy.record_stream(cur)
         # S1-S4 deformable clustering (:53-67)
         mn, mx, c0 = ops.minmax_centres(P, self.grid_size, w["lin"])
         idx1, _ = ops.ball_query(c0, P, K)
@@ -324,6 +344,8 @@ class ProxyTransformationNormReverse(nn.Module):
         # S9 image proxies (:449) and image branch -> transform (:450-455)
         if img_proxy is None:
             img_proxy = ops.img_attnpool(img_feat, w["img"], self.num_heads, params=w["img_struct"])
+        if side is not None:
+            torch.cuda.current_stream(P.device).wait_stream(side)
         ig = ops.proxy_block(pp, img_proxy, None, w["imgb"], self.num_heads, params=w["imgb_struct"])
         ih = w["img_head"]
         transform = ops.heads(ig, ih["lin_w"], ih["lin_b"], ih["bn_scale"], ih["bn_shift"])
