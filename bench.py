@@ -174,6 +174,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def measured_traffic(kernel: str, batch: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
+    (profiles/ncu_traffic.json, measured at a stated batch and scaled linearly in the batch); None if not captured."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
+        return t["dram_bytes_per_launch"] * batch / t["batch"]
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
     import torch.distributed as dist
@@ -296,16 +306,11 @@ def run_b200(args):
                "d2h_bytes_per_step": int(d2h) * world, "steps": e_steps, "ms_per_step": e_ms / e_steps,
                "timer": "host perf_counter around forward() incl. copies, max over ranks"}
 
-    # ---- the one collective of the path: all_gather of per-rank metric tensors
-    cnt = counts.to(torch.float64)
-    mine = torch.tensor([float(B), cnt.sum().item(), out[0, :int(counts[0])].double().sum().item(), ms, float(launches)],
-                        device=dev, dtype=torch.float64)
-    if world > 1:
-        gathered = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine)
-        allm = torch.stack(gathered).cpu()
-    else:
-        allm = mine[None].cpu()
+    # ---- the one collective of the path: all_gather of per-rank metric tensors (sharding.py)
+    from proxytransformation_b200 import sharding
+    cnt_host = counts.cpu().tolist()
+    mine = sharding.scene_metrics([out[b, :cnt_host[b]] for b in range(B)], elapsed_ms=ms, launches=launches, device=dev)
+    allm = sharding.gather_metrics(mine).cpu()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -334,7 +339,8 @@ def run_b200(args):
         t_ms, n = prof[dom]
         ach = alg_bytes[dom] / (t_ms / n / 1e3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "avg_launch_ms": t_ms / n, "algorithmic_bytes_per_launch": alg_bytes[dom]}
+                "traffic": measured_traffic(dom, B), "peak_source": peak_src, "avg_launch_ms": t_ms / n,
+                "algorithmic_bytes_per_launch": alg_bytes[dom]}
     elif dom in prof:
         t_ms, n = prof[dom]
         roof = {"bound": "latency", "kernel": dom, "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,
