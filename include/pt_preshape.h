@@ -153,6 +153,10 @@ size_t pt_img_attnpool_ws_bytes(int BV, int C, int HW, int c, int heads);
 int pt_img_attnpool(const void* img_feat, int img_dtype, const pt_img_pool_params* p, int BV, int C, int HW, int c,
                     int heads, float* img_proxy, void* ws, size_t ws_bytes, pt_stream_t stream);
 
+/* Debug only: per-phase SM-clock cycles of CTA 0 of the bf16 image-pool kernel, accumulated while PT_POOL_DEBUG has bit 8
+ * set: [0] view barrier, [1] operand wait, [2] fragment conversion, [3] score MMAs, [4] softmax, [5] weighted sums. */
+int pt_debug_pool_trace(unsigned long long* out8, int reset);
+
 /* ---- S10-S12 affine (:459-462) + pt_replace (:472-498) + remove_points_by_index (:501-525) ------------
  * new = (T[m] @ (p - centre[m]) + centre[m]) + t[m] for every valid (m,k); duplicate destinations resolved by the
  * pinned rule "largest flat m*K+k wins"; points listed in drop_idx (>= 0) are removed; survivors are written in

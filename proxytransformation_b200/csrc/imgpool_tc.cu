@@ -177,6 +177,17 @@ __global__ void __launch_bounds__(256) img_mean_bf16_kernel(const uint4* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ pass B
+// Debug timeline (PT_POOL_DEBUG bit 8): SM-clock cycles spent by CTA 0 / warp 0 in each phase, summed over its views.
+__device__ unsigned long long g_pool_trace[8];
+#define POOL_TRACE(slot)                                                                   \
+    do {                                                                                   \
+        if ((a.debug_skip & 8) && blockIdx.x == 0 && tid == 0) {                           \
+            const long long now_ = clock64();                                              \
+            atomicAdd(&g_pool_trace[slot], (unsigned long long)(now_ - t_prev));           \
+            t_prev = now_;                                                                 \
+        }                                                                                  \
+    } while (0)
+
 struct PoolArgs {
     const uint8_t* img;          // (BV, 512, 225) bf16
     const float* w_eff;          // (BV, 8, 512) fp32
@@ -187,7 +198,7 @@ struct PoolArgs {
     int BV;
     float scale;
     int pf_dist;                 // L2 prefetch distance of the producer in ring loads (0 = off)
-    int debug_skip;              // PT_POOL_DEBUG=1: consumers only wait/release (load-pipeline ceiling), results are garbage
+    int debug_skip;              // PT_POOL_DEBUG bit mask (results are garbage): 1 skip score MMAs, 4 skip sum MMAs, 2 no slab data (16-byte loads)
 };
 
 __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const PoolArgs a) {
@@ -232,8 +243,9 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
                         if (a.pf_dist > 0 && k2 < NSLAB && bv2 < a.BV) ip_prefetch_l2(a.img + (size_t)bv2 * C * HW * 2 + (size_t)k2 * SLAB_BYTES, SLAB_BYTES);
                     }
                     ip_mbar_wait(empty + b, ph ^ 1u);
-                    ip_mbar_expect_tx(full + b, SLAB_BYTES);
-                    ip_bulk_load(smem + OFF_RING + b * SLAB_BYTES, view + (size_t)slab * SLAB_BYTES, SLAB_BYTES, full + b);
+                    const uint32_t nbytes = (a.debug_skip & 2) ? 16u : (uint32_t)SLAB_BYTES;
+                    ip_mbar_expect_tx(full + b, nbytes);
+                    ip_bulk_load(smem + OFF_RING + b * SLAB_BYTES, view + (size_t)slab * SLAB_BYTES, nbytes, full + b);
                 }
             }
         }
@@ -257,11 +269,14 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
     const int nt = warp & 7, kh = warp >> 3;
     unsigned cnt = 0, vi = 0;      // loads consumed so far (ring position / parity), views done
 
+    long long t_prev = clock64();
     for (int bv = blockIdx.x; bv < a.BV; bv += gridDim.x, ++vi) {
         // ---- (0) per-view operands (staged by the producer): w_eff -> bf16 hi/lo A fragments, s0 = w_eff . xbar
         ip_consumer_sync();                                   // every warp is done with the previous view's Wfrag / ypart / scores
         const float* sxbar = reinterpret_cast<const float*>(smem + OFF_XBAR + (vi & 1u) * C * 4);
+        POOL_TRACE(0);                                        // barrier (0)
         ip_mbar_wait(wfull, vi & 1u);
+        POOL_TRACE(1);                                        // wait for the staged operands
         {
             // 8 consecutive channels ch..ch+7 of head g -> two fragment entries: k-block 4*sl+jj takes the even channels,
             // k-block 4*sl+2+jj the odd ones (k-slot s <-> channel ch + 2s + parity), see the score loop
@@ -294,6 +309,7 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
             }
         ip_consumer_sync();
         if (tid == 0) ip_mbar_arrive(wempty);                 // staging may be refilled with the next view's w_eff
+        POOL_TRACE(2);                                        // conversion + barrier (1)
 
         // ---- (1) scores: S[h][tok] = sum_ch w_eff[h][ch] X[ch][tok].
         // A B register packs two k-consecutive bf16, i.e. the same token of two channels (two rows of the slab), so every
@@ -311,7 +327,7 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
             const unsigned k = cnt + sl, b = k % RING, ph = (k / RING) & 1u;
             ip_mbar_wait(full + b, ph);
             const uint32_t* X0 = reinterpret_cast<const uint32_t*>(smem + OFF_RING + b * SLAB_BYTES) + 1800 * q + g + 8 * gp + (par ? 112 : 0);
-            if (!a.debug_skip)
+            if (!(a.debug_skip & 1))
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const uint4 af = wfrag[(sl * 4 + 2 * par + jj) * 32 + lane];
@@ -331,6 +347,7 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
                 if (lane == 0) ip_mbar_arrive(empty + b);
             }
         }
+        POOL_TRACE(3);                                        // score MMAs (incl. waiting for slabs)
         // unscaled scores (hi + lo rows of the accumulators): even-parity warps store E, O (+ cterm), then odd-parity warps
         // add their E and O' contributions
         if (par == 0) {
@@ -421,6 +438,7 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
         }
         ip_consumer_sync();
 
+        POOL_TRACE(4);                                        // score exchange + softmax + barriers
         // ---- (3) weighted sums: Y[h][ch] = sum_tok P[h][tok] X[ch][tok]  (+ p0[h] xbar[ch]).
         // warp <-> (8 channels of the slab, half of the tokens); the two halves meet through ypart + a 64-thread barrier
         uint32_t PA[8][4];
@@ -441,7 +459,7 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
             const int cl = 8 * nt + g;                          // channel within the slab
             const uint32_t* Xw = reinterpret_cast<const uint32_t*>(smem + OFF_RING + b * SLAB_BYTES) + ((cl * HW + 8 * q) >> 1) + 64 * kh;
             float y[4] = {0.f, 0.f, 0.f, 0.f}, y2[4] = {0.f, 0.f, 0.f, 0.f};     // two independent MMA chains
-            if (!a.debug_skip)
+            if (!(a.debug_skip & 4))
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 uint32_t w[5];
@@ -477,8 +495,20 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
             }
         }
         cnt += LOADS_PER_VIEW;
+        POOL_TRACE(5);                                        // weighted sums
     }
 }
+
+}  // namespace pt
+extern "C" int pt_debug_pool_trace(unsigned long long* out8, int reset) {
+    if (out8 && cudaMemcpyFromSymbol(out8, pt::g_pool_trace, sizeof(pt::g_pool_trace)) != cudaSuccess) return PT_ERR_CUDA;
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (cudaMemcpyToSymbol(pt::g_pool_trace, z, sizeof(z)) != cudaSuccess) return PT_ERR_CUDA;
+    }
+    return PT_OK;
+}
+namespace pt {
 
 // ------------------------------------------------------------------------------------------------ host
 struct ImgTcWs {
