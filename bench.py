@@ -287,7 +287,7 @@ def run_b200(args):
         h2d = sum(p.numel() * 4 for p in hsets[0][0]) + hsets[0][1]["text_feats"].numel() * 4 + hsets[0][1]["text_token_mask"].numel() + \
             hsets[0][2].numel() * hsets[0][2].element_size()
         res = m(*hsets[0])
-        d2h = sum(r.numel() * 4 for r in res) + 4 * B
+        d2h = B * cfg.n_points * 12 + 4 * B          # the packed (B,N,3) result block + B counts are copied back
         for i in range(max(1, args.warmup - 1)):
             m(*hsets[(i + 1) % 2])
         sync_all()
@@ -304,7 +304,8 @@ def run_b200(args):
             e_ms = t.item()
         e2e = {"value": world * B * e_steps / (e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world,
                "d2h_bytes_per_step": int(d2h) * world, "steps": e_steps, "ms_per_step": e_ms / e_steps,
-               "timer": "host perf_counter around forward() incl. copies, max over ranks"}
+               "timer": "host perf_counter around forward() incl. copies, max over ranks",
+               "pipeline": f"{m.host_chunk_scenes}-scene chunks over H2D / compute / D2H streams, one host sync per call"}
 
     # ---- the one collective of the path: all_gather of per-rank metric tensors (sharding.py)
     from proxytransformation_b200 import sharding
@@ -377,8 +378,18 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def _guard_stdout():
+    """Libraries (NCCL's version banner, torchrun) write to fd 1; the contract is ONE JSON line on stdout.  Route fd 1 to
+    stderr for the duration of the run and give print() a private handle on the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
     a = parse()
+    _guard_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:

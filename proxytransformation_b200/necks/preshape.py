@@ -158,6 +158,7 @@ class ProxyTransformationNormReverse(nn.Module):
         self.overlap_image_stage = False  # option: image proxies on a side CUDA stream; measured SLOWER on B200 (3.04 vs 2.86 ms/step)
         # because the persistent pool kernel owns every SM's shared memory and the small kernels queue behind it
         self._streams: Dict[str, torch.cuda.Stream] = {}
+        self.host_chunk_scenes = 8       # scenes per pipeline chunk when forward() is fed host tensors
 
     # ------------------------------------------------------------------ reference helper API (same names, :332-350)
     def get_text_proxy(self, text_dict):
@@ -274,6 +275,8 @@ class ProxyTransformationNormReverse(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("ProxyTransformationNormReverse (B200) has no CPU path: move the module to a CUDA device")
         in_dev = points[0].device
+        if in_dev.type != "cuda":
+            return self._forward_from_host(points, text_dict, img_feat, img_proxy, dev, trace)
         P = self._stack_points(points, dev)                                                     # :426-427
         text, mask = tuple(self.get_text_proxy(text_dict))                                      # :440
         text = text.to(dev, torch.float32, non_blocking=True).contiguous()
@@ -287,10 +290,67 @@ class ProxyTransformationNormReverse(nn.Module):
             img_proxy = img_proxy.to(dev, torch.float32, non_blocking=True).contiguous()
         out, counts = self.forward_packed(P, text, mask, img_feat, img_proxy=img_proxy, trace=trace)
         cnt = counts.cpu().tolist()                                                             # the one D2H sync
-        res = [out[b, :cnt[b]] for b in range(len(cnt))]
-        if in_dev.type != "cuda":
-            res = [r.to(in_dev) for r in res]
-        return res
+        return [out[b, :cnt[b]] for b in range(len(cnt))]
+
+    def _forward_from_host(self, points, text_dict, img_feat, img_proxy, dev, trace) -> List[torch.Tensor]:
+        """Host inputs -> host results.  The batch is cut into chunks of ``host_chunk_scenes`` scenes that flow through three
+        streams: H2D copies of chunk j+1 (pinned inputs make them asynchronous) overlap the kernels of chunk j and the D2H
+        copy of chunk j-1, so a call costs about the PCIe time of its inputs instead of copy + compute + copy.  One host
+        synchronisation at the end; the results are views of one pinned host block."""
+        B = len(points)
+        N = points[0].shape[0]
+        for p in points:
+            if p.dim() != 2 or p.shape[1] != 3:
+                raise ValueError(f"points must be (N,3) xyz per scene, got {tuple(p.shape)}")
+            if p.shape[0] != N:
+                raise RuntimeError(f"all scenes must have the same number of points (got {p.shape[0]} vs {N})")
+        text, mask = tuple(self.get_text_proxy(text_dict))                                      # :440
+        if img_proxy is None and img_feat.dtype not in (torch.float32, torch.bfloat16):
+            img_feat = img_feat.float()
+        cur = torch.cuda.current_stream(dev)
+        h2d, d2h = self._side_stream(dev, "h2d"), self._side_stream(dev, "d2h")
+        h2d.wait_stream(cur)
+        d2h.wait_stream(cur)
+        host_out = torch.empty(B, N, 3, dtype=torch.float32, pin_memory=True)
+        host_cnt = torch.empty(B, dtype=torch.int32, pin_memory=True)
+        chunk = max(1, min(B, int(self.host_chunk_scenes)))
+        traces = [] if trace is not None else None
+        for s0 in range(0, B, chunk):
+            s1 = min(B, s0 + chunk)
+            with torch.cuda.stream(h2d):
+                P = torch.empty(s1 - s0, N, 3, dtype=torch.float32, device=dev)
+                for b in range(s0, s1):
+                    P[b - s0].copy_(points[b], non_blocking=True)                               # :426-427
+                tx = text[s0:s1].to(dev, non_blocking=True).float().contiguous()
+                mk = mask[s0:s1].to(dev, non_blocking=True).to(torch.uint8).contiguous() if mask is not None else None
+                if img_proxy is None:
+                    im, ip = img_feat[s0:s1].to(dev, non_blocking=True).contiguous(), None
+                else:
+                    im, ip = None, img_proxy[s0:s1].to(dev, non_blocking=True).float().contiguous()
+                ready = torch.cuda.Event()
+                ready.record(h2d)
+            cur.wait_event(ready)
+            for t in (P, tx, mk, im, ip):
+                if t is not None:
+                    t.record_stream(cur)
+            tr = {} if traces is not None else None
+            out, counts = self.forward_packed(P, tx, mk, im, img_proxy=ip, trace=tr)
+            if traces is not None:
+                traces.append(tr)
+            done = torch.cuda.Event()
+            done.record(cur)
+            d2h.wait_event(done)
+            out.record_stream(d2h)
+            counts.record_stream(d2h)
+            with torch.cuda.stream(d2h):
+                host_out[s0:s1].copy_(out, non_blocking=True)
+                host_cnt[s0:s1].copy_(counts, non_blocking=True)
+        d2h.synchronize()                                                                       # the one host sync
+        if trace is not None:
+            for k in traces[0]:
+                trace[k] = torch.cat([t[k] for t in traces], 0)
+        cnt = host_cnt.tolist()
+        return [host_out[b, :cnt[b]] for b in range(B)]
 
     @staticmethod
     def _stack_points(points, dev) -> torch.Tensor:
@@ -306,8 +366,8 @@ class ProxyTransformationNormReverse(nn.Module):
             raise ValueError(f"points must be (N,3) xyz per scene, got {tuple(P.shape)}")
         return P.to(dev, torch.float32, non_blocking=True).contiguous()
 
-    def _side_stream(self, device) -> "torch.cuda.Stream":
-        key = str(device)
+    def _side_stream(self, device, name: str = "img") -> "torch.cuda.Stream":
+        key = f"{device}/{name}"
         if key not in self._streams:
             self._streams[key] = torch.cuda.Stream(device=device)
         return self._streams[key]

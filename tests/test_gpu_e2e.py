@@ -87,6 +87,24 @@ def test_forward_accepts_host_tensors_and_returns_host_results():
         np.testing.assert_allclose(o.numpy(), g[f"out_{b}"], rtol=0, atol=1e-4)
 
 
+@pytest.mark.parametrize("chunk", [1, 2, 8])
+def test_host_pipeline_chunks_equal_device_path(chunk):
+    """forward() on host tensors streams the batch in chunks over three CUDA streams; scenes are independent, so every
+    chunking must give exactly the device-resident result (pageable and pinned inputs alike)."""
+    cfg, sd, pts, text_dict, img, g = load_case("gs5_ragged")
+    pts, img = pts + pts[::-1] + pts, torch.cat([img, img.flip(0), img], 0)
+    text_dict = {k: torch.cat([v, v.flip(0), v], 0) for k, v in text_dict.items()}
+    m = build_module(cfg, sd)
+    want = m([p.to(DEV) for p in pts], {k: v.to(DEV) for k, v in text_dict.items()}, img.to(DEV))
+    m.host_chunk_scenes = chunk
+    for pin in (False, True):
+        f = (lambda t: t.pin_memory()) if pin else (lambda t: t)
+        got = m([f(p) for p in pts], {k: f(v) for k, v in text_dict.items()}, f(img))
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert not a.is_cuda and torch.equal(a, b.cpu())
+
+
 def test_forward_does_not_mutate_inputs_and_is_deterministic():
     cfg, sd, pts, text_dict, img, g = load_case("gs5_ragged")
     m = build_module(cfg, sd)
