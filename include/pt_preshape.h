@@ -142,10 +142,15 @@ typedef struct pt_img_pool_params {
     /* Optional bf16 hi/lo planes ([2][rows][cols], see pt_split_bf16) for the tensor-core fast path taken when img_feat
      * is bf16 and (C, HW, c, heads) = (512, 225, 256, 8); all five or none:
      *   w_qc_split   (c, C)            W_qc
-     *   wk_pad_split (heads*C, 64)     row h*C + ch, col e < hd: (Wk Wc)[h*hd+e][ch]; cols >= hd zero
+     *   wk_pad_split (heads*C, 64)     row h*C + j, col e < hd: (Wk Wc)[h*hd+e][score_order[j]]; cols >= hd zero
      *   gk_pad_split (heads*228, 64)   row h*228 + t, col e < hd: g_k[t][h*hd+e]; rows t >= T and cols >= hd zero
-     *   wv_cat_split (c, 768)          cols [0,C): Wv Wc ; cols C + t: h_v[t][row] (t < T), rest zero
-     *   cproj_split  (c, c)            c_proj weight */
+     *   wv_cat_split (c, 768)          cols j < C: (Wv Wc)[row][sum_order[j]] ; cols C + t: h_v[t][row] (t < T), rest zero
+     *   cproj_split  (c, c)            c_proj weight
+     * The pool kernel reads the raw 450-byte-pitch channel rows with ldmatrix, which forces it to walk the channels by
+     * residue class s = channel mod 8 (225 = 1 mod 8: a class shares its 16-byte alignment).  The channel orders that
+     * follow are absorbed into the two weight matrices above:
+     *   score_order[((p*8 + s)*4 + q)*4 + e] = 128 p + 64 (e >> 1) + s + 16 q + 8 (e & 1)      p<4, s<8, q<4, e<4
+     *   sum_order[((sl*8 + s)*4 + q)*2 + e]  = 64 sl + s + 16 q + 8 e                          sl<8, s<8, q<4, e<2 */
     const void *w_qc_split, *wk_pad_split, *gk_pad_split, *wv_cat_split, *cproj_split;
 } pt_img_pool_params;
 
@@ -154,8 +159,11 @@ int pt_img_attnpool(const void* img_feat, int img_dtype, const pt_img_pool_param
                     int heads, float* img_proxy, void* ws, size_t ws_bytes, pt_stream_t stream);
 
 /* Debug only: per-phase SM-clock cycles of CTA 0 of the bf16 image-pool kernel, accumulated while PT_POOL_DEBUG has bit 8
- * set: [0] view barrier, [1] operand wait, [2] fragment conversion, [3] score MMAs, [4] softmax, [5] weighted sums. */
+ * set: [0] view barrier, [1] operand wait, [2] score MMAs, [3] score exchange + softmax, [4] weighted sums. */
 int pt_debug_pool_trace(unsigned long long* out8, int reset);
+/* Debug only (PT_POOL_DEBUG bit 32): (id, SM clock) event pairs logged by CTA 0 for views 40..43; returns the count and
+ * clears the log.  Decoded by tools/pool_events.py. */
+int pt_debug_pool_events(long long* out, int max_events);
 
 /* ---- S10-S12 affine (:459-462) + pt_replace (:472-498) + remove_points_by_index (:501-525) ------------
  * new = (T[m] @ (p - centre[m]) + centre[m]) + t[m] for every valid (m,k); duplicate destinations resolved by the

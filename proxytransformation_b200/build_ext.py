@@ -38,14 +38,15 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+    extra = os.environ.get("PT_NVCC_DEFINES", "").split()       # debug builds only, e.g. PT_NVCC_DEFINES=-DPT_POOL_EVENTS
+    if not force and not extra and not needs_build():
         return LIB
     objs = []
     procs = []
     for src in sources():
         obj = src[:-3] + ".o"
         objs.append(obj)
-        cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + (["-Xptxas", "-v"] if verbose else []) + extra + ["-c", src, "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()

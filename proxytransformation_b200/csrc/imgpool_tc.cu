@@ -10,9 +10,14 @@
 //             * scores S[8 heads][225] = W_eff X and sums Y[8][512] = P X^T run on the tensor cores (mma.sync m16n8k16
 //               bf16, fp32 accumulate): the fp32 operand (w_eff / probabilities) is split into bf16 hi + lo halves that
 //               occupy rows 0-7 / 8-15 of the 16-row A tile, X is already bf16, so the products are exact to ~2^-17;
-//             * the k index of every MMA is permuted so that the B fragments can be read straight from the raw
-//               [channel][225] bf16 rows (450-byte pitch, not 16-byte aligned: no ldmatrix / UMMA layout possible)
-//               without shared-memory bank conflicts.
+//             * X fragments come from ldmatrix on the RAW [channel][225] rows.  A row pitch of 450 B is not 16-byte
+//               aligned, but 225 = 1 (mod 8): channel c starts at element c (mod 8) of a 16-byte chunk, so the channels
+//               of one residue class s = c mod 8 share their alignment.  Every MMA therefore works on one class: its
+//               8 (sums: n index) or 16 (scores: k index, 8 from each slab of a pair) channels are s, s+8, s+16, ... and
+//               its token axis runs over the aligned chunks u = token + s.  Chunk columns that belong to the neighbouring
+//               channel meet zero probabilities (sums) or land in score columns nobody reads (scores).  The channel
+//               order this induces on w_eff and on the weighted sums is absorbed into the GEMM weights on the host
+//               (pt_img_pool_params: wk_pad_split rows, wv_cat_split columns).
 //   G4-G5   z_h = [y_h | a_h] [W_vc_h | h_v_h]^T ; o = W_c z + b_c ; LayerNorm                      (gemm_tc.cu, dense.cu)
 #include "common.cuh"
 #include "gemm_tc.cuh"
@@ -32,24 +37,34 @@ constexpr int TP = 228;                    // cterm row pitch
 constexpr int YA = 768;                    // per (view, head) row of the value GEMM: 512 weighted sums + 256 probabilities
 constexpr int SLAB_CH = 64, NSLAB = C / SLAB_CH;
 constexpr int SLAB_BYTES = SLAB_CH * HW * 2;          // 28800
-constexpr int RING = 6, REFETCH = NSLAB - RING;       // 2 slabs are streamed a second time per view
+constexpr int RING = 6, REFETCH = NSLAB - RING;       // 2 slabs (the first slab pair) are streamed a second time per view
 constexpr int LOADS_PER_VIEW = NSLAB + REFETCH;
 constexpr int PF_DIST = 4;                 // L2 prefetch distance of the producer, in ring loads
-constexpr int NT_SCORE = 29;               // 8-token score tiles (232 >= 225)
-constexpr int CONSUMER_WARPS = 16, THREADS = 32 * (CONSUMER_WARPS + 1);
+constexpr int NCHUNK = 29;                 // aligned 8-token chunks per channel row in u = token + class coordinates (232 >= 225 + 7)
+constexpr int CONSUMER_WARPS = 16, THREADS = 32 * (CONSUMER_WARPS + 4);   // + a warpgroup whose first warp is the producer
+constexpr int WPITCH = 528;                // w_eff plane row pitch in bf16 (512 + 16: lanes of different heads hit different banks)
+constexpr int WPLANE = HEADS * WPITCH;     // elements per plane; a view's operand block is [hi plane][lo plane]
+constexpr int WBYTES = 2 * WPLANE * 2;     // 16896
+constexpr int PPITCH = 264;                // probability row pitch in bf16 (8-token zero margins on both sides)
+constexpr int PBYTES = 2 * 2 * HEADS * PPITCH * 2;    // [hi|lo][token parity copy][head][PPITCH] = 16896
+constexpr int SPITCH = 232;                // partial-score row pitch (floats)
+constexpr int SBUF = HEADS * SPITCH;       // floats per partial-score buffer; 4 buffers (class s and s+4 share one)
 // shared memory carve-up (bytes)
 constexpr int OFF_RING = 0;
-constexpr int OFF_PAD = OFF_RING + RING * SLAB_BYTES;                 // 128 B of zeros behind the ring (fragment over-reads)
-constexpr int OFF_WFRAG = OFF_PAD + 128;                              // [32 k-blocks][32 lanes][4 x u32]
-constexpr int OFF_PFRAG = OFF_WFRAG + 32 * 32 * 16;                   // [16 k-blocks][32 lanes][4 x u32]
-constexpr int OFF_S = OFF_PFRAG + 16 * 32 * 16;                       // fp32 scores [8][232]
-constexpr int OFF_XBAR = OFF_S + HEADS * 232 * 4;                     // fp32 [2][512]  (double-buffered by view parity)
-constexpr int OFF_WSTAGE = OFF_XBAR + 2 * C * 4;                      // fp32 [8][512]  next view's w_eff (bulk-copied)
-constexpr int OFF_MISC = OFF_WSTAGE + HEADS * C * 4;                  // s0 partials [16 warps][8], p0 [8], softmax exchange [32]
-constexpr int OFF_BAR = OFF_MISC + (128 + 8 + 32) * 4;                      // full[RING], empty[RING], wfull, wempty
-constexpr int SMEM_BYTES = OFF_BAR + (2 * RING + 2) * 8 + 16;
+constexpr int OFF_W0 = OFF_RING + RING * SLAB_BYTES;                  // w_eff planes of even views
+constexpr int OFF_P = OFF_W0 + WBYTES;                                // probabilities (bf16 hi/lo, two token alignments)
+constexpr int OFF_W1 = OFF_P + PBYTES;                                // w_eff planes of odd views
+constexpr int OFF_XBAR = OFF_W1 + WBYTES;                             // fp32 [2][512]  (double-buffered by view parity)
+constexpr int OFF_MISC = OFF_XBAR + 2 * C * 4;                        // s0 partials [16 warps][8], p0 [8], softmax exchange [32]
+constexpr int OFF_BAR = OFF_MISC + (128 + 8 + 32) * 4;                // full[RING], empty[RING], wfull[2], wempty[2]
+constexpr int SMEM_BYTES = OFF_BAR + (2 * RING + 4) * 8;
+// The four partial-score buffers (29.7 KB) live only between the score MMAs and the softmax; they overlay the (dead) w_eff
+// planes of the current view plus the adjacent part of the (dead) probability arrays.
+constexpr int SPART_BYTES = 4 * SBUF * 4;
+constexpr int OFF_SPART_EVEN = OFF_W0, OFF_SPART_ODD = OFF_W1 + WBYTES - SPART_BYTES;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(OFF_WFRAG % 16 == 0 && OFF_PFRAG % 16 == 0 && OFF_BAR % 8 == 0 && OFF_WSTAGE % 16 == 0 && OFF_XBAR % 16 == 0, "alignment");
+static_assert(SPART_BYTES <= WBYTES + PBYTES && OFF_SPART_ODD >= OFF_P && OFF_SPART_ODD % 16 == 0, "partial-score overlay");
+static_assert(OFF_W0 % 16 == 0 && OFF_P % 16 == 0 && OFF_W1 % 16 == 0 && OFF_XBAR % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
 }  // namespace ip
 
 __device__ __forceinline__ uint32_t ip_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -86,6 +101,18 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x1(uint32_t& r, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x1.shared.b16 {%0}, [%1];" : "=r"(r) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t (&r)[2], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
 }
 // fp32 -> (bf16 hi, bf16 lo) with hi + lo == x to ~2^-17
 __device__ __forceinline__ void split_hi_lo(float x, uint32_t& hi, uint32_t& lo) {
@@ -188,48 +215,89 @@ __device__ unsigned long long g_pool_trace[8];
         }                                                                                  \
     } while (0)
 
+// Debug event log (build with PT_NVCC_DEFINES=-DPT_POOL_EVENTS, run with PT_POOL_DEBUG bit 32): (id, SM clock) pairs of
+// CTA 0 for views 40..43, kept in shared memory by the three logging threads (producer lane, warp 0, warp 8) and dumped at
+// the end of the kernel; decoded by tools/pool_events.py.
+__device__ long long g_pool_ev[2 * 4096];
+__device__ unsigned int g_pool_evn;
+#ifdef PT_POOL_EVENTS
+#define POOL_EV_MAX 96
+#define POOL_EV_DECL(logger) unsigned int ev_n = 0; unsigned int* ev_buf = reinterpret_cast<unsigned int*>(smem + ip::SMEM_BYTES) + (logger) * 2 * POOL_EV_MAX
+#define POOL_EV(id)                                                                                        \
+    do {                                                                                                   \
+        if ((a.debug_skip & 32) && blockIdx.x == 0 && vi >= 40 && vi < 44 && ev_n < POOL_EV_MAX) {         \
+            ev_buf[2 * ev_n] = (unsigned int)(id); ev_buf[2 * ev_n + 1] = (unsigned int)clock64(); ++ev_n; \
+        }                                                                                                  \
+    } while (0)
+#define POOL_EV_DUMP()                                                                                     \
+    do {                                                                                                   \
+        if ((a.debug_skip & 32) && blockIdx.x == 0) {                                                      \
+            const unsigned int e0_ = atomicAdd(&g_pool_evn, ev_n);                                         \
+            for (unsigned int i_ = 0; i_ < ev_n && e0_ + i_ < 4096; ++i_) {                                \
+                g_pool_ev[2 * (e0_ + i_)] = ev_buf[2 * i_]; g_pool_ev[2 * (e0_ + i_) + 1] = ev_buf[2 * i_ + 1]; \
+            }                                                                                              \
+        }                                                                                                  \
+    } while (0)
+#define POOL_EV_SMEM (3 * 2 * POOL_EV_MAX * 4)
+#else
+#define POOL_EV_DECL(logger)
+#define POOL_EV(id)
+#define POOL_EV_DUMP()
+#define POOL_EV_SMEM 0
+#endif
+
 struct PoolArgs {
     const uint8_t* img;          // (BV, 512, 225) bf16
-    const float* w_eff;          // (BV, 8, 512) fp32
+    const __nv_bfloat16* wpl;    // (BV, 2, 8, WPITCH) bf16: w_eff hi / lo planes, columns in score order (see header)
     const float* cterm;          // (BV, 8, TP) fp32: q_h . g_k[t,h]
     const float* xbar;           // (BV, 512) fp32
-    __nv_bfloat16* ya_hi;        // (BV, 8, 768) bf16 hi plane: [0,512) weighted sums, [512,768) probabilities (zero padded)
+    __nv_bfloat16* ya_hi;        // (BV, 8, 768) bf16 hi plane: [0,512) weighted sums (sum order), [512,768) probabilities (zero padded)
     long long ya_plane;          // elements between the hi and lo planes
     int BV;
     float scale;
     int pf_dist;                 // L2 prefetch distance of the producer in ring loads (0 = off)
-    int debug_skip;              // PT_POOL_DEBUG bit mask (results are garbage): 1 skip score MMAs, 4 skip sum MMAs, 2 no slab data (16-byte loads)
+    int debug_skip;              // PT_POOL_DEBUG bit mask (1, 2, 4, 16 give garbage results): 1 skip score MMAs, 2 slabs are 16-byte loads
+                                 // (no HBM traffic), 4 skip sum MMAs, 8 per-phase cycle trace of CTA 0, 16 skip exchange + softmax
 };
 
+// Channel orders (host side: pt_img_pool_score_order / pt_img_pool_sum_order in api.cu mirror these):
+//   score column ((p*8 + s)*4 + q)*4 + e  <->  channel 128 p + 64 (e >> 1) + s + 16 q + 8 (e & 1)
+//   sum   column ((sl*8 + s)*4 + q)*2 + e <->  channel 64 sl + s + 16 q + 8 e
 __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const PoolArgs a) {
     using namespace ip;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* empty = full + RING;
-    uint64_t* wfull = empty + RING;
-    uint64_t* wempty = wfull + 1;
+    uint64_t* wfull = empty + RING;      // [2]
+    uint64_t* wempty = wfull + 2;        // [2]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) {
         for (int b = 0; b < RING; ++b) { ip_mbar_init(full + b, 1); ip_mbar_init(empty + b, CONSUMER_WARPS); }
-        ip_mbar_init(wfull, 1);
-        ip_mbar_init(wempty, 1);
+        for (int b = 0; b < 2; ++b) { ip_mbar_init(wfull + b, 1); ip_mbar_init(wempty + b, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 32) reinterpret_cast<uint32_t*>(smem + OFF_PAD)[tid] = 0u;
     __syncthreads();
 
-    if (warp == CONSUMER_WARPS) {
+    // 5 warps per SM sub-partition cap the kernel at 96 registers per thread; the producer needs almost none, so its
+    // warpgroup (setmaxnreg is warpgroup-wide: three idle warps keep the producer company and exit at once) hands its share
+    // to the consumers.  The pool is what the launch allocated (640 x 96): 4 warps x 72 released registers = 16 per consumer thread
+    if (warp >= CONSUMER_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;" ::: "memory");
+        if (warp > CONSUMER_WARPS) return;
         // ===== producer: slabs 0..7 of the view, then slabs 0..REFETCH-1 again (FIFO ring, see header) =====
         if (lane == 0) {
             unsigned cnt = 0, vi = 0;
+            POOL_EV_DECL(0);
             for (int bv = blockIdx.x; bv < a.BV; bv += gridDim.x, ++vi) {
-                // per-view operands (w_eff 16 KB -> staging, xbar 2 KB -> buffer vi & 1); they are requested as soon as the
-                // previous view's slab loads are all in flight, i.e. while the consumers are still in its weighted-sum phase
-                ip_mbar_wait(wempty, (vi & 1u) ^ 1u);
-                ip_mbar_expect_tx(wfull, HEADS * C * 4 + C * 4);
-                ip_bulk_load(smem + OFF_WSTAGE, a.w_eff + (size_t)bv * HEADS * C, HEADS * C * 4, wfull);
-                ip_bulk_load(smem + OFF_XBAR + (vi & 1u) * C * 4, a.xbar + (size_t)bv * C, C * 4, wfull);
+                // per-view operands: w_eff planes (16.5 KB) + xbar (2 KB) into the buffers of this view's parity; they are
+                // requested as soon as the previous view's slab loads are all in flight
+                const unsigned wb = vi & 1u;
+                ip_mbar_wait(wempty + wb, ((vi >> 1) & 1u) ^ 1u);
+                ip_mbar_expect_tx(wfull + wb, WBYTES + C * 4);
+                ip_bulk_load(smem + (wb ? OFF_W1 : OFF_W0), a.wpl + (size_t)bv * 2 * WPLANE, WBYTES, wfull + wb);
+                ip_bulk_load(smem + OFF_XBAR + wb * C * 4, a.xbar + (size_t)bv * C, C * 4, wfull + wb);
+                POOL_EV(100 * (int)vi + 50);                       // operand load issued
                 const uint8_t* view = a.img + (size_t)bv * C * HW * 2;
                 for (int k = 0; k < LOADS_PER_VIEW; ++k, ++cnt) {
                     const int slab = k < NSLAB ? k : k - NSLAB;
@@ -246,260 +314,267 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
                     const uint32_t nbytes = (a.debug_skip & 2) ? 16u : (uint32_t)SLAB_BYTES;
                     ip_mbar_expect_tx(full + b, nbytes);
                     ip_bulk_load(smem + OFF_RING + b * SLAB_BYTES, view + (size_t)slab * SLAB_BYTES, nbytes, full + b);
+                    POOL_EV(100 * (int)vi + k);                // slab load k of view vi issued
                 }
             }
+            POOL_EV_DUMP();
         }
         return;
     }
 
     // ===== consumers: 16 warps =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
     const int g = lane >> 2, q = lane & 3;
-    uint4* wfrag = reinterpret_cast<uint4*>(smem + OFF_WFRAG);
-    uint32_t* pfrag32 = reinterpret_cast<uint32_t*>(smem + OFF_PFRAG);
-    float* S = reinterpret_cast<float*>(smem + OFF_S);
-    const float* wstage = reinterpret_cast<const float*>(smem + OFF_WSTAGE);
+    const int mi = lane >> 3, r8 = lane & 7;                            // ldmatrix: this lane addresses row r8 of matrix mi
     float* s0part = reinterpret_cast<float*>(smem + OFF_MISC);          // [16 warps][8 heads]
     float* p0 = s0part + 128;                                           // [8]
     float* red = p0 + 8;                                                // [2][16] softmax max / sum exchange
-    float4* ypart = reinterpret_cast<float4*>(smem + OFF_WFRAG);        // [2][8 n-tiles][32 lanes], aliases Wfrag (dead in phase 3)
-    // scores: warp <-> (pair of 16-token groups gp, gp + 8 ; channel parity)
-    const int gp = warp & 7, par = warp >> 3;
-    const int ngrp = gp + 8 < 15 ? 2 : 1;                               // 15 groups = 240 tokens >= 225
-    // sums: warp <-> (8-channel tile nt of the slab ; token half kh: tokens [128 kh, 128 kh + 128))
-    const int nt = warp & 7, kh = warp >> 3;
+    const uint32_t ring_u32 = ip_smem_u32(smem + OFF_RING);
+    // every MMA works on the channels of one residue class s = channel mod 8 (see header)
+    const int s = warp & 7;
+    // scores: warp <-> (class s ; token-chunk half nh: chunks [15 nh, 15 nh + 15) of the 29)
+    const int nh = warp >> 3, i0 = 15 * nh;
+    const uint32_t sc_off = 448u * s + 3600u * r8 + 16u * (i0 + (mi >> 1));   // + 32 per chunk pair; slab of the pair = mi & 1
+    // sums: warp <-> (class s ; slab parity hb in processing order)
+    const int hb = warp >> 3;
+    const uint32_t sm_off = 448u * s + 3600u * r8 + 16u * mi;                  // + 64 per pair of k-blocks
+    // softmax: warp <-> (head ; half of the 256 padded attention tokens)
+    const int sh = warp & 7, shalf = warp >> 3;
     unsigned cnt = 0, vi = 0;      // loads consumed so far (ring position / parity), views done
+    POOL_EV_DECL(1 + (tid >> 8));
 
     long long t_prev = clock64();
     for (int bv = blockIdx.x; bv < a.BV; bv += gridDim.x, ++vi) {
-        // ---- (0) per-view operands (staged by the producer): w_eff -> bf16 hi/lo A fragments, s0 = w_eff . xbar
-        ip_consumer_sync();                                   // every warp is done with the previous view's Wfrag / ypart / scores
-        const float* sxbar = reinterpret_cast<const float*>(smem + OFF_XBAR + (vi & 1u) * C * 4);
-        POOL_TRACE(0);                                        // barrier (0)
-        ip_mbar_wait(wfull, vi & 1u);
-        POOL_TRACE(1);                                        // wait for the staged operands
-        {
-            // 8 consecutive channels ch..ch+7 of head g -> two fragment entries: k-block 4*sl+jj takes the even channels,
-            // k-block 4*sl+2+jj the odd ones (k-slot s <-> channel ch + 2s + parity), see the score loop
-            const int sl = warp >> 1, jj = warp & 1;
-            const int ch = 64 * sl + 16 * q + 8 * jj;
-            float f[8], x[8];
-            *reinterpret_cast<float4*>(f) = *reinterpret_cast<const float4*>(wstage + g * C + ch);
-            *reinterpret_cast<float4*>(f + 4) = *reinterpret_cast<const float4*>(wstage + g * C + ch + 4);
-            *reinterpret_cast<float4*>(x) = *reinterpret_cast<const float4*>(sxbar + ch);
-            *reinterpret_cast<float4*>(x + 4) = *reinterpret_cast<const float4*>(sxbar + ch + 4);
-            uint32_t hi[8], lo[8];
-            float dotp = 0.f;
+        const unsigned wb = vi & 1u;
+        const uint8_t* wbuf = smem + (wb ? OFF_W1 : OFF_W0);
+        const float* sxbar = reinterpret_cast<const float*>(smem + OFF_XBAR + wb * C * 4);
+        float* spart = reinterpret_cast<float*>(smem + (wb ? OFF_SPART_ODD : OFF_SPART_EVEN));
+        // position terms of the attention tokens this thread owns in the softmax (global; in flight during the score phase)
+        float ct[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { dotp = fmaf(f[e], x[e], dotp); split_hi_lo(f[e], hi[e], lo[e]); }
-            // a0 = (row g: hi, k-slots 2q,2q+1), a1 = (row g+8: lo), a2 = (row g: hi, slots 2q+8,2q+9), a3 = lo
-            wfrag[(4 * sl + jj) * 32 + lane] = make_uint4(hi[0] | (hi[2] << 16), lo[0] | (lo[2] << 16), hi[4] | (hi[6] << 16), lo[4] | (lo[6] << 16));
-            wfrag[(4 * sl + 2 + jj) * 32 + lane] = make_uint4(hi[1] | (hi[3] << 16), lo[1] | (lo[3] << 16), hi[5] | (hi[7] << 16), lo[5] | (lo[7] << 16));
+        for (int i = 0; i < 4; ++i) {
+            const int t = 128 * shalf + lane + 32 * i;
+            ct[i] = t < T ? __ldg(a.cterm + ((size_t)bv * HEADS + sh) * TP + t) : 0.f;
+        }
+        ip_consumer_sync();                                   // every warp is done with the previous view (probabilities, s0part, red)
+        POOL_TRACE(0);
+        ip_mbar_wait(wfull + wb, (vi >> 1) & 1u);
+        POOL_TRACE(1);                                        // wait for the staged operands
+        if ((tid & 255) == 0) POOL_EV(10000 * (1 + (tid >> 8)) + 100 * (int)vi + 90);      // view start (warp 0 / warp 8)
+
+        // ---- (1) scores: S_s[h][u] = sum over the channels c of class s of w_eff[h][c] X[c][u - s].
+        // k-block = 8 class-s channels of slab 2p + 8 of slab 2p+1; B fragments by ldmatrix.trans (rows = channels,
+        // 16-byte chunks = 8 tokens), two token chunks per x4.
+        float acc[15][4];
+#pragma unroll
+        for (int i = 0; i < 15; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+        float dotp = 0.f;                                      // this lane's share of s0[g] = w_eff[g] . xbar
+        for (int p = 0; p < NSLAB / 2; ++p) {
+            const unsigned k0 = cnt + 2 * p, k1 = k0 + 1, b0 = k0 % RING, b1 = k1 % RING;
+            // A fragments straight from the bf16 planes: 4 consecutive columns = k slots 2q, 2q+1, 2q+8, 2q+9
+            const int col = ((p * 8 + s) * 4 + q) * 4;
+            const uint2 ah = *reinterpret_cast<const uint2*>(wbuf + (g * WPITCH + col) * 2);
+            const uint2 al = *reinterpret_cast<const uint2*>(wbuf + (WPLANE + g * WPITCH + col) * 2);
+            const uint32_t A[4] = {ah.x, al.x, ah.y, al.y};
+            if (nh == 1) {                                     // mean-token score (the upper-half warps have one chunk less to do)
+                const int ch = 128 * p + s + 16 * q;
+                const float w0 = __uint_as_float(ah.x << 16) + __uint_as_float(al.x << 16), w1 = __uint_as_float(ah.x & 0xffff0000u) + __uint_as_float(al.x & 0xffff0000u);
+                const float w2 = __uint_as_float(ah.y << 16) + __uint_as_float(al.y << 16), w3 = __uint_as_float(ah.y & 0xffff0000u) + __uint_as_float(al.y & 0xffff0000u);
+                dotp = fmaf(w0, sxbar[ch], dotp); dotp = fmaf(w1, sxbar[ch + 8], dotp);
+                dotp = fmaf(w2, sxbar[ch + 64], dotp); dotp = fmaf(w3, sxbar[ch + 72], dotp);
+            }
+            ip_mbar_wait(full + b0, (k0 / RING) & 1u);
+            ip_mbar_wait(full + b1, (k1 / RING) & 1u);
+            if ((tid & 255) == 0) POOL_EV(10000 * (1 + (tid >> 8)) + 100 * (int)vi + 2 * p + 1);   // pair p has landed
+            const uint32_t base = ring_u32 + ((mi & 1) ? b1 : b0) * SLAB_BYTES + sc_off;
+            if (!(a.debug_skip & 1)) {
+                uint32_t bf[2][4];                             // fragment loads run one step ahead of the MMAs
+                ldsm_x4_t(bf[0], base);
+#pragma unroll
+                for (int m = 0; m < 7; ++m) {
+                    if (m < 6) ldsm_x4_t(bf[(m + 1) & 1], base + 32 * (m + 1));
+                    else if (nh == 0) ldsm_x2_t(reinterpret_cast<uint32_t(&)[2]>(bf[1][0]), base + 32 * 7);   // 15th chunk of the lower half
+                    mma_bf16_16816(acc[2 * m], A, bf[m & 1][0], bf[m & 1][1]);
+                    mma_bf16_16816(acc[2 * m + 1], A, bf[m & 1][2], bf[m & 1][3]);
+                }
+                if (nh == 0) mma_bf16_16816(acc[14], A, bf[1][0], bf[1][1]);
+            }
+            if (p == 0) {                                      // the first pair is not kept: hand the buffers back
+                __syncwarp();
+                if (lane == 0) { ip_mbar_arrive(empty + b0); ip_mbar_arrive(empty + b1); }
+            }
+        }
+        if (nh == 1) {
             dotp += __shfl_xor_sync(FULL, dotp, 1);
             dotp += __shfl_xor_sync(FULL, dotp, 2);
-            if (q == 0) s0part[warp * 8 + g] = dotp;
+            if (q == 0) s0part[s * 8 + g] = dotp;             // 8 class partials per head
         }
-        // cterm of the score columns the even-parity warps own: tokens 16 i + 4 q + {0,1,2,3} (attention token = spatial + 1)
-        float ctv[2][4];
+        POOL_TRACE(2);                                        // score MMAs (incl. waiting for slabs)
+        if ((tid & 255) == 0) POOL_EV(10000 * (1 + (tid >> 8)) + 100 * (int)vi + 91);      // score MMAs done
+        ip_consumer_sync();                                   // w_eff planes are dead: the partial-score overlay may be written
+        if (!(a.debug_skip & 16)) {
+        // hi + lo rows of the accumulators; classes 0-3 store S_s[h][u], then classes 4-7 add theirs four columns lower so
+        // that buffer j holds S_j[h][u] + S_{j+4}[h][u+4]: token t sits at column t + j in buffer j
+        if (s < 4) {
+            float* dst = spart + s * SBUF + g * SPITCH + 2 * q;
 #pragma unroll
-        for (int t = 0; t < 2; ++t)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int tok = 16 * (gp + 8 * t) + 4 * q + e;
-                ctv[t][e] = (par == 0 && t < ngrp && tok < HW) ? __ldg(a.cterm + ((size_t)bv * HEADS + g) * TP + 1 + tok) : 0.f;
-            }
-        ip_consumer_sync();
-        if (tid == 0) ip_mbar_arrive(wempty);                 // staging may be refilled with the next view's w_eff
-        POOL_TRACE(2);                                        // conversion + barrier (1)
-
-        // ---- (1) scores: S[h][tok] = sum_ch w_eff[h][ch] X[ch][tok].
-        // A B register packs two k-consecutive bf16, i.e. the same token of two channels (two rows of the slab), so every
-        // aligned 32-bit word read from a row carries TWO tokens: one k-block (16 channels of one parity, chosen so that the
-        // words are aligned and the 32 lanes hit 32 different banks) feeds two 8-token tiles at once.  Even channels see
-        // tokens (16i+2g, +1) -> tiles E_i, O_i; odd channels (rows start on an odd bf16) see (16i+2g-1, 16i+2g) -> O'_i, E_i;
-        // O' is O shifted by one token (its first column, token -1, is the previous row's tail and is dropped).
-        // Warps 0-7 take the even channels, warps 8-15 the odd ones; the partial scores meet in shared memory.
-        float accA[2][4], accB[2][4];            // first / second token of the words
-#pragma unroll
-        for (int t = 0; t < 2; ++t)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { accA[t][e] = 0.f; accB[t][e] = 0.f; }
-        for (int sl = 0; sl < NSLAB; ++sl) {
-            const unsigned k = cnt + sl, b = k % RING, ph = (k / RING) & 1u;
-            ip_mbar_wait(full + b, ph);
-            const uint32_t* X0 = reinterpret_cast<const uint32_t*>(smem + OFF_RING + b * SLAB_BYTES) + 1800 * q + g + 8 * gp + (par ? 112 : 0);
-            if (!(a.debug_skip & 1))
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                const uint4 af = wfrag[(sl * 4 + 2 * par + jj) * 32 + lane];
-                const uint32_t A[4] = {af.x, af.y, af.z, af.w};
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    if (t < ngrp) {
-                        const uint32_t* x = X0 + (4 * jj) * HW + 64 * t;
-                        const uint32_t wa = x[0], wb = x[HW], wc = x[2 * HW], wd = x[3 * HW];
-                        mma_bf16_16816(accA[t], A, __byte_perm(wa, wb, 0x5410), __byte_perm(wc, wd, 0x5410));
-                        mma_bf16_16816(accB[t], A, __byte_perm(wa, wb, 0x7632), __byte_perm(wc, wd, 0x7632));
-                    }
-                }
-            }
-            if (sl < REFETCH) {                                // this slab is not kept: hand the buffer back
-                __syncwarp();
-                if (lane == 0) ip_mbar_arrive(empty + b);
-            }
-        }
-        POOL_TRACE(3);                                        // score MMAs (incl. waiting for slabs)
-        // unscaled scores (hi + lo rows of the accumulators): even-parity warps store E, O (+ cterm), then odd-parity warps
-        // add their E and O' contributions
-        if (par == 0) {
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                if (t < ngrp) {
-                    const int tok = 16 * (gp + 8 * t) + 4 * q;
-                    float* Sr = S + g * 232 + 1 + tok;
-                    if (tok < HW) Sr[0] = (accA[t][0] + accA[t][2]) + ctv[t][0];
-                    if (tok + 1 < HW) Sr[1] = (accB[t][0] + accB[t][2]) + ctv[t][1];
-                    if (tok + 2 < HW) Sr[2] = (accA[t][1] + accA[t][3]) + ctv[t][2];
-                    if (tok + 3 < HW) Sr[3] = (accB[t][1] + accB[t][3]) + ctv[t][3];
-                }
-            }
+            for (int i = 0; i < 15; ++i)
+                if (i < 14 || nh == 0)
+                    *reinterpret_cast<float2*>(dst + 8 * (i0 + i)) = make_float2(acc[i][0] + acc[i][2], acc[i][1] + acc[i][3]);
         }
         ip_consumer_sync();
-        if (par == 1) {
+        if (s >= 4) {
+            float* dst = spart + (s - 4) * SBUF + g * SPITCH + 2 * q - 4;
+            float2 v[15];
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                if (t < ngrp) {
-                    const int tok = 16 * (gp + 8 * t) + 4 * q;
-                    float* Sr = S + g * 232 + 1 + tok;
-                    // each (head, token) below is touched by exactly one thread: O' columns are tokens tok-1, tok+1
-                    float o_prev = accA[t][0] + accA[t][2], o_next = accA[t][1] + accA[t][3];
-                    if (tok < HW) Sr[0] += accB[t][0] + accB[t][2];
-                    if (tok + 2 < HW) Sr[2] += accB[t][1] + accB[t][3];
-                    if (tok >= 1 && tok - 1 < HW) Sr[-1] += o_prev;
-                    if (tok + 1 < HW) Sr[1] += o_next;
-                }
-            }
-        }
-        if (warp < HEADS && lane == 0) {                        // token 0 = mean token
-            float s0 = 0.f;
+            for (int i = 0; i < 15; ++i)
+                if ((i < 14 || nh == 0) && (8 * (i0 + i) + 2 * q >= 4)) v[i] = *reinterpret_cast<const float2*>(dst + 8 * (i0 + i));
 #pragma unroll
-            for (int w = 0; w < CONSUMER_WARPS; ++w) s0 += s0part[w * 8 + warp];
-            S[warp * 232] = s0 + __ldg(a.cterm + ((size_t)bv * HEADS + warp) * TP);
+            for (int i = 0; i < 15; ++i)
+                if ((i < 14 || nh == 0) && (8 * (i0 + i) + 2 * q >= 4))
+                    *reinterpret_cast<float2*>(dst + 8 * (i0 + i)) = make_float2(v[i].x + (acc[i][0] + acc[i][2]), v[i].y + (acc[i][1] + acc[i][3]));
         }
         ip_consumer_sync();
 
-        // ---- (2) softmax over the 226 tokens, two warps per head ; probabilities -> bf16 hi/lo A fragments + global
+        // ---- (2) softmax over the 226 tokens, two warps per head ; probabilities -> bf16 hi/lo arrays + global
         {
-            const int h = warp & 7, half = warp >> 3;
             float sv[4];
             float mx = -INFINITY;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int t = 128 * half + lane + 32 * i;
-                sv[i] = t < T ? a.scale * S[h * 232 + t] : -INFINITY;
-                mx = fmaxf(mx, sv[i]);
+                const int t = 128 * shalf + lane + 32 * i;     // attention token; spatial token tau = t - 1
+                float v = -INFINITY;
+                if (t == 0) {
+                    float s0 = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) s0 += s0part[w * 8 + sh];
+                    v = a.scale * (s0 + ct[i]);
+                } else if (t < T) {
+                    const float* sp = spart + sh * SPITCH + (t - 1);
+                    v = a.scale * ((((sp[0] + sp[SBUF + 1]) + sp[2 * SBUF + 2]) + sp[3 * SBUF + 3]) + ct[i]);
+                }
+                sv[i] = v;
+                mx = fmaxf(mx, v);
             }
             mx = warp_max(mx);
             if (lane == 0) red[warp] = mx;
-            ip_consumer_sync();
-            mx = fmaxf(red[h], red[h + 8]);
+            ip_consumer_sync();                                // all partial scores have been read
+            if (tid == 0) ip_mbar_arrive(wempty + wb);         // the w_eff buffer (and the overlay) may be refilled
+            {   // zero the margins of the probability rows (the overlay clobbered them): words [0,5) and [116,132) of 32 rows
+                const int row = tid >> 4, j = tid & 15;        // 512 threads = 32 rows x 16
+                uint32_t* prow = reinterpret_cast<uint32_t*>(smem + OFF_P) + row * (PPITCH / 2);
+                prow[116 + j] = 0u;
+                if (j < 5) prow[j] = 0u;
+            }
+            mx = fmaxf(red[sh], red[sh + 8]);
             float sum = 0.f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { sv[i] = (128 * half + lane + 32 * i) < T ? expf(sv[i] - mx) : 0.f; sum += sv[i]; }
+            for (int i = 0; i < 4; ++i) { sv[i] = (128 * shalf + lane + 32 * i) < T ? expf(sv[i] - mx) : 0.f; sum += sv[i]; }
             sum = warp_sum(sum);
             if (lane == 0) red[16 + warp] = sum;
             ip_consumer_sync();
-            const float inv = 1.0f / (red[16 + h] + red[16 + h + 8]);
-            __nv_bfloat16* ya = a.ya_hi + ((size_t)bv * HEADS + h) * YA + C;
-            unsigned short* pf16 = reinterpret_cast<unsigned short*>(pfrag32);
+            const float inv = 1.0f / (red[16 + sh] + red[16 + sh + 8]);
+            __nv_bfloat16* ya = a.ya_hi + ((size_t)bv * HEADS + sh) * YA + C;
+            // copy e of plane pl: element tau + 8 + e of row ((pl*2 + e)*8 + head) holds token tau, so that both token
+            // parities can be fetched as aligned 32-bit pairs
+            unsigned short* pq = reinterpret_cast<unsigned short*>(smem + OFF_P) + sh * PPITCH;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int t = 128 * half + lane + 32 * i;      // attention token 0..255 (>= 226: zero padding)
-                const float p = sv[i] * inv;
+                const int t = 128 * shalf + lane + 32 * i;      // attention token 0..255 (>= 226: zero padding)
+                const float pr = sv[i] * inv;
                 uint32_t hi, lo;
-                split_hi_lo(p, hi, lo);
+                split_hi_lo(pr, hi, lo);
                 ya[t] = __ushort_as_bfloat16((unsigned short)hi);
                 ya[a.ya_plane + t] = __ushort_as_bfloat16((unsigned short)lo);
-                if (t == 0) p0[h] = p;
-                // spatial token tau = t - 1 -> fragment slot
-                const int tau = t - 1;
-                if (tau >= 0) {
-                    const int kb = 2 * (tau >> 5) + ((tau >> 2) & 1), fl = 4 * h + ((tau >> 3) & 3), reg = (tau & 2);
-                    const int o16 = ((kb * 32 + fl) * 4 + reg) * 2 + (tau & 1);
-                    pf16[o16] = (unsigned short)hi;
-                    pf16[o16 + 2] = (unsigned short)lo;       // reg + 1
+                if (t == 0) p0[sh] = pr;
+                if (t >= 1 && t < T) {
+                    const int x = t - 1 + 8;
+                    pq[x] = (unsigned short)hi;                               // hi, even copy
+                    pq[HEADS * PPITCH + x + 1] = (unsigned short)hi;           // hi, odd copy
+                    pq[2 * HEADS * PPITCH + x] = (unsigned short)lo;           // lo, even copy
+                    pq[3 * HEADS * PPITCH + x + 1] = (unsigned short)lo;       // lo, odd copy
                 }
             }
-            if (half == 1 && lane == 0) {                       // tau = 255 (t = 256) is not covered by the loop above
-                const int tau = 255;
-                const int kb = 2 * (tau >> 5) + ((tau >> 2) & 1), fl = 4 * h + ((tau >> 3) & 3), reg = (tau & 2);
-                const int o16 = ((kb * 32 + fl) * 4 + reg) * 2 + (tau & 1);
-                pf16[o16] = 0; pf16[o16 + 2] = 0;
+        }
+        } else if (tid == 0) ip_mbar_arrive(wempty + wb);
+        ip_consumer_sync();
+        POOL_TRACE(3);                                        // score exchange + softmax + barriers
+        if ((tid & 255) == 0) POOL_EV(10000 * (1 + (tid >> 8)) + 100 * (int)vi + 92);      // softmax done
+
+        // ---- (3) weighted sums: Y[h][c] = sum_tok P[h][tok] X[c][tok]  (+ p0[h] xbar[c]) for the 8 class-s channels of a slab
+        // per MMA column tile; k runs over the aligned chunks u = tok + s, so the A fragments are the probabilities shifted
+        // by s (zero outside [0,225)), held in registers for the whole view.
+        uint32_t PA[15][4];
+        {
+            const int e = s & 1;
+            const uint32_t* ph = reinterpret_cast<const uint32_t*>(smem + OFF_P) + (e * HEADS + g) * (PPITCH / 2) + q + ((8 + e - s) >> 1);
+            const uint32_t* pl = ph + 2 * HEADS * (PPITCH / 2);
+#pragma unroll
+            for (int kb = 0; kb < 15; ++kb) {
+                PA[kb][0] = ph[8 * kb]; PA[kb][1] = pl[8 * kb]; PA[kb][2] = ph[8 * kb + 4]; PA[kb][3] = pl[8 * kb + 4];
             }
         }
-        ip_consumer_sync();
-
-        POOL_TRACE(4);                                        // score exchange + softmax + barriers
-        // ---- (3) weighted sums: Y[h][ch] = sum_tok P[h][tok] X[ch][tok]  (+ p0[h] xbar[ch]).
-        // warp <-> (8 channels of the slab, half of the tokens); the two halves meet through ypart + a 64-thread barrier
-        uint32_t PA[8][4];
-#pragma unroll
-        for (int kb = 0; kb < 8; ++kb) {
-            const uint4 pf = reinterpret_cast<const uint4*>(pfrag32)[(8 * kh + kb) * 32 + lane];
-            PA[kb][0] = pf.x; PA[kb][1] = pf.y; PA[kb][2] = pf.z; PA[kb][3] = pf.w;
-        }
         const float p0g = p0[g];
-        const uint32_t shift = (g & 1) * 16;                   // rows of odd channels start on an odd bf16 (225 is odd)
         __nv_bfloat16* yrow = a.ya_hi + ((size_t)bv * HEADS + g) * YA;
         for (int s2 = 0; s2 < NSLAB; ++s2) {
             // resident slabs REFETCH..7 first (FIFO release order), then the re-fetched slabs 0..REFETCH-1
             const int sl = s2 < NSLAB - REFETCH ? s2 + REFETCH : s2 - (NSLAB - REFETCH);
             const unsigned k = s2 < NSLAB - REFETCH ? cnt + sl : cnt + NSLAB + sl;
             const unsigned b = k % RING;
-            if (s2 >= NSLAB - REFETCH) ip_mbar_wait(full + b, (k / RING) & 1u);
-            const int cl = 8 * nt + g;                          // channel within the slab
-            const uint32_t* Xw = reinterpret_cast<const uint32_t*>(smem + OFF_RING + b * SLAB_BYTES) + ((cl * HW + 8 * q) >> 1) + 64 * kh;
-            float y[4] = {0.f, 0.f, 0.f, 0.f}, y2[4] = {0.f, 0.f, 0.f, 0.f};     // two independent MMA chains
-            if (!(a.debug_skip & 4))
+            if (s2 >= NSLAB - REFETCH) ip_mbar_wait(full + b, (k / RING) & 1u);     // readers and non-readers alike (arrival order)
+            if ((tid & 255) == 0) POOL_EV(10000 * (1 + (tid >> 8)) + 100 * (int)vi + 20 + s2);     // sums step s2 starts
+            if ((s2 & 1) == hb && !(a.debug_skip & 4)) {
+                const uint32_t base = ring_u32 + b * SLAB_BYTES + sm_off;
+                float y0[4] = {0.f, 0.f, 0.f, 0.f}, y1[4] = {0.f, 0.f, 0.f, 0.f}, y2[4] = {0.f, 0.f, 0.f, 0.f};   // independent MMA chains
+                uint32_t bf[2][4];                             // fragment loads run one step ahead of the MMAs
+                ldsm_x4(bf[0], base);
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                uint32_t w[5];
-#pragma unroll
-                for (int i = 0; i < 5; ++i) w[i] = Xw[16 * p + i];
-                uint32_t r[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) r[i] = __funnelshift_r(w[i], w[i + 1], shift);
-                if (p == 3 && kh == 1) {                       // tokens 224..255: only 224 is real, the rest must not leak NaNs
-                    r[0] = q == 0 ? (r[0] & 0xffffu) : 0u;
-                    r[1] = 0u; r[2] = 0u; r[3] = 0u;
+                for (int m = 0; m < 7; ++m) {
+                    if (m < 6) ldsm_x4(bf[(m + 1) & 1], base + 64 * (m + 1));
+                    else ldsm_x1(bf[1][0], base + 64 * 7);     // chunk 28; the k-block's upper half (u >= 232) is empty
+                    const uint32_t* f = bf[m & 1];
+                    if (m % 3 == 0) { mma_bf16_16816(y0, PA[2 * m], f[0], f[1]); mma_bf16_16816(y1, PA[2 * m + 1], f[2], f[3]); }
+                    else if (m % 3 == 1) { mma_bf16_16816(y2, PA[2 * m], f[0], f[1]); mma_bf16_16816(y0, PA[2 * m + 1], f[2], f[3]); }
+                    else { mma_bf16_16816(y1, PA[2 * m], f[0], f[1]); mma_bf16_16816(y2, PA[2 * m + 1], f[2], f[3]); }
                 }
-                mma_bf16_16816(y, PA[2 * p], r[0], r[1]);
-                mma_bf16_16816(y2, PA[2 * p + 1], r[2], r[3]);
-            }
-            __syncwarp();
-            if (lane == 0) ip_mbar_arrive(empty + b);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) y[e] += y2[e];
-            float4* yp = ypart + ((s2 & 1) * 8 + nt) * 32 + lane;
-            if (kh == 1) *yp = make_float4(y[0], y[1], y[2], y[3]);
-            asm volatile("bar.sync %0, 64;" ::"r"(2 + nt) : "memory");
-            if (kh == 0) {
-                const float4 o4 = *yp;
-                // accumulator rows g (hi part) / g+8 (lo part), columns = channels 8*nt + 2q, +1 of slab sl
-                const int ch = sl * SLAB_CH + 8 * nt + 2 * q;
-                const float y0 = ((y[0] + o4.x) + (y[2] + o4.z)) + p0g * sxbar[ch], y1 = ((y[1] + o4.y) + (y[3] + o4.w)) + p0g * sxbar[ch + 1];
+                mma_bf16_16816(y0, PA[14], bf[1][0], 0u);
+                __syncwarp();
+                if (lane == 0) ip_mbar_arrive(empty + b);
+                // accumulator rows g (hi part) / g+8 (lo part), columns 2q, 2q+1 = channels s + 16 q, s + 16 q + 8 of slab sl
+                const int ch = sl * SLAB_CH + s + 16 * q;
+                const float v0 = (((y0[0] + y1[0]) + y2[0]) + ((y0[2] + y1[2]) + y2[2])) + p0g * sxbar[ch];
+                const float v1 = (((y0[1] + y1[1]) + y2[1]) + ((y0[3] + y1[3]) + y2[3])) + p0g * sxbar[ch + 8];
                 uint32_t h0, l0, h1, l1;
-                split_hi_lo(y0, h0, l0);
-                split_hi_lo(y1, h1, l1);
-                *reinterpret_cast<uint32_t*>(yrow + ch) = h0 | (h1 << 16);
-                *reinterpret_cast<uint32_t*>(yrow + a.ya_plane + ch) = l0 | (l1 << 16);
+                split_hi_lo(v0, h0, l0);
+                split_hi_lo(v1, h1, l1);
+                const int col = ((sl * 8 + s) * 4 + q) * 2;
+                *reinterpret_cast<uint32_t*>(yrow + col) = h0 | (h1 << 16);
+                *reinterpret_cast<uint32_t*>(yrow + a.ya_plane + col) = l0 | (l1 << 16);
+            } else {
+                __syncwarp();
+                if (lane == 0) ip_mbar_arrive(empty + b);
             }
         }
         cnt += LOADS_PER_VIEW;
-        POOL_TRACE(5);                                        // weighted sums
+        POOL_TRACE(4);                                        // weighted sums
+        if ((tid & 255) == 0) POOL_EV(10000 * (1 + (tid >> 8)) + 100 * (int)vi + 93);      // sums done
     }
+    if ((tid & 255) == 0) POOL_EV_DUMP();
 }
 
 }  // namespace pt
+extern "C" int pt_debug_pool_events(long long* out, int max_events) {
+    unsigned int n = 0;
+    if (cudaMemcpyFromSymbol(&n, pt::g_pool_evn, sizeof(n)) != cudaSuccess) return PT_ERR_CUDA;
+    if (n > 4096u) n = 4096u;
+    if ((int)n > max_events) n = (unsigned int)max_events;
+    if (n && cudaMemcpyFromSymbol(out, pt::g_pool_ev, (size_t)n * 16) != cudaSuccess) return PT_ERR_CUDA;
+    const unsigned int z = 0;
+    if (cudaMemcpyToSymbol(pt::g_pool_evn, &z, sizeof(z)) != cudaSuccess) return PT_ERR_CUDA;
+    return (int)n;
+}
 extern "C" int pt_debug_pool_trace(unsigned long long* out8, int reset) {
     if (out8 && cudaMemcpyFromSymbol(out8, pt::g_pool_trace, sizeof(pt::g_pool_trace)) != cudaSuccess) return PT_ERR_CUDA;
     if (reset) {
@@ -512,8 +587,8 @@ namespace pt {
 
 // ------------------------------------------------------------------------------------------------ host
 struct ImgTcWs {
-    float *xbar, *w_eff, *cterm, *o;
-    __nv_bfloat16 *xbar_split, *q_split, *ya_split, *z_split;
+    float *xbar, *cterm, *o;
+    __nv_bfloat16 *xbar_split, *q_split, *wpl, *ya_split, *z_split;
     size_t total;
 };
 
@@ -525,7 +600,7 @@ static ImgTcWs carve_tc(void* ws, int BV) {
     r.xbar = (float*)take((size_t)BV * C * 4);
     r.xbar_split = (__nv_bfloat16*)take((size_t)2 * BV * C * 2);
     r.q_split = (__nv_bfloat16*)take((size_t)2 * BV * EMB * 2);
-    r.w_eff = (float*)take((size_t)BV * HEADS * C * 4);
+    r.wpl = (__nv_bfloat16*)take((size_t)BV * 2 * WPLANE * 2);
     r.cterm = (float*)take((size_t)BV * HEADS * TP * 4);
     r.ya_split = (__nv_bfloat16*)take((size_t)2 * BV * HEADS * YA * 2);
     r.z_split = (__nv_bfloat16*)take((size_t)2 * BV * EMB * 2);
@@ -567,12 +642,13 @@ int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, in
         gp.c_split = w.q_split; gp.cs_plane = (long long)BV * EMB; gp.ldcs = EMB;
         if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
     }
-    {   // G2: w_eff[:, h, :] = q[:, 32h:32h+32] W_kc_h   (K = 32 real + 32 columns that hit zero weights)
+    {   // G2: w_eff[:, h, :] = q[:, 32h:32h+32] W_kc_h   (K = 32 real + 32 columns that hit zero weights), emitted as the
+        // bf16 hi / lo planes the pool kernel bulk-copies per view: [view][hi|lo][head][WPITCH], columns in score order
         GemmTc gp;
         gp.M = BV; gp.N = C; gp.K = 64; gp.batch = HEADS;
         gp.a_split = w.q_split; gp.a_rows = BV; gp.a_cols = EMB; gp.lda = EMB; gp.a_koff_z = HD;
         gp.w_split = p->wk_pad_split; gp.w_rows = HEADS * C; gp.ldw = 64; gp.w_row_z = C;
-        gp.C = w.w_eff; gp.ldc = HEADS * C; gp.c_off_z = C;
+        gp.c_split = w.wpl; gp.cs_plane = WPLANE; gp.ldcs = 2 * WPLANE; gp.cs_off_z = WPITCH;
         if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
     }
     {   // G3: cterm[:, h, t] = q[:, 32h:32h+32] . g_k[t, 32h:32h+32]
@@ -586,11 +662,11 @@ int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, in
     {   // pass B
         static bool attr_set = false;
         if (!attr_set) {
-            PT_CUDA_OK(cudaFuncSetAttribute(img_pool_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+            PT_CUDA_OK(cudaFuncSetAttribute(img_pool_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + POOL_EV_SMEM));
             attr_set = true;
         }
         PoolArgs a;
-        a.img = (const uint8_t*)img_feat; a.w_eff = w.w_eff; a.cterm = w.cterm; a.xbar = w.xbar;
+        a.img = (const uint8_t*)img_feat; a.wpl = w.wpl; a.cterm = w.cterm; a.xbar = w.xbar;
         a.ya_hi = w.ya_split; a.ya_plane = (long long)BV * HEADS * YA; a.BV = BV;
         a.scale = (float)(1.0 / sqrt((double)HD));
         const char* dbg = getenv("PT_POOL_DEBUG");
@@ -598,7 +674,7 @@ int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, in
         const char* pf = getenv("PT_POOL_PF");
         a.pf_dist = pf ? atoi(pf) : PF_DIST;
         const int grid = BV < sms ? BV : sms;
-        { ProfScope prof_(PROF_IMG_POOL, s); img_pool_mma_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(a); }
+        { ProfScope prof_(PROF_IMG_POOL, s); img_pool_mma_kernel<<<grid, THREADS, SMEM_BYTES + POOL_EV_SMEM, s>>>(a); }
         PT_LAUNCH_CHECK();
     }
     {   // G4: z[:, 32h:32h+32] = [y_h | a_h] [W_vc_h | h_v_h]^T   -> split planes only

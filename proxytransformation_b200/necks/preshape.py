@@ -249,12 +249,15 @@ class ProxyTransformationNormReverse(nn.Module):
         if self.use_tensor_cores and (C, self.img_spacial_dim, c, heads) == (512, 15, 256, 8):
             # operands of the bf16 tensor-core fast path (csrc/imgpool_tc.cu), layouts in include/pt_preshape.h
             TPc = 228
+            # the pool kernel walks the channels residue class by residue class (channel mod 8, csrc/imgpool_tc.cu): w_eff
+            # columns and weighted-sum columns come in the orders below, absorbed here into the GEMM weights
+            score_order, sum_order = ops.img_pool_channel_orders(device)
             wk_pad = torch.zeros(heads * C, 64, dtype=torch.float64, device=device)
-            wk_pad[:, :hd] = w_kc.reshape(heads * C, hd)
+            wk_pad[:, :hd] = w_kc[:, score_order, :].reshape(heads * C, hd)
             gk_pad = torch.zeros(heads, TPc, 64, dtype=torch.float64, device=device)
             gk_pad[:, :T, :hd] = (posb @ Wk.T).reshape(T, heads, hd).transpose(0, 1)
             wv_cat = torch.zeros(c, 768, dtype=torch.float64, device=device)
-            wv_cat[:, :C] = Wv @ Wc
+            wv_cat[:, :C] = (Wv @ Wc)[:, sum_order]
             wv_cat[:, C:C + T] = (posb @ Wv.T + bv).T
             out.update(w_qc_split=ops.split_bf16(out["w_qc"]), wk_pad_split=ops.split_bf16(f(wk_pad)),
                        gk_pad_split=ops.split_bf16(f(gk_pad.reshape(heads * TPc, 64))), wv_cat_split=ops.split_bf16(f(wv_cat)),

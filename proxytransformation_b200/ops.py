@@ -195,6 +195,18 @@ def make_img_params(w: Dict[str, torch.Tensor]) -> ImgPoolParams:
     return p
 
 
+def img_pool_channel_orders(device=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Channel orders of the bf16 image-pool kernel (C=512), see csrc/imgpool_tc.cu and include/pt_preshape.h:
+    score_order[((p*8 + s)*4 + q)*4 + e] = 128 p + 64 (e >> 1) + s + 16 q + 8 (e & 1)   (w_eff columns)
+    sum_order[((sl*8 + s)*4 + q)*2 + e]  = 64 sl + s + 16 q + 8 e                       (weighted-sum columns)."""
+    p, s, q, e = torch.meshgrid(torch.arange(4), torch.arange(8), torch.arange(4), torch.arange(4), indexing="ij")
+    score = (128 * p + 64 * (e >> 1) + s + 16 * q + 8 * (e & 1)).reshape(-1)
+    sl, s, q, e = torch.meshgrid(torch.arange(8), torch.arange(8), torch.arange(4), torch.arange(2), indexing="ij")
+    sums = (64 * sl + s + 16 * q + 8 * e).reshape(-1)
+    assert sorted(score.tolist()) == list(range(512)) and sorted(sums.tolist()) == list(range(512))
+    return score.to(device), sums.to(device)
+
+
 def img_attnpool(img_feat, w: Dict[str, torch.Tensor], heads: int, ws: Optional[torch.Tensor] = None,
                  params: Optional[ImgPoolParams] = None):
     """S9 (:335-342, :154-177).  img_feat (B,V,C,H,W) fp32/bf16 -> (B,V,c)."""

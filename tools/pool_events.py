@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Timeline of the image-pool kernel's load pipeline (CTA 0, views 40..43): PT_POOL_DEBUG=32 python tools/pool_events.py [batch]
+Prints every logged event with its SM-clock offset: producer issue times of each ring load, and when warp 0 / warp 8
+saw each slab pair land (scores) or started each weighted-sum step."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["PT_POOL_DEBUG"] = str(int(os.environ.get("PT_POOL_DEBUG", "0")) | 32)
+import torch
+from proxytransformation_b200 import ProxyTransformationNormReverse, _lib, synthetic as syn
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+cfg = syn.C2_WIDE
+m = ProxyTransformationNormReverse(**cfg.module_kwargs()).eval()
+m.load_state_dict(syn.make_state_dict(cfg, 0, bf16_round=True))
+m = m.cuda()
+img = (torch.relu(torch.randn(B, cfg.n_views, 512, 15, 15, device="cuda")) * 1.5).bfloat16()
+L = _lib.load()
+buf = (ctypes.c_longlong * 8192)()
+m.get_img_proxy(img); torch.cuda.synchronize()
+L.pt_debug_pool_events(buf, 4096)
+m.get_img_proxy(img); torch.cuda.synchronize()
+n = L.pt_debug_pool_events(buf, 4096)
+ev = sorted((buf[2 * i + 1], buf[2 * i]) for i in range(n))      # 32-bit SM clock (a 0.9 ms kernel cannot wrap twice)
+t0 = ev[0][0]
+def name(i):
+    if i >= 10000:
+        w, r = divmod(i, 10000); vi, c = divmod(r, 100)
+        who = "warp0" if w == 1 else "warp8"
+        what = {90: "view start", 91: "score MMAs done", 92: "softmax done", 93: "sums done"}.get(c) or (f"pair {(c - 1) // 2} landed" if c < 20 else f"sums step {c - 20} starts")
+        return f"{who} view {vi}: {what}"
+    vi, k = divmod(i, 100)
+    if k == 50:
+        return f"producer: operands of view {vi} issued"
+    return f"producer: load {k} of view {vi} issued" + (" (refetch)" if k >= 8 else "")
+for t, i in ev:
+    print(f"{t - t0:8d}  {name(i)}")
