@@ -340,7 +340,8 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
     const uint32_t sm_off = 448u * s + 3600u * r8 + 16u * mi;                  // + 64 per pair of k-blocks
     // softmax: warp <-> (head ; half of the 256 padded attention tokens)
     const int sh = warp & 7, shalf = warp >> 3;
-    unsigned cnt = 0, vi = 0;      // loads consumed so far (ring position / parity), views done
+    unsigned vi = 0;               // views done
+    unsigned slot0 = 0, wrap0 = 0; // ring slot and wrap count of this view's load 0 (kept incrementally: no division in the loops)
     POOL_EV_DECL(1 + (tid >> 8));
 
     long long t_prev = clock64();
@@ -349,6 +350,9 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
         const uint8_t* wbuf = smem + (wb ? OFF_W1 : OFF_W0);
         const float* sxbar = reinterpret_cast<const float*>(smem + OFF_XBAR + wb * C * 4);
         float* spart = reinterpret_cast<float*>(smem + (wb ? OFF_SPART_ODD : OFF_SPART_EVEN));
+        // ring slot / mbarrier parity of this view's load j (j < 10 is a compile-time constant wherever this is used)
+        auto slot_of = [&](int j) -> unsigned { const unsigned x = slot0 + j; return x >= 2 * RING ? x - 2 * RING : (x >= RING ? x - RING : x); };
+        auto par_of = [&](int j) -> unsigned { const unsigned x = slot0 + j; return (wrap0 + (x >= 2 * RING ? 2u : (x >= RING ? 1u : 0u))) & 1u; };
         // position terms of the attention tokens this thread owns in the softmax (global; in flight during the score phase)
         float ct[4];
 #pragma unroll
@@ -371,8 +375,9 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
         float dotp = 0.f;                                      // this lane's share of s0[g] = w_eff[g] . xbar
+#pragma unroll
         for (int p = 0; p < NSLAB / 2; ++p) {
-            const unsigned k0 = cnt + 2 * p, k1 = k0 + 1, b0 = k0 % RING, b1 = k1 % RING;
+            const unsigned b0 = slot_of(2 * p), b1 = slot_of(2 * p + 1);
             // A fragments straight from the bf16 planes: 4 consecutive columns = k slots 2q, 2q+1, 2q+8, 2q+9
             const int col = ((p * 8 + s) * 4 + q) * 4;
             const uint2 ah = *reinterpret_cast<const uint2*>(wbuf + (g * WPITCH + col) * 2);
@@ -385,8 +390,8 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
                 dotp = fmaf(w0, sxbar[ch], dotp); dotp = fmaf(w1, sxbar[ch + 8], dotp);
                 dotp = fmaf(w2, sxbar[ch + 64], dotp); dotp = fmaf(w3, sxbar[ch + 72], dotp);
             }
-            ip_mbar_wait(full + b0, (k0 / RING) & 1u);
-            ip_mbar_wait(full + b1, (k1 / RING) & 1u);
+            ip_mbar_wait(full + b0, par_of(2 * p));
+            ip_mbar_wait(full + b1, par_of(2 * p + 1));
             if ((tid & 255) == 0) POOL_EV(10000 * (1 + (tid >> 8)) + 100 * (int)vi + 2 * p + 1);   // pair p has landed
             const uint32_t base = ring_u32 + ((mi & 1) ? b1 : b0) * SLAB_BYTES + sc_off;
             if (!(a.debug_skip & 1)) {
@@ -518,16 +523,31 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
         }
         const float p0g = p0[g];
         __nv_bfloat16* yrow = a.ya_hi + ((size_t)bv * HEADS + g) * YA;
+        // Processing order: resident slabs 2..7 (FIFO release order), then the re-fetched slabs 0, 1 (loads 8, 9).  A warp
+        // reads every other slab of that order (parity hb); the slots of the slabs it does not read are handed back up
+        // front (the arrival only counts, the readers still hold the slot), the re-fetched one after its load has landed
+        // so that the arrival cannot fall into the slot's previous phase.
+#pragma unroll
+        for (int s2 = 0; s2 < NSLAB - REFETCH; ++s2)
+            if ((s2 & 1) != hb && lane == 0) ip_mbar_arrive(empty + slot_of(s2 + REFETCH));
+#pragma unroll
         for (int s2 = 0; s2 < NSLAB; ++s2) {
-            // resident slabs REFETCH..7 first (FIFO release order), then the re-fetched slabs 0..REFETCH-1
             const int sl = s2 < NSLAB - REFETCH ? s2 + REFETCH : s2 - (NSLAB - REFETCH);
-            const unsigned k = s2 < NSLAB - REFETCH ? cnt + sl : cnt + NSLAB + sl;
-            const unsigned b = k % RING;
-            if (s2 >= NSLAB - REFETCH) ip_mbar_wait(full + b, (k / RING) & 1u);     // readers and non-readers alike (arrival order)
+            const int j = s2 < NSLAB - REFETCH ? sl : NSLAB + sl;            // load index within the view
+            const unsigned b = slot_of(j);
+            if ((s2 & 1) != hb) {
+                if (s2 >= NSLAB - REFETCH) {
+                    ip_mbar_wait(full + b, par_of(j));
+                    __syncwarp();
+                    if (lane == 0) ip_mbar_arrive(empty + b);
+                }
+                continue;
+            }
+            if (s2 >= NSLAB - REFETCH) ip_mbar_wait(full + b, par_of(j));
             if ((tid & 255) == 0) POOL_EV(10000 * (1 + (tid >> 8)) + 100 * (int)vi + 20 + s2);     // sums step s2 starts
-            if ((s2 & 1) == hb && !(a.debug_skip & 4)) {
+            float y0[4] = {0.f, 0.f, 0.f, 0.f}, y1[4] = {0.f, 0.f, 0.f, 0.f}, y2[4] = {0.f, 0.f, 0.f, 0.f};   // independent MMA chains
+            if (!(a.debug_skip & 4)) {
                 const uint32_t base = ring_u32 + b * SLAB_BYTES + sm_off;
-                float y0[4] = {0.f, 0.f, 0.f, 0.f}, y1[4] = {0.f, 0.f, 0.f, 0.f}, y2[4] = {0.f, 0.f, 0.f, 0.f};   // independent MMA chains
                 uint32_t bf[2][4];                             // fragment loads run one step ahead of the MMAs
                 ldsm_x4(bf[0], base);
 #pragma unroll
@@ -540,24 +560,23 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
                     else { mma_bf16_16816(y1, PA[2 * m], f[0], f[1]); mma_bf16_16816(y2, PA[2 * m + 1], f[2], f[3]); }
                 }
                 mma_bf16_16816(y0, PA[14], bf[1][0], 0u);
-                __syncwarp();
-                if (lane == 0) ip_mbar_arrive(empty + b);
-                // accumulator rows g (hi part) / g+8 (lo part), columns 2q, 2q+1 = channels s + 16 q, s + 16 q + 8 of slab sl
-                const int ch = sl * SLAB_CH + s + 16 * q;
-                const float v0 = (((y0[0] + y1[0]) + y2[0]) + ((y0[2] + y1[2]) + y2[2])) + p0g * sxbar[ch];
-                const float v1 = (((y0[1] + y1[1]) + y2[1]) + ((y0[3] + y1[3]) + y2[3])) + p0g * sxbar[ch + 8];
-                uint32_t h0, l0, h1, l1;
-                split_hi_lo(v0, h0, l0);
-                split_hi_lo(v1, h1, l1);
-                const int col = ((sl * 8 + s) * 4 + q) * 2;
-                *reinterpret_cast<uint32_t*>(yrow + col) = h0 | (h1 << 16);
-                *reinterpret_cast<uint32_t*>(yrow + a.ya_plane + col) = l0 | (l1 << 16);
-            } else {
-                __syncwarp();
-                if (lane == 0) ip_mbar_arrive(empty + b);
             }
+            __syncwarp();
+            if (lane == 0) ip_mbar_arrive(empty + b);
+            // accumulator rows g (hi part) / g+8 (lo part), columns 2q, 2q+1 = channels s + 16 q, s + 16 q + 8 of slab sl
+            const int ch = sl * SLAB_CH + s + 16 * q;
+            const float v0 = (((y0[0] + y1[0]) + y2[0]) + ((y0[2] + y1[2]) + y2[2])) + p0g * sxbar[ch];
+            const float v1 = (((y0[1] + y1[1]) + y2[1]) + ((y0[3] + y1[3]) + y2[3])) + p0g * sxbar[ch + 8];
+            uint32_t h0, l0, h1, l1;
+            split_hi_lo(v0, h0, l0);
+            split_hi_lo(v1, h1, l1);
+            const int col = ((sl * 8 + s) * 4 + q) * 2;
+            *reinterpret_cast<uint32_t*>(yrow + col) = h0 | (h1 << 16);
+            *reinterpret_cast<uint32_t*>(yrow + a.ya_plane + col) = l0 | (l1 << 16);
         }
-        cnt += LOADS_PER_VIEW;
+        slot0 += LOADS_PER_VIEW - RING;                        // 10 loads per view on a ring of 6
+        wrap0 += 1;
+        if (slot0 >= RING) { slot0 -= RING; wrap0 += 1; }
         POOL_TRACE(4);                                        // weighted sums
         if ((tid & 255) == 0) POOL_EV(10000 * (1 + (tid >> 8)) + 100 * (int)vi + 93);      // sums done
     }
