@@ -158,6 +158,15 @@ size_t pt_img_attnpool_ws_bytes(int BV, int C, int HW, int c, int heads);
 int pt_img_attnpool(const void* img_feat, int img_dtype, const pt_img_pool_params* p, int BV, int C, int HW, int c,
                     int heads, float* img_proxy, void* ws, size_t ws_bytes, pt_stream_t stream);
 
+/* The same stage in two calls, so that the host can run the first one concurrently with the geometric stages on another
+ * stream: FRONT = pass over the features for the spatial means + the query-side projections (HBM-bound, few SM resources),
+ * BACK = pooling pass + value-side projections + LayerNorm.  Both calls get the same arguments and the same workspace, whose
+ * contents carry the state between them; stages = FRONT | BACK is pt_img_attnpool. */
+#define PT_IMG_STAGE_FRONT 1
+#define PT_IMG_STAGE_BACK 2
+int pt_img_attnpool_stage(const void* img_feat, int img_dtype, const pt_img_pool_params* p, int BV, int C, int HW, int c,
+                          int heads, float* img_proxy, void* ws, size_t ws_bytes, int stages, pt_stream_t stream);
+
 /* Debug only: per-phase SM-clock cycles of CTA 0 of the bf16 image-pool kernel, accumulated while PT_POOL_DEBUG has bit 8
  * set: [0] view barrier, [1] operand wait, [2] score MMAs, [3] score exchange + softmax, [4] weighted sums. */
 int pt_debug_pool_trace(unsigned long long* out8, int reset);
@@ -175,6 +184,19 @@ int pt_affine_scatter_compact(const float* points, const int32_t* kept_idx, cons
                               const float* kept_centres, const float* transform, const float* translate, int B, int N,
                               int n, int K, int n_drop_entries, float* out, int32_t* counts, void* ws, size_t ws_bytes,
                               pt_stream_t stream);
+
+/* ---- N1 hand-off to the sparse backbone (detectors/sparse_featfusion_grounder_preshape.py:388-391) ------------
+ * ME.utils.batch_sparse_collate([(p[:, :3] / voxel_size, p) for p in points]) on the packed result of
+ * pt_affine_scatter_compact: coords (T,4) int32 rows [scene, x, y, z], feats (T,3) fp32 rows = the coordinates themselves,
+ * scenes in order, T = sum(counts) written to *total.  coords / feats must hold B*N rows.  float -> int32 truncates
+ * toward zero (tensor assignment in MinkowskiEngine's sparse_collate) unless PT_COLLATE_FLOOR; the quotient is the IEEE
+ * division torch performs on the CPU, or with PT_COLLATE_RECIPROCAL the multiplication by fp32(1/voxel_size) of torch's
+ * CUDA kernel.  MinkowskiEngine is not vendored by the reference (version unpinned): its semantics are restated, parity for
+ * this entry point is pinned against the torch expression only. */
+#define PT_COLLATE_RECIPROCAL 1
+#define PT_COLLATE_FLOOR 2
+int pt_sparse_collate(const float* packed, const int32_t* counts, int B, int N, float voxel_size, int flags,
+                      int32_t* coords, float* feats, int32_t* total, pt_stream_t stream);
 
 /* ---- building blocks exposed for tests ------------------------------------------------------------------ */
 /* C (M,N) = act(A (M,K) @ W (N,K)^T + bias) + residual ; act: 0 none, 1 GELU(erf).  bias/residual may be NULL.

@@ -295,6 +295,27 @@ def remove_points(P: torch.Tensor, drop_idx: torch.Tensor) -> List[torch.Tensor]
 
 # ----------------------------------------------------------------------------- driver
 @torch.no_grad()
+def batch_sparse_collate(points: List[torch.Tensor], voxel_size: float, reciprocal: bool = False, floor: bool = False):
+    """Caller hand-off (detectors/sparse_featfusion_grounder_preshape.py:388-391):
+    ``ME.utils.batch_sparse_collate([(p[:, :3] / voxel_size, p) for p in points])`` -> (coordinates (T,4) int32, features (T,3)).
+    MinkowskiEngine (un-vendored, unpinned) is restated from its published ``sparse_collate``: an int32 (T, 1+D) tensor whose
+    column 0 is the batch index and whose other columns receive the float coordinates by tensor assignment (= truncation toward
+    zero); features are concatenated.  ``reciprocal`` restates torch's CUDA division by a Python scalar (multiply by the fp32
+    reciprocal); the default is the CPU kernel's IEEE division, which is what ``p / voxel_size`` evaluates to here."""
+    n = sum(len(p) for p in points)
+    coords = torch.zeros(n, 4, dtype=torch.int32)
+    s = 0
+    for b, p in enumerate(points):
+        xyz = p[:, :3].float()
+        quot = xyz * (torch.tensor(1.0, dtype=torch.float32) / torch.tensor(voxel_size, dtype=torch.float32)) if reciprocal else xyz / voxel_size
+        if floor:
+            quot = torch.floor(quot)
+        coords[s:s + len(p), 1:] = quot          # the assignment MinkowskiEngine performs: float -> int32 truncates
+        coords[s:s + len(p), 0] = b
+        s += len(p)
+    return coords, torch.cat([p.float() for p in points], 0)
+
+
 def forward(sd: Dict[str, torch.Tensor], points: List[torch.Tensor], text_dict, img_feat: Optional[torch.Tensor], *,
             grid_size: int, dynamic_drop_radio: float, text_blocks: int, img_blocks: int, num_sub: int = 30,
             num_heads: int = 8, img_proxy: Optional[torch.Tensor] = None, faithful_cost: bool = False,

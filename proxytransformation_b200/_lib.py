@@ -61,10 +61,12 @@ _SIGNATURES = {
     "pt_heads": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "pt_img_attnpool_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "pt_img_attnpool": (c_int, [_P, c_int, POINTER(ImgPoolParams), c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "pt_img_attnpool_stage": (c_int, [_P, c_int, POINTER(ImgPoolParams), c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, c_int, _P]),
     "pt_debug_pool_trace": (c_int, [POINTER(ctypes.c_ulonglong), c_int]),
     "pt_debug_pool_events": (c_int, [POINTER(ctypes.c_longlong), c_int]),
     "pt_scatter_ws_bytes": (c_size_t, [c_int, c_int]),
     "pt_affine_scatter_compact": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "pt_sparse_collate": (c_int, [_P, _P, c_int, c_int, ctypes.c_float, c_int, _P, _P, _P, _P]),
     "pt_gemm_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pt_gemm_nt": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "pt_gemm_tc": (c_int, [POINTER(GemmTcDesc), _P]),

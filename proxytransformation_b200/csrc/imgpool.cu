@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(PB_THREADS) img_pool_kernel(const void* __rest
 
 size_t img_attnpool_tc_ws_bytes(int BV);
 bool img_attnpool_tc_supported(int img_dtype, const pt_img_pool_params* p, int C, int HW, int c, int heads);
-int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, int BV, float* img_proxy, void* ws, size_t ws_bytes,
+int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, int BV, float* img_proxy, void* ws, size_t ws_bytes, int stages,
                            cudaStream_t s);
 
 static size_t pool_smem_bytes(int HW, int Tp) {
@@ -240,10 +240,18 @@ extern "C" size_t pt_img_attnpool_ws_bytes(int BV, int C, int HW, int c, int hea
 // w_vc (c,C); h_v consumed TRANSPOSED PER HEAD as h_vT (heads, hd, Tp) zero-padded.
 extern "C" int pt_img_attnpool(const void* img_feat, int img_dtype, const pt_img_pool_params* p, int BV, int C, int HW,
                                int c, int heads, float* img_proxy, void* ws, size_t ws_bytes, pt_stream_t stream) {
+    return pt_img_attnpool_stage(img_feat, img_dtype, p, BV, C, HW, c, heads, img_proxy, ws, ws_bytes,
+                                 PT_IMG_STAGE_FRONT | PT_IMG_STAGE_BACK, stream);
+}
+
+extern "C" int pt_img_attnpool_stage(const void* img_feat, int img_dtype, const pt_img_pool_params* p, int BV, int C, int HW,
+                                     int c, int heads, float* img_proxy, void* ws, size_t ws_bytes, int stages, pt_stream_t stream) {
     PT_REQUIRE(img_feat && p && img_proxy && ws, "pt_img_attnpool: null pointer");
     PT_REQUIRE(img_dtype == PT_DTYPE_F32 || img_dtype == PT_DTYPE_BF16, "pt_img_attnpool: dtype %d", img_dtype);
+    PT_REQUIRE(stages >= 1 && stages <= 3, "pt_img_attnpool_stage: stages=%d", stages);
     if (BV > 0 && img_attnpool_tc_supported(img_dtype, p, C, HW, c, heads))      // bf16 tensor-core fast path (imgpool_tc.cu)
-        return launch_img_attnpool_tc(img_feat, p, BV, img_proxy, ws, ws_bytes, (cudaStream_t)stream);
+        return launch_img_attnpool_tc(img_feat, p, BV, img_proxy, ws, ws_bytes, stages, (cudaStream_t)stream);
+    if (!(stages & PT_IMG_STAGE_BACK)) return PT_OK;                              // generic path: everything runs in the back stage
     PT_REQUIRE(heads == PB_HEADS, "pt_img_attnpool: heads=%d unsupported (8)", heads);
     PT_REQUIRE(BV > 0 && C % PB_CH == 0 && c % heads == 0 && HW >= 1 && HW <= PB_THREADS,
                "pt_img_attnpool: BV=%d C=%d HW=%d c=%d unsupported", BV, C, HW, c);

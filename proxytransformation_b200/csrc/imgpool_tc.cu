@@ -636,22 +636,26 @@ bool img_attnpool_tc_supported(int img_dtype, const pt_img_pool_params* p, int C
 }
 
 int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, int BV, float* img_proxy, void* ws, size_t ws_bytes,
-                           cudaStream_t s) {
+                           int stages, cudaStream_t s) {
     using namespace ip;
     PT_REQUIRE(((uintptr_t)img_feat & 15) == 0, "pt_img_attnpool: img_feat must be 16-byte aligned");
     ImgTcWs w = carve_tc(ws, BV);
     if (ws_bytes < w.total) { set_error("pt_img_attnpool: workspace %zu < %zu", ws_bytes, w.total); return PT_ERR_WORKSPACE; }
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int rc;
+    if (stages & PT_IMG_STAGE_FRONT) {
     {   // pass A
         const long long groups = (long long)BV * (C / 8);
         const long long blocks = (groups + 7) / 8;
-        const int grid = (int)(blocks < (long long)sms * 8 ? blocks : (long long)sms * 8);
+        // CTAs per SM: 8 saturate HBM when the kernel runs alone; fewer leave room for the geometry kernels that the host
+        // module runs concurrently on another stream (they are latency / ALU bound and barely touch HBM)
+        static const int per_sm = [] { const char* e = getenv("PT_MEAN_CTAS"); const int v = e ? atoi(e) : 8; return v >= 1 && v <= 8 ? v : 8; }();
+        const int grid = (int)(blocks < (long long)sms * per_sm ? blocks : (long long)sms * per_sm);
         ProfScope prof_(PROF_IMG_MEAN, s);
         img_mean_bf16_kernel<<<grid, 256, 0, s>>>((const uint4*)img_feat, groups, w.xbar, w.xbar_split, w.xbar_split + (size_t)BV * C);
     }
     PT_LAUNCH_CHECK();
-    int rc;
     {   // G1: q = xbar W_qc^T + q0  -> split planes only
         GemmTc gp;
         gp.M = BV; gp.N = EMB; gp.K = C;
@@ -678,6 +682,8 @@ int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, in
         gp.C = w.cterm; gp.ldc = HEADS * TP; gp.c_off_z = TP;
         if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
     }
+    }
+    if (!(stages & PT_IMG_STAGE_BACK)) return PT_OK;
     {   // pass B
         static bool attr_set = false;
         if (!attr_set) {

@@ -78,9 +78,61 @@ __global__ void __launch_bounds__(SC_BLOCK) compact_kernel(const float* __restri
     if (blk == nblk - 1 && tid == SC_BLOCK - 1) counts[b] = off + __popc(mask);
 }
 
+// N1 hand-off to the sparse backbone (detectors/sparse_featfusion_grounder_preshape.py:388-391):
+//   ME.utils.batch_sparse_collate([(p[:, :3] / voxel_size, p) for p in points]) -> coordinates (T,4) int32 [batch, x, y, z],
+//   features (T,3) fp32, T = sum of the per-scene counts, scenes in order.
+// The float -> int32 step is the tensor assignment `bcoords[s:s+n, 1:] = coord` of MinkowskiEngine's sparse_collate, i.e.
+// truncation toward zero (floor is offered for callers that quantise with sparse_quantize).  The division follows torch:
+// `tensor / python_float` is a true IEEE division on the CPU and a multiplication by the fp32 reciprocal in torch's CUDA
+// kernel (div_true_kernel_cuda, CPU-scalar divisor); `recip` selects which one is reproduced bit for bit.
+__global__ void __launch_bounds__(256) collate_kernel(const float* __restrict__ packed, const int32_t* __restrict__ counts, int B,
+                                                      int N, float voxel_size, float inv_voxel, int recip, int use_floor,
+                                                      int32_t* __restrict__ coords, float* __restrict__ feats,
+                                                      int32_t* __restrict__ total) {
+    __shared__ long long base_s;
+    const int b = blockIdx.y;
+    if (threadIdx.x < 32) {
+        long long s = 0, all = 0;
+        for (int j = threadIdx.x; j < B; j += 32) { const int c = __ldg(counts + j); all += c; if (j < b) s += c; }
+        for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(FULL, s, o); all += __shfl_xor_sync(FULL, all, o); }
+        if (threadIdx.x == 0) { base_s = s; if (b == 0 && blockIdx.x == 0) *total = (int32_t)all; }
+    }
+    __syncthreads();
+    const int cnt = __ldg(counts + b);
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= cnt) return;
+    const float* p = packed + ((size_t)b * N + i) * 3;
+    const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    const float qx = recip ? __fmul_rn(x, inv_voxel) : __fdiv_rn(x, voxel_size);
+    const float qy = recip ? __fmul_rn(y, inv_voxel) : __fdiv_rn(y, voxel_size);
+    const float qz = recip ? __fmul_rn(z, inv_voxel) : __fdiv_rn(z, voxel_size);
+    const long long r = base_s + i;
+    int4 c;
+    c.x = b;
+    c.y = use_floor ? __float2int_rd(qx) : __float2int_rz(qx);
+    c.z = use_floor ? __float2int_rd(qy) : __float2int_rz(qy);
+    c.w = use_floor ? __float2int_rd(qz) : __float2int_rz(qz);
+    reinterpret_cast<int4*>(coords)[r] = c;
+    float* f = feats + r * 3;
+    f[0] = x; f[1] = y; f[2] = z;
+}
+
 }  // namespace pt
 
 using namespace pt;
+
+extern "C" int pt_sparse_collate(const float* packed, const int32_t* counts, int B, int N, float voxel_size, int flags,
+                                 int32_t* coords, float* feats, int32_t* total, pt_stream_t stream) {
+    PT_REQUIRE(packed && counts && coords && feats && total, "pt_sparse_collate: null pointer");
+    PT_REQUIRE(B > 0 && N > 0 && voxel_size > 0.f && (flags & ~3) == 0, "pt_sparse_collate: bad argument");
+    PT_REQUIRE(((uintptr_t)coords & 15) == 0, "pt_sparse_collate: coords must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    { ProfScope prof_(PROF_MISC, s);
+      collate_kernel<<<dim3(ceil_div(N, 256), B), 256, 0, s>>>(packed, counts, B, N, voxel_size, 1.0f / voxel_size, flags & PT_COLLATE_RECIPROCAL,
+                                                               flags & PT_COLLATE_FLOOR, coords, feats, total); }
+    PT_LAUNCH_CHECK();
+    return PT_OK;
+}
 
 extern "C" size_t pt_scatter_ws_bytes(int B, int N) {
     return align_up((size_t)B * N * sizeof(int), 256) + align_up((size_t)B * ceil_div(N, SC_BLOCK) * sizeof(int), 256);

@@ -16,6 +16,7 @@ Algorithmic differences from the reference, all output-preserving:
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -155,8 +156,10 @@ class ProxyTransformationNormReverse(nn.Module):
         self._packed_key = None
         self._ws: Dict[str, torch.Tensor] = {}
         self.use_tensor_cores = True     # 3xBF16 tcgen05 GEMMs for the dense layers (falls back per shape inside the C side)
-        self.overlap_image_stage = False  # option: image proxies on a side CUDA stream; measured SLOWER on B200 (3.04 vs 2.86 ms/step)
-        # because the persistent pool kernel owns every SM's shared memory and the small kernels queue behind it
+        # first half of the image stage (feature means + query-side projections) on a side stream, concurrent with the
+        # geometric stages.  (The whole image stage on a side stream measured slower, 3.04 vs 2.86 ms/step: the persistent
+        # pool kernel owns every SM's shared memory and the small kernels queue behind it.)
+        self.overlap_mean_pass = os.environ.get("PT_OVERLAP_MEAN", "0") != "0"    # measured: 2.735 vs 2.765 ms/step at best, off by default
         self._streams: Dict[str, torch.cuda.Stream] = {}
         self.host_chunk_scenes = 8       # scenes per pipeline chunk when forward() is fed host tensors
 
@@ -355,6 +358,26 @@ class ProxyTransformationNormReverse(nn.Module):
         cnt = host_cnt.tolist()
         return [host_out[b, :cnt[b]] for b in range(B)]
 
+    @torch.no_grad()
+    def forward_sparse(self, points, text_dict, img_feat, voxel_size: float, *, reciprocal: bool = True, floor: bool = False):
+        """forward() followed by the caller's hand-off to the sparse backbone
+        (detectors/sparse_featfusion_grounder_preshape.py:385-391, ``use_xyz_feat=True``):
+        ``ME.utils.batch_sparse_collate([(p[:, :3] / voxel_size, p) for p in self(points, ...)])`` without the per-scene Python
+        list in between.  Device inputs; returns (coordinates (T,4) int32 [scene,x,y,z], features (T,3) fp32) on the device.
+        ``reciprocal=True`` reproduces the quotient of torch's CUDA kernel (the reference's production path)."""
+        dev = next(self.parameters()).device
+        P = self._stack_points(points, dev)
+        text, mask = tuple(self.get_text_proxy(text_dict))
+        text = text.to(dev, torch.float32).contiguous()
+        mask = mask.to(dev).to(torch.uint8).contiguous() if mask is not None else None
+        img_feat = img_feat.to(dev)
+        if img_feat.dtype not in (torch.float32, torch.bfloat16):
+            img_feat = img_feat.float()
+        out, counts = self.forward_packed(P, text, mask, img_feat.contiguous())
+        coords, feats, total = ops.sparse_collate(out, counts, voxel_size, reciprocal=reciprocal, floor=floor)
+        t = int(total.item())                                                                    # the one D2H sync
+        return coords[:t], feats[:t]
+
     @staticmethod
     def _stack_points(points, dev) -> torch.Tensor:
         if isinstance(points, torch.Tensor):          # already (B,N,3)
@@ -380,17 +403,20 @@ class ProxyTransformationNormReverse(nn.Module):
         (out (B,N,3) packed per scene, counts (B,) int32), no host synchronisation."""
         w = self._weights(P.device)
         K, n = self.num_sub, self.real_cluster_num
-        # S9 image proxies (:449) depend on nothing but img_feat and are HBM-bound, the geometric stages are latency/ALU
-        # bound: run them concurrently on a side stream and join before the image ProxyBlock.
-        side = None
-        if img_proxy is None and self.overlap_image_stage:
+        # S9 image proxies (:449) depend on nothing but img_feat.  Their first half (pass over the features for the spatial
+        # means + query-side projections) is HBM-bound and light on SM resources, the geometric stages S1-S6 are latency /
+        # ALU bound and barely touch HBM: the two run concurrently on two streams.  The second half (the persistent pooling
+        # kernel, which owns every SM's shared memory) stays on the main stream.
+        side = img_state = None
+        if img_proxy is None and self.overlap_mean_pass:
             cur = torch.cuda.current_stream(P.device)
             side = self._side_stream(P.device)
             side.wait_stream(cur)
-            img_feat.record_stream(side)
             with torch.cuda.stream(side):
-                img_proxy = ops.img_attnpool(img_feat, w["img"], self.num_heads, params=w["img_struct"])
-            img_proxy.record_stream(cur)
+                img_state = ops.img_attnpool(img_feat, w["img"], self.num_heads, params=w["img_struct"], stages=ops.IMG_STAGE_FRONT)
+            img_feat.record_stream(side)
+            for t in img_state:                     # allocated on the side stream, finished on the main one
+                t.record_stream(cur)
         # S1-S4 deformable clustering (:53-67)
         mn, mx, c0 = ops.minmax_centres(P, self.grid_size, w["lin"])
         idx1, _ = ops.ball_query(c0, P, K)
@@ -405,10 +431,12 @@ class ProxyTransformationNormReverse(nn.Module):
         th = w["text_head"]
         translate = ops.heads(tg, th["lin_w"], th["lin_b"], th["bn_scale"], th["bn_shift"])
         # S9 image proxies (:449) and image branch -> transform (:450-455)
-        if img_proxy is None:
-            img_proxy = ops.img_attnpool(img_feat, w["img"], self.num_heads, params=w["img_struct"])
         if side is not None:
             torch.cuda.current_stream(P.device).wait_stream(side)
+            img_proxy = ops.img_attnpool(img_feat, w["img"], self.num_heads, params=w["img_struct"], stages=ops.IMG_STAGE_BACK,
+                                         out=img_state[0], ws=img_state[1])[0]
+        elif img_proxy is None:
+            img_proxy = ops.img_attnpool(img_feat, w["img"], self.num_heads, params=w["img_struct"])
         ig = ops.proxy_block(pp, img_proxy, None, w["imgb"], self.num_heads, params=w["imgb_struct"])
         ih = w["img_head"]
         transform = ops.heads(ig, ih["lin_w"], ih["lin_b"], ih["bn_scale"], ih["bn_shift"])

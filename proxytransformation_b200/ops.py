@@ -207,9 +207,15 @@ def img_pool_channel_orders(device=None) -> Tuple[torch.Tensor, torch.Tensor]:
     return score.to(device), sums.to(device)
 
 
+IMG_STAGE_FRONT, IMG_STAGE_BACK = 1, 2
+
+
 def img_attnpool(img_feat, w: Dict[str, torch.Tensor], heads: int, ws: Optional[torch.Tensor] = None,
-                 params: Optional[ImgPoolParams] = None):
-    """S9 (:335-342, :154-177).  img_feat (B,V,C,H,W) fp32/bf16 -> (B,V,c)."""
+                 params: Optional[ImgPoolParams] = None, stages: int = IMG_STAGE_FRONT | IMG_STAGE_BACK,
+                 out: Optional[torch.Tensor] = None):
+    """S9 (:335-342, :154-177).  img_feat (B,V,C,H,W) fp32/bf16 -> (B,V,c).
+    ``stages``: FRONT (spatial means + query-side projections) and BACK (pooling + value side + LayerNorm) may be issued
+    as two calls with the same ``ws`` / ``out`` (pt_img_attnpool_stage); returns (out, ws)."""
     L = _lib.load()
     B, V, C, H, W = img_feat.shape
     c = w["cproj_w"].shape[0]
@@ -223,10 +229,13 @@ def img_attnpool(img_feat, w: Dict[str, torch.Tensor], heads: int, ws: Optional[
     need = L.pt_img_attnpool_ws_bytes(B * V, C, H * W, c, heads)
     if ws is None or ws.numel() < need:
         ws = _ws(need, img_feat.device)
-    out = torch.empty(B, V, c, dtype=torch.float32, device=img_feat.device)
-    check(L.pt_img_attnpool(_chk(img_feat, img_feat.dtype, "img_feat"), dt, ctypes.byref(p), B * V, C, H * W, c, heads,
-                            out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "pt_img_attnpool")
-    return out
+    if out is None:
+        out = torch.empty(B, V, c, dtype=torch.float32, device=img_feat.device)
+    check(L.pt_img_attnpool_stage(_chk(img_feat, img_feat.dtype, "img_feat"), dt, ctypes.byref(p), B * V, C, H * W, c, heads,
+                                  out.data_ptr(), ws.data_ptr(), ws.numel(), stages, _stream()), "pt_img_attnpool_stage")
+    if stages == (IMG_STAGE_FRONT | IMG_STAGE_BACK):
+        return out
+    return out, ws
 
 
 def affine_scatter_compact(points, kept_idx, drop_idx, kept_centres, transform, translate, ws: Optional[torch.Tensor] = None):
@@ -248,6 +257,26 @@ def affine_scatter_compact(points, kept_idx, drop_idx, kept_centres, transform, 
                                       out.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
           "pt_affine_scatter_compact")
     return out, counts
+
+
+COLLATE_RECIPROCAL, COLLATE_FLOOR = 1, 2
+
+
+def sparse_collate(out, counts, voxel_size: float, reciprocal: bool = True, floor: bool = False):
+    """N1 hand-off (detectors/sparse_featfusion_grounder_preshape.py:388-391): packed (B,N,3) + counts (B,) ->
+    coords (B*N,4) int32 [scene,x,y,z], feats (B*N,3) fp32, total (1,) int32 (device); rows >= total are unspecified.
+    ``reciprocal``: quotient as torch's CUDA kernel computes ``p / voxel_size`` (p * fp32(1/voxel_size)); False = IEEE
+    division (torch CPU).  ``floor``: round down instead of the truncation of MinkowskiEngine's tensor assignment."""
+    L = _lib.load()
+    B, N, _ = out.shape
+    dev = out.device
+    coords = torch.empty(B * N, 4, dtype=torch.int32, device=dev)
+    feats = torch.empty(B * N, 3, dtype=torch.float32, device=dev)
+    total = torch.empty(1, dtype=torch.int32, device=dev)
+    flags = (COLLATE_RECIPROCAL if reciprocal else 0) | (COLLATE_FLOOR if floor else 0)
+    check(L.pt_sparse_collate(_chk(out, torch.float32, "out"), _chk(counts, torch.int32, "counts"), B, N, float(voxel_size), flags,
+                              coords.data_ptr(), feats.data_ptr(), total.data_ptr(), _stream()), "pt_sparse_collate")
+    return coords, feats, total
 
 
 def gemm_nt(A, W, bias=None, residual=None, act: int = 0, w_split=None):

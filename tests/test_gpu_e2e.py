@@ -170,3 +170,14 @@ def test_full_size_batch_properties():
         untouched = ~is_touched[surv]
         assert torch.equal(o[untouched], P[surv][untouched]), "untouched survivors must be copied bit-exactly, in order"
         assert (o[~untouched] != P[surv][~untouched]).any(-1).float().mean() > 0.99
+
+
+def test_forward_sparse_equals_collate_of_forward():
+    """N1: forward_sparse == batch_sparse_collate(forward(...)) (oracle restatement of the caller's hand-off)."""
+    cfg, sd, pts, text_dict, img, g = load_case("gs5_ragged")
+    m = build_module(cfg, sd)
+    dpts, td, dimg = [p.to(DEV) for p in pts], {k: v.to(DEV) for k, v in text_dict.items()}, img.to(DEV)
+    out = m(dpts, td, dimg)
+    want_c, want_f = po.batch_sparse_collate([o.cpu() for o in out], 0.01, reciprocal=True)
+    coords, feats = m.forward_sparse(dpts, td, dimg, 0.01)
+    assert torch.equal(coords.cpu(), want_c) and torch.equal(feats.cpu(), want_f)

@@ -170,6 +170,25 @@ def test_image_proxies_single_query_form(name, dtype):
     np.testing.assert_allclose(np_(got), want.numpy(), rtol=0, atol=3e-5)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_image_proxies_two_stage_call_equals_single_call(dtype):
+    """pt_img_attnpool_stage: FRONT then BACK on one workspace (what the module does when the feature-mean pass runs on a
+    side stream) must give exactly pt_img_attnpool's result; so must the module with the overlap switched on."""
+    cfg, sd, pts, text_dict, img, g = load_case("c2_wide_b1")
+    m = build_module(cfg, sd)
+    x = img.to(dtype).to(DEV)
+    w = m._weights(x.device)
+    want = m.get_img_proxy(x)
+    out, ws = ops.img_attnpool(x, w["img"], cfg.num_heads, params=w["img_struct"], stages=ops.IMG_STAGE_FRONT)
+    got, _ = ops.img_attnpool(x, w["img"], cfg.num_heads, params=w["img_struct"], stages=ops.IMG_STAGE_BACK, out=out, ws=ws)
+    assert torch.equal(got, want)
+    dpts, td = [p.to(DEV) for p in pts], {k: v.to(DEV) for k, v in text_dict.items()}
+    a = m(dpts, td, x)
+    m.overlap_mean_pass = True
+    b = m(dpts, td, x)
+    assert all(torch.equal(p, q) for p, q in zip(a, b))
+
+
 @pytest.mark.parametrize("name", ALL)
 def test_affine_scatter_compact_on_golden_inputs(name):
     """duplicates resolved by the pinned rule (largest flat (m,k) wins); coords within 2e-5 of the reference; survivor
@@ -260,3 +279,21 @@ def test_gemm_tensor_core_batched_head_slices():
     ops.gemm_tc(ops.split_bf16(cu(q)), ops.split_bf16(cu(wpad)), BV, C, 64, batch=heads, a_koff_z=hd, w_row_z=C, C=out,
                 ldc=heads * C, c_off_z=C)
     np.testing.assert_allclose(np_(out), want.numpy(), rtol=0, atol=6e-5)
+
+
+@pytest.mark.parametrize("reciprocal,floor", [(False, False), (True, False), (False, True), (True, True)])
+def test_sparse_collate_handoff_bit_exact(reciprocal, floor):
+    """N1: packed result + counts -> (coordinates int32 [scene,x,y,z], features) exactly as the oracle's restatement of
+    ME.utils.batch_sparse_collate on the ragged per-scene list, negative coordinates and voxel-boundary values included."""
+    g = torch.Generator().manual_seed(5)
+    B, N, vs = 5, 3000, 0.01
+    P = (torch.rand(B, N, 3, generator=g) - 0.3) * 20.0
+    P[0, :64] = torch.arange(-32, 32).float()[:, None] * vs                  # exact multiples of the voxel size
+    P[1, :64] = torch.nextafter(P[0, :64], torch.full_like(P[0, :64], -100.0))
+    counts = torch.tensor([N, 0, 1234, 1, 2999], dtype=torch.int32)
+    want_c, want_f = po.batch_sparse_collate([P[b, :counts[b]] for b in range(B)], vs, reciprocal=reciprocal, floor=floor)
+    coords, feats, total = ops.sparse_collate(cu(P), cu(counts), vs, reciprocal=reciprocal, floor=floor)
+    t = int(total.item())
+    assert t == int(counts.sum())
+    assert torch.equal(coords[:t].cpu(), want_c)
+    assert torch.equal(feats[:t].cpu(), want_f)

@@ -132,3 +132,25 @@ def test_oracle_live_against_reference_faithful_cost():
     for a, b in zip(out, want):
         assert a.shape == b.shape
         assert (a - b).abs().max().item() < 1e-5
+
+
+def test_sparse_collate_restatement_matches_the_torch_expression():
+    """N1 oracle pin: the caller evaluates ``p[:, :3] / voxel_size`` with torch and MinkowskiEngine assigns it into an int32
+    tensor; the restatement must agree with exactly that expression (CPU semantics), batch column and ordering included."""
+    g = torch.Generator().manual_seed(11)
+    pts = [(torch.rand(n, 3, generator=g) - 0.4) * 30.0 for n in (7, 0, 129)]
+    coords, feats = po.batch_sparse_collate(pts, 0.01)
+    s = 0
+    for b, p in enumerate(pts):
+        ref = torch.zeros(len(p), 4, dtype=torch.int32)
+        ref[:, 1:] = p[:, :3] / 0.01
+        ref[:, 0] = b
+        assert torch.equal(coords[s:s + len(p)], ref)
+        assert torch.equal(feats[s:s + len(p)], p)
+        s += len(p)
+    assert s == len(coords)
+    # truncation, not floor, for negative quotients; floor only on request
+    c2, _ = po.batch_sparse_collate([torch.tensor([[-0.015, 0.015, -0.0]])], 0.01)
+    assert c2[0].tolist() == [0, -1, 1, 0]
+    c3, _ = po.batch_sparse_collate([torch.tensor([[-0.015, 0.015, -0.0]])], 0.01, floor=True)
+    assert c3[0].tolist() == [0, -2, 1, 0]
