@@ -13,7 +13,7 @@
 
 namespace pt {
 
-constexpr int AM_THREADS = 256, AM_WARPS = 8, AM_HD = 32, AM_KP = 40;   // KP: bf16 pitch of the [rows][32] operand planes
+constexpr int AM_THREADS = 512, AM_WARPS = 16, AM_HD = 32, AM_KP = 40;   // KP: bf16 pitch of the [rows][32] operand planes
 
 __device__ __forceinline__ void am_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"

@@ -221,11 +221,12 @@ __device__ unsigned long long g_pool_trace[8];
 __device__ long long g_pool_ev[2 * 4096];
 __device__ unsigned int g_pool_evn;
 #ifdef PT_POOL_EVENTS
-#define POOL_EV_MAX 96
+#define POOL_EV_MAX 16
+#define POOL_EV_LOGGERS 17
 #define POOL_EV_DECL(logger) unsigned int ev_n = 0; unsigned int* ev_buf = reinterpret_cast<unsigned int*>(smem + ip::SMEM_BYTES) + (logger) * 2 * POOL_EV_MAX
 #define POOL_EV(id)                                                                                        \
     do {                                                                                                   \
-        if ((a.debug_skip & 32) && blockIdx.x == 0 && vi >= 40 && vi < 44 && ev_n < POOL_EV_MAX) {         \
+        if ((a.debug_skip & 32) && blockIdx.x == 0 && vi >= 40 && vi < 43 && ev_n < POOL_EV_MAX) {         \
             ev_buf[2 * ev_n] = (unsigned int)(id); ev_buf[2 * ev_n + 1] = (unsigned int)clock64(); ++ev_n; \
         }                                                                                                  \
     } while (0)
@@ -238,7 +239,7 @@ __device__ unsigned int g_pool_evn;
             }                                                                                              \
         }                                                                                                  \
     } while (0)
-#define POOL_EV_SMEM (3 * 2 * POOL_EV_MAX * 4)
+#define POOL_EV_SMEM (POOL_EV_LOGGERS * 2 * POOL_EV_MAX * 4)
 #else
 #define POOL_EV_DECL(logger)
 #define POOL_EV(id)
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
         // ===== producer: slabs 0..7 of the view, then slabs 0..REFETCH-1 again (FIFO ring, see header) =====
         if (lane == 0) {
             unsigned cnt = 0, vi = 0;
-            POOL_EV_DECL(0);
+            POOL_EV_DECL(16);
             for (int bv = blockIdx.x; bv < a.BV; bv += gridDim.x, ++vi) {
                 // per-view operands: w_eff planes (16.5 KB) + xbar (2 KB) into the buffers of this view's parity; they are
                 // requested as soon as the previous view's slab loads are all in flight
@@ -297,7 +298,6 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
                 ip_mbar_expect_tx(wfull + wb, WBYTES + C * 4);
                 ip_bulk_load(smem + (wb ? OFF_W1 : OFF_W0), a.wpl + (size_t)bv * 2 * WPLANE, WBYTES, wfull + wb);
                 ip_bulk_load(smem + OFF_XBAR + wb * C * 4, a.xbar + (size_t)bv * C, C * 4, wfull + wb);
-                POOL_EV(100 * (int)vi + 50);                       // operand load issued
                 const uint8_t* view = a.img + (size_t)bv * C * HW * 2;
                 for (int k = 0; k < LOADS_PER_VIEW; ++k, ++cnt) {
                     const int slab = k < NSLAB ? k : k - NSLAB;
@@ -314,7 +314,6 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
                     const uint32_t nbytes = (a.debug_skip & 2) ? 16u : (uint32_t)SLAB_BYTES;
                     ip_mbar_expect_tx(full + b, nbytes);
                     ip_bulk_load(smem + OFF_RING + b * SLAB_BYTES, view + (size_t)slab * SLAB_BYTES, nbytes, full + b);
-                    POOL_EV(100 * (int)vi + k);                // slab load k of view vi issued
                 }
             }
             POOL_EV_DUMP();
@@ -342,7 +341,7 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
     const int sh = warp & 7, shalf = warp >> 3;
     unsigned vi = 0;               // views done
     unsigned slot0 = 0, wrap0 = 0; // ring slot and wrap count of this view's load 0 (kept incrementally: no division in the loops)
-    POOL_EV_DECL(1 + (tid >> 8));
+    POOL_EV_DECL(warp);
 
     long long t_prev = clock64();
     for (int bv = blockIdx.x; bv < a.BV; bv += gridDim.x, ++vi) {
@@ -360,11 +359,13 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
             const int t = 128 * shalf + lane + 32 * i;
             ct[i] = t < T ? __ldg(a.cterm + ((size_t)bv * HEADS + sh) * TP + t) : 0.f;
         }
+        if (lane == 0) POOL_EV(1000 * warp + 10 * ((int)vi - 40) + 0);                    // reached the top of the view
         ip_consumer_sync();                                   // every warp is done with the previous view (probabilities, s0part, red)
         POOL_TRACE(0);
+        if (lane == 0) POOL_EV(1000 * warp + 10 * ((int)vi - 40) + 1);                    // past the view barrier
         ip_mbar_wait(wfull + wb, (vi >> 1) & 1u);
         POOL_TRACE(1);                                        // wait for the staged operands
-        if ((tid & 255) == 0) POOL_EV(10000 * (1 + (tid >> 8)) + 100 * (int)vi + 90);      // view start (warp 0 / warp 8)
+        if (lane == 0) POOL_EV(1000 * warp + 10 * ((int)vi - 40) + 2);                    // operands landed
 
         // ---- (1) scores: S_s[h][u] = sum over the channels c of class s of w_eff[h][c] X[c][u - s].
         // k-block = 8 class-s channels of slab 2p + 8 of slab 2p+1; B fragments by ldmatrix.trans (rows = channels,
@@ -392,7 +393,6 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
             }
             ip_mbar_wait(full + b0, par_of(2 * p));
             ip_mbar_wait(full + b1, par_of(2 * p + 1));
-            if ((tid & 255) == 0) POOL_EV(10000 * (1 + (tid >> 8)) + 100 * (int)vi + 2 * p + 1);   // pair p has landed
             const uint32_t base = ring_u32 + ((mi & 1) ? b1 : b0) * SLAB_BYTES + sc_off;
             if (!(a.debug_skip & 1)) {
                 uint32_t bf[2][4];                             // fragment loads run one step ahead of the MMAs
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
             if (q == 0) s0part[s * 8 + g] = dotp;             // 8 class partials per head
         }
         POOL_TRACE(2);                                        // score MMAs (incl. waiting for slabs)
-        if ((tid & 255) == 0) POOL_EV(10000 * (1 + (tid >> 8)) + 100 * (int)vi + 91);      // score MMAs done
+        if (lane == 0) POOL_EV(1000 * warp + 10 * ((int)vi - 40) + 3);                    // score MMAs done
         ip_consumer_sync();                                   // w_eff planes are dead: the partial-score overlay may be written
         if (!(a.debug_skip & 16)) {
         // hi + lo rows of the accumulators; classes 0-3 store S_s[h][u], then classes 4-7 add theirs four columns lower so
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
         } else if (tid == 0) ip_mbar_arrive(wempty + wb);
         ip_consumer_sync();
         POOL_TRACE(3);                                        // score exchange + softmax + barriers
-        if ((tid & 255) == 0) POOL_EV(10000 * (1 + (tid >> 8)) + 100 * (int)vi + 92);      // softmax done
+        if (lane == 0) POOL_EV(1000 * warp + 10 * ((int)vi - 40) + 4);                    // softmax done
 
         // ---- (3) weighted sums: Y[h][c] = sum_tok P[h][tok] X[c][tok]  (+ p0[h] xbar[c]) for the 8 class-s channels of a slab
         // per MMA column tile; k runs over the aligned chunks u = tok + s, so the A fragments are the probabilities shifted
@@ -544,7 +544,6 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
                 continue;
             }
             if (s2 >= NSLAB - REFETCH) ip_mbar_wait(full + b, par_of(j));
-            if ((tid & 255) == 0) POOL_EV(10000 * (1 + (tid >> 8)) + 100 * (int)vi + 20 + s2);     // sums step s2 starts
             float y0[4] = {0.f, 0.f, 0.f, 0.f}, y1[4] = {0.f, 0.f, 0.f, 0.f}, y2[4] = {0.f, 0.f, 0.f, 0.f};   // independent MMA chains
             if (!(a.debug_skip & 4)) {
                 const uint32_t base = ring_u32 + b * SLAB_BYTES + sm_off;
@@ -578,9 +577,8 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
         wrap0 += 1;
         if (slot0 >= RING) { slot0 -= RING; wrap0 += 1; }
         POOL_TRACE(4);                                        // weighted sums
-        if ((tid & 255) == 0) POOL_EV(10000 * (1 + (tid >> 8)) + 100 * (int)vi + 93);      // sums done
     }
-    if ((tid & 255) == 0) POOL_EV_DUMP();
+    if (lane == 0) POOL_EV_DUMP();
 }
 
 }  // namespace pt

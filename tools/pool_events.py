@@ -21,15 +21,12 @@ m.get_img_proxy(img); torch.cuda.synchronize()
 n = L.pt_debug_pool_events(buf, 4096)
 ev = sorted((buf[2 * i + 1], buf[2 * i]) for i in range(n))      # 32-bit SM clock (a 0.9 ms kernel cannot wrap twice)
 t0 = ev[0][0]
-def name(i):
-    if i >= 10000:
-        w, r = divmod(i, 10000); vi, c = divmod(r, 100)
-        who = "warp0" if w == 1 else "warp8"
-        what = {90: "view start", 91: "score MMAs done", 92: "softmax done", 93: "sums done"}.get(c) or (f"pair {(c - 1) // 2} landed" if c < 20 else f"sums step {c - 20} starts")
-        return f"{who} view {vi}: {what}"
-    vi, k = divmod(i, 100)
-    if k == 50:
-        return f"producer: operands of view {vi} issued"
-    return f"producer: load {k} of view {vi} issued" + (" (refetch)" if k >= 8 else "")
+CODES = {0: "top of view", 1: "past view barrier", 2: "operands landed", 3: "score MMAs done", 4: "softmax done"}
+rows = {}
 for t, i in ev:
-    print(f"{t - t0:8d}  {name(i)}")
+    w, r = divmod(i, 1000); v, c = divmod(r, 10)
+    rows.setdefault((v, c), {})[w] = t - t0
+print("cycles since the first event; one column per consumer warp (lane 0)")
+print("view event              " + " ".join(f"w{w:<6d}" for w in range(16)))
+for (v, c) in sorted(rows):
+    print(f"{40 + v:4d} {CODES.get(c, c):18s} " + " ".join(f"{rows[(v, c)].get(w, -1):7d}" for w in range(16)))
