@@ -120,6 +120,15 @@ int pt_proxy_block_fused(const float* x, const float* proxy, const uint8_t* mask
  * + pc[m,r] + pr[m,q]   (:212-215).  pb (n,4,4), pc (n,s), pr (n,s). */
 int pt_position_bias(const float* pb, const float* pc, const float* pr, int n, int s, float* out, pt_stream_t stream);
 
+/* The two-stage proxy attention core (:225-252) alone, tcgen05 / TMEM form, on pre-split bf16 hi/lo operand planes
+ * (heads of 32 channels, n <= 256, n % 8 == 0, l <= 256): qk_split [rows][ldq] holds Q at column 0 and K at column c,
+ * vt_split [c][ldv] holds V^T (column = scene*n + cluster), pt_split [B*l][c] the projected proxies; every lo plane lies
+ * *_plane elements behind its hi plane.  Writes o (fp32, optional) and / or o_split hi/lo planes, (B*n, c).
+ * pt_proxy_block_fused uses it when the shape fits and the mma.sync kernel otherwise. */
+int pt_proxy_attention_tc(const void* qk_split, long long qk_plane, int ldq, const void* vt_split, long long vt_plane, long long ldv,
+                          const void* pt_split, long long pt_plane, const uint8_t* mask, int B, int n, int l, int c, int heads,
+                          float* o, void* o_split, long long o_plane, pt_stream_t stream);
+
 /* ---- S8 heads — Linear + BatchNorm1d(eval) (:445-446, :454-455) ---------------------------------------
  * out (rows,o) = (guide (rows,c) @ lin_w(o,c)^T + lin_b) * bn_scale + bn_shift, o <= 16. */
 int pt_heads(const float* guide, const float* lin_w, const float* lin_b, const float* bn_scale, const float* bn_shift,

@@ -6,6 +6,7 @@
 #include <mutex>
 #include <vector>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace pt {
@@ -56,6 +57,10 @@ int launch_layernorm_split(const float* x, const float* w, const float* b, const
 bool proxy_attention_mma_supported(int n, int l, int c, int heads);
 int launch_proxy_attention_mma(const float* qkv, const float* pt_tok, const uint8_t* mask, int B, int n, int l, int c, int heads,
                                float* o, void* o_split, long long o_plane, cudaStream_t s);
+bool proxy_attention_tc_supported(int n, int l, int c, int heads);
+int launch_proxy_attention_tc(const void* qk_split, long long qk_plane, int ldq, const void* vt_split, long long vt_plane, long long ldv,
+                              const void* pt_split, long long pt_plane, const uint8_t* mask, int B, int n, int l, int c, int heads,
+                              float* o, void* o_split, long long o_plane, cudaStream_t s);
 int launch_gemm_f32(const float* A, const float* W, const float* bias, const float* residual, int act, int M, int N, int K,
                     float* C, cudaStream_t s);
 int launch_proxy_attention(const float* qkv, const float* pt_tok, const uint8_t* mask, int B, int n, int l, int c,
@@ -166,6 +171,47 @@ extern "C" int pt_proxy_block_fused(const float* x, const float* proxy, const ui
         };
         // u = LN1(x) + bias[m]                                        (:274, :212-217)
         if ((rc = launch_layernorm_split(x, p->ln1_w, p->ln1_b, p->pos_bias, n, rows, c, nullptr, w.u_s, (long long)rows * c, s))) return rc;
+        static const bool no_tc_attn = getenv("PT_ATTN_MMA") != nullptr;          // debug: force the mma.sync attention kernel
+        if (!no_tc_attn && proxy_attention_tc_supported(n, l, c, heads)) {
+            // tcgen05 / TMEM attention (attn_tc.cu): every operand is a bf16 hi/lo plane pair written by a projection GEMM.
+            // The fp32 qkv buffer (rows x 3c x 4 B) holds [Q|K] planes (2 x rows x 2c) followed by the V^T planes (2 x c x rows).
+            __nv_bfloat16* qk_s = (__nv_bfloat16*)w.qkv;
+            __nv_bfloat16* vt_s = qk_s + (size_t)2 * rows * 2 * c;
+            __nv_bfloat16* pt_s = (__nv_bfloat16*)w.pt;
+            {   // [Q|K] = u Wqk^T                                      (:221, rows 0..2c-1 of the qkv weight)
+                GemmTc gp;
+                gp.M = rows; gp.N = 2 * c; gp.K = c;
+                gp.a_split = w.u_s; gp.a_rows = rows; gp.a_cols = c; gp.lda = c;
+                gp.w_split = p->qkv_w_split; gp.w_rows = 3 * c; gp.ldw = c;
+                gp.c_split = qk_s; gp.cs_plane = (long long)rows * 2 * c; gp.ldcs = 2 * c;
+                if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
+            }
+            {   // V^T = Wv u^T: the same GEMM with the operand roles swapped, so that the value planes come out K-major over
+                // the clusters (the B operand layout of the value contraction).  A = rows 2c..3c-1 of the qkv weight planes
+                // (hi plane + 3c rows = lo plane); the tensor map nominally extends 2c rows past the planes, never touched.
+                GemmTc gp;
+                gp.M = c; gp.N = rows; gp.K = c;
+                gp.a_split = (const __nv_bfloat16*)p->qkv_w_split + (size_t)2 * c * c; gp.a_rows = 3 * c; gp.a_cols = c; gp.lda = c;
+                gp.w_split = w.u_s; gp.w_rows = rows; gp.ldw = c;
+                gp.c_split = vt_s; gp.cs_plane = (long long)c * rows; gp.ldcs = rows;
+                if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
+            }
+            // Pt = proxy Wp^T + bp                                     (:223)
+            if ((rc = split_rows_bf16(proxy, (long long)B * l * c, w.proxy_s, w.proxy_s + (size_t)B * l * c, s))) return rc;
+            {
+                GemmTc gp;
+                gp.M = B * l; gp.N = c; gp.K = c;
+                gp.a_split = w.proxy_s; gp.a_rows = B * l; gp.a_cols = c; gp.lda = c;
+                gp.w_split = p->pp_w_split; gp.w_rows = c; gp.ldw = c;
+                gp.bias = p->pp_b;
+                gp.c_split = pt_s; gp.cs_plane = (long long)B * l * c; gp.ldcs = c;
+                if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
+            }
+            // two-stage proxy attention                                (:225-252)
+            if ((rc = launch_proxy_attention_tc(qk_s, (long long)rows * 2 * c, 2 * c, vt_s, (long long)c * rows, rows, pt_s,
+                                                (long long)B * l * c, mask, B, n, l, c, heads, nullptr, w.o_s, (long long)rows * c, s)))
+                return rc;
+        } else {
         // [Q|K|V] = u Wqkv^T                                          (:221)
         if ((rc = gemm(w.u_s, rows, c, p->qkv_w_split, 3 * c, nullptr, nullptr, 0, w.qkv, nullptr))) return rc;
         // Pt = proxy Wp^T + bp                                        (:223)
@@ -173,6 +219,7 @@ extern "C" int pt_proxy_block_fused(const float* x, const float* proxy, const ui
         if ((rc = gemm(w.proxy_s, B * l, c, p->pp_w_split, c, p->pp_b, nullptr, 0, w.pt, nullptr))) return rc;
         // two-stage proxy attention                                   (:225-252)
         if ((rc = launch_proxy_attention_mma(w.qkv, w.pt, mask, B, n, l, c, heads, nullptr, w.o_s, (long long)rows * c, s))) return rc;
+        }
         // x1 = x + (o Wo^T + bo)                                      (:255, :274)
         if ((rc = gemm(w.o_s, rows, c, p->proj_w_split, c, p->proj_b, x, 0, w.x1, nullptr))) return rc;
         // x2 = x1 + fc2(GELU(fc1(LN2(x1))))                           (:275)

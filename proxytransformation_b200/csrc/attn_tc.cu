@@ -1,0 +1,393 @@
+// tcgen05 / TMEM form of the two-stage proxy attention core of ProxyAttention.forward (:225-252), one CTA per (scene, head):
+//   stage 1 (proxy as query, :232-238):  Pv = softmax_n((Pt*scale) K^T) V          (l x hd), unmasked
+//   stage 2 (proxy as key,   :241-250):  O  = softmax_l(mask((Q*scale) Pt^T)) Pv   (n x hd)
+// for heads of 32 channels, n <= 256 point proxies and l <= 256 text / image proxies (the benchmark shape; larger n fall
+// back to the mma.sync kernel in attn_mma.cu).
+//
+// Every contraction is a tcgen05.mma (cta_group::1, kind::f16, M = 128) with fp32 accumulation in TMEM and 3xBF16 operand
+// splitting (hi*hi + lo*hi + hi*lo), so scores and outputs keep ~2^-17 relative accuracy:
+//   * Q, K, Pt arrive as bf16 hi/lo planes straight from the projection GEMMs and are staged as K-major SWIZZLE_128B
+//     tiles whose 128-byte rows are [hi 32 | lo 32]: the three products are descriptor offsets into the same tile;
+//   * the score tile S (128 rows x <= 256 keys, fp32) lives in TMEM; four threads per row (four warps per lane quarter,
+//     interleaved 32-column chunks) reads it with tcgen05.ld, applies scale / mask / softmax and writes the probabilities
+//     back IN PLACE as packed bf16 hi and lo halves (tcgen05.st), where the second MMA reads them as its TMEM A operand —
+//     the probabilities never touch shared memory;
+//   * V^T (from a transposed projection GEMM) and Pv^T (written by the stage-1 epilogue) are the K-major B operands of
+//     the value contractions; the 1/rowsum normalisation is applied to the 32-column accumulator in the epilogue.
+// Cost is O(n*l*hd), never n^2.
+#include "common.cuh"
+
+#include <math.h>
+
+namespace pt {
+
+namespace at {
+constexpr int THREADS = 512, HD = 32, MAXR = 256;   // 16 warps: 4 per TMEM lane quarter, each takes every 4th 32-column chunk
+constexpr int ROW_BYTES = 128;                        // [hi 32 | lo 32] bf16
+constexpr int TILE_BYTES = MAXR * ROW_BYTES;          // 32768: Q / K / Pt operand tiles (256 rows)
+constexpr int VT_TILE = HD * ROW_BYTES;               // 4096: one 64-key k-tile of V^T / Pv^T (32 rows)
+constexpr int VT_PLANE = 4 * VT_TILE;                 // 16384: 256 keys
+constexpr int OFF_K = 0, OFF_Q = OFF_K + TILE_BYTES, OFF_P = OFF_Q + TILE_BYTES;
+constexpr int OFF_VT = OFF_P + TILE_BYTES;            // hi plane, then lo plane
+constexpr int OFF_PV = OFF_VT + 2 * VT_PLANE;         // hi plane, then lo plane
+constexpr int OFF_MISC = OFF_PV + 2 * VT_PLANE;       // rowmax [4][128], rowsum [4][128], keyflag [256] floats
+constexpr int OFF_BAR = OFF_MISC + (8 * 128 + 256) * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 16 + 1024;       // + alignment slack
+constexpr int TMEM_COLS = 512, ACC_COL = 256;
+}  // namespace at
+
+__device__ __forceinline__ uint32_t at_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t at_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__host__ __device__ constexpr uint32_t at_idesc(int n) {     // D=f32, A=B=bf16, K-major, M=128
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void at_mma_ss(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(da),
+                 "l"(db), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+__device__ __forceinline__ void at_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a_tmem),
+                 "l"(db), "r"(idesc), "r"(acc)
+                 : "memory");
+}
+__device__ __forceinline__ void at_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(at_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void at_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(at_smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ void at_ld32(uint32_t (&v)[32], uint32_t taddr) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void at_ld16(uint32_t (&v)[16], uint32_t taddr) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void at_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+                 "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                 : "memory");
+}
+__device__ __forceinline__ void at_ld8(uint32_t (&v)[8], uint32_t taddr) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float at_ex2(float x) {            // 2^x, ~2 ulp; x <= 0 here
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// (x0, x1) -> packed bf16x2 hi word (x0 in the low half) and lo word, with one packed conversion each
+__device__ __forceinline__ void at_split2_fast(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
+__device__ __forceinline__ void at_split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+    hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+}
+
+struct AtArgs {
+    const __nv_bfloat16* qk;      // hi plane of [rows][ldq]: Q at column 0, K at column c; lo plane qk_plane elements later
+    long long qk_plane;
+    int ldq;
+    const __nv_bfloat16* vt;      // hi plane of V^T [c][ldv] (column = global row b*n + j); lo plane vt_plane later
+    long long vt_plane;
+    long long ldv;
+    const __nv_bfloat16* pt;      // hi plane of Pt [B*l][c]; lo plane pt_plane later
+    long long pt_plane;
+    const uint8_t* mask;          // (B,l) 1 = real token, or null
+    int n, l, c;
+    float scale;
+    float* o;                     // optional fp32 (B*n, c)
+    __nv_bfloat16* o_hi;          // optional bf16 hi plane (B*n, c); lo plane o_plane later
+    long long o_plane;
+};
+
+// One score tile: scale / mask / softmax of the 128 rows in TMEM columns [0, ncols), probabilities written back in place
+// (chunk j of 32 keys -> 16 hi columns, 16 lo columns).  nvalid = real keys; flag (smem) != 0 marks masked keys (-1e9).
+// Each of the 4 warps of a lane quarter (hh) takes every 4th chunk; the row maximum and the row sum meet in shared memory.
+// softmax(scale*s) is evaluated as 2^(s*c1 - max*c1) with c1 = scale*log2(e): one FFMA and one MUFU per element.
+__device__ __forceinline__ void at_softmax_tile(uint32_t tmem_row, int ncols, int nvalid, const float* __restrict__ flag, float scale,
+                                                int hh, float* __restrict__ rowmax, float* __restrict__ rowsum, int row) {
+    const int nch = (ncols + 31) >> 5;
+    const float c1 = scale * 1.4426950408889634f;
+    float mx = -INFINITY;                                      // maximum of the UNSCALED scores of the real, unmasked keys
+    bool any_masked = false;
+    for (int ch = hh; ch < nch; ch += 4) {
+        uint32_t v[32];
+        at_ld32(v, tmem_row + 32 * ch);
+        const int kv = nvalid - 32 * ch;                       // real keys in this chunk (>= 32: all)
+        if (flag == nullptr && kv >= 32) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+        } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                if (e < kv) {
+                    if (flag != nullptr && flag[32 * ch + e] != 0.f) any_masked = true;
+                    else mx = fmaxf(mx, __uint_as_float(v[e]));
+                }
+            }
+        }
+    }
+    // scaled maximum; a masked key contributes the literal -1e9 of masked_fill (:247)
+    float ms = mx * scale;
+    if (any_masked) ms = fmaxf(ms, -1e9f);
+    rowmax[hh * 128 + row] = ms;
+    __syncthreads();
+    ms = fmaxf(fmaxf(rowmax[row], rowmax[128 + row]), fmaxf(rowmax[256 + row], rowmax[384 + row]));    // finite: key 0 is a real key
+    const float mc = ms * 1.4426950408889634f;
+    const float pmask = at_ex2(-1e9f * 1.4426950408889634f - mc);      // probability weight of a masked key (1 if every key is masked)
+    float sum = 0.f;
+    for (int ch = hh; ch < nch; ch += 4) {
+        uint32_t v[32];
+        at_ld32(v, tmem_row + 32 * ch);
+        uint32_t ph[16], pl[16];
+        const int kv = nvalid - 32 * ch;
+        if (flag == nullptr && kv >= 32) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+                const float p0 = at_ex2(fmaf(__uint_as_float(v[e]), c1, -mc)), p1 = at_ex2(fmaf(__uint_as_float(v[e + 1]), c1, -mc));
+                sum += p0 + p1;
+                at_split2_fast(p0, p1, ph[e >> 1], pl[e >> 1]);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+                float p[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int key = 32 * ch + e + u;
+                    p[u] = 0.f;
+                    if (e + u < kv) p[u] = (flag != nullptr && flag[key] != 0.f) ? pmask : at_ex2(fmaf(__uint_as_float(v[e + u]), c1, -mc));
+                    sum += p[u];
+                }
+                at_split2_fast(p[0], p[1], ph[e >> 1], pl[e >> 1]);
+            }
+        }
+        at_st16(tmem_row + 32 * ch, ph);
+        at_st16(tmem_row + 32 * ch + 16, pl);
+    }
+    rowsum[hh * 128 + row] = sum;
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(at::THREADS, 1) proxy_attention_tc_kernel(const AtArgs a) {
+    using namespace at;
+    extern __shared__ uint8_t at_smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)at_smem_raw + 1023) & ~(uintptr_t)1023);
+    float* rowmax = reinterpret_cast<float*>(smem + OFF_MISC);
+    float* rowsum = rowmax + 512;
+    float* keyflag = rowsum + 512;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = a.n, l = a.l, c = a.c;
+    const int npad = (n + 15) & ~15, lpad = (l + 15) & ~15;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(at_smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(at_smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+
+    // ---- stage the operand tiles (K-major, SWIZZLE_128B: 16-byte chunk ch of row r sits at chunk ch ^ (r & 7))
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < MAXR * 8; i += THREADS) {
+        const int r = i >> 3, ch = i & 7, half = ch >> 2, col = h * HD + 8 * (ch & 3);
+        const uint32_t dst = r * ROW_BYTES + ((ch ^ (r & 7)) << 4);
+        uint4 kq = z4, qq = z4, pp = z4;
+        if (r < n) {
+            const __nv_bfloat16* src = a.qk + (half ? a.qk_plane : 0) + ((size_t)b * n + r) * a.ldq + col;
+            qq = __ldg(reinterpret_cast<const uint4*>(src));
+            kq = __ldg(reinterpret_cast<const uint4*>(src + c));
+        }
+        if (r < l) pp = __ldg(reinterpret_cast<const uint4*>(a.pt + (half ? a.pt_plane : 0) + ((size_t)b * l + r) * c + col));
+        *reinterpret_cast<uint4*>(smem + OFF_K + dst) = kq;
+        *reinterpret_cast<uint4*>(smem + OFF_Q + dst) = qq;
+        *reinterpret_cast<uint4*>(smem + OFF_P + dst) = pp;
+    }
+    for (int i = tid; i < 2 * HD * 32; i += THREADS) {          // V^T: plane, row e, 8-key chunk j8
+        const int plane = i >> 10, e = (i >> 5) & 31, j8 = i & 31;
+        uint4 v = z4;
+        if (8 * j8 < n) v = __ldg(reinterpret_cast<const uint4*>(a.vt + (plane ? a.vt_plane : 0) + (size_t)(h * HD + e) * a.ldv + (size_t)b * n + 8 * j8));
+        *reinterpret_cast<uint4*>(smem + OFF_VT + plane * VT_PLANE + (j8 >> 3) * VT_TILE + e * ROW_BYTES + (((j8 & 7) ^ (e & 7)) << 4)) = v;
+    }
+    for (int i = tid; i < 2 * VT_PLANE / 16; i += THREADS) *reinterpret_cast<uint4*>(smem + OFF_PV + 16 * i) = z4;
+    for (int i = tid; i < 256; i += THREADS) keyflag[i] = (a.mask != nullptr && i < l && a.mask[(size_t)b * l + i] == 0) ? 1.f : 0.f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const int q4 = warp & 3, hh = warp >> 2;                    // TMEM lane quarter, which of its 4 warps
+    const int row = 32 * q4 + lane;                             // row of the 128-row tile this thread owns
+    const uint32_t tmem_row = tmem + ((uint32_t)(32 * q4) << 16);
+    const uint32_t sK = at_smem_u32(smem + OFF_K), sQ = at_smem_u32(smem + OFF_Q), sP = at_smem_u32(smem + OFF_P);
+    const uint32_t sVT = at_smem_u32(smem + OFF_VT), sPV = at_smem_u32(smem + OFF_PV);
+    uint32_t phase = 0;
+
+    // one (scores -> softmax -> values) pass over a 128-row tile
+    //   sA: operand tile of the rows, sB: operand tile of the keys (nkeys_pad rows), sV: value planes (K-major over the keys)
+    auto pass = [&](uint32_t sA, uint32_t sB, int nkeys, int nkeys_pad, uint32_t sV, const float* flag) {
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t idesc = at_idesc(nkeys_pad);
+            const uint64_t da = at_desc_sw128(sA), db = at_desc_sw128(sB);
+            // k-steps of 16 inside the 128-byte rows: +0/+2 (16-byte units) = hi, +4/+6 = lo
+            at_mma_ss(tmem, da + 0, db + 0, idesc, 0u);
+            at_mma_ss(tmem, da + 2, db + 2, idesc, 1u);
+            at_mma_ss(tmem, da + 4, db + 0, idesc, 1u);
+            at_mma_ss(tmem, da + 6, db + 2, idesc, 1u);
+            at_mma_ss(tmem, da + 0, db + 4, idesc, 1u);
+            at_mma_ss(tmem, da + 2, db + 6, idesc, 1u);
+            at_commit(bar);
+        }
+        at_wait(bar, phase); phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        at_softmax_tile(tmem_row, nkeys_pad, nkeys, flag, a.scale, hh, rowmax, rowsum, row);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t idesc = at_idesc(HD);
+            for (int ks = 0; ks < nkeys_pad / 16; ++ks) {
+                const uint32_t a_hi = tmem + 32 * (ks >> 1) + 8 * (ks & 1), a_lo = a_hi + 16;
+                const uint32_t voff = (uint32_t)((ks >> 2) * VT_TILE + (ks & 3) * 32);
+                const uint64_t dv_hi = at_desc_sw128(sV + voff), dv_lo = at_desc_sw128(sV + VT_PLANE + voff);
+                at_mma_ts(tmem + ACC_COL, a_hi, dv_hi, idesc, ks != 0 ? 1u : 0u);
+                at_mma_ts(tmem + ACC_COL, a_lo, dv_hi, idesc, 1u);
+                at_mma_ts(tmem + ACC_COL, a_hi, dv_lo, idesc, 1u);
+            }
+            at_commit(bar);
+        }
+        at_wait(bar, phase); phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+
+    // ---- stage 1: rows = proxies, keys = clusters, values = V  ->  Pv^T (normalised) as K-major operand planes
+    for (int mt = 0; mt * 128 < lpad; ++mt) {
+        pass(sP + mt * 128 * ROW_BYTES, sK, n, npad, sVT, nullptr);
+        uint32_t v[8];
+        at_ld8(v, tmem_row + ACC_COL + 8 * hh);
+        const int i = mt * 128 + row;                           // proxy index
+        if (i < l) {
+            const float inv = 1.0f / ((rowsum[row] + rowsum[128 + row]) + (rowsum[256 + row] + rowsum[384 + row]));
+            uint8_t* base = smem + OFF_PV + (i >> 6) * VT_TILE + (i & 7) * 2;
+            const int ch = (i & 63) >> 3;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int ee = 8 * hh + e;
+                const float y = __uint_as_float(v[e]) * inv;
+                const __nv_bfloat16 yh = __float2bfloat16_rn(y), yl = __float2bfloat16_rn(y - __bfloat162float(yh));
+                uint8_t* p = base + ee * ROW_BYTES + ((ch ^ (ee & 7)) << 4);
+                *reinterpret_cast<__nv_bfloat16*>(p) = yh;
+                *reinterpret_cast<__nv_bfloat16*>(p + VT_PLANE) = yl;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                        // accumulator drained, Pv^T visible, rowmax / rowsum reusable
+    }
+
+    // ---- stage 2: rows = clusters (Q), keys = proxies (masked), values = Pv
+    for (int mt = 0; mt * 128 < npad; ++mt) {
+        pass(sQ + mt * 128 * ROW_BYTES, sP, l, lpad, sPV, a.mask != nullptr ? keyflag : nullptr);
+        uint32_t v[8];
+        at_ld8(v, tmem_row + ACC_COL + 8 * hh);
+        const int r = mt * 128 + row;                           // cluster index
+        if (r < n) {
+            const float inv = 1.0f / ((rowsum[row] + rowsum[128 + row]) + (rowsum[256 + row] + rowsum[384 + row]));
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(v[e]) * inv;
+            const size_t off = ((size_t)b * n + r) * c + h * HD + 8 * hh;
+            if (a.o != nullptr) {
+                *reinterpret_cast<float4*>(a.o + off) = make_float4(y[0], y[1], y[2], y[3]);
+                *reinterpret_cast<float4*>(a.o + off + 4) = make_float4(y[4], y[5], y[6], y[7]);
+            }
+            if (a.o_hi != nullptr) {
+                uint32_t wh[4], wl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) at_split2(y[2 * e], y[2 * e + 1], wh[e], wl[e]);
+                *reinterpret_cast<uint4*>(a.o_hi + off) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                *reinterpret_cast<uint4*>(a.o_hi + a.o_plane + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
+bool proxy_attention_tc_supported(int n, int l, int c, int heads) {
+    return c % heads == 0 && c / heads == at::HD && c % 8 == 0 && n >= 1 && n <= at::MAXR && n % 8 == 0 && l >= 1 && l <= at::MAXR;
+}
+
+// qk_split: [2][rows][ldq] bf16 (Q | K); vt_split: [2][c][ldv] bf16 (V^T, column = b*n + j); pt_split: [2][B*l][c] bf16.
+int launch_proxy_attention_tc(const void* qk_split, long long qk_plane, int ldq, const void* vt_split, long long vt_plane, long long ldv,
+                              const void* pt_split, long long pt_plane, const uint8_t* mask, int B, int n, int l, int c, int heads,
+                              float* o, void* o_split, long long o_plane, cudaStream_t s) {
+    PT_REQUIRE(proxy_attention_tc_supported(n, l, c, heads), "attention(tcgen05): n=%d l=%d c=%d heads=%d unsupported", n, l, c, heads);
+    PT_REQUIRE(qk_split && vt_split && pt_split && (o || o_split), "attention(tcgen05): null operand");
+    PT_REQUIRE(((uintptr_t)qk_split & 15) == 0 && ((uintptr_t)vt_split & 15) == 0 && ((uintptr_t)pt_split & 15) == 0 && ldq % 8 == 0 &&
+                   ldv % 8 == 0 && qk_plane % 8 == 0 && vt_plane % 8 == 0 && pt_plane % 8 == 0 && o_plane % 8 == 0,
+               "attention(tcgen05): operand planes must be 16-byte aligned");
+    static bool attr = false;
+    if (!attr) {
+        PT_CUDA_OK(cudaFuncSetAttribute(proxy_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, at::SMEM_BYTES));
+        attr = true;
+    }
+    AtArgs a;
+    a.qk = (const __nv_bfloat16*)qk_split; a.qk_plane = qk_plane; a.ldq = ldq;
+    a.vt = (const __nv_bfloat16*)vt_split; a.vt_plane = vt_plane; a.ldv = ldv;
+    a.pt = (const __nv_bfloat16*)pt_split; a.pt_plane = pt_plane;
+    a.mask = mask; a.n = n; a.l = l; a.c = c;
+    a.scale = (float)(1.0 / sqrt((double)at::HD));              // python float head_dim ** -0.5 (:186), rounded to fp32 once
+    a.o = o; a.o_hi = (__nv_bfloat16*)o_split; a.o_plane = o_plane;
+    { ProfScope prof_(PROF_ATTENTION, s); proxy_attention_tc_kernel<<<dim3(heads, B), at::THREADS, at::SMEM_BYTES, s>>>(a); }
+    PT_LAUNCH_CHECK();
+    return PT_OK;
+}
+
+}  // namespace pt
+
+// Stand-alone entry point (tests, tools): the attention core on pre-split operands.
+extern "C" int pt_proxy_attention_tc(const void* qk_split, long long qk_plane, int ldq, const void* vt_split, long long vt_plane,
+                                     long long ldv, const void* pt_split, long long pt_plane, const uint8_t* mask, int B, int n, int l,
+                                     int c, int heads, float* o, void* o_split, long long o_plane, pt_stream_t stream) {
+    return pt::launch_proxy_attention_tc(qk_split, qk_plane, ldq, vt_split, vt_plane, ldv, pt_split, pt_plane, mask, B, n, l, c, heads, o,
+                                         o_split, o_plane, (cudaStream_t)stream);
+}

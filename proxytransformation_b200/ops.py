@@ -259,6 +259,23 @@ def affine_scatter_compact(points, kept_idx, drop_idx, kept_centres, transform, 
     return out, counts
 
 
+def proxy_attention_tc(q, k, v, pt, mask, heads: int):
+    """The tcgen05 / TMEM attention core on fp32 inputs (test / tool entry): q, k, v (B,n,c), pt (B,l,c), mask (B,l) uint8 or
+    None -> o (B,n,c) fp32.  Splits the operands into the bf16 hi/lo planes pt_proxy_attention_tc expects."""
+    L = _lib.load()
+    B, n, c = q.shape
+    l = pt.shape[1]
+    rows = B * n
+    qk = split_bf16(torch.cat([q, k], -1).reshape(rows, 2 * c).contiguous())                  # (2, rows, 2c)
+    vt = split_bf16(v.reshape(rows, c).t().contiguous())                                        # (2, c, rows)
+    pts = split_bf16(pt.reshape(B * l, c).contiguous())                                         # (2, B*l, c)
+    o = torch.empty(B, n, c, dtype=torch.float32, device=q.device)
+    check(L.pt_proxy_attention_tc(qk.data_ptr(), rows * 2 * c, 2 * c, vt.data_ptr(), c * rows, rows, pts.data_ptr(), B * l * c,
+                                  _chk(mask, torch.uint8, "mask", optional=True), B, n, l, c, heads, o.data_ptr(), None, 0, _stream()),
+          "pt_proxy_attention_tc")
+    return o
+
+
 COLLATE_RECIPROCAL, COLLATE_FLOOR = 1, 2
 
 
