@@ -178,22 +178,14 @@ extern "C" int pt_proxy_block_fused(const float* x, const float* proxy, const ui
             __nv_bfloat16* qk_s = (__nv_bfloat16*)w.qkv;
             __nv_bfloat16* vt_s = qk_s + (size_t)2 * rows * 2 * c;
             __nv_bfloat16* pt_s = (__nv_bfloat16*)w.pt;
-            {   // [Q|K] = u Wqk^T                                      (:221, rows 0..2c-1 of the qkv weight)
+            {   // [Q|K|V] = u Wqkv^T (:221): Q and K as row-major planes, V TRANSPOSED (V^T planes, K-major over the clusters:
+                // the B operand layout of the value contraction) straight from the epilogue
                 GemmTc gp;
-                gp.M = rows; gp.N = 2 * c; gp.K = c;
+                gp.M = rows; gp.N = 3 * c; gp.K = c;
                 gp.a_split = w.u_s; gp.a_rows = rows; gp.a_cols = c; gp.lda = c;
                 gp.w_split = p->qkv_w_split; gp.w_rows = 3 * c; gp.ldw = c;
                 gp.c_split = qk_s; gp.cs_plane = (long long)rows * 2 * c; gp.ldcs = 2 * c;
-                if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
-            }
-            {   // V^T = Wv u^T: the same GEMM with the operand roles swapped, so that the value planes come out K-major over
-                // the clusters (the B operand layout of the value contraction).  A = rows 2c..3c-1 of the qkv weight planes
-                // (hi plane + 3c rows = lo plane); the tensor map nominally extends 2c rows past the planes, never touched.
-                GemmTc gp;
-                gp.M = c; gp.N = rows; gp.K = c;
-                gp.a_split = (const __nv_bfloat16*)p->qkv_w_split + (size_t)2 * c * c; gp.a_rows = 3 * c; gp.a_cols = c; gp.lda = c;
-                gp.w_split = w.u_s; gp.w_rows = rows; gp.ldw = c;
-                gp.c_split = vt_s; gp.cs_plane = (long long)c * rows; gp.ldcs = rows;
+                gp.ct_split = vt_s; gp.ct_col0 = 2 * c; gp.ct_ld = rows; gp.ct_plane = (long long)c * rows;
                 if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
             }
             // Pt = proxy Wp^T + bp                                     (:223)

@@ -99,6 +99,7 @@ struct TcKernelArgs {
     const float* residual;                 // same layout as C (ldc, c_off_z); may alias C
     float* C; int ldc; long long c_off_z;
     __nv_bfloat16* Cs; long long cs_plane; int ldcs; long long cs_off_z;     // optional bf16 hi/lo planes of the result
+    __nv_bfloat16* Ct; int ct_col0; long long ct_ld, ct_plane;               // optional transposed planes for columns >= ct_col0
     int act;
     int tiles_m, tiles_n, stages;
 };
@@ -208,6 +209,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             const int row0 = m0 + q * 32;
 #pragma unroll 1
             for (int cc = half; cc < BN / 32; cc += 2) {
+                if (g.Ct != nullptr && n0 + cc * 32 >= g.ct_col0) {
+                    // transposed columns: lane = row already, so a fixed register is a 64-byte run of one output row of C^T
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cc * 32);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const int row = row0 + lane;
+                    if (row < g.M) {
+                        __nv_bfloat16* dst = g.Ct + (size_t)(n0 + cc * 32 - g.ct_col0) * g.ct_ld + row;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (n0 + cc * 32 + j < g.N) {
+                                const float y = __uint_as_float(v[j]);
+                                const __nv_bfloat16 hh = __float2bfloat16_rn(y);
+                                dst[(size_t)j * g.ct_ld] = hh;
+                                dst[(size_t)j * g.ct_ld + g.ct_plane] = __float2bfloat16_rn(y - __bfloat162float(hh));
+                            }
+                        }
+                    }
+                    continue;
+                }
                 {
                     uint32_t v[32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cc * 32);
@@ -373,6 +401,8 @@ static int launch_bn(const CUtensorMap& mapA, const CUtensorMap& mapW, TcKernelA
 int launch_gemm_tc_ex(const GemmTc& p, cudaStream_t s) {
     PT_REQUIRE(gemm_tc_supported(p.M, p.N, p.K) && p.batch >= 1, "gemm_tc: M=%d N=%d K=%d batch=%d unsupported", p.M, p.N, p.K, p.batch);
     PT_REQUIRE(p.a_split && p.w_split && (p.C || p.c_split), "gemm_tc: null operand");
+    PT_REQUIRE(!p.ct_split || (p.ct_col0 % 32 == 0 && p.ct_col0 >= 0 && p.ct_ld >= p.M && p.batch == 1 && !p.act),
+               "gemm_tc: transposed output needs ct_col0 %% 32 == 0, ct_ld >= M, batch 1, no activation");
     PT_REQUIRE(((uintptr_t)p.a_split & 15) == 0 && ((uintptr_t)p.w_split & 15) == 0 && (p.lda % 8) == 0 && (p.ldw % 8) == 0,
                "gemm_tc: operand planes must be 16-byte aligned with pitches that are multiples of 8");
     PT_REQUIRE(!p.C || (((uintptr_t)p.C & 15) == 0 && p.ldc % 4 == 0 && p.c_off_z % 4 == 0), "gemm_tc: C alignment");
@@ -395,6 +425,7 @@ int launch_gemm_tc_ex(const GemmTc& p, cudaStream_t s) {
     k.C = p.C; k.ldc = p.ldc; k.c_off_z = p.c_off_z;
     k.Cs = (__nv_bfloat16*)p.c_split; k.cs_plane = p.cs_plane; k.ldcs = p.ldcs; k.cs_off_z = p.cs_off_z;
     k.act = p.act;
+    k.Ct = (__nv_bfloat16*)p.ct_split; k.ct_col0 = p.ct_col0; k.ct_ld = p.ct_ld; k.ct_plane = p.ct_plane;
     k.tiles_m = ceil_div(p.M, TC_BM);
     switch (bn) {
         case 32: return launch_bn<32>(mapA, mapW, k, s);

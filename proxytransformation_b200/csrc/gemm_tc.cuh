@@ -26,6 +26,12 @@ struct GemmTc {
     long long cs_plane = 0;
     int ldcs = 0;
     long long cs_off_z = 0;
+    // optional TRANSPOSED bf16 hi/lo planes for the output columns n >= ct_col0 (those columns are then written nowhere
+    // else): element (row, n) goes to ct_split[(n - ct_col0) * ct_ld + row], lo plane ct_plane elements later.  No bias /
+    // activation / residual on these columns.  Used for V^T, the K-major value operand of the tcgen05 attention.
+    void* ct_split = nullptr;
+    int ct_col0 = 0;
+    long long ct_ld = 0, ct_plane = 0;
     int bn = 0;                           // tile width override (32/64/128/256), 0 = auto
 };
 
