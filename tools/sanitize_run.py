@@ -1,0 +1,20 @@
+#!/usr/bin/env python
+"""One small forward through every sm_100a kernel (bf16 image features -> tensor-core pool kernel, tcgen05 GEMMs and
+attention, geometry, scatter) for compute-sanitizer:
+    compute-sanitizer --tool memcheck  python tools/sanitize_run.py
+    compute-sanitizer --tool racecheck python tools/sanitize_run.py
+    compute-sanitizer --tool synccheck python tools/sanitize_run.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from proxytransformation_b200 import ProxyTransformationNormReverse, synthetic as syn
+
+cfg = syn.C2_WIDE.replace(n_views=6, n_points=20000)
+m = ProxyTransformationNormReverse(**cfg.module_kwargs()).eval()
+m.load_state_dict(syn.make_state_dict(cfg, 0, bf16_round=True))
+m = m.cuda()
+pts, text_dict, img = syn.make_inputs(cfg, 2, first_scene=0, img_dtype=torch.bfloat16)
+out = m([p.cuda() for p in pts], {k: v.cuda() for k, v in text_dict.items()}, img.cuda())
+coords, feats = m.forward_sparse([p.cuda() for p in pts], {k: v.cuda() for k, v in text_dict.items()}, img.cuda(), 0.01)
+torch.cuda.synchronize()
+print("ok", [tuple(o.shape) for o in out], tuple(coords.shape))
