@@ -162,6 +162,9 @@ class ProxyTransformationNormReverse(nn.Module):
         self.overlap_mean_pass = os.environ.get("PT_OVERLAP_MEAN", "0") != "0"    # measured: 2.735 vs 2.765 ms/step at best, off by default
         self._streams: Dict[str, torch.cuda.Stream] = {}
         self.host_chunk_scenes = 8       # scenes per pipeline chunk when forward() is fed host tensors
+        self.cuda_graphs = os.environ.get("PT_CUDA_GRAPHS", "0") != "0"     # replay small device-resident batches as one CUDA graph
+        self.cuda_graph_max_bytes = 256 << 20
+        self._graphs: Dict[tuple, tuple] = {}
 
     # ------------------------------------------------------------------ reference helper API (same names, :332-350)
     def get_text_proxy(self, text_dict):
@@ -294,9 +297,50 @@ class ProxyTransformationNormReverse(nn.Module):
             img_feat = img_feat.contiguous()
         else:
             img_proxy = img_proxy.to(dev, torch.float32, non_blocking=True).contiguous()
-        out, counts = self.forward_packed(P, text, mask, img_feat, img_proxy=img_proxy, trace=trace)
+        if self._use_graph(P, img_feat, img_proxy, trace):
+            out, counts = self._forward_graphed(P, text, mask, img_feat)
+        else:
+            out, counts = self.forward_packed(P, text, mask, img_feat, img_proxy=img_proxy, trace=trace)
         cnt = counts.cpu().tolist()                                                             # the one D2H sync
         return [out[b, :cnt[b]] for b in range(len(cnt))]
+
+    # ------------------------------------------------------------------ CUDA graphs for small batches
+    def _use_graph(self, P, img_feat, img_proxy, trace) -> bool:
+        """Small batches are launch-latency bound (about 40 dependent kernels of a few microseconds each): replaying the whole
+        forward as one CUDA graph removes the gaps.  The inputs have to be copied into the graph's static buffers, so the
+        mode is limited to batches whose inputs are small (``cuda_graph_max_bytes``); off unless ``cuda_graphs`` is set."""
+        if not self.cuda_graphs or trace is not None or img_proxy is not None or torch.cuda.is_current_stream_capturing():
+            return False
+        return P.numel() * 4 + img_feat.numel() * img_feat.element_size() <= self.cuda_graph_max_bytes
+
+    def _forward_graphed(self, P, text, mask, img_feat):
+        key = (tuple(P.shape), tuple(text.shape), mask is not None, tuple(img_feat.shape), img_feat.dtype, self._weight_key(P.device))
+        entry = self._graphs.get(key)
+        if entry is None:
+            if len(self._graphs) >= 8:                       # shapes normally repeat; do not hoard graph memory pools
+                self._graphs.clear()
+            static = [torch.empty_like(P), torch.empty_like(text), torch.empty_like(mask) if mask is not None else None,
+                      torch.empty_like(img_feat)]
+            for dst, src in zip(static, (P, text, mask, img_feat)):
+                if dst is not None:
+                    dst.copy_(src)
+            cur = torch.cuda.current_stream(P.device)
+            side = self._side_stream(P.device, "graph-warmup")
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                    # warm-up outside the capture: weight packing, function attributes
+                for _ in range(2):
+                    self.forward_packed(*static)
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out, counts = self.forward_packed(*static)
+            entry = self._graphs[key] = (graph, static, out, counts)
+        graph, static, out, counts = entry
+        for dst, src in zip(static, (P, text, mask, img_feat)):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        graph.replay()
+        return out.clone(), counts.clone()                   # the graph owns its outputs: hand out copies
 
     def _forward_from_host(self, points, text_dict, img_feat, img_proxy, dev, trace) -> List[torch.Tensor]:
         """Host inputs -> host results.  The batch is cut into chunks of ``host_chunk_scenes`` scenes that flow through three

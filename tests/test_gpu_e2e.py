@@ -181,3 +181,23 @@ def test_forward_sparse_equals_collate_of_forward():
     want_c, want_f = po.batch_sparse_collate([o.cpu() for o in out], 0.01, reciprocal=True)
     coords, feats = m.forward_sparse(dpts, td, dimg, 0.01)
     assert torch.equal(coords.cpu(), want_c) and torch.equal(feats.cpu(), want_f)
+
+
+def test_cuda_graph_replay_equals_eager_forward():
+    """cuda_graphs=True replays the captured forward for small device-resident batches: same results as the eager path,
+    also on new inputs of the same shape (the static buffers are refilled) and after a shape change."""
+    cfg, sd, pts, text_dict, img, g = load_case("gs5_ragged")
+    m = build_module(cfg, sd)
+    dpts, td, dimg = [p.to(DEV) for p in pts], {k: v.to(DEV) for k, v in text_dict.items()}, img.to(DEV)
+    want = m(dpts, td, dimg)
+    rolled = [p.roll(7, 0) for p in dpts]
+    want_rolled = m(rolled, td, dimg)
+    m.cuda_graphs = True
+    for _ in range(2):
+        got = m(dpts, td, dimg)
+        assert all(torch.equal(a, b) for a, b in zip(got, want))
+        got = m(rolled, td, dimg)
+        assert all(torch.equal(a, b) for a, b in zip(got, want_rolled))
+    assert len(m._graphs) == 1
+    one = m(dpts[:1], {k: v[:1] for k, v in td.items()}, dimg[:1])      # another batch size: a second graph
+    assert torch.equal(one[0], want[0]) and len(m._graphs) == 2
