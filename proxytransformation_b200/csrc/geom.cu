@@ -325,23 +325,35 @@ __global__ void cluster_dropout_kernel(const float* __restrict__ centres, const 
     if (tid == 0) sel[0] = 0;
     for (int k = 1; k < n_drop; ++k) {
         const float lx = ux[last], ly = uy[last], lz = uz[last];
-        unsigned long long best = 0ull;
+        // arg-max key = (distance bits, ~index): non-negative floats order like their bit patterns, ~index makes the FIRST
+        // maximum win; the two halves are reduced with redux.sync (one instruction each) instead of 64-bit shuffle trees
+        unsigned bh = 0u, bl = 0u;
 #pragma unroll
         for (int r = 0; r < FPS_PER; ++r) {
             const int p = tid + r * T;
             if (p < keep1) {
                 const float d = dist2_rn(lx, ly, lz, px[r], py[r], pz[r]);
                 dmin[r] = d < dmin[r] ? d : dmin[r];
-                const unsigned long long key = ((unsigned long long)__float_as_uint(dmin[r]) << 32) | (unsigned)(0xffffffffu - (unsigned)p);
-                best = key > best ? key : best;
+                const unsigned kh = __float_as_uint(dmin[r]), kl2 = 0xffffffffu - (unsigned)p;
+                if (kh > bh || (kh == bh && kl2 > bl)) { bh = kh; bl = kl2; }
             }
         }
-        best = warp_max_u64(best);
-        unsigned long long* slot = red + (k & 1) * 32;
-        if (lane == 0) slot[wid] = best;
+        {
+            const unsigned mh = __reduce_max_sync(FULL, bh);
+            const unsigned ml = __reduce_max_sync(FULL, bh == mh ? bl : 0u);
+            unsigned long long* slot = red + (k & 1) * 32;
+            if (lane == 0) slot[wid] = ((unsigned long long)mh << 32) | ml;
+        }
         __syncthreads();
-        unsigned long long v = lane < (T >> 5) ? slot[lane] : 0ull;
-        v = warp_max_u64(v);
+        unsigned long long v;
+        {
+            const unsigned long long* slot = red + (k & 1) * 32;
+            const unsigned long long w = lane < (T >> 5) ? slot[lane] : 0ull;
+            const unsigned wh = (unsigned)(w >> 32), wl = (unsigned)w;
+            const unsigned mh = __reduce_max_sync(FULL, wh);
+            const unsigned ml = __reduce_max_sync(FULL, wh == mh ? wl : 0u);
+            v = ((unsigned long long)mh << 32) | ml;
+        }
         last = (int)(0xffffffffu - (unsigned)(v & 0xffffffffull));
         if (tid == 0) sel[k] = last;
     }
