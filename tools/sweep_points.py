@@ -29,7 +29,8 @@ for N in [int(x) for x in a.sizes.split(",")]:
     text = torch.randn(B, cfg.n_text, cfg.embed_dim, generator=g, device=dev)
     mask = torch.ones(B, cfg.n_text, dtype=torch.uint8, device=dev)
     img_proxy = torch.randn(B, cfg.n_views, cfg.embed_dim, generator=g, device=dev)
-    for _ in range(3):
+    for _ in range(5):                  # warm-up with the flush in place: the caching allocator reaches its steady state
+        flush.fill_(1)
         m.forward_packed(P, text, mask, None, img_proxy=img_proxy)
     torch.cuda.synchronize()
     tot = 0.0
@@ -68,3 +69,5 @@ for N in [int(x) for x in a.sizes.split(",")]:
                       "algorithmic_GBps": 24 * N * sps / 1e9, "hbm_frac_of_measured_peak": 24 * N * sps / 1e9 / peak,
                       "bandwidth_kernels_ms": bw_ms, "bandwidth_kernels_GBps": 24 * N * B / (bw_ms / 1e3) / 1e9 if bw_ms else None,
                       "ball_query_ms": bq_ms, "cpu_oracle_scenes_per_s": cpu, "cpu_cores": os.cpu_count()}), flush=True)
+    del m, P, text, mask, img_proxy, out, counts
+    torch.cuda.empty_cache()            # the next size starts from a clean allocator (no cudaMalloc inside a timed iteration)
