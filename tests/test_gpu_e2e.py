@@ -201,3 +201,42 @@ def test_cuda_graph_replay_equals_eager_forward():
     assert len(m._graphs) == 1
     one = m(dpts[:1], {k: v[:1] for k, v in td.items()}, dimg[:1])      # another batch size: a second graph
     assert torch.equal(one[0], want[0]) and len(m._graphs) == 2
+
+
+@pytest.mark.parametrize("gs,ddr,N,V,L,B,dtype,box", [
+    (4, 0.75, 1500, 1, 1, 1, torch.float32, 14.0),
+    (4, 0.5, 3000, 3, 5, 3, torch.bfloat16, 12.0),
+    (5, 0.6, 4000, 7, 17, 2, torch.bfloat16, 20.0),
+    (6, 0.55, 6000, 2, 77, 1, torch.float32, 30.0),
+    (7, 0.6, 9000, 5, 33, 2, torch.bfloat16, 40.0),          # n = 137 clusters: not a multiple of 8 -> mma.sync attention
+    (4, 0.5, 2000, 9, 8, 5, torch.bfloat16, 9.0),
+])
+def test_odd_shapes_against_oracle_chain(gs, ddr, N, V, L, B, dtype, box):
+    """Shapes the fixtures do not cover (one view / one token, odd cluster counts, batches that are not powers of two):
+    every index-producing stage must agree bit for bit with the oracle run on the CUDA path's own inputs, and the final
+    coordinates with the oracle's evaluation of the rest of the path on the CUDA path's clusters, within 1e-4."""
+    cfg = syn.PreshapeConfig(f"odd-gs{gs}", n_points=N, grid_size=gs, dynamic_drop_radio=ddr, text_blocks=1, img_blocks=2,
+                             n_text=L, n_views=V, box=(box, box, box))
+    sd = syn.make_state_dict(cfg, 7 + gs, bf16_round=dtype == torch.bfloat16)
+    pts, text_dict, img = syn.make_inputs(cfg, B, first_scene=10 * gs, img_dtype=dtype)
+    m = build_module(cfg, sd)
+    tr = {}
+    out = m([p.to(DEV) for p in pts], {k: v.to(DEV) for k, v in text_dict.items()}, img.to(DEV), trace=tr)
+    P = torch.stack(pts, 0)
+    _chain_check(cfg, sd, P, tr)
+    kc, kidx = tr["kept_centres"].cpu(), tr["kept_idx"].cpu().long()
+    cl = po.masked_gather(P, kidx)
+    pp = po.point_encoder(sd, kc, cl)
+    np.testing.assert_allclose(np_(tr["point_proxy"]), pp.numpy(), rtol=0, atol=1e-5 + 2e-6 * pp.abs().max().item())
+    ip = po.image_proxies(sd, img.float(), cfg.num_heads)
+    np.testing.assert_allclose(np_(tr["img_proxy"]), ip.numpy(), rtol=0, atol=3e-5)
+    tg = po.branch(sd, "textformer", "text_norm", cfg.text_blocks, pp, text_dict["text_feats"], text_dict["text_token_mask"], cfg.num_heads)
+    ig = po.branch(sd, "imgformer", "img_norm", cfg.img_blocks, pp, ip, None, cfg.num_heads)
+    translate, transform = po.head(sd, "text_trans", "text_trans_norm", tg), po.head(sd, "img_trans", "img_trans_norm", ig)
+    np.testing.assert_allclose(np_(tr["translate"]), translate.numpy(), rtol=0, atol=5e-5)
+    np.testing.assert_allclose(np_(tr["transform"]).reshape(B, -1, 9), transform.reshape(B, -1, 9).numpy(), rtol=0, atol=5e-5)
+    new = po.affine(tr["transform"].cpu(), tr["translate"].cpu(), kc, cl)
+    want = po.remove_points(po.scatter_last_writer_wins(P, kidx, new), tr["drop_idx"].cpu().long())
+    for o, w in zip(out, want):
+        assert o.shape == w.shape
+        np.testing.assert_allclose(np_(o), w.numpy(), rtol=0, atol=1e-4)
