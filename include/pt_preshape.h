@@ -194,6 +194,14 @@ int pt_affine_scatter_compact(const float* points, const int32_t* kept_idx, cons
                               int n, int K, int n_drop_entries, float* out, int32_t* counts, void* ws, size_t ws_bytes,
                               pt_stream_t stream);
 
+/* ---- N3 input side: AggregateMultiViewPoints (datasets/transforms/multiview.py:224-241) + the gather of PointSample
+ * (datasets/transforms/points.py:411-417), fused so that only the sampled points are transformed.
+ * points_cat (T,3): per-view ego-frame points back to back; view_off (V+1) int64 row offsets; ego2global (V,16) row-major
+ * inverses of the views' `extrinsic` matrices (the reference solves extrinsic x = [p;1]); choices (n) int64 indices into
+ * the concatenation, drawn by the data loader (np.random.choice stays on the host); out (n,3) in the order of choices. */
+int pt_aggregate_sample(const float* points_cat, const long long* view_off, int V, const float* ego2global,
+                        const long long* choices, long long n, float* out, pt_stream_t stream);
+
 /* ---- N1 hand-off to the sparse backbone (detectors/sparse_featfusion_grounder_preshape.py:388-391) ------------
  * ME.utils.batch_sparse_collate([(p[:, :3] / voxel_size, p) for p in points]) on the packed result of
  * pt_affine_scatter_compact: coords (T,4) int32 rows [scene, x, y, z], feats (T,3) fp32 rows = the coordinates themselves,

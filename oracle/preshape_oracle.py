@@ -295,6 +295,19 @@ def remove_points(P: torch.Tensor, drop_idx: torch.Tensor) -> List[torch.Tensor]
 
 # ----------------------------------------------------------------------------- driver
 @torch.no_grad()
+def aggregate_sample(view_points: List[torch.Tensor], extrinsics: torch.Tensor, choices: torch.Tensor) -> torch.Tensor:
+    """Input side, restated from the reference's data pipeline: ``AggregateMultiViewPoints.transform``
+    (datasets/transforms/multiview.py:224-241: per view ``torch.linalg.solve(global2ego, [p;1]^T)^T``, first three
+    columns, views concatenated in order) followed by ``points[choices]`` of ``PointSample._points_random_sampling``
+    (datasets/transforms/points.py:411-417; ``choices`` = the np.random.choice the data loader draws)."""
+    glob = []
+    for v, p in enumerate(view_points):
+        point = torch.cat([p[:, :3].float(), p.new_ones(p.shape[0], 1).float()], dim=1)
+        global2ego = extrinsics[v].to(point.dtype)
+        glob.append(torch.linalg.solve(global2ego, point.transpose(0, 1)).transpose(0, 1)[:, :3])
+    return torch.cat(glob)[choices.long()]
+
+
 def batch_sparse_collate(points: List[torch.Tensor], voxel_size: float, reciprocal: bool = False, floor: bool = False):
     """Caller hand-off (detectors/sparse_featfusion_grounder_preshape.py:388-391):
     ``ME.utils.batch_sparse_collate([(p[:, :3] / voxel_size, p) for p in points])`` -> (coordinates (T,4) int32, features (T,3)).

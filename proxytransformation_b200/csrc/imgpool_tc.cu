@@ -419,6 +419,7 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
         POOL_TRACE(2);                                        // score MMAs (incl. waiting for slabs)
         if (lane == 0) POOL_EV(1000 * warp + 10 * ((int)vi - 40) + 3);                    // score MMAs done
         ip_consumer_sync();                                   // w_eff planes are dead: the partial-score overlay may be written
+        if (lane == 0 && vi == 41) POOL_EV(100000 + 1000 * warp + 20);
         if (!(a.debug_skip & 16)) {
         // hi + lo rows of the accumulators; classes 0-3 store S_s[h][u], then classes 4-7 add theirs four columns lower so
         // that buffer j holds S_j[h][u] + S_{j+4}[h][u+4]: token t sits at column t + j in buffer j
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
                     *reinterpret_cast<float2*>(dst + 8 * (i0 + i)) = make_float2(acc[i][0] + acc[i][2], acc[i][1] + acc[i][3]);
         }
         ip_consumer_sync();
+        if (lane == 0 && vi == 41) POOL_EV(100000 + 1000 * warp + 21);
         if (s >= 4) {
             float* dst = spart + (s - 4) * SBUF + g * SPITCH + 2 * q - 4;
             float2 v[15];
@@ -442,6 +444,7 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
                     *reinterpret_cast<float2*>(dst + 8 * (i0 + i)) = make_float2(v[i].x + (acc[i][0] + acc[i][2]), v[i].y + (acc[i][1] + acc[i][3]));
         }
         ip_consumer_sync();
+        if (lane == 0 && vi == 41) POOL_EV(100000 + 1000 * warp + 22);
 
         // ---- (2) softmax over the 226 tokens, two warps per head ; probabilities -> bf16 hi/lo arrays + global
         {
@@ -466,6 +469,7 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
             mx = warp_max(mx);
             if (lane == 0) red[warp] = mx;
             ip_consumer_sync();                                // all partial scores have been read
+        if (lane == 0 && vi == 41) POOL_EV(100000 + 1000 * warp + 23);
             if (tid == 0) ip_mbar_arrive(wempty + wb);         // the w_eff buffer (and the overlay) may be refilled
             {   // zero the margins of the probability rows (the overlay clobbered them): words [0,5) and [116,132) of 32 rows
                 const int row = tid >> 4, j = tid & 15;        // 512 threads = 32 rows x 16
@@ -480,6 +484,7 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
             sum = warp_sum(sum);
             if (lane == 0) red[16 + warp] = sum;
             ip_consumer_sync();
+        if (lane == 0 && vi == 41) POOL_EV(100000 + 1000 * warp + 24);
             const float inv = 1.0f / (red[16 + sh] + red[16 + sh + 8]);
             __nv_bfloat16* ya = a.ya_hi + ((size_t)bv * HEADS + sh) * YA + C;
             // copy e of plane pl: element tau + 8 + e of row ((pl*2 + e)*8 + head) holds token tau, so that both token
@@ -522,6 +527,7 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
             }
         }
         const float p0g = p0[g];
+        if (lane == 0 && vi == 41) POOL_EV(100000 + 1000 * warp + 25);
         __nv_bfloat16* yrow = a.ya_hi + ((size_t)bv * HEADS + g) * YA;
         // Processing order: resident slabs 2..7 (FIFO release order), then the re-fetched slabs 0, 1 (loads 8, 9).  A warp
         // reads every other slab of that order (parity hb); the slots of the slabs it does not read are handed back up

@@ -117,9 +117,44 @@ __global__ void __launch_bounds__(256) collate_kernel(const float* __restrict__ 
     f[0] = x; f[1] = y; f[2] = z;
 }
 
+// N3 input side: AggregateMultiViewPoints (datasets/transforms/multiview.py:224-241) + the gather of PointSample
+// (datasets/transforms/points.py:411-417) fused: only the SAMPLED points are moved to the global frame.
+//   points_cat (T,3): the per-view ego-frame points back to back, view v owns rows [view_off[v], view_off[v+1])
+//   ego2global (V,16): row-major 4x4 inverse of the view's `extrinsic` (the reference solves extrinsic . x = [p;1] per view)
+//   choices (n): indices into the concatenation (the data loader's np.random.choice: RNG stays on the host)
+//   out (n,3) = (ego2global[view(choices[i])] . [p;1])[:3], in the order of `choices`
+__global__ void __launch_bounds__(256) aggregate_sample_kernel(const float* __restrict__ pts, const long long* __restrict__ view_off, int V,
+                                                               const float* __restrict__ ego2global, const long long* __restrict__ choices,
+                                                               long long n, float* __restrict__ out) {
+    extern __shared__ long long s_off[];              // V + 1 offsets
+    for (int i = threadIdx.x; i <= V; i += blockDim.x) s_off[i] = view_off[i];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long c = __ldg(choices + i);
+    int lo = 0, hi = V;                               // largest v with s_off[v] <= c
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= c) lo = mid; else hi = mid; }
+    const float* M = ego2global + (size_t)lo * 16;
+    const float x = __ldg(pts + c * 3), y = __ldg(pts + c * 3 + 1), z = __ldg(pts + c * 3 + 2);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        out[i * 3 + r] = fmaf(__ldg(M + 4 * r + 2), z, fmaf(__ldg(M + 4 * r + 1), y, fmaf(__ldg(M + 4 * r), x, __ldg(M + 4 * r + 3))));
+}
+
 }  // namespace pt
 
 using namespace pt;
+
+extern "C" int pt_aggregate_sample(const float* points_cat, const long long* view_off, int V, const float* ego2global,
+                                   const long long* choices, long long n, float* out, pt_stream_t stream) {
+    PT_REQUIRE(points_cat && view_off && ego2global && choices && out, "pt_aggregate_sample: null pointer");
+    PT_REQUIRE(V >= 1 && V <= 4096 && n >= 1, "pt_aggregate_sample: V=%d n=%lld", V, n);
+    cudaStream_t s = (cudaStream_t)stream;
+    { ProfScope prof_(PROF_MISC, s);
+      aggregate_sample_kernel<<<(unsigned)((n + 255) / 256), 256, (size_t)(V + 1) * sizeof(long long), s>>>(points_cat, view_off, V, ego2global, choices, n, out); }
+    PT_LAUNCH_CHECK();
+    return PT_OK;
+}
 
 extern "C" int pt_sparse_collate(const float* packed, const int32_t* counts, int B, int N, float voxel_size, int flags,
                                  int32_t* coords, float* feats, int32_t* total, pt_stream_t stream) {

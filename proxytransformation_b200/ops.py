@@ -276,6 +276,28 @@ def proxy_attention_tc(q, k, v, pt, mask, heads: int):
     return o
 
 
+def aggregate_sample(view_points, extrinsics: torch.Tensor, choices: torch.Tensor) -> torch.Tensor:
+    """N3 input side: ``AggregateMultiViewPoints`` (datasets/transforms/multiview.py:224-241) followed by the gather of
+    ``PointSample`` (points.py:411-417) on the device.  view_points: list of V (n_v, >=3) ego-frame tensors (or one
+    concatenated (T,3) tensor plus ``extrinsics`` per view and offsets inferred from the list); extrinsics (V,4,4) the
+    reference's ``depth2img['extrinsic']`` (global -> ego); choices (n,) int64 indices into the concatenation, drawn on the
+    host exactly as the reference draws them.  Returns (n,3) fp32 global-frame points in the order of ``choices``."""
+    L = _lib.load()
+    dev = choices.device
+    V = len(view_points)
+    cat = torch.cat([p[:, :3].to(dev, torch.float32) for p in view_points], 0).contiguous()
+    sizes = torch.tensor([0] + [int(p.shape[0]) for p in view_points], dtype=torch.int64)
+    off = torch.cumsum(sizes, 0).to(dev)
+    inv = torch.linalg.inv(extrinsics.to(torch.float64)).to(dev, torch.float32).reshape(V, 16).contiguous()
+    ch = choices.to(dev, torch.int64).contiguous()
+    if ch.numel() and (int(ch.min()) < 0 or int(ch.max()) >= cat.shape[0]):
+        raise IndexError("choices out of range")
+    out = torch.empty(ch.numel(), 3, dtype=torch.float32, device=dev)
+    check(L.pt_aggregate_sample(cat.data_ptr(), off.data_ptr(), V, inv.data_ptr(), ch.data_ptr(), ch.numel(), out.data_ptr(), _stream()),
+          "pt_aggregate_sample")
+    return out
+
+
 COLLATE_RECIPROCAL, COLLATE_FLOOR = 1, 2
 
 

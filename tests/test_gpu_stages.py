@@ -325,3 +325,23 @@ def test_proxy_attention_tcgen05_core(B, n, l, masked):
     want = (torch.softmax(s2, -1) @ pv).permute(0, 2, 1, 3).reshape(B, n, c)
     got = ops.proxy_attention_tc(cu(q), cu(k), cu(v), cu(pt), cu(mask) if mask is not None else None, heads)
     np.testing.assert_allclose(np_(got), want.numpy(), rtol=0, atol=6e-5)
+
+
+def test_aggregate_sample_input_side():
+    """N3: multi-view aggregation + PointSample gather on the device against the restatement of the reference's
+    transforms (per-view torch.linalg.solve with the 4x4 extrinsic, concatenate, index with the sampled choices)."""
+    g = torch.Generator().manual_seed(3)
+    V, n = 7, 5000
+    views = [torch.rand(int(torch.randint(200, 3000, (1,), generator=g)), 3, generator=g) * 6 - 3 for _ in range(V)]
+    ext = torch.eye(4).repeat(V, 1, 1)
+    for v in range(V):                                   # rigid global -> ego transforms
+        a = torch.rand(3, generator=g) * 6.28
+        rz = torch.tensor([[torch.cos(a[0]), -torch.sin(a[0]), 0], [torch.sin(a[0]), torch.cos(a[0]), 0], [0, 0, 1.0]])
+        ry = torch.tensor([[torch.cos(a[1]), 0, torch.sin(a[1])], [0, 1.0, 0], [-torch.sin(a[1]), 0, torch.cos(a[1])]])
+        ext[v, :3, :3] = rz @ ry
+        ext[v, :3, 3] = torch.rand(3, generator=g) * 10 - 5
+    total = sum(len(p) for p in views)
+    choices = torch.randperm(total, generator=g)[:n]
+    want = po.aggregate_sample(views, ext, choices)
+    got = ops.aggregate_sample([p.to(DEV) for p in views], ext, choices.to(DEV))
+    np.testing.assert_allclose(np_(got), want.numpy(), rtol=0, atol=2e-5)      # fp32 LU solve vs fp64 inverse applied in fp32

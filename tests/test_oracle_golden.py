@@ -154,3 +154,17 @@ def test_sparse_collate_restatement_matches_the_torch_expression():
     assert c2[0].tolist() == [0, -1, 1, 0]
     c3, _ = po.batch_sparse_collate([torch.tensor([[-0.015, 0.015, -0.0]])], 0.01, floor=True)
     assert c3[0].tolist() == [0, -2, 1, 0]
+
+
+def test_aggregate_sample_restatement_is_the_inverse_transform():
+    """N3 oracle sanity: solving extrinsic . x = [p;1] moves ego points back to where the global points were."""
+    g = torch.Generator().manual_seed(8)
+    glob = [torch.rand(50, 3, generator=g) * 8 for _ in range(3)]
+    ext = torch.eye(4).repeat(3, 1, 1)
+    for v in range(3):
+        q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+        ext[v, :3, :3], ext[v, :3, 3] = q, torch.randn(3, generator=g)
+    ego = [(ext[v, :3, :3] @ glob[v].T).T + ext[v, :3, 3] for v in range(3)]
+    choices = torch.tensor([149, 0, 75, 75, 3])
+    got = po.aggregate_sample(ego, ext, choices)
+    assert torch.allclose(got, torch.cat(glob)[choices], atol=1e-5)

@@ -22,11 +22,18 @@ n = L.pt_debug_pool_events(buf, 4096)
 ev = sorted((buf[2 * i + 1], buf[2 * i]) for i in range(n))      # 32-bit SM clock (a 0.9 ms kernel cannot wrap twice)
 t0 = ev[0][0]
 CODES = {0: "top of view", 1: "past view barrier", 2: "operands landed", 3: "score MMAs done", 4: "softmax done"}
+FINE = {20: "41 after barrier (planes dead)", 21: "41 after store round + barrier", 22: "41 after add round + barrier", 23: "41 after row max + barrier",
+        24: "41 after row sum + barrier", 25: "41 probabilities in registers"}
 rows = {}
 for t, i in ev:
+    if i >= 100000:
+        w, c = divmod(i - 100000, 1000)
+        rows.setdefault((1, 100 + c), {})[w] = t - t0
+        continue
     w, r = divmod(i, 1000); v, c = divmod(r, 10)
     rows.setdefault((v, c), {})[w] = t - t0
 print("cycles since the first event; one column per consumer warp (lane 0)")
-print("view event              " + " ".join(f"w{w:<6d}" for w in range(16)))
+print(f"{'view event':34s} " + " ".join(f"w{w:<6d}" for w in range(16)))
 for (v, c) in sorted(rows):
-    print(f"{40 + v:4d} {CODES.get(c, c):18s} " + " ".join(f"{rows[(v, c)].get(w, -1):7d}" for w in range(16)))
+    label = FINE[c - 100] if c >= 100 else f"{40 + v:4d} {CODES.get(c, c)}"
+    print(f"{label:34s} " + " ".join(f"{rows[(v, c)].get(w, -1):7d}" for w in range(16)))
