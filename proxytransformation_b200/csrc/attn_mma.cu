@@ -310,11 +310,8 @@ int launch_proxy_attention_mma(const float* qkv, const float* pt_tok, const uint
                                float* o, void* o_split, long long o_plane, cudaStream_t s) {
     PT_REQUIRE(proxy_attention_mma_supported(n, l, c, heads), "attention(mma): n=%d l=%d c=%d heads=%d unsupported", n, l, c, heads);
     const size_t smem = am_layout(n, l).total;
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
+    if (smem > 48 * 1024)      // per device and size-dependent: set on every launch (a host-side call of a few hundred ns)
         PT_CUDA_OK(cudaFuncSetAttribute(proxy_attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
     const float scale = (float)(1.0 / sqrt((double)AM_HD));     // python float head_dim ** -0.5 (:186), rounded to fp32 once
     { ProfScope prof_(PROF_ATTENTION, s); proxy_attention_mma_kernel<<<dim3(heads, B), AM_THREADS, smem, s>>>(qkv, pt_tok, mask, n, l, c, scale, o, (__nv_bfloat16*)o_split, o_plane); }
     PT_LAUNCH_CHECK();

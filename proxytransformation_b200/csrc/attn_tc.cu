@@ -365,11 +365,9 @@ int launch_proxy_attention_tc(const void* qk_split, long long qk_plane, int ldq,
     PT_REQUIRE(((uintptr_t)qk_split & 15) == 0 && ((uintptr_t)vt_split & 15) == 0 && ((uintptr_t)pt_split & 15) == 0 && ldq % 8 == 0 &&
                    ldv % 8 == 0 && qk_plane % 8 == 0 && vt_plane % 8 == 0 && pt_plane % 8 == 0 && o_plane % 8 == 0,
                "attention(tcgen05): operand planes must be 16-byte aligned");
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[PT_MAX_DEVICES] = {};
+    if (first_use_on_current_device(attr))
         PT_CUDA_OK(cudaFuncSetAttribute(proxy_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, at::SMEM_BYTES));
-        attr = true;
-    }
     AtArgs a;
     a.qk = (const __nv_bfloat16*)qk_split; a.qk_plane = qk_plane; a.ldq = ldq;
     a.vt = (const __nv_bfloat16*)vt_split; a.vt_plane = vt_plane; a.ldv = ldv;

@@ -80,6 +80,17 @@ __device__ __forceinline__ float dist2_rn(float ax, float ay, float az, float bx
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// cudaFuncSetAttribute is per device: remember per (call site, device) whether it has been done (a process normally drives
+// one GPU, but nothing here may assume it).  `done` is a call-site static array of PT_MAX_DEVICES flags.
+constexpr int PT_MAX_DEVICES = 64;
+inline bool first_use_on_current_device(bool* done) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PT_MAX_DEVICES) return true;     // unknown: always (re)apply
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -363,12 +363,11 @@ int split_rows_bf16(const float* x, long long count, __nv_bfloat16* hi, __nv_bfl
 }
 
 static int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
+    static int n[PT_MAX_DEVICES] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PT_MAX_DEVICES) return 148;
+    if (n[dev] == 0 && (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0)) n[dev] = 148;
+    return n[dev];
 }
 
 template <int BN, int ACT, bool SPLIT>
@@ -377,11 +376,9 @@ static int launch_variant(const CUtensorMap& mapA, const CUtensorMap& mapW, TcKe
     int stages = TC_SMEM_BUDGET / STAGE_BYTES;
     if (stages > 6) stages = 6;
     const int smem = stages * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + TC_EPI_SMEM;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[PT_MAX_DEVICES] = {};
+    if (first_use_on_current_device(attr_set))
         PT_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, ACT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048 + TC_EPI_SMEM));
-        attr_set = true;
-    }
     k.stages = stages;
     k.tiles_n = ceil_div(k.N, BN);
     const int total = k.tiles_m * k.tiles_n * k.batch;

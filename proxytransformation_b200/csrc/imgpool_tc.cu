@@ -689,11 +689,9 @@ int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, in
     }
     if (!(stages & PT_IMG_STAGE_BACK)) return PT_OK;
     {   // pass B
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool attr_set[PT_MAX_DEVICES] = {};
+        if (first_use_on_current_device(attr_set))
             PT_CUDA_OK(cudaFuncSetAttribute(img_pool_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + POOL_EV_SMEM));
-            attr_set = true;
-        }
         PoolArgs a;
         a.img = (const uint8_t*)img_feat; a.wpl = w.wpl; a.cterm = w.cterm; a.xbar = w.xbar;
         a.ya_hi = w.ya_split; a.ya_plane = (long long)BV * HEADS * YA; a.BV = BV;
