@@ -61,6 +61,7 @@ constexpr int SMEM_BYTES = OFF_BAR + (2 * RING + 4) * 8;
 // The four partial-score buffers (29.7 KB) live only between the score MMAs and the softmax; they overlay the (dead) w_eff
 // planes of the current view plus the adjacent part of the (dead) probability arrays.
 constexpr int SPART_BYTES = 4 * SBUF * 4;
+constexpr int DBG_PER_VIEW = HEADS * 256 + 8 * SBUF;   // floats per view of the PT_POOL_DEBUG=64 dump (PoolArgs::dbg)
 constexpr int OFF_SPART_EVEN = OFF_W0, OFF_SPART_ODD = OFF_W1 + WBYTES - SPART_BYTES;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(SPART_BYTES <= WBYTES + PBYTES && OFF_SPART_ODD >= OFF_P && OFF_SPART_ODD % 16 == 0, "partial-score overlay");
@@ -257,6 +258,8 @@ struct PoolArgs {
     int BV;
     float scale;
     int pf_dist;                 // L2 prefetch distance of the producer in ring loads (0 = off)
+    float* dbg;                  // debug dump area behind the workspace (null unless the caller over-allocated it): per view
+                                 // [8 heads][256] scaled scores, then (two-group kernel) [8 classes][8 heads][232] partial scores
     int debug_skip;              // PT_POOL_DEBUG bit mask (1, 2, 4, 16 give garbage results): 1 skip score MMAs, 2 slabs are 16-byte loads
                                  // (no HBM traffic), 4 skip sum MMAs, 8 per-phase cycle trace of CTA 0, 16 skip exchange + softmax
 };
@@ -466,6 +469,10 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
                 sv[i] = v;
                 mx = fmaxf(mx, v);
             }
+            if ((a.debug_skip & 64) && a.dbg) {                // debug: dump the scaled scores
+                float* dbg = a.dbg + (size_t)bv * DBG_PER_VIEW + sh * 256;
+                for (int i = 0; i < 4; ++i) dbg[128 * shalf + lane + 32 * i] = sv[i];
+            }
             mx = warp_max(mx);
             if (lane == 0) red[warp] = mx;
             ip_consumer_sync();                                // all partial scores have been read
@@ -587,6 +594,301 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
     if (lane == 0) POOL_EV_DUMP();
 }
 
+
+// ------------------------------------------------------------------------------------------------ pass B, two-group form
+// Same algebra, fragment layouts and channel orders as img_pool_mma_kernel, different schedule (PT_POOL_V2=1): the consumer
+// warps are split into two specialised groups that work on two different views at the same time, and both passes over a
+// view are streamed (nothing stays resident: the weighted-sum pass re-reads the view from L2):
+//   group A (warps 0-7, one residue class each): scores of view j (all 29 token chunks), score exchange, softmax -> probabilities
+//   group B (warps 8-15, one residue class each): weighted sums of view j-1 with the probabilities A handed over
+//   warp 16 / 17: producers of ring A (4 slots: pass 1, from HBM) and ring B (2 slots: pass 2, from L2)
+// so HBM requests are issued all the time (ring A drains continuously) instead of only while the weighted-sum phase frees
+// slots.  Registers are redistributed with setmaxnreg: A 136 (116 score accumulators), B 80, producers 40
+// (8 x 256 x 40 needed by A <= 8 x 256 x 16 + 128 x 56 released; 2 x 136 + 2 x 80 + 40 <= 512 per lane and sub-partition).
+namespace ip2 {
+using namespace ip;
+constexpr int RA = 4, RB = 2;
+constexpr int OFF_RA = 0;
+constexpr int OFF_RB = OFF_RA + RA * SLAB_BYTES;
+constexpr int OFF_WA = OFF_RB + RB * SLAB_BYTES;                       // w_eff planes, double-buffered by view parity
+constexpr int OFF_PP = OFF_WA + 2 * WBYTES;                            // probabilities (bf16 hi/lo, two token alignments)
+constexpr int OFF_MS = OFF_PP + PBYTES;                                // s0 partials [8 classes][8 heads], p0 [8]
+constexpr int OFF_BR = OFF_MS + 512;                                   // fullA[4] emptyA[4] fullB[2] emptyB[2] wfull[2] wempty[2] pfull pempty
+constexpr int SMEM2_BYTES = OFF_BR + 18 * 8;
+constexpr int SP2_BYTES = 2 * SBUF * 4;                                // two partial-score buffers (token parity of the class)
+static_assert(SMEM2_BYTES <= 227 * 1024 && SP2_BYTES <= WBYTES, "shared memory budget (v2)");
+}  // namespace ip2
+
+__global__ void __launch_bounds__(ip::THREADS, 1) img_pool_split_kernel(const PoolArgs a) {
+    using namespace ip2;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + OFF_BR);
+    uint64_t* emptyA = fullA + RA;
+    uint64_t* fullB = emptyA + RA;
+    uint64_t* emptyB = fullB + RB;
+    uint64_t* wfull = emptyB + RB;
+    uint64_t* wempty = wfull + 2;
+    uint64_t* pfull = wempty + 2;
+    uint64_t* pempty = pfull + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int b = 0; b < RA; ++b) { ip_mbar_init(fullA + b, 1); ip_mbar_init(emptyA + b, 8); }
+        for (int b = 0; b < RB; ++b) { ip_mbar_init(fullB + b, 1); ip_mbar_init(emptyB + b, 8); }
+        for (int b = 0; b < 2; ++b) { ip_mbar_init(wfull + b, 1); ip_mbar_init(wempty + b, 1); }
+        ip_mbar_init(pfull, 8);
+        ip_mbar_init(pempty, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < PBYTES / 4; i += THREADS) reinterpret_cast<uint32_t*>(smem + OFF_PP)[i] = 0u;    // margins stay zero for good
+    __syncthreads();
+    const int nviews = blockIdx.x < a.BV ? (a.BV - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp >= 16) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+        if (lane != 0 || warp > 17) return;
+        if (warp == 16) {
+            // ===== producer of ring A: w_eff planes + the eight slabs of every view, pass 1 (HBM) =====
+            for (int j = 0; j < nviews; ++j) {
+                const int bv = blockIdx.x + j * gridDim.x;
+                const unsigned wb = j & 1;
+                ip_mbar_wait(wempty + wb, ((j >> 1) & 1u) ^ 1u);
+                ip_mbar_expect_tx(wfull + wb, WBYTES);
+                ip_bulk_load(smem + OFF_WA + wb * WBYTES, a.wpl + (size_t)bv * 2 * WPLANE, WBYTES, wfull + wb);
+                const uint8_t* view = a.img + (size_t)bv * C * HW * 2;
+                for (int k = 0; k < NSLAB; ++k) {
+                    {   // L2 prefetch a.pf_dist slabs ahead (into the next view if need be)
+                        int k2 = k + a.pf_dist, bv2 = bv;
+                        if (k2 >= NSLAB) { k2 -= NSLAB; bv2 += gridDim.x; }
+                        if (a.pf_dist > 0 && bv2 < a.BV) ip_prefetch_l2(a.img + (size_t)bv2 * C * HW * 2 + (size_t)k2 * SLAB_BYTES, SLAB_BYTES);
+                    }
+                    const unsigned slot = k & 3, n = 2u * j + (k >> 2);
+                    ip_mbar_wait(emptyA + slot, (n & 1u) ^ 1u);
+                    ip_mbar_expect_tx(fullA + slot, SLAB_BYTES);
+                    ip_bulk_load(smem + OFF_RA + slot * SLAB_BYTES, view + (size_t)k * SLAB_BYTES, SLAB_BYTES, fullA + slot);
+                }
+            }
+        } else {
+            // ===== producer of ring B: the same slabs again for the weighted-sum pass (L2 hits) =====
+            for (int j = 0; j < nviews; ++j) {
+                const uint8_t* view = a.img + (size_t)(blockIdx.x + j * gridDim.x) * C * HW * 2;
+                for (int k = 0; k < NSLAB; ++k) {
+                    const unsigned slot = k & 1, n = 4u * j + (k >> 1);
+                    ip_mbar_wait(emptyB + slot, (n & 1u) ^ 1u);
+                    ip_mbar_expect_tx(fullB + slot, SLAB_BYTES);
+                    ip_bulk_load(smem + OFF_RB + slot * SLAB_BYTES, view + (size_t)k * SLAB_BYTES, SLAB_BYTES, fullB + slot);
+                }
+            }
+        }
+        return;
+    }
+
+    const int g = lane >> 2, q = lane & 3;
+    const int mi = lane >> 3, r8 = lane & 7;                            // ldmatrix: this lane addresses row r8 of matrix mi
+    float* s0part = reinterpret_cast<float*>(smem + OFF_MS);            // [8 classes][8 heads]
+    float* p0 = s0part + 64;                                            // [8]
+
+    if (warp >= 8) {
+        // ===== group B: weighted sums of the view whose probabilities group A has handed over =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;" ::: "memory");
+        const int s = warp - 8;
+        const uint32_t ringB = ip_smem_u32(smem + OFF_RB);
+        const uint32_t sm_off = 448u * s + 3600u * r8 + 16u * mi;
+        for (int j = 0; j < nviews; ++j) {
+            const int bv = blockIdx.x + j * gridDim.x;
+            ip_mbar_wait(pfull, j & 1u);
+            uint32_t PA[15][4];
+            {
+                const int e = s & 1;
+                const uint32_t* ph = reinterpret_cast<const uint32_t*>(smem + OFF_PP) + (e * HEADS + g) * (PPITCH / 2) + q + ((8 + e - s) >> 1);
+                const uint32_t* pl = ph + 2 * HEADS * (PPITCH / 2);
+#pragma unroll
+                for (int kb = 0; kb < 15; ++kb) {
+                    PA[kb][0] = ph[8 * kb]; PA[kb][1] = pl[8 * kb]; PA[kb][2] = ph[8 * kb + 4]; PA[kb][3] = pl[8 * kb + 4];
+                }
+            }
+            const float p0g = p0[g];
+            __syncwarp();
+            if (lane == 0) ip_mbar_arrive(pempty);                      // group A may publish the next view's probabilities
+            __nv_bfloat16* yrow = a.ya_hi + ((size_t)bv * HEADS + g) * YA;
+            const float* xb = a.xbar + (size_t)bv * C;
+#pragma unroll 1
+            for (int k = 0; k < NSLAB; ++k) {
+                const unsigned slot = k & 1, n = 4u * j + (k >> 1);
+                const int ch = k * SLAB_CH + s + 16 * q;
+                const float x0 = __ldg(xb + ch), x1 = __ldg(xb + ch + 8);
+                ip_mbar_wait(fullB + slot, n & 1u);
+                const uint32_t base = ringB + slot * SLAB_BYTES + sm_off;
+                float y0[4] = {0.f, 0.f, 0.f, 0.f}, y1[4] = {0.f, 0.f, 0.f, 0.f};
+                uint32_t bf[4];
+#pragma unroll
+                for (int m = 0; m < 7; ++m) {
+                    ldsm_x4(bf, base + 64 * m);
+                    mma_bf16_16816(y0, PA[2 * m], bf[0], bf[1]);
+                    mma_bf16_16816(y1, PA[2 * m + 1], bf[2], bf[3]);
+                }
+                ldsm_x1(bf[0], base + 64 * 7);                           // chunk 28; the k-block's upper half (u >= 232) is empty
+                mma_bf16_16816(y0, PA[14], bf[0], 0u);
+                __syncwarp();
+                if (lane == 0) ip_mbar_arrive(emptyB + slot);
+                const float v0 = ((y0[0] + y1[0]) + (y0[2] + y1[2])) + p0g * x0;
+                const float v1 = ((y0[1] + y1[1]) + (y0[3] + y1[3])) + p0g * x1;
+                uint32_t h0, l0, h1, l1;
+                split_hi_lo(v0, h0, l0);
+                split_hi_lo(v1, h1, l1);
+                const int col = ((k * 8 + s) * 4 + q) * 2;
+                *reinterpret_cast<uint32_t*>(yrow + col) = h0 | (h1 << 16);
+                *reinterpret_cast<uint32_t*>(yrow + a.ya_plane + col) = l0 | (l1 << 16);
+            }
+        }
+        return;
+    }
+
+    // ===== group A: scores (all 29 chunks of one residue class per warp), exchange, softmax =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;" ::: "memory");
+    const int s = warp;                                                  // residue class for the scores; head for the softmax
+    const uint32_t ringA = ip_smem_u32(smem + OFF_RA);
+    const uint32_t sc_off = 448u * s + 3600u * r8 + 16u * (mi >> 1);    // + 32 per chunk pair; slab of the pair = mi & 1
+    for (int j = 0; j < nviews; ++j) {
+        const int bv = blockIdx.x + j * gridDim.x;
+        const unsigned wb = j & 1;
+        const uint8_t* wbuf = smem + OFF_WA + wb * WBYTES;
+        float* spart = reinterpret_cast<float*>(smem + OFF_WA + wb * WBYTES);       // overlay: the planes are dead after the MMAs
+        const float* xb = a.xbar + (size_t)bv * C;
+        float ct[8];                                                     // position terms of this warp's head (softmax role)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int t = lane + 32 * i;
+            ct[i] = t < T ? __ldg(a.cterm + ((size_t)bv * HEADS + s) * TP + t) : 0.f;
+        }
+        ip_mbar_wait(wfull + wb, (j >> 1) & 1u);
+        float acc[29][4];
+#pragma unroll
+        for (int i = 0; i < 29; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+        float dotp = 0.f;
+#pragma unroll 1
+        for (int p = 0; p < NSLAB / 2; ++p) {
+            const unsigned s0 = (2 * p) & 3, s1 = s0 + 1, n = 2u * j + (p >> 1);
+            const int col = ((p * 8 + s) * 4 + q) * 4;
+            const uint2 ah = *reinterpret_cast<const uint2*>(wbuf + (g * WPITCH + col) * 2);
+            const uint2 al = *reinterpret_cast<const uint2*>(wbuf + (WPLANE + g * WPITCH + col) * 2);
+            const uint32_t A[4] = {ah.x, al.x, ah.y, al.y};
+            {   // mean-token score s0[g] = w_eff[g] . xbar, this (class, pair) column block
+                const int ch = 128 * p + s + 16 * q;
+                const float w0 = __uint_as_float(ah.x << 16) + __uint_as_float(al.x << 16), w1 = __uint_as_float(ah.x & 0xffff0000u) + __uint_as_float(al.x & 0xffff0000u);
+                const float w2 = __uint_as_float(ah.y << 16) + __uint_as_float(al.y << 16), w3 = __uint_as_float(ah.y & 0xffff0000u) + __uint_as_float(al.y & 0xffff0000u);
+                dotp = fmaf(w0, __ldg(xb + ch), dotp); dotp = fmaf(w1, __ldg(xb + ch + 8), dotp);
+                dotp = fmaf(w2, __ldg(xb + ch + 64), dotp); dotp = fmaf(w3, __ldg(xb + ch + 72), dotp);
+            }
+            ip_mbar_wait(fullA + s0, n & 1u);
+            ip_mbar_wait(fullA + s1, n & 1u);
+            const uint32_t base = ringA + ((mi & 1) ? s1 : s0) * SLAB_BYTES + sc_off;
+            uint32_t bf[4];
+#pragma unroll
+            for (int m = 0; m < 14; ++m) {
+                ldsm_x4_t(bf, base + 32 * m);
+                mma_bf16_16816(acc[2 * m], A, bf[0], bf[1]);
+                mma_bf16_16816(acc[2 * m + 1], A, bf[2], bf[3]);
+            }
+            ldsm_x2_t(reinterpret_cast<uint32_t(&)[2]>(bf[0]), base + 32 * 14);      // chunk 28
+            mma_bf16_16816(acc[28], A, bf[0], bf[1]);
+            __syncwarp();
+            if (lane == 0) { ip_mbar_arrive(emptyA + s0); ip_mbar_arrive(emptyA + s1); }
+        }
+        dotp += __shfl_xor_sync(FULL, dotp, 1);
+        dotp += __shfl_xor_sync(FULL, dotp, 2);
+        if (q == 0) s0part[s * 8 + g] = dotp;
+        if ((a.debug_skip & 64) && a.dbg) {                              // debug: dump this class's partial scores S_s[h][u]
+            float* dbg = a.dbg + (size_t)bv * DBG_PER_VIEW + HEADS * 256 + s * SBUF + g * SPITCH + 2 * q;
+#pragma unroll
+            for (int i = 0; i < 29; ++i) { dbg[8 * i] = acc[i][0] + acc[i][2]; dbg[8 * i + 1] = acc[i][1] + acc[i][3]; }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");                   // every A warp is done with the planes: the overlay may be written
+        // Partial scores: class s holds S_s[h][u] (token t = u - s).  Two buffers by class parity j2 = s & 1; a class writes
+        // its value for token t at column t + j2, i.e. u - (s - j2): classes 0/1 store, 2/3, 4/5, 6/7 add, one round each.
+        {
+            const int j2 = s & 1, sh2 = s - j2;                          // even column shift: float2 accesses stay aligned
+            // (the column offset goes through an opaque asm: nvcc 12.9 turned `g * SPITCH + (2q - sh2)` into a bitwise OR, which
+            // drops the row term whenever 2q < sh2)
+            int coff = 2 * q + 8 - sh2;
+            asm volatile("" : "+r"(coff));
+            float* dst = spart + j2 * SBUF + g * SPITCH + coff;
+#pragma unroll 1
+            for (int r = 0; r < 4; ++r) {
+                if ((s >> 1) == r) {
+#pragma unroll
+                    for (int i = 0; i < 29; ++i) {
+                        if (8 * i + 2 * q >= sh2) {
+                            float2* d2 = reinterpret_cast<float2*>(dst + 8 * i - 8);
+                            float2 v = make_float2(acc[i][0] + acc[i][2], acc[i][1] + acc[i][3]);
+                            if (r > 0) { const float2 o = *d2; v.x += o.x; v.y += o.y; }
+                            *d2 = v;
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+        }
+        // softmax of head s over the 226 tokens (this warp alone: lane owns tokens lane + 32 i)
+        float sv[8];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int t = lane + 32 * i;                                 // attention token; spatial token tau = t - 1
+            float v = -INFINITY;
+            if (t == 0) {
+                float s0v = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) s0v += s0part[w * 8 + s];
+                v = a.scale * (s0v + ct[i]);
+            } else if (t < T) {
+                const float* sp = spart + s * SPITCH + (t - 1);
+                v = a.scale * ((sp[0] + sp[SBUF + 1]) + ct[i]);
+            }
+            sv[i] = v;
+            mx = fmaxf(mx, v);
+        }
+        if ((a.debug_skip & 64) && a.dbg) {                              // debug: dump the scaled scores
+            float* dbg = a.dbg + (size_t)bv * DBG_PER_VIEW + s * 256;
+            for (int i = 0; i < 8; ++i) dbg[lane + 32 * i] = sv[i];
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sv[i] = (lane + 32 * i) < T ? expf(sv[i] - mx) : 0.f; sum += sv[i]; }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");                   // all partial scores and s0 partials have been read
+        if (tid == 0) ip_mbar_arrive(wempty + wb);                       // the planes buffer (and the overlay) may be refilled
+        ip_mbar_wait(pempty, (j & 1u) ^ 1u);                             // group B has taken the previous view's probabilities
+        {
+            __nv_bfloat16* ya = a.ya_hi + ((size_t)bv * HEADS + s) * YA + C;
+            unsigned short* pq = reinterpret_cast<unsigned short*>(smem + OFF_PP) + s * PPITCH;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int t = lane + 32 * i;                             // attention token 0..255 (>= 226: zero padding)
+                const float pr = sv[i] * inv;
+                uint32_t hi, lo;
+                split_hi_lo(pr, hi, lo);
+                ya[t] = __ushort_as_bfloat16((unsigned short)hi);
+                ya[a.ya_plane + t] = __ushort_as_bfloat16((unsigned short)lo);
+                if (t == 0) p0[s] = pr;
+                if (t >= 1 && t < T) {
+                    const int x = t - 1 + 8;
+                    pq[x] = (unsigned short)hi;                               // hi, even copy
+                    pq[HEADS * PPITCH + x + 1] = (unsigned short)hi;           // hi, odd copy
+                    pq[2 * HEADS * PPITCH + x] = (unsigned short)lo;           // lo, even copy
+                    pq[3 * HEADS * PPITCH + x + 1] = (unsigned short)lo;       // lo, odd copy
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) ip_mbar_arrive(pfull);
+    }
+}
+
 }  // namespace pt
 extern "C" int pt_debug_pool_events(long long* out, int max_events) {
     unsigned int n = 0;
@@ -698,10 +1000,20 @@ int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, in
         a.scale = (float)(1.0 / sqrt((double)HD));
         const char* dbg = getenv("PT_POOL_DEBUG");
         a.debug_skip = dbg ? atoi(dbg) : 0;
+        a.dbg = ws_bytes >= w.total + (size_t)BV * DBG_PER_VIEW * 4 ? reinterpret_cast<float*>((char*)ws + w.total) : nullptr;
         const char* pf = getenv("PT_POOL_PF");
         a.pf_dist = pf ? atoi(pf) : PF_DIST;
         const int grid = BV < sms ? BV : sms;
-        { ProfScope prof_(PROF_IMG_POOL, s); img_pool_mma_kernel<<<grid, THREADS, SMEM_BYTES + POOL_EV_SMEM, s>>>(a); }
+        const char* v2e = getenv("PT_POOL_V2");                         // experimental two-group schedule
+        const bool v2 = v2e && atoi(v2e) != 0;
+        if (v2) {
+            static bool attr2[PT_MAX_DEVICES] = {};
+            if (first_use_on_current_device(attr2))
+                PT_CUDA_OK(cudaFuncSetAttribute(img_pool_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ip2::SMEM2_BYTES));
+            { ProfScope prof_(PROF_IMG_POOL, s); img_pool_split_kernel<<<grid, THREADS, ip2::SMEM2_BYTES, s>>>(a); }
+        } else {
+            { ProfScope prof_(PROF_IMG_POOL, s); img_pool_mma_kernel<<<grid, THREADS, SMEM_BYTES + POOL_EV_SMEM, s>>>(a); }
+        }
         PT_LAUNCH_CHECK();
     }
     {   // G4: z[:, 32h:32h+32] = [y_h | a_h] [W_vc_h | h_v_h]^T   -> split planes only

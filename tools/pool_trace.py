@@ -19,7 +19,7 @@ m.get_img_proxy(img); torch.cuda.synchronize()
 L.pt_debug_pool_trace(buf, 0)
 views = -(-B * cfg.n_views // 148)
 names = ["view barrier", "operand wait", "score MMAs", "exchange+softmax", "weighted sums"]
-tot = sum(buf[:5])
+tot = sum(buf[:5]) or 1
 for n, v in zip(names, buf[:5]):
     print(f"{n:22s} {v / views:9.0f} cycles/view  {100.0 * v / tot:5.1f}%")
 print(f"total {tot / views:.0f} cycles/view over {views} views")
