@@ -596,37 +596,47 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
 
 
 // ------------------------------------------------------------------------------------------------ pass B, two-group form
-// Same algebra, fragment layouts and channel orders as img_pool_mma_kernel, different schedule (PT_POOL_V2=1): the consumer
-// warps are split into two specialised groups that work on two different views at the same time, and both passes over a
-// view are streamed (nothing stays resident: the weighted-sum pass re-reads the view from L2):
-//   group A (warps 0-7, one residue class each): scores of view j (all 29 token chunks), score exchange, softmax -> probabilities
-//   group B (warps 8-15, one residue class each): weighted sums of view j-1 with the probabilities A handed over
-//   warp 16 / 17: producers of ring A (4 slots: pass 1, from HBM) and ring B (2 slots: pass 2, from L2)
-// so HBM requests are issued all the time (ring A drains continuously) instead of only while the weighted-sum phase frees
-// slots.  Registers are redistributed with setmaxnreg: A 136 (116 score accumulators), B 80, producers 40
-// (8 x 256 x 40 needed by A <= 8 x 256 x 16 + 128 x 56 released; 2 x 136 + 2 x 80 + 40 <= 512 per lane and sub-partition).
+// Same algebra and channel orders as img_pool_mma_kernel, different schedule (PT_POOL_V2=1): the consumer warps are split
+// into two specialised groups that work on two different views at the same time, and nothing stays resident:
+//   group A (warps 0-7, one residue class each): scores of view j (all 29 token chunks) from a 6-slot ring fed by the
+//            producer (HBM), score exchange, softmax -> probabilities
+//   group B (warps 8-15, one residue class each): weighted sums of view j-1 with the probabilities A handed over.  Its MMA
+//            B operand (k = token, n = channel) needs consecutive tokens of ONE channel per thread, which is how the rows
+//            lie in memory: every thread reads its fragments straight from global memory (L2 hits: group A's pass has just
+//            pulled the view through L2) as 16-byte loads of the aligned chunks u = token + class, no shared memory and no
+//            ldmatrix.  A 16-byte load feeds two MMAs; the token order inside a k-block this induces (thread q of a 32-token
+//            group G holds tokens 32 G + 8 q + 0..7) is matched by the order in which the probability fragments are read.
+//   warp 16: producer of the ring (pass 1)
+// so HBM requests are issued all the time (the ring drains continuously) instead of only while the weighted-sum phase frees
+// slots, and shared memory sees one pass of writes and one of ldmatrix reads per view instead of two each.
+// Registers are redistributed with setmaxnreg: A 128 (116 score accumulators), B 96, producer warpgroup 24
+// (2 x 128 + 2 x 96 + 24 <= 480 per lane and sub-partition, the launch allocation of 5 warps x 96).
 namespace ip2 {
 using namespace ip;
-constexpr int RA = 4, RB = 2;
+constexpr int RA = 6;
 constexpr int OFF_RA = 0;
-constexpr int OFF_RB = OFF_RA + RA * SLAB_BYTES;
-constexpr int OFF_WA = OFF_RB + RB * SLAB_BYTES;                       // w_eff planes, double-buffered by view parity
+constexpr int OFF_WA = OFF_RA + RA * SLAB_BYTES;                       // w_eff planes, double-buffered by view parity
 constexpr int OFF_PP = OFF_WA + 2 * WBYTES;                            // probabilities (bf16 hi/lo, two token alignments)
 constexpr int OFF_MS = OFF_PP + PBYTES;                                // s0 partials [8 classes][8 heads], p0 [8]
-constexpr int OFF_BR = OFF_MS + 512;                                   // fullA[4] emptyA[4] fullB[2] emptyB[2] wfull[2] wempty[2] pfull pempty
+constexpr int OFF_BR = OFF_MS + 512;                                   // fullA[6] emptyA[6] wfull[2] wempty[2] pfull pempty
 constexpr int SMEM2_BYTES = OFF_BR + 18 * 8;
 constexpr int SP2_BYTES = 2 * SBUF * 4;                                // two partial-score buffers (token parity of the class)
+constexpr int LDG_DEPTH = 4;                                           // 16-byte loads in flight per thread of group B
 static_assert(SMEM2_BYTES <= 227 * 1024 && SP2_BYTES <= WBYTES, "shared memory budget (v2)");
 }  // namespace ip2
+
+__device__ __forceinline__ uint4 ip_ldg_stream(const uint8_t* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 
 __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_split_kernel(const PoolArgs a) {
     using namespace ip2;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + OFF_BR);
     uint64_t* emptyA = fullA + RA;
-    uint64_t* fullB = emptyA + RA;
-    uint64_t* emptyB = fullB + RB;
-    uint64_t* wfull = emptyB + RB;
+    uint64_t* wfull = emptyA + RA;
     uint64_t* wempty = wfull + 2;
     uint64_t* pfull = wempty + 2;
     uint64_t* pempty = pfull + 1;
@@ -634,7 +644,6 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_split_kernel(const Po
 
     if (tid == 0) {
         for (int b = 0; b < RA; ++b) { ip_mbar_init(fullA + b, 1); ip_mbar_init(emptyA + b, 8); }
-        for (int b = 0; b < RB; ++b) { ip_mbar_init(fullB + b, 1); ip_mbar_init(emptyB + b, 8); }
         for (int b = 0; b < 2; ++b) { ip_mbar_init(wfull + b, 1); ip_mbar_init(wempty + b, 1); }
         ip_mbar_init(pfull, 8);
         ip_mbar_init(pempty, 8);
@@ -645,92 +654,92 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_split_kernel(const Po
     const int nviews = blockIdx.x < a.BV ? (a.BV - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (warp >= 16) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
-        if (lane != 0 || warp > 17) return;
-        if (warp == 16) {
-            // ===== producer of ring A: w_eff planes + the eight slabs of every view, pass 1 (HBM) =====
-            for (int j = 0; j < nviews; ++j) {
-                const int bv = blockIdx.x + j * gridDim.x;
-                const unsigned wb = j & 1;
-                ip_mbar_wait(wempty + wb, ((j >> 1) & 1u) ^ 1u);
-                ip_mbar_expect_tx(wfull + wb, WBYTES);
-                ip_bulk_load(smem + OFF_WA + wb * WBYTES, a.wpl + (size_t)bv * 2 * WPLANE, WBYTES, wfull + wb);
-                const uint8_t* view = a.img + (size_t)bv * C * HW * 2;
-                for (int k = 0; k < NSLAB; ++k) {
-                    {   // L2 prefetch a.pf_dist slabs ahead (into the next view if need be)
-                        int k2 = k + a.pf_dist, bv2 = bv;
-                        if (k2 >= NSLAB) { k2 -= NSLAB; bv2 += gridDim.x; }
-                        if (a.pf_dist > 0 && bv2 < a.BV) ip_prefetch_l2(a.img + (size_t)bv2 * C * HW * 2 + (size_t)k2 * SLAB_BYTES, SLAB_BYTES);
-                    }
-                    const unsigned slot = k & 3, n = 2u * j + (k >> 2);
-                    ip_mbar_wait(emptyA + slot, (n & 1u) ^ 1u);
-                    ip_mbar_expect_tx(fullA + slot, SLAB_BYTES);
-                    ip_bulk_load(smem + OFF_RA + slot * SLAB_BYTES, view + (size_t)k * SLAB_BYTES, SLAB_BYTES, fullA + slot);
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;" ::: "memory");
+        if (lane != 0 || warp > 16) return;
+        // ===== producer: w_eff planes + the eight slabs of every view (HBM) through the ring =====
+        unsigned slot = 0, ph = 0;
+        for (int j = 0; j < nviews; ++j) {
+            const int bv = blockIdx.x + j * gridDim.x;
+            const unsigned wb = j & 1;
+            ip_mbar_wait(wempty + wb, ((j >> 1) & 1u) ^ 1u);
+            ip_mbar_expect_tx(wfull + wb, WBYTES);
+            ip_bulk_load(smem + OFF_WA + wb * WBYTES, a.wpl + (size_t)bv * 2 * WPLANE, WBYTES, wfull + wb);
+            const uint8_t* view = a.img + (size_t)bv * C * HW * 2;
+            for (int k = 0; k < NSLAB; ++k) {
+                {   // L2 prefetch a.pf_dist slabs ahead (into the next view if need be)
+                    int k2 = k + a.pf_dist, bv2 = bv;
+                    if (k2 >= NSLAB) { k2 -= NSLAB; bv2 += gridDim.x; }
+                    if (a.pf_dist > 0 && bv2 < a.BV) ip_prefetch_l2(a.img + (size_t)bv2 * C * HW * 2 + (size_t)k2 * SLAB_BYTES, SLAB_BYTES);
                 }
-            }
-        } else {
-            // ===== producer of ring B: the same slabs again for the weighted-sum pass (L2 hits) =====
-            for (int j = 0; j < nviews; ++j) {
-                const uint8_t* view = a.img + (size_t)(blockIdx.x + j * gridDim.x) * C * HW * 2;
-                for (int k = 0; k < NSLAB; ++k) {
-                    const unsigned slot = k & 1, n = 4u * j + (k >> 1);
-                    ip_mbar_wait(emptyB + slot, (n & 1u) ^ 1u);
-                    ip_mbar_expect_tx(fullB + slot, SLAB_BYTES);
-                    ip_bulk_load(smem + OFF_RB + slot * SLAB_BYTES, view + (size_t)k * SLAB_BYTES, SLAB_BYTES, fullB + slot);
-                }
+                ip_mbar_wait(emptyA + slot, ph ^ 1u);
+                ip_mbar_expect_tx(fullA + slot, SLAB_BYTES);
+                ip_bulk_load(smem + OFF_RA + slot * SLAB_BYTES, view + (size_t)k * SLAB_BYTES, SLAB_BYTES, fullA + slot);
+                if (++slot == RA) { slot = 0; ph ^= 1u; }
             }
         }
         return;
     }
 
     const int g = lane >> 2, q = lane & 3;
-    const int mi = lane >> 3, r8 = lane & 7;                            // ldmatrix: this lane addresses row r8 of matrix mi
     float* s0part = reinterpret_cast<float*>(smem + OFF_MS);            // [8 classes][8 heads]
     float* p0 = s0part + 64;                                            // [8]
 
     if (warp >= 8) {
         // ===== group B: weighted sums of the view whose probabilities group A has handed over =====
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;" ::: "memory");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;" ::: "memory");
         const int s = warp - 8;
-        const uint32_t ringB = ip_smem_u32(smem + OFF_RB);
-        const uint32_t sm_off = 448u * s + 3600u * r8 + 16u * mi;
+        // this thread's fragments: channel 64 k + s + 8 g of slab k, chunk 4 G + q of 32-token group G (byte 64 G from here)
+        const size_t lane_off = 448u * s + 3600u * g + 16u * q;
         for (int j = 0; j < nviews; ++j) {
             const int bv = blockIdx.x + j * gridDim.x;
+            const uint8_t* vb = a.img + (size_t)bv * C * HW * 2 + lane_off;
+            uint4 buf[LDG_DEPTH];                                        // the first loads of the view do not depend on the probabilities
+#pragma unroll
+            for (int d = 0; d < LDG_DEPTH; ++d) buf[d] = ip_ldg_stream(vb + 64 * d);
             ip_mbar_wait(pfull, j & 1u);
-            uint32_t PA[15][4];
+            // A fragments: rows g / g + 8 = hi / lo part of head g's probabilities, k slots (2q, 2q+1 | 2q+8, 2q+9) of MMA jj of
+            // group G = tokens u0, u0 + 1 | u0 + 2, u0 + 3 with u0 = 32 G + 8 q + 4 jj (token = u - s, zero outside [0,225))
+            uint32_t PA[8][2][4];
             {
                 const int e = s & 1;
-                const uint32_t* ph = reinterpret_cast<const uint32_t*>(smem + OFF_PP) + (e * HEADS + g) * (PPITCH / 2) + q + ((8 + e - s) >> 1);
+                const uint32_t* ph = reinterpret_cast<const uint32_t*>(smem + OFF_PP) + (e * HEADS + g) * (PPITCH / 2) + 4 * q + ((8 + e - s) >> 1);
                 const uint32_t* pl = ph + 2 * HEADS * (PPITCH / 2);
 #pragma unroll
-                for (int kb = 0; kb < 15; ++kb) {
-                    PA[kb][0] = ph[8 * kb]; PA[kb][1] = pl[8 * kb]; PA[kb][2] = ph[8 * kb + 4]; PA[kb][3] = pl[8 * kb + 4];
-                }
+                for (int G = 0; G < 8; ++G)
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const int wd = 16 * G + 2 * jj;
+                        const bool live = G < 7 || q == 0;               // chunks 29..31 do not exist
+                        PA[G][jj][0] = live ? ph[wd] : 0u; PA[G][jj][1] = live ? pl[wd] : 0u;
+                        PA[G][jj][2] = live ? ph[wd + 1] : 0u; PA[G][jj][3] = live ? pl[wd + 1] : 0u;
+                    }
             }
             const float p0g = p0[g];
             __syncwarp();
             if (lane == 0) ip_mbar_arrive(pempty);                      // group A may publish the next view's probabilities
             __nv_bfloat16* yrow = a.ya_hi + ((size_t)bv * HEADS + g) * YA;
             const float* xb = a.xbar + (size_t)bv * C;
+            float x0n = __ldg(xb + s + 16 * q), x1n = __ldg(xb + s + 16 * q + 8);    // feature means, fetched one slab ahead
 #pragma unroll 1
             for (int k = 0; k < NSLAB; ++k) {
-                const unsigned slot = k & 1, n = 4u * j + (k >> 1);
-                const int ch = k * SLAB_CH + s + 16 * q;
-                const float x0 = __ldg(xb + ch), x1 = __ldg(xb + ch + 8);
-                ip_mbar_wait(fullB + slot, n & 1u);
-                const uint32_t base = ringB + slot * SLAB_BYTES + sm_off;
+                const float x0 = x0n, x1 = x1n;
+                if (k + 1 < NSLAB) { const int ch = (k + 1) * SLAB_CH + s + 16 * q; x0n = __ldg(xb + ch); x1n = __ldg(xb + ch + 8); }
+                const uint8_t* sb = vb + (size_t)k * SLAB_BYTES;
                 float y0[4] = {0.f, 0.f, 0.f, 0.f}, y1[4] = {0.f, 0.f, 0.f, 0.f};
-                uint32_t bf[4];
 #pragma unroll
-                for (int m = 0; m < 7; ++m) {
-                    ldsm_x4(bf, base + 64 * m);
-                    mma_bf16_16816(y0, PA[2 * m], bf[0], bf[1]);
-                    mma_bf16_16816(y1, PA[2 * m + 1], bf[2], bf[3]);
+                for (int G = 0; G < 8; ++G) {
+                    const uint4 cur = buf[G % LDG_DEPTH];
+                    mma_bf16_16816(y0, PA[G][0], cur.x, cur.y);
+                    mma_bf16_16816(y1, PA[G][1], cur.z, cur.w);
+                    const int G2 = G + LDG_DEPTH;                        // refill the register slot: this slab, then the next one
+                    uint4 nx = make_uint4(0u, 0u, 0u, 0u);
+                    if (G2 < 7) nx = ip_ldg_stream(sb + 64 * G2);
+                    else if (G2 == 7) { if (q == 0) nx = ip_ldg_stream(sb + 64 * 7); }
+                    else if (k + 1 < NSLAB) {
+                        if (G2 - 8 < 7 || q == 0) nx = ip_ldg_stream(sb + SLAB_BYTES + 64 * (G2 - 8));
+                    }
+                    buf[G % LDG_DEPTH] = nx;
                 }
-                ldsm_x1(bf[0], base + 64 * 7);                           // chunk 28; the k-block's upper half (u >= 232) is empty
-                mma_bf16_16816(y0, PA[14], bf[0], 0u);
-                __syncwarp();
-                if (lane == 0) ip_mbar_arrive(emptyB + slot);
                 const float v0 = ((y0[0] + y1[0]) + (y0[2] + y1[2])) + p0g * x0;
                 const float v1 = ((y0[1] + y1[1]) + (y0[3] + y1[3])) + p0g * x1;
                 uint32_t h0, l0, h1, l1;
@@ -745,22 +754,18 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_split_kernel(const Po
     }
 
     // ===== group A: scores (all 29 chunks of one residue class per warp), exchange, softmax =====
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;" ::: "memory");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;" ::: "memory");
+    const int mi = lane >> 3, r8 = lane & 7;                            // ldmatrix: this lane addresses row r8 of matrix mi
     const int s = warp;                                                  // residue class for the scores; head for the softmax
     const uint32_t ringA = ip_smem_u32(smem + OFF_RA);
     const uint32_t sc_off = 448u * s + 3600u * r8 + 16u * (mi >> 1);    // + 32 per chunk pair; slab of the pair = mi & 1
+    unsigned slot0 = 0, wrap0 = 0;                                       // ring slot / wrap count of this view's slab 0
     for (int j = 0; j < nviews; ++j) {
         const int bv = blockIdx.x + j * gridDim.x;
         const unsigned wb = j & 1;
         const uint8_t* wbuf = smem + OFF_WA + wb * WBYTES;
         float* spart = reinterpret_cast<float*>(smem + OFF_WA + wb * WBYTES);       // overlay: the planes are dead after the MMAs
         const float* xb = a.xbar + (size_t)bv * C;
-        float ct[8];                                                     // position terms of this warp's head (softmax role)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int t = lane + 32 * i;
-            ct[i] = t < T ? __ldg(a.cterm + ((size_t)bv * HEADS + s) * TP + t) : 0.f;
-        }
         ip_mbar_wait(wfull + wb, (j >> 1) & 1u);
         float acc[29][4];
 #pragma unroll
@@ -770,7 +775,8 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_split_kernel(const Po
         float dotp = 0.f;
 #pragma unroll 1
         for (int p = 0; p < NSLAB / 2; ++p) {
-            const unsigned s0 = (2 * p) & 3, s1 = s0 + 1, n = 2u * j + (p >> 1);
+            const unsigned x = slot0 + 2 * p, over = x >= RA ? 1u : 0u;
+            const unsigned b0 = x - over * RA, b1 = b0 + 1, par = (wrap0 + over) & 1u;
             const int col = ((p * 8 + s) * 4 + q) * 4;
             const uint2 ah = *reinterpret_cast<const uint2*>(wbuf + (g * WPITCH + col) * 2);
             const uint2 al = *reinterpret_cast<const uint2*>(wbuf + (WPLANE + g * WPITCH + col) * 2);
@@ -782,9 +788,9 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_split_kernel(const Po
                 dotp = fmaf(w0, __ldg(xb + ch), dotp); dotp = fmaf(w1, __ldg(xb + ch + 8), dotp);
                 dotp = fmaf(w2, __ldg(xb + ch + 64), dotp); dotp = fmaf(w3, __ldg(xb + ch + 72), dotp);
             }
-            ip_mbar_wait(fullA + s0, n & 1u);
-            ip_mbar_wait(fullA + s1, n & 1u);
-            const uint32_t base = ringA + ((mi & 1) ? s1 : s0) * SLAB_BYTES + sc_off;
+            ip_mbar_wait(fullA + b0, par);
+            ip_mbar_wait(fullA + b1, par);
+            const uint32_t base = ringA + ((mi & 1) ? b1 : b0) * SLAB_BYTES + sc_off;
             uint32_t bf[4];
 #pragma unroll
             for (int m = 0; m < 14; ++m) {
@@ -795,8 +801,11 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_split_kernel(const Po
             ldsm_x2_t(reinterpret_cast<uint32_t(&)[2]>(bf[0]), base + 32 * 14);      // chunk 28
             mma_bf16_16816(acc[28], A, bf[0], bf[1]);
             __syncwarp();
-            if (lane == 0) { ip_mbar_arrive(emptyA + s0); ip_mbar_arrive(emptyA + s1); }
+            if (lane == 0) { ip_mbar_arrive(emptyA + b0); ip_mbar_arrive(emptyA + b1); }
         }
+        slot0 += NSLAB - RA;                                             // 8 loads per view on a ring of 6
+        wrap0 += 1;
+        if (slot0 >= RA) { slot0 -= RA; wrap0 += 1; }
         dotp += __shfl_xor_sync(FULL, dotp, 1);
         dotp += __shfl_xor_sync(FULL, dotp, 2);
         if (q == 0) s0part[s * 8 + g] = dotp;
@@ -837,21 +846,23 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_split_kernel(const Po
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int t = lane + 32 * i;                                 // attention token; spatial token tau = t - 1
+            const float ct = t < T ? __ldg(a.cterm + ((size_t)bv * HEADS + s) * TP + t) : 0.f;   // position term of head s
             float v = -INFINITY;
             if (t == 0) {
                 float s0v = 0.f;
 #pragma unroll
                 for (int w = 0; w < 8; ++w) s0v += s0part[w * 8 + s];
-                v = a.scale * (s0v + ct[i]);
+                v = a.scale * (s0v + ct);
             } else if (t < T) {
                 const float* sp = spart + s * SPITCH + (t - 1);
-                v = a.scale * ((sp[0] + sp[SBUF + 1]) + ct[i]);
+                v = a.scale * ((sp[0] + sp[SBUF + 1]) + ct);
             }
             sv[i] = v;
             mx = fmaxf(mx, v);
         }
         if ((a.debug_skip & 64) && a.dbg) {                              // debug: dump the scaled scores
             float* dbg = a.dbg + (size_t)bv * DBG_PER_VIEW + s * 256;
+#pragma unroll
             for (int i = 0; i < 8; ++i) dbg[lane + 32 * i] = sv[i];
         }
         mx = warp_max(mx);
