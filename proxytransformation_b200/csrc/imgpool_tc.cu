@@ -61,7 +61,7 @@ constexpr int SMEM_BYTES = OFF_BAR + (2 * RING + 4) * 8;
 // The four partial-score buffers (29.7 KB) live only between the score MMAs and the softmax; they overlay the (dead) w_eff
 // planes of the current view plus the adjacent part of the (dead) probability arrays.
 constexpr int SPART_BYTES = 4 * SBUF * 4;
-constexpr int DBG_PER_VIEW = HEADS * 256 + 8 * SBUF;   // floats per view of the PT_POOL_DEBUG=64 dump (PoolArgs::dbg)
+constexpr int DBG_PER_VIEW = HEADS * 256;              // floats per view of the PT_POOL_DEBUG=64 dump (PoolArgs::dbg)
 constexpr int OFF_SPART_EVEN = OFF_W0, OFF_SPART_ODD = OFF_W1 + WBYTES - SPART_BYTES;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(SPART_BYTES <= WBYTES + PBYTES && OFF_SPART_ODD >= OFF_P && OFF_SPART_ODD % 16 == 0, "partial-score overlay");
@@ -259,7 +259,7 @@ struct PoolArgs {
     float scale;
     int pf_dist;                 // L2 prefetch distance of the producer in ring loads (0 = off)
     float* dbg;                  // debug dump area behind the workspace (null unless the caller over-allocated it): per view
-                                 // [8 heads][256] scaled scores, then (two-group kernel) [8 classes][8 heads][232] partial scores
+                                 // [8 heads][256] scaled scores (PT_POOL_DEBUG bit 64; tools/pool_check.py)
     int debug_skip;              // PT_POOL_DEBUG bit mask (1, 2, 4, 16 give garbage results): 1 skip score MMAs, 2 slabs are 16-byte loads
                                  // (no HBM traffic), 4 skip sum MMAs, 8 per-phase cycle trace of CTA 0, 16 skip exchange + softmax
 };
@@ -595,311 +595,6 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
 }
 
 
-// ------------------------------------------------------------------------------------------------ pass B, two-group form
-// Same algebra and channel orders as img_pool_mma_kernel, different schedule (PT_POOL_V2=1): the consumer warps are split
-// into two specialised groups that work on two different views at the same time, and nothing stays resident:
-//   group A (warps 0-7, one residue class each): scores of view j (all 29 token chunks) from a 6-slot ring fed by the
-//            producer (HBM), score exchange, softmax -> probabilities
-//   group B (warps 8-15, one residue class each): weighted sums of view j-1 with the probabilities A handed over.  Its MMA
-//            B operand (k = token, n = channel) needs consecutive tokens of ONE channel per thread, which is how the rows
-//            lie in memory: every thread reads its fragments straight from global memory (L2 hits: group A's pass has just
-//            pulled the view through L2) as 16-byte loads of the aligned chunks u = token + class, no shared memory and no
-//            ldmatrix.  A 16-byte load feeds two MMAs; the token order inside a k-block this induces (thread q of a 32-token
-//            group G holds tokens 32 G + 8 q + 0..7) is matched by the order in which the probability fragments are read.
-//   warp 16: producer of the ring (pass 1)
-// so HBM requests are issued all the time (the ring drains continuously) instead of only while the weighted-sum phase frees
-// slots, and shared memory sees one pass of writes and one of ldmatrix reads per view instead of two each.
-// Registers are redistributed with setmaxnreg: A 128 (116 score accumulators), B 96, producer warpgroup 24
-// (2 x 128 + 2 x 96 + 24 <= 480 per lane and sub-partition, the launch allocation of 5 warps x 96).
-namespace ip2 {
-using namespace ip;
-constexpr int RA = 6;
-constexpr int OFF_RA = 0;
-constexpr int OFF_WA = OFF_RA + RA * SLAB_BYTES;                       // w_eff planes, double-buffered by view parity
-constexpr int OFF_PP = OFF_WA + 2 * WBYTES;                            // probabilities (bf16 hi/lo, two token alignments)
-constexpr int OFF_MS = OFF_PP + PBYTES;                                // s0 partials [8 classes][8 heads], p0 [8]
-constexpr int OFF_BR = OFF_MS + 512;                                   // fullA[6] emptyA[6] wfull[2] wempty[2] pfull pempty
-constexpr int SMEM2_BYTES = OFF_BR + 18 * 8;
-constexpr int SP2_BYTES = 2 * SBUF * 4;                                // two partial-score buffers (token parity of the class)
-constexpr int LDG_DEPTH = 4;                                           // 16-byte loads in flight per thread of group B
-static_assert(SMEM2_BYTES <= 227 * 1024 && SP2_BYTES <= WBYTES, "shared memory budget (v2)");
-}  // namespace ip2
-
-__device__ __forceinline__ uint4 ip_ldg_stream(const uint8_t* p) {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-
-__global__ void __launch_bounds__(ip::THREADS, 1) img_pool_split_kernel(const PoolArgs a) {
-    using namespace ip2;
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* fullA = reinterpret_cast<uint64_t*>(smem + OFF_BR);
-    uint64_t* emptyA = fullA + RA;
-    uint64_t* wfull = emptyA + RA;
-    uint64_t* wempty = wfull + 2;
-    uint64_t* pfull = wempty + 2;
-    uint64_t* pempty = pfull + 1;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    if (tid == 0) {
-        for (int b = 0; b < RA; ++b) { ip_mbar_init(fullA + b, 1); ip_mbar_init(emptyA + b, 8); }
-        for (int b = 0; b < 2; ++b) { ip_mbar_init(wfull + b, 1); ip_mbar_init(wempty + b, 1); }
-        ip_mbar_init(pfull, 8);
-        ip_mbar_init(pempty, 8);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < PBYTES / 4; i += THREADS) reinterpret_cast<uint32_t*>(smem + OFF_PP)[i] = 0u;    // margins stay zero for good
-    __syncthreads();
-    const int nviews = blockIdx.x < a.BV ? (a.BV - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
-    if (warp >= 16) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;" ::: "memory");
-        if (lane != 0 || warp > 16) return;
-        // ===== producer: w_eff planes + the eight slabs of every view (HBM) through the ring =====
-        unsigned slot = 0, ph = 0;
-        for (int j = 0; j < nviews; ++j) {
-            const int bv = blockIdx.x + j * gridDim.x;
-            const unsigned wb = j & 1;
-            ip_mbar_wait(wempty + wb, ((j >> 1) & 1u) ^ 1u);
-            ip_mbar_expect_tx(wfull + wb, WBYTES);
-            ip_bulk_load(smem + OFF_WA + wb * WBYTES, a.wpl + (size_t)bv * 2 * WPLANE, WBYTES, wfull + wb);
-            const uint8_t* view = a.img + (size_t)bv * C * HW * 2;
-            for (int k = 0; k < NSLAB; ++k) {
-                {   // L2 prefetch a.pf_dist slabs ahead (into the next view if need be)
-                    int k2 = k + a.pf_dist, bv2 = bv;
-                    if (k2 >= NSLAB) { k2 -= NSLAB; bv2 += gridDim.x; }
-                    if (a.pf_dist > 0 && bv2 < a.BV) ip_prefetch_l2(a.img + (size_t)bv2 * C * HW * 2 + (size_t)k2 * SLAB_BYTES, SLAB_BYTES);
-                }
-                ip_mbar_wait(emptyA + slot, ph ^ 1u);
-                ip_mbar_expect_tx(fullA + slot, SLAB_BYTES);
-                ip_bulk_load(smem + OFF_RA + slot * SLAB_BYTES, view + (size_t)k * SLAB_BYTES, SLAB_BYTES, fullA + slot);
-                if (++slot == RA) { slot = 0; ph ^= 1u; }
-            }
-        }
-        return;
-    }
-
-    const int g = lane >> 2, q = lane & 3;
-    float* s0part = reinterpret_cast<float*>(smem + OFF_MS);            // [8 classes][8 heads]
-    float* p0 = s0part + 64;                                            // [8]
-
-    if (warp >= 8) {
-        // ===== group B: weighted sums of the view whose probabilities group A has handed over =====
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;" ::: "memory");
-        const int s = warp - 8;
-        // this thread's fragments: channel 64 k + s + 8 g of slab k, chunk 4 G + q of 32-token group G (byte 64 G from here)
-        const size_t lane_off = 448u * s + 3600u * g + 16u * q;
-        for (int j = 0; j < nviews; ++j) {
-            const int bv = blockIdx.x + j * gridDim.x;
-            const uint8_t* vb = a.img + (size_t)bv * C * HW * 2 + lane_off;
-            uint4 buf[LDG_DEPTH];                                        // the first loads of the view do not depend on the probabilities
-#pragma unroll
-            for (int d = 0; d < LDG_DEPTH; ++d) buf[d] = ip_ldg_stream(vb + 64 * d);
-            ip_mbar_wait(pfull, j & 1u);
-            // A fragments: rows g / g + 8 = hi / lo part of head g's probabilities, k slots (2q, 2q+1 | 2q+8, 2q+9) of MMA jj of
-            // group G = tokens u0, u0 + 1 | u0 + 2, u0 + 3 with u0 = 32 G + 8 q + 4 jj (token = u - s, zero outside [0,225))
-            uint32_t PA[8][2][4];
-            {
-                const int e = s & 1;
-                const uint32_t* ph = reinterpret_cast<const uint32_t*>(smem + OFF_PP) + (e * HEADS + g) * (PPITCH / 2) + 4 * q + ((8 + e - s) >> 1);
-                const uint32_t* pl = ph + 2 * HEADS * (PPITCH / 2);
-#pragma unroll
-                for (int G = 0; G < 8; ++G)
-#pragma unroll
-                    for (int jj = 0; jj < 2; ++jj) {
-                        const int wd = 16 * G + 2 * jj;
-                        const bool live = G < 7 || q == 0;               // chunks 29..31 do not exist
-                        PA[G][jj][0] = live ? ph[wd] : 0u; PA[G][jj][1] = live ? pl[wd] : 0u;
-                        PA[G][jj][2] = live ? ph[wd + 1] : 0u; PA[G][jj][3] = live ? pl[wd + 1] : 0u;
-                    }
-            }
-            const float p0g = p0[g];
-            __syncwarp();
-            if (lane == 0) ip_mbar_arrive(pempty);                      // group A may publish the next view's probabilities
-            __nv_bfloat16* yrow = a.ya_hi + ((size_t)bv * HEADS + g) * YA;
-            const float* xb = a.xbar + (size_t)bv * C;
-            float x0n = __ldg(xb + s + 16 * q), x1n = __ldg(xb + s + 16 * q + 8);    // feature means, fetched one slab ahead
-#pragma unroll 1
-            for (int k = 0; k < NSLAB; ++k) {
-                const float x0 = x0n, x1 = x1n;
-                if (k + 1 < NSLAB) { const int ch = (k + 1) * SLAB_CH + s + 16 * q; x0n = __ldg(xb + ch); x1n = __ldg(xb + ch + 8); }
-                const uint8_t* sb = vb + (size_t)k * SLAB_BYTES;
-                float y0[4] = {0.f, 0.f, 0.f, 0.f}, y1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int G = 0; G < 8; ++G) {
-                    const uint4 cur = buf[G % LDG_DEPTH];
-                    mma_bf16_16816(y0, PA[G][0], cur.x, cur.y);
-                    mma_bf16_16816(y1, PA[G][1], cur.z, cur.w);
-                    const int G2 = G + LDG_DEPTH;                        // refill the register slot: this slab, then the next one
-                    uint4 nx = make_uint4(0u, 0u, 0u, 0u);
-                    if (G2 < 7) nx = ip_ldg_stream(sb + 64 * G2);
-                    else if (G2 == 7) { if (q == 0) nx = ip_ldg_stream(sb + 64 * 7); }
-                    else if (k + 1 < NSLAB) {
-                        if (G2 - 8 < 7 || q == 0) nx = ip_ldg_stream(sb + SLAB_BYTES + 64 * (G2 - 8));
-                    }
-                    buf[G % LDG_DEPTH] = nx;
-                }
-                const float v0 = ((y0[0] + y1[0]) + (y0[2] + y1[2])) + p0g * x0;
-                const float v1 = ((y0[1] + y1[1]) + (y0[3] + y1[3])) + p0g * x1;
-                uint32_t h0, l0, h1, l1;
-                split_hi_lo(v0, h0, l0);
-                split_hi_lo(v1, h1, l1);
-                const int col = ((k * 8 + s) * 4 + q) * 2;
-                *reinterpret_cast<uint32_t*>(yrow + col) = h0 | (h1 << 16);
-                *reinterpret_cast<uint32_t*>(yrow + a.ya_plane + col) = l0 | (l1 << 16);
-            }
-        }
-        return;
-    }
-
-    // ===== group A: scores (all 29 chunks of one residue class per warp), exchange, softmax =====
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;" ::: "memory");
-    const int mi = lane >> 3, r8 = lane & 7;                            // ldmatrix: this lane addresses row r8 of matrix mi
-    const int s = warp;                                                  // residue class for the scores; head for the softmax
-    const uint32_t ringA = ip_smem_u32(smem + OFF_RA);
-    const uint32_t sc_off = 448u * s + 3600u * r8 + 16u * (mi >> 1);    // + 32 per chunk pair; slab of the pair = mi & 1
-    unsigned slot0 = 0, wrap0 = 0;                                       // ring slot / wrap count of this view's slab 0
-    for (int j = 0; j < nviews; ++j) {
-        const int bv = blockIdx.x + j * gridDim.x;
-        const unsigned wb = j & 1;
-        const uint8_t* wbuf = smem + OFF_WA + wb * WBYTES;
-        float* spart = reinterpret_cast<float*>(smem + OFF_WA + wb * WBYTES);       // overlay: the planes are dead after the MMAs
-        const float* xb = a.xbar + (size_t)bv * C;
-        ip_mbar_wait(wfull + wb, (j >> 1) & 1u);
-        float acc[29][4];
-#pragma unroll
-        for (int i = 0; i < 29; ++i)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
-        float dotp = 0.f;
-#pragma unroll 1
-        for (int p = 0; p < NSLAB / 2; ++p) {
-            const unsigned x = slot0 + 2 * p, over = x >= RA ? 1u : 0u;
-            const unsigned b0 = x - over * RA, b1 = b0 + 1, par = (wrap0 + over) & 1u;
-            const int col = ((p * 8 + s) * 4 + q) * 4;
-            const uint2 ah = *reinterpret_cast<const uint2*>(wbuf + (g * WPITCH + col) * 2);
-            const uint2 al = *reinterpret_cast<const uint2*>(wbuf + (WPLANE + g * WPITCH + col) * 2);
-            const uint32_t A[4] = {ah.x, al.x, ah.y, al.y};
-            {   // mean-token score s0[g] = w_eff[g] . xbar, this (class, pair) column block
-                const int ch = 128 * p + s + 16 * q;
-                const float w0 = __uint_as_float(ah.x << 16) + __uint_as_float(al.x << 16), w1 = __uint_as_float(ah.x & 0xffff0000u) + __uint_as_float(al.x & 0xffff0000u);
-                const float w2 = __uint_as_float(ah.y << 16) + __uint_as_float(al.y << 16), w3 = __uint_as_float(ah.y & 0xffff0000u) + __uint_as_float(al.y & 0xffff0000u);
-                dotp = fmaf(w0, __ldg(xb + ch), dotp); dotp = fmaf(w1, __ldg(xb + ch + 8), dotp);
-                dotp = fmaf(w2, __ldg(xb + ch + 64), dotp); dotp = fmaf(w3, __ldg(xb + ch + 72), dotp);
-            }
-            ip_mbar_wait(fullA + b0, par);
-            ip_mbar_wait(fullA + b1, par);
-            const uint32_t base = ringA + ((mi & 1) ? b1 : b0) * SLAB_BYTES + sc_off;
-            uint32_t bf[4];
-#pragma unroll
-            for (int m = 0; m < 14; ++m) {
-                ldsm_x4_t(bf, base + 32 * m);
-                mma_bf16_16816(acc[2 * m], A, bf[0], bf[1]);
-                mma_bf16_16816(acc[2 * m + 1], A, bf[2], bf[3]);
-            }
-            ldsm_x2_t(reinterpret_cast<uint32_t(&)[2]>(bf[0]), base + 32 * 14);      // chunk 28
-            mma_bf16_16816(acc[28], A, bf[0], bf[1]);
-            __syncwarp();
-            if (lane == 0) { ip_mbar_arrive(emptyA + b0); ip_mbar_arrive(emptyA + b1); }
-        }
-        slot0 += NSLAB - RA;                                             // 8 loads per view on a ring of 6
-        wrap0 += 1;
-        if (slot0 >= RA) { slot0 -= RA; wrap0 += 1; }
-        dotp += __shfl_xor_sync(FULL, dotp, 1);
-        dotp += __shfl_xor_sync(FULL, dotp, 2);
-        if (q == 0) s0part[s * 8 + g] = dotp;
-        if ((a.debug_skip & 64) && a.dbg) {                              // debug: dump this class's partial scores S_s[h][u]
-            float* dbg = a.dbg + (size_t)bv * DBG_PER_VIEW + HEADS * 256 + s * SBUF + g * SPITCH + 2 * q;
-#pragma unroll
-            for (int i = 0; i < 29; ++i) { dbg[8 * i] = acc[i][0] + acc[i][2]; dbg[8 * i + 1] = acc[i][1] + acc[i][3]; }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");                   // every A warp is done with the planes: the overlay may be written
-        // Partial scores: class s holds S_s[h][u] (token t = u - s).  Two buffers by class parity j2 = s & 1; a class writes
-        // its value for token t at column t + j2, i.e. u - (s - j2): classes 0/1 store, 2/3, 4/5, 6/7 add, one round each.
-        {
-            const int j2 = s & 1, sh2 = s - j2;                          // even column shift: float2 accesses stay aligned
-            // (the column offset goes through an opaque asm: nvcc 12.9 turned `g * SPITCH + (2q - sh2)` into a bitwise OR, which
-            // drops the row term whenever 2q < sh2)
-            int coff = 2 * q + 8 - sh2;
-            asm volatile("" : "+r"(coff));
-            float* dst = spart + j2 * SBUF + g * SPITCH + coff;
-#pragma unroll 1
-            for (int r = 0; r < 4; ++r) {
-                if ((s >> 1) == r) {
-#pragma unroll
-                    for (int i = 0; i < 29; ++i) {
-                        if (8 * i + 2 * q >= sh2) {
-                            float2* d2 = reinterpret_cast<float2*>(dst + 8 * i - 8);
-                            float2 v = make_float2(acc[i][0] + acc[i][2], acc[i][1] + acc[i][3]);
-                            if (r > 0) { const float2 o = *d2; v.x += o.x; v.y += o.y; }
-                            *d2 = v;
-                        }
-                    }
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-            }
-        }
-        // softmax of head s over the 226 tokens (this warp alone: lane owns tokens lane + 32 i)
-        float sv[8];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int t = lane + 32 * i;                                 // attention token; spatial token tau = t - 1
-            const float ct = t < T ? __ldg(a.cterm + ((size_t)bv * HEADS + s) * TP + t) : 0.f;   // position term of head s
-            float v = -INFINITY;
-            if (t == 0) {
-                float s0v = 0.f;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) s0v += s0part[w * 8 + s];
-                v = a.scale * (s0v + ct);
-            } else if (t < T) {
-                const float* sp = spart + s * SPITCH + (t - 1);
-                v = a.scale * ((sp[0] + sp[SBUF + 1]) + ct);
-            }
-            sv[i] = v;
-            mx = fmaxf(mx, v);
-        }
-        if ((a.debug_skip & 64) && a.dbg) {                              // debug: dump the scaled scores
-            float* dbg = a.dbg + (size_t)bv * DBG_PER_VIEW + s * 256;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dbg[lane + 32 * i] = sv[i];
-        }
-        mx = warp_max(mx);
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { sv[i] = (lane + 32 * i) < T ? expf(sv[i] - mx) : 0.f; sum += sv[i]; }
-        sum = warp_sum(sum);
-        const float inv = 1.0f / sum;
-        asm volatile("bar.sync 1, 256;" ::: "memory");                   // all partial scores and s0 partials have been read
-        if (tid == 0) ip_mbar_arrive(wempty + wb);                       // the planes buffer (and the overlay) may be refilled
-        ip_mbar_wait(pempty, (j & 1u) ^ 1u);                             // group B has taken the previous view's probabilities
-        {
-            __nv_bfloat16* ya = a.ya_hi + ((size_t)bv * HEADS + s) * YA + C;
-            unsigned short* pq = reinterpret_cast<unsigned short*>(smem + OFF_PP) + s * PPITCH;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int t = lane + 32 * i;                             // attention token 0..255 (>= 226: zero padding)
-                const float pr = sv[i] * inv;
-                uint32_t hi, lo;
-                split_hi_lo(pr, hi, lo);
-                ya[t] = __ushort_as_bfloat16((unsigned short)hi);
-                ya[a.ya_plane + t] = __ushort_as_bfloat16((unsigned short)lo);
-                if (t == 0) p0[s] = pr;
-                if (t >= 1 && t < T) {
-                    const int x = t - 1 + 8;
-                    pq[x] = (unsigned short)hi;                               // hi, even copy
-                    pq[HEADS * PPITCH + x + 1] = (unsigned short)hi;           // hi, odd copy
-                    pq[2 * HEADS * PPITCH + x] = (unsigned short)lo;           // lo, even copy
-                    pq[3 * HEADS * PPITCH + x + 1] = (unsigned short)lo;       // lo, odd copy
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) ip_mbar_arrive(pfull);
-    }
-}
-
 }  // namespace pt
 extern "C" int pt_debug_pool_events(long long* out, int max_events) {
     unsigned int n = 0;
@@ -1015,16 +710,7 @@ int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, in
         const char* pf = getenv("PT_POOL_PF");
         a.pf_dist = pf ? atoi(pf) : PF_DIST;
         const int grid = BV < sms ? BV : sms;
-        const char* v2e = getenv("PT_POOL_V2");                         // experimental two-group schedule
-        const bool v2 = v2e && atoi(v2e) != 0;
-        if (v2) {
-            static bool attr2[PT_MAX_DEVICES] = {};
-            if (first_use_on_current_device(attr2))
-                PT_CUDA_OK(cudaFuncSetAttribute(img_pool_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ip2::SMEM2_BYTES));
-            { ProfScope prof_(PROF_IMG_POOL, s); img_pool_split_kernel<<<grid, THREADS, ip2::SMEM2_BYTES, s>>>(a); }
-        } else {
-            { ProfScope prof_(PROF_IMG_POOL, s); img_pool_mma_kernel<<<grid, THREADS, SMEM_BYTES + POOL_EV_SMEM, s>>>(a); }
-        }
+        { ProfScope prof_(PROF_IMG_POOL, s); img_pool_mma_kernel<<<grid, THREADS, SMEM_BYTES + POOL_EV_SMEM, s>>>(a); }
         PT_LAUNCH_CHECK();
     }
     {   // G4: z[:, 32h:32h+32] = [y_h | a_h] [W_vc_h | h_v_h]^T   -> split planes only

@@ -1,7 +1,7 @@
 """Stage-level check of the image pool kernels (pass B of S9) against a float64 torch evaluation of the same algebra from
 the kernel's own inputs (w_eff planes, cterm, xbar in the workspace): scaled scores, probabilities, weighted sums.
-Runs img_pool_mma_kernel (PT_POOL_V2=0) and the two-group img_pool_split_kernel (PT_POOL_V2=1) in one process.
-Usage (GPU box): PT_POOL_DEBUG=64 python tools/pool_check.py [views_per_scene] [scenes]"""
+With a third argument it also times the BACK stage at bench size over a sweep of the producer's L2-prefetch distance (PT_POOL_PF).
+Usage (GPU box): python tools/pool_check.py [views_per_scene] [scenes] [time]"""
 import os, sys, torch, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("PT_POOL_DEBUG", "64")
@@ -11,7 +11,7 @@ V = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 C, HW, EMB, HEADS, TP, YA, WPITCH, SP = 512, 225, 256, 8, 228, 768, 528, 232
 WPLANE, SBUF = HEADS * WPITCH, HEADS * SP
-DBG = HEADS * 256 + 8 * SBUF
+DBG = HEADS * 256
 cfg = syn.C2_WIDE.replace(n_views=V)
 m = ProxyTransformationNormReverse(**cfg.module_kwargs()).eval()
 m.load_state_dict(syn.make_state_dict(cfg, 0, bf16_round=True))
@@ -37,8 +37,7 @@ score_ch = torch.tensor(128 * p_ + 64 * (e_ >> 1) + s_ + 16 * q_ + 8 * (e_ & 1),
 sl_, s2_, q2_, e2_ = j // 64, (j // 8) % 8, (j // 2) % 4, j % 2
 sum_ch = torch.tensor(64 * sl_ + s2_ + 16 * q2_ + 8 * e2_, device="cuda")
 
-def run(v2):
-    os.environ["PT_POOL_V2"] = "1" if v2 else "0"
+def run():
     ws = torch.zeros(need + BV * DBG * 4, dtype=torch.uint8, device="cuda")
     out, ws = ops.img_attnpool(img, w["img"], HEADS, params=w["img_struct"], stages=1, ws=ws)
     out, ws = ops.img_attnpool(img, w["img"], HEADS, params=w["img_struct"], stages=2, out=out, ws=ws)
@@ -48,10 +47,8 @@ def run(v2):
 def f32(ws, o, n): return ws[o:o + 4 * n].view(torch.float32)
 def bf(ws, o, n): return ws[o:o + 2 * n].view(torch.bfloat16)
 
-outs = []
-for v2 in (0, 1):
-    out, ws = run(v2)
-    outs.append(out)
+for _ in (0,):
+    out, ws = run()
     X = img.reshape(BV, C, HW).double()
     wpl = bf(ws, o_wpl, BV * 2 * WPLANE).double().reshape(BV, 2, HEADS, WPITCH)[..., :512].sum(1)      # (BV, 8, 512) score order
     weff = torch.zeros(BV, HEADS, C, dtype=torch.float64, device="cuda")
@@ -67,7 +64,7 @@ for v2 in (0, 1):
     ya = bf(ws, o_ya, 2 * BV * HEADS * YA).double().reshape(2, BV, HEADS, YA).sum(0)
     P_k = ya[..., 512:512 + 226]
     Y_k = torch.zeros_like(Y); Y_k[:, :, sum_ch] = ya[..., :512]
-    name = "split" if v2 else "mma"
+    name = "mma"
     print(f"[{name}] scores max err {float((sv_k - sv).abs().max()):.3e}  probs max err {float((P_k - P).abs().max()):.3e}  "
           f"sums max rel err {float(((Y_k - Y).abs().max() / Y.abs().max())):.3e}")
     d = (sv_k - sv).abs()
@@ -75,32 +72,21 @@ for v2 in (0, 1):
     print(f"[{name}] worst view score err {float(d.amax(dim=(1, 2)).max()):.2e} (view {int(d.amax(dim=(1, 2)).argmax())})")
     dy = (Y_k - Y).abs().amax(dim=(0, 1)).reshape(8, 64)
     print(f"[{name}] sums err by slab:", [f"{float(dy[k].max()):.1e}" for k in range(8)])
-    if v2:
-        part = dbg[:, HEADS * 256:].reshape(BV, 8, HEADS, SP).double()                                # [view][class][head][u]
-        for s in range(8):
-            ch = torch.arange(s, C, 8, device="cuda")
-            exp = torch.einsum("vhc,vct->vht", weff[:, :, ch], X[:, ch, :])                           # (BV, 8, 225), tau = u - s
-            got = part[:, s, :, s:s + 225]
-            e = (got - exp).abs()
-            print(f"  class {s}: partial max err {float(e.max()):.2e}  by (u mod 8):", [f"{float(e[..., (r - s) % 8::8].max()):.1e}" for r in range(8)])
-print("final proxies: max |split - mma| =", float((outs[1] - outs[0]).abs().max()))
 
 if len(sys.argv) > 3:                                             # timing: BACK stage (pool + value GEMMs + LayerNorm) at bench size
     Bt, Vt = 64, 196
     imgs = [(torch.relu(torch.randn(Bt, Vt, C, 15, 15, device="cuda")) * 1.5).bfloat16() for _ in range(2)]   # 2 x 2.9 GB >> L2
     needt = _lib.load().pt_img_attnpool_ws_bytes(Bt * Vt, C, HW, EMB, HEADS)
-    for v2 in (0, 1, 0, 1):
-        os.environ["PT_POOL_V2"] = str(v2)
-        wss = [torch.zeros(needt, dtype=torch.uint8, device="cuda") for _ in range(2)]
-        outs_t = [ops.img_attnpool(imgs[k], w["img"], HEADS, params=w["img_struct"], stages=1, ws=wss[k])[0] for k in range(2)]
-        for pf in ([4] if not v2 else [4, 0, 2, 8]):
-            os.environ["PT_POOL_PF"] = str(pf)
-            for k in range(4):
-                ops.img_attnpool(imgs[k & 1], w["img"], HEADS, params=w["img_struct"], stages=2, out=outs_t[k & 1], ws=wss[k & 1])
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for k in range(20):
-                ops.img_attnpool(imgs[k & 1], w["img"], HEADS, params=w["img_struct"], stages=2, out=outs_t[k & 1], ws=wss[k & 1])
-            e1.record(); torch.cuda.synchronize()
-            print(f"BACK stage, {'split' if v2 else 'mma'} kernel, pf={pf}: {e0.elapsed_time(e1) / 20:.4f} ms per {Bt} scenes")
+    wss = [torch.zeros(needt, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    outs_t = [ops.img_attnpool(imgs[k], w["img"], HEADS, params=w["img_struct"], stages=1, ws=wss[k])[0] for k in range(2)]
+    for pf in (4, 0, 2, 6, 8, 10, 4):
+        os.environ["PT_POOL_PF"] = str(pf)
+        for k in range(4):
+            ops.img_attnpool(imgs[k & 1], w["img"], HEADS, params=w["img_struct"], stages=2, out=outs_t[k & 1], ws=wss[k & 1])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(20):
+            ops.img_attnpool(imgs[k & 1], w["img"], HEADS, params=w["img_struct"], stages=2, out=outs_t[k & 1], ws=wss[k & 1])
+        e1.record(); torch.cuda.synchronize()
+        print(f"BACK stage (pool + value GEMMs + LayerNorm), PT_POOL_PF={pf}: {e0.elapsed_time(e1) / 20:.4f} ms per {Bt} scenes")
