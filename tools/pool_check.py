@@ -1,7 +1,7 @@
 """Stage-level check of the image pool kernels (pass B of S9) against a float64 torch evaluation of the same algebra from
 the kernel's own inputs (w_eff planes, cterm, xbar in the workspace): scaled scores, probabilities, weighted sums.
 With a third argument it also times the BACK stage at bench size over a sweep of the producer's L2-prefetch distance (PT_POOL_PF).
-Usage (GPU box): python tools/pool_check.py [views_per_scene] [scenes] [time]"""
+Usage (GPU box): python tools/pool_check.py [views_per_scene] [scenes] [time | comma-separated PT_POOL_PF values]"""
 import os, sys, torch, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("PT_POOL_DEBUG", "64")
@@ -79,14 +79,14 @@ if len(sys.argv) > 3:                                             # timing: BACK
     needt = _lib.load().pt_img_attnpool_ws_bytes(Bt * Vt, C, HW, EMB, HEADS)
     wss = [torch.zeros(needt, dtype=torch.uint8, device="cuda") for _ in range(2)]
     outs_t = [ops.img_attnpool(imgs[k], w["img"], HEADS, params=w["img_struct"], stages=1, ws=wss[k])[0] for k in range(2)]
-    for pf in (4, 0, 2, 6, 8, 10, 4):
+    for pf in ([int(x) for x in sys.argv[3].split(',')] if sys.argv[3][0].isdigit() else (4, 0, 2, 6, 8, 10, 4)):
         os.environ["PT_POOL_PF"] = str(pf)
         for k in range(4):
             ops.img_attnpool(imgs[k & 1], w["img"], HEADS, params=w["img_struct"], stages=2, out=outs_t[k & 1], ws=wss[k & 1])
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for k in range(20):
+        for k in range(40):
             ops.img_attnpool(imgs[k & 1], w["img"], HEADS, params=w["img_struct"], stages=2, out=outs_t[k & 1], ws=wss[k & 1])
         e1.record(); torch.cuda.synchronize()
-        print(f"BACK stage (pool + value GEMMs + LayerNorm), PT_POOL_PF={pf}: {e0.elapsed_time(e1) / 20:.4f} ms per {Bt} scenes")
+        print(f"BACK stage (pool + value GEMMs + LayerNorm), PT_POOL_PF={pf}: {e0.elapsed_time(e1) / 40:.4f} ms per {Bt} scenes")
