@@ -99,7 +99,8 @@ int pt_point_encoder_fused(const float* points, const int32_t* kept_idx, const f
 typedef struct pt_proxy_block_params {
     const float *ln1_w, *ln1_b;       /* (c) */
     const float* pos_bias;            /* (n,c) */
-    const float* qkv_w;               /* (3c,c), no bias */
+    const float* qkv_w;               /* (3c,c) */
+    const float* qkv_b;               /* (3c) or NULL (qkv_bias=False, every shipped config) */
     const float *pp_w, *pp_b;         /* proxy_proj (c,c),(c) */
     const float *proj_w, *proj_b;     /* (c,c),(c) */
     const float *ln2_w, *ln2_b;       /* (c) */

@@ -193,7 +193,7 @@ def proxy_attention(sd, prefix, x, proxy, mask, num_heads):
     hd = c // num_heads
     scale = hd ** -0.5
     x = x + position_bias(sd, prefix, int(c ** 0.5))[None]
-    qkv = F.linear(x, sd[f"{prefix}.qkv.weight"]).reshape(b, n, 3, c).permute(2, 0, 1, 3)
+    qkv = F.linear(x, sd[f"{prefix}.qkv.weight"], sd.get(f"{prefix}.qkv.bias")).reshape(b, n, 3, c).permute(2, 0, 1, 3)   # bias iff qkv_bias (:199)
     pt = F.linear(proxy, sd[f"{prefix}.proxy_proj.weight"], sd[f"{prefix}.proxy_proj.bias"])
     q, k, v = (t.reshape(b, n, num_heads, hd).permute(0, 2, 1, 3) for t in (qkv[0], qkv[1], qkv[2]))
     pt = pt.reshape(b, l, num_heads, hd).permute(0, 2, 1, 3)

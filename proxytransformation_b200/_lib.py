@@ -20,7 +20,7 @@ class PtError(RuntimeError):
 
 class ProxyBlockParams(Structure):
     _fields_ = [(n, c_void_p) for n in (
-        "ln1_w", "ln1_b", "pos_bias", "qkv_w", "pp_w", "pp_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b",
+        "ln1_w", "ln1_b", "pos_bias", "qkv_w", "qkv_b", "pp_w", "pp_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b",
         "fc2_w", "fc2_b", "lno_w", "lno_b", "qkv_w_split", "proj_w_split", "fc1_w_split", "fc2_w_split", "pp_w_split")]
 
 

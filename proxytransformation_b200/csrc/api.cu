@@ -184,6 +184,7 @@ extern "C" int pt_proxy_block_fused(const float* x, const float* proxy, const ui
                 gp.M = rows; gp.N = 3 * c; gp.K = c;
                 gp.a_split = w.u_s; gp.a_rows = rows; gp.a_cols = c; gp.lda = c;
                 gp.w_split = p->qkv_w_split; gp.w_rows = 3 * c; gp.ldw = c;
+                gp.bias = p->qkv_b;
                 gp.c_split = qk_s; gp.cs_plane = (long long)rows * 2 * c; gp.ldcs = 2 * c;
                 gp.ct_split = vt_s; gp.ct_col0 = 2 * c; gp.ct_ld = rows; gp.ct_plane = (long long)c * rows;
                 if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
@@ -205,7 +206,7 @@ extern "C" int pt_proxy_block_fused(const float* x, const float* proxy, const ui
                 return rc;
         } else {
         // [Q|K|V] = u Wqkv^T                                          (:221)
-        if ((rc = gemm(w.u_s, rows, c, p->qkv_w_split, 3 * c, nullptr, nullptr, 0, w.qkv, nullptr))) return rc;
+        if ((rc = gemm(w.u_s, rows, c, p->qkv_w_split, 3 * c, p->qkv_b, nullptr, 0, w.qkv, nullptr))) return rc;
         // Pt = proxy Wp^T + bp                                        (:223)
         if ((rc = split_rows_bf16(proxy, (long long)B * l * c, w.proxy_s, w.proxy_s + (size_t)B * l * c, s))) return rc;
         if ((rc = gemm(w.proxy_s, B * l, c, p->pp_w_split, c, p->pp_b, nullptr, 0, w.pt, nullptr))) return rc;
@@ -224,7 +225,7 @@ extern "C" int pt_proxy_block_fused(const float* x, const float* proxy, const ui
     // u = LN1(x) + bias[m]                                           (:274, :212-217)
     if ((rc = launch_layernorm(x, p->ln1_w, p->ln1_b, p->pos_bias, n, rows, c, w.u, s))) return rc;
     // [Q|K|V] = u Wqkv^T                                             (:221)
-    if ((rc = gemm_any(w.u, p->qkv_w, p->qkv_w_split, nullptr, nullptr, 0, rows, 3 * c, c, w.qkv, w.gemm, w.gemm_bytes, s))) return rc;
+    if ((rc = gemm_any(w.u, p->qkv_w, p->qkv_w_split, p->qkv_b, nullptr, 0, rows, 3 * c, c, w.qkv, w.gemm, w.gemm_bytes, s))) return rc;
     // Pt = proxy Wp^T + bp                                           (:223)
     if ((rc = gemm_any(proxy, p->pp_w, p->pp_w_split, p->pp_b, nullptr, 0, B * l, c, c, w.pt, w.gemm, w.gemm_bytes, s))) return rc;
     // two-stage proxy attention                                      (:225-252)

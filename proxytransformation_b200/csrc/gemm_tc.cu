@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             if (n0 + cc * 32 + j < g.N) {
-                                const float y = __uint_as_float(v[j]);
+                                const float y = __uint_as_float(v[j]) + (bias != nullptr ? __ldg(bias + n0 + cc * 32 + j) : 0.f);
                                 const __nv_bfloat16 hh = __float2bfloat16_rn(y);
                                 dst[(size_t)j * g.ct_ld] = hh;
                                 dst[(size_t)j * g.ct_ld + g.ct_plane] = __float2bfloat16_rn(y - __bfloat162float(hh));

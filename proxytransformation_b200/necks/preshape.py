@@ -112,8 +112,6 @@ class ProxyTransformationNormReverse(nn.Module):
         super().__init__()
         if act_layer is not nn.GELU or norm_layer is not nn.LayerNorm:
             raise NotImplementedError("the CUDA path implements the shipped configuration: GELU(erf) + LayerNorm")
-        if qkv_bias:
-            raise NotImplementedError("qkv_bias=True is not used by any shipped config and is not implemented")
         if embed_dim != 256:
             # the reference hard-wires 256 in SimplifiedPointNet()/OffsetNetwork (:31,:110,:302): any other embed_dim
             # fails at norm1 there as well
@@ -210,6 +208,8 @@ class ProxyTransformationNormReverse(nn.Module):
                          ln2_b=f32(blk.norm2.bias), fc1_w=f32(blk.mlp.fc1.weight), fc1_b=f32(blk.mlp.fc1.bias),
                          fc2_w=f32(blk.mlp.fc2.weight), fc2_b=f32(blk.mlp.fc2.bias), lno_w=f32(out_norm.weight),
                          lno_b=f32(out_norm.bias))
+                if a.qkv.bias is not None:                               # qkv_bias=True (:199; no shipped config sets it)
+                    d["qkv_b"] = f32(a.qkv.bias)
                 if self.use_tensor_cores:
                     for k in ("qkv_w", "proj_w", "fc1_w", "fc2_w", "pp_w"):
                         d[k + "_split"] = ops.split_bf16(d[k])

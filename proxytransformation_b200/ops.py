@@ -131,6 +131,8 @@ def make_block_params(w: Dict[str, torch.Tensor]) -> ProxyBlockParams:
     p = ProxyBlockParams()
     for k in _BLOCK_F32:
         setattr(p, k, _chk(w[k], torch.float32, k))
+    qb = w.get("qkv_b")
+    p.qkv_b = _chk(qb, torch.float32, "qkv_b") if qb is not None else None
     for k in _BLOCK_SPLIT:
         t = w.get(k)
         setattr(p, k, _chk(t, torch.bfloat16, k) if t is not None else None)

@@ -40,6 +40,7 @@ class PreshapeConfig:
     n_text: int = 64          # L
     n_views: int = 196        # V
     box: Tuple[float, float, float] = (24.0, 24.0, 24.0)
+    qkv_bias: bool = False    # :285 (no shipped config sets it)
 
     @property
     def num_cluster(self) -> int:          # M
@@ -61,7 +62,7 @@ class PreshapeConfig:
         return dict(embed_dim=self.embed_dim, num_heads=self.num_heads, n_points=self.n_points,
                     grid_size=self.grid_size, text_blocks=self.text_blocks, img_blocks=self.img_blocks,
                     dynamic_drop_radio=self.dynamic_drop_radio, num_sub=self.num_sub,
-                    input_dim=self.input_dim, img_spacial_dim=self.img_spacial_dim)
+                    input_dim=self.input_dim, img_spacial_dim=self.img_spacial_dim, qkv_bias=self.qkv_bias)
 
     def replace(self, **kw) -> "PreshapeConfig":
         d = asdict(self)
@@ -121,7 +122,7 @@ def state_dict_spec(cfg: PreshapeConfig) -> List[Tuple[str, Tuple[int, ...], str
             spec.append((f"{p}.attn.pb_bias", (1, n, 4, 4), "tn"))
             spec.append((f"{p}.attn.pc_bias", (1, n, s, 1), "tn"))
             spec.append((f"{p}.attn.pr_bias", (1, n, 1, s), "tn"))
-            lin(f"{p}.attn.qkv", 3 * c, c, bias=False)
+            lin(f"{p}.attn.qkv", 3 * c, c, bias=cfg.qkv_bias)
             lin(f"{p}.attn.proxy_proj", c, c)
             lin(f"{p}.attn.proj", c, c)
             ln(f"{p}.norm2")

@@ -3,7 +3,7 @@
 deterministic synthetic scenes/weights of proxytransformation_b200.synthetic.
 
 Run in the build container only (the reference tree does not exist on the GPU box):
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case names ...]
 Each fixture stores the seeds/config needed to regenerate the inputs, every
 intermediate of the path captured from the reference itself, and either the
 full outputs (small cases) or their digests (100k-point cases).
@@ -80,7 +80,10 @@ def capture(net, ref_mod, pts, text_dict, img):
 
 def main():
     ref_mod = ref_shim.load()
+    only = set(sys.argv[1:])          # optional: generate just the named cases (fixtures of the others stay untouched)
     for name, (cfg, batch, first, wseed, mutate, full) in CASES.items():
+        if only and name not in only:
+            continue
         sd = syn.make_state_dict(cfg, wseed)
         pts, text_dict, img = syn.make_inputs(cfg, batch, first)
         if mutate is not None:

@@ -50,6 +50,7 @@ CASES = {
     "c1_blocks3": (C1.replace(name="C1-b3", text_blocks=3, img_blocks=2, n_text=9, n_views=3), 1, 13, 5, None, True),
     "gs5_ragged": (C1.replace(name="gs5", n_points=5003, grid_size=5, dynamic_drop_radio=0.6, n_text=7, n_views=5,
                               num_sub=17), 3, 17, 6, None, True),
+    "c1_qkv_bias": (C1.replace(name="C1-qkvb", qkv_bias=True, text_blocks=2, n_text=11, n_views=3), 2, 21, 10, None, True),
     "c2_wide_b1": (syn.C2_WIDE.replace(n_views=8), 1, 0, 7, None, False),
     "c2_room_b1": (syn.C2_ROOM.replace(n_views=8), 1, 1, 8, None, False),
     "c3_wide_b1": (syn.C3_WIDE.replace(n_views=6), 1, 2, 9, None, False),

@@ -113,10 +113,12 @@ def _block_weights(sd, stack, norm, i):
              ln2_b=cu(sd[f"{p}.norm2.bias"]), fc1_w=cu(sd[f"{p}.mlp.fc1.weight"]), fc1_b=cu(sd[f"{p}.mlp.fc1.bias"]),
              fc2_w=cu(sd[f"{p}.mlp.fc2.weight"]), fc2_b=cu(sd[f"{p}.mlp.fc2.bias"]), lno_w=cu(sd[f"{norm}.{i}.weight"]),
              lno_b=cu(sd[f"{norm}.{i}.bias"]))
+    if f"{a}.qkv.bias" in sd:                      # qkv_bias=True (:199)
+        w["qkv_b"] = cu(sd[f"{a}.qkv.bias"])
     return w
 
 
-@pytest.mark.parametrize("name", ["c1_b2", "c1_blocks3", "gs5_ragged", "c2_wide_b1", "c3_wide_b1"])
+@pytest.mark.parametrize("name", ["c1_b2", "c1_blocks3", "c1_qkv_bias", "gs5_ragged", "c2_wide_b1", "c3_wide_b1"])
 @pytest.mark.parametrize("tc", [False, True], ids=["fp32", "tc3xbf16"])
 def test_proxy_block_on_golden_point_proxies(name, tc):
     """LayerNorm-ed outputs are O(1); tolerance 3e-5 absolute (fp32 CUDA cores) / 1e-4 (3xBF16 tensor cores)."""
