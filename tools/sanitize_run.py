@@ -18,3 +18,17 @@ out = m([p.cuda() for p in pts], {k: v.cuda() for k, v in text_dict.items()}, im
 coords, feats = m.forward_sparse([p.cuda() for p in pts], {k: v.cuda() for k, v in text_dict.items()}, img.cuda(), 0.01)
 torch.cuda.synchronize()
 print("ok", [tuple(o.shape) for o in out], tuple(coords.shape))
+# qkv_bias=True (bias inside the transposed-V epilogue of the QKV GEMM) and the N3 input-side kernel
+cfgb = syn.C1.replace(qkv_bias=True)
+mb = ProxyTransformationNormReverse(**cfgb.module_kwargs()).eval()
+mb.load_state_dict(syn.make_state_dict(cfgb, 1))
+mb = mb.cuda()
+ptsb, tdb, imgb = syn.make_inputs(cfgb, 2, first_scene=3)
+outb = mb([p.cuda() for p in ptsb], {k: v.cuda() for k, v in tdb.items()}, imgb.cuda())        # fp32 features: generic pool kernels
+from proxytransformation_b200 import ops
+views = [torch.rand(300 + 97 * v, 3) for v in range(5)]
+ext = torch.eye(4).repeat(5, 1, 1)
+ext[:, :3, 3] = torch.rand(5, 3)
+agg = ops.aggregate_sample([v.cuda() for v in views], ext, torch.randint(0, sum(len(v) for v in views), (4096,)).cuda())
+torch.cuda.synchronize()
+print("ok", [tuple(o.shape) for o in outb], tuple(agg.shape))
