@@ -313,49 +313,73 @@ __global__ void cluster_dropout_kernel(const float* __restrict__ centres, const 
         flag[i] = 0;
     }
     __syncthreads();
-    // :393 farthest point sampling of n_drop centres (pytorch3d semantics; in-tree pin :577-614)
-    float px[FPS_PER], py[FPS_PER], pz[FPS_PER], dmin[FPS_PER];
-#pragma unroll
-    for (int r = 0; r < FPS_PER; ++r) {
-        const int p = tid + r * T;
-        px[r] = p < keep1 ? ux[p] : 0.f; py[r] = p < keep1 ? uy[p] : 0.f; pz[r] = p < keep1 ? uz[p] : 0.f;
-        dmin[r] = INFINITY;
-    }
-    int last = 0;
-    if (tid == 0) sel[0] = 0;
-    for (int k = 1; k < n_drop; ++k) {
-        const float lx = ux[last], ly = uy[last], lz = uz[last];
-        // arg-max key = (distance bits, ~index): non-negative floats order like their bit patterns, ~index makes the FIRST
-        // maximum win; the two halves are reduced with redux.sync (one instruction each) instead of 64-bit shuffle trees
-        unsigned bh = 0u, bl = 0u;
+    // :393 farthest point sampling of n_drop centres (pytorch3d semantics; in-tree pin :577-614).  A round is a dependent
+    // chain (distances -> arg-max -> next centre), so its latency is what counts: only the first TF threads take part
+    // (TF = 128 / 256 / T by keep1: fewer warps make the cross-warp step cheaper, nper slots per thread actually used) and
+    // they meet at a named barrier of their own.
+    const int TF = keep1 <= 128 * FPS_PER ? 128 : (keep1 <= 256 * FPS_PER ? 256 : T);
+    if (tid < TF) {
+        const int nper = (keep1 + TF - 1) / TF, nwf = TF >> 5;
+        float px[FPS_PER], py[FPS_PER], pz[FPS_PER], dmin[FPS_PER];
 #pragma unroll
         for (int r = 0; r < FPS_PER; ++r) {
-            const int p = tid + r * T;
-            if (p < keep1) {
-                const float d = dist2_rn(lx, ly, lz, px[r], py[r], pz[r]);
-                dmin[r] = d < dmin[r] ? d : dmin[r];
-                const unsigned kh = __float_as_uint(dmin[r]), kl2 = 0xffffffffu - (unsigned)p;
-                if (kh > bh || (kh == bh && kl2 > bl)) { bh = kh; bl = kl2; }
+            const int p = tid + r * TF;
+            px[r] = p < keep1 ? ux[p] : 0.f; py[r] = p < keep1 ? uy[p] : 0.f; pz[r] = p < keep1 ? uz[p] : 0.f;
+            dmin[r] = INFINITY;
+        }
+        int last = 0;
+        if (tid == 0) sel[0] = 0;
+        for (int k = 1; k < n_drop; ++k) {
+            const float lx = ux[last], ly = uy[last], lz = uz[last];
+            // arg-max key = (distance bits, ~index): non-negative floats order like their bit patterns, ~index makes the FIRST
+            // maximum win; the two halves are reduced with redux.sync (one instruction each) instead of 64-bit shuffle trees
+            unsigned long long best = 0ull;
+#pragma unroll
+            for (int r = 0; r < FPS_PER; ++r) {
+                if (r < nper) {                                // uniform
+                    const int p = tid + r * TF;
+                    const float d = dist2_rn(lx, ly, lz, px[r], py[r], pz[r]);
+                    dmin[r] = d < dmin[r] ? d : dmin[r];
+                    const unsigned long long key = p < keep1 ? (((unsigned long long)__float_as_uint(dmin[r]) << 32) | (0xffffffffu - (unsigned)p)) : 0ull;
+                    best = key > best ? key : best;
+                }
             }
-        }
-        {
-            const unsigned mh = __reduce_max_sync(FULL, bh);
-            const unsigned ml = __reduce_max_sync(FULL, bh == mh ? bl : 0u);
             unsigned long long* slot = red + (k & 1) * 32;
-            if (lane == 0) slot[wid] = ((unsigned long long)mh << 32) | ml;
+            {
+                // warp arg-max: one redux on the distance bits; the index half needs a second one only when several lanes
+                // hold the maximal distance (duplicated centres), otherwise the single winner lane publishes its own key
+                const unsigned bh = (unsigned)(best >> 32), bl = (unsigned)best;
+                const unsigned mh = __reduce_max_sync(FULL, bh);
+                const unsigned tie = __ballot_sync(FULL, bh == mh);
+                if (__popc(tie) == 1) {
+                    if (bh == mh) slot[wid] = best;
+                } else {
+                    const unsigned ml = __reduce_max_sync(FULL, bh == mh ? bl : 0u);
+                    if (lane == 0) slot[wid] = ((unsigned long long)mh << 32) | ml;
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(TF) : "memory");
+            unsigned long long v;
+            if (nwf <= 8) {                                    // every thread combines the 4 / 8 warp results itself
+                const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(slot);
+                const ulonglong2 a = s2[0], b2 = s2[1];
+                unsigned long long m0 = a.x > a.y ? a.x : a.y, m1 = b2.x > b2.y ? b2.x : b2.y;
+                if (nwf == 8) {
+                    const ulonglong2 c = s2[2], d = s2[3];
+                    const unsigned long long m2 = c.x > c.y ? c.x : c.y, m3 = d.x > d.y ? d.x : d.y;
+                    m0 = m0 > m2 ? m0 : m2; m1 = m1 > m3 ? m1 : m3;
+                }
+                v = m0 > m1 ? m0 : m1;
+            } else {
+                const unsigned long long w = lane < nwf ? slot[lane] : 0ull;
+                const unsigned wh = (unsigned)(w >> 32), wl = (unsigned)w;
+                const unsigned mh = __reduce_max_sync(FULL, wh);
+                const unsigned ml = __reduce_max_sync(FULL, wh == mh ? wl : 0u);
+                v = ((unsigned long long)mh << 32) | ml;
+            }
+            last = (int)(0xffffffffu - (unsigned)(v & 0xffffffffull));
+            if (tid == 0) sel[k] = last;
         }
-        __syncthreads();
-        unsigned long long v;
-        {
-            const unsigned long long* slot = red + (k & 1) * 32;
-            const unsigned long long w = lane < (T >> 5) ? slot[lane] : 0ull;
-            const unsigned wh = (unsigned)(w >> 32), wl = (unsigned)w;
-            const unsigned mh = __reduce_max_sync(FULL, wh);
-            const unsigned ml = __reduce_max_sync(FULL, wh == mh ? wl : 0u);
-            v = ((unsigned long long)mh << 32) | ml;
-        }
-        last = (int)(0xffffffffu - (unsigned)(v & 0xffffffffull));
-        if (tid == 0) sel[k] = last;
     }
     __syncthreads();
     for (int k = tid; k < n_drop; k += T) flag[sel[k]] = 1;
