@@ -262,6 +262,81 @@ __global__ void __launch_bounds__(MLP_WARPS * 32) cluster_mlp_kernel(
 // ordered complement -> gathers.
 constexpr int FPS_PER = 8;
 
+// The FPS rounds of one scene, run by the first TF threads of the CTA (a multiple of 32; they meet at named barrier 1).
+// A round is one dependent chain (distances to the last pick -> running minima -> arg-max -> next pick) and the kernel is
+// bound by its latency (ncu: ~5 cycles per issued instruction with two warps per scheduler), so the body is straight-line
+// code with NPER independent distance chains per thread and as few instructions as possible: slots past keep1 keep a
+// running minimum of 0 and therefore lose every comparison (a valid point with distance 0 still wins on the index half),
+// no per-round validity test.  Arg-max key = (distance bits, ~index): non-negative floats order like their bit patterns and
+// ~index makes the FIRST maximum win (pytorch3d / the in-tree pin :577-614).
+template <int NPER>
+__device__ __forceinline__ void fps_rounds(const float* ux, const float* uy, const float* uz, int keep1, int n_drop, int TF,
+                                           unsigned long long* red, int* sel) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwf = TF >> 5;
+    float px[NPER], py[NPER], pz[NPER], dmin[NPER];
+#pragma unroll
+    for (int r = 0; r < NPER; ++r) {
+        const int p = tid + r * TF;
+        const bool ok = p < keep1;
+        px[r] = ok ? ux[p] : 0.f; py[r] = ok ? uy[p] : 0.f; pz[r] = ok ? uz[p] : 0.f;
+        dmin[r] = ok ? INFINITY : 0.f;
+    }
+    const unsigned nt = 0xffffffffu - (unsigned)tid;
+    int last = 0;
+    if (tid == 0) sel[0] = 0;
+    for (int k = 1; k < n_drop; ++k) {
+        const float lx = ux[last], ly = uy[last], lz = uz[last];
+        unsigned kh[NPER];
+#pragma unroll
+        for (int r = 0; r < NPER; ++r) {
+            const float d = dist2_rn(lx, ly, lz, px[r], py[r], pz[r]);
+            dmin[r] = fminf(d, dmin[r]);
+            kh[r] = __float_as_uint(dmin[r]);
+        }
+        unsigned bh = kh[0], bl = nt;                         // lower slots hold lower indices: strict > keeps the first maximum
+#pragma unroll
+        for (int r = 1; r < NPER; ++r) {
+            const bool gt = kh[r] > bh;
+            bh = gt ? kh[r] : bh;
+            bl = gt ? nt - (unsigned)(r * TF) : bl;
+        }
+        unsigned long long* slot = red + (k & 1) * 32;
+        {
+            // warp arg-max: one redux on the distance bits; the index half needs a second one only when several lanes hold the
+            // maximal distance (duplicated centres), otherwise the single winner lane publishes its own key
+            const unsigned mh = __reduce_max_sync(FULL, bh);
+            const unsigned tie = __ballot_sync(FULL, bh == mh);
+            if (__popc(tie) == 1) {
+                if (bh == mh) slot[wid] = ((unsigned long long)bh << 32) | bl;
+            } else {
+                const unsigned ml = __reduce_max_sync(FULL, bh == mh ? bl : 0u);
+                if (lane == 0) slot[wid] = ((unsigned long long)mh << 32) | ml;
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(TF) : "memory");
+        unsigned long long v;
+        if (nwf <= 8) {                                        // every thread combines the 4 / 8 warp results itself
+            const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(slot);
+            const ulonglong2 a = s2[0], b2 = s2[1];
+            unsigned long long m0 = a.x > a.y ? a.x : a.y, m1 = b2.x > b2.y ? b2.x : b2.y;
+            if (nwf == 8) {
+                const ulonglong2 c = s2[2], d = s2[3];
+                const unsigned long long m2 = c.x > c.y ? c.x : c.y, m3 = d.x > d.y ? d.x : d.y;
+                m0 = m0 > m2 ? m0 : m2; m1 = m1 > m3 ? m1 : m3;
+            }
+            v = m0 > m1 ? m0 : m1;
+        } else {
+            const unsigned long long w = lane < nwf ? slot[lane] : 0ull;
+            const unsigned wh = (unsigned)(w >> 32), wl = (unsigned)w;
+            const unsigned mh = __reduce_max_sync(FULL, wh);
+            const unsigned ml = __reduce_max_sync(FULL, wh == mh ? wl : 0u);
+            v = ((unsigned long long)mh << 32) | ml;
+        }
+        last = (int)(0xffffffffu - (unsigned)(v & 0xffffffffull));
+        if (tid == 0) sel[k] = last;
+    }
+}
+
 __global__ void cluster_dropout_kernel(const float* __restrict__ centres, const int32_t* __restrict__ idx, int M, int K,
                                        int keep1, int n_keep, int32_t* __restrict__ kept_src,
                                        float* __restrict__ kept_centres, int32_t* __restrict__ kept_idx,
@@ -319,66 +394,15 @@ __global__ void cluster_dropout_kernel(const float* __restrict__ centres, const 
     // they meet at a named barrier of their own.
     const int TF = keep1 <= 128 * FPS_PER ? 128 : (keep1 <= 256 * FPS_PER ? 256 : T);
     if (tid < TF) {
-        const int nper = (keep1 + TF - 1) / TF, nwf = TF >> 5;
-        float px[FPS_PER], py[FPS_PER], pz[FPS_PER], dmin[FPS_PER];
-#pragma unroll
-        for (int r = 0; r < FPS_PER; ++r) {
-            const int p = tid + r * TF;
-            px[r] = p < keep1 ? ux[p] : 0.f; py[r] = p < keep1 ? uy[p] : 0.f; pz[r] = p < keep1 ? uz[p] : 0.f;
-            dmin[r] = INFINITY;
-        }
-        int last = 0;
-        if (tid == 0) sel[0] = 0;
-        for (int k = 1; k < n_drop; ++k) {
-            const float lx = ux[last], ly = uy[last], lz = uz[last];
-            // arg-max key = (distance bits, ~index): non-negative floats order like their bit patterns, ~index makes the FIRST
-            // maximum win; the two halves are reduced with redux.sync (one instruction each) instead of 64-bit shuffle trees
-            unsigned long long best = 0ull;
-#pragma unroll
-            for (int r = 0; r < FPS_PER; ++r) {
-                if (r < nper) {                                // uniform
-                    const int p = tid + r * TF;
-                    const float d = dist2_rn(lx, ly, lz, px[r], py[r], pz[r]);
-                    dmin[r] = d < dmin[r] ? d : dmin[r];
-                    const unsigned long long key = p < keep1 ? (((unsigned long long)__float_as_uint(dmin[r]) << 32) | (0xffffffffu - (unsigned)p)) : 0ull;
-                    best = key > best ? key : best;
-                }
-            }
-            unsigned long long* slot = red + (k & 1) * 32;
-            {
-                // warp arg-max: one redux on the distance bits; the index half needs a second one only when several lanes
-                // hold the maximal distance (duplicated centres), otherwise the single winner lane publishes its own key
-                const unsigned bh = (unsigned)(best >> 32), bl = (unsigned)best;
-                const unsigned mh = __reduce_max_sync(FULL, bh);
-                const unsigned tie = __ballot_sync(FULL, bh == mh);
-                if (__popc(tie) == 1) {
-                    if (bh == mh) slot[wid] = best;
-                } else {
-                    const unsigned ml = __reduce_max_sync(FULL, bh == mh ? bl : 0u);
-                    if (lane == 0) slot[wid] = ((unsigned long long)mh << 32) | ml;
-                }
-            }
-            asm volatile("bar.sync 1, %0;" ::"r"(TF) : "memory");
-            unsigned long long v;
-            if (nwf <= 8) {                                    // every thread combines the 4 / 8 warp results itself
-                const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(slot);
-                const ulonglong2 a = s2[0], b2 = s2[1];
-                unsigned long long m0 = a.x > a.y ? a.x : a.y, m1 = b2.x > b2.y ? b2.x : b2.y;
-                if (nwf == 8) {
-                    const ulonglong2 c = s2[2], d = s2[3];
-                    const unsigned long long m2 = c.x > c.y ? c.x : c.y, m3 = d.x > d.y ? d.x : d.y;
-                    m0 = m0 > m2 ? m0 : m2; m1 = m1 > m3 ? m1 : m3;
-                }
-                v = m0 > m1 ? m0 : m1;
-            } else {
-                const unsigned long long w = lane < nwf ? slot[lane] : 0ull;
-                const unsigned wh = (unsigned)(w >> 32), wl = (unsigned)w;
-                const unsigned mh = __reduce_max_sync(FULL, wh);
-                const unsigned ml = __reduce_max_sync(FULL, wh == mh ? wl : 0u);
-                v = ((unsigned long long)mh << 32) | ml;
-            }
-            last = (int)(0xffffffffu - (unsigned)(v & 0xffffffffull));
-            if (tid == 0) sel[k] = last;
+        switch ((keep1 + TF - 1) / TF) {               // slots per thread, compile-time inside the rounds
+            case 1: fps_rounds<1>(ux, uy, uz, keep1, n_drop, TF, red, sel); break;
+            case 2: fps_rounds<2>(ux, uy, uz, keep1, n_drop, TF, red, sel); break;
+            case 3: fps_rounds<3>(ux, uy, uz, keep1, n_drop, TF, red, sel); break;
+            case 4: fps_rounds<4>(ux, uy, uz, keep1, n_drop, TF, red, sel); break;
+            case 5: fps_rounds<5>(ux, uy, uz, keep1, n_drop, TF, red, sel); break;
+            case 6: fps_rounds<6>(ux, uy, uz, keep1, n_drop, TF, red, sel); break;
+            case 7: fps_rounds<7>(ux, uy, uz, keep1, n_drop, TF, red, sel); break;
+            default: fps_rounds<FPS_PER>(ux, uy, uz, keep1, n_drop, TF, red, sel); break;
         }
     }
     __syncthreads();
