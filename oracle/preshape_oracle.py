@@ -11,7 +11,13 @@ Pinned semantics where the reference is order-dependent:
   * ``torch.argsort`` at :378 -> ``stable=True`` (ties broken by cluster index);
   * ``pt_replace`` :495 (index_put_ with duplicate destinations) -> the write
     with the largest flat ``(m, k)`` index wins;
-  * eval mode, fp32, no autograd.
+  * eval mode, fp32, no autograd — the mode the CUDA path implements.
+
+Training mode (oracle side only so far): ``forward(..., train={})`` evaluates the BatchNorm layers with
+batch statistics (:72,:112,:326-330 in ``train()``), returns their updated running statistics in ``train["bn"]`` and keeps
+the whole computation differentiable for torch autograd (index work is done on detached tensors, the scatter is an
+index_put on unique destinations), with every stochastic layer at rate 0 (Dropout / DropPath need the reference's RNG
+stream and are not restated).  Pinned against the reference in ``train()`` mode by tests/golden/c1_train.npz.
 """
 from __future__ import annotations
 
@@ -49,9 +55,11 @@ def _geom():
 # ----------------------------------------------------------------------------- pytorch3d boundary
 def ball_query(p1: torch.Tensor, p2: torch.Tensor, K: int, radius: float = RADIUS, want_scanned: bool = False):
     """pytorch3d.ops.ball_query(p1, p2, K, radius) semantics (:56, :65): first K
-    indices of p2 in ascending order with d2 < r^2; idx pad -1; knn pad 0.0."""
-    p1 = p1.contiguous().float()
-    p2 = p2.contiguous().float()
+    indices of p2 in ascending order with d2 < r^2; idx pad -1; knn pad 0.0.
+    Index work on detached tensors: no gradient flows through the search (idx is an integer output and the gathered
+    points come from p2, which carries no gradient on this path)."""
+    p1 = p1.detach().contiguous().float()
+    p2 = p2.detach().contiguous().float()
     B, M, _ = p1.shape
     N = p2.shape[1]
     idx = torch.empty(B, M, K, dtype=torch.int64)
@@ -87,7 +95,7 @@ def masked_gather(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 
 def farthest_point_indices(pts: torch.Tensor, K: int) -> torch.Tensor:
     """pytorch3d.ops.sample_farthest_points(points, K=K)[1] (:393; in-tree pin :527-625)."""
-    pts = pts.contiguous().float()
+    pts = pts.detach().contiguous().float()
     B, P, _ = pts.shape
     out = torch.empty(B, K, dtype=torch.int64)
     scratch = torch.empty(P, dtype=torch.float32)
@@ -116,26 +124,39 @@ def _cluster_features(centre: torch.Tensor, cluster: torch.Tensor) -> torch.Tens
     return torch.cat([rel, cluster], dim=-1)
 
 
-def _conv_bn_relu(sd: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor) -> torch.Tensor:
-    """nn.Sequential(Conv2d(6,256,1), BatchNorm2d(256) [eval], ReLU) on (b,m,k,6) -> (b,256,m,k)."""
+def _batch_norm(sd: Dict[str, torch.Tensor], prefix: str, y: torch.Tensor, train: Optional[dict]) -> torch.Tensor:
+    """BatchNorm over dim 1.  eval (``train is None``): running statistics.  train(): batch statistics (biased variance)
+    and the running statistics after this step (momentum 0.1, unbiased variance, num_batches_tracked + 1) recorded in
+    ``train["bn"]`` under the state_dict keys — what nn.BatchNorm{1,2}d does in train() mode."""
+    if train is None:
+        return F.batch_norm(y, sd[f"{prefix}.running_mean"], sd[f"{prefix}.running_var"], sd[f"{prefix}.weight"],
+                            sd[f"{prefix}.bias"], training=False, eps=BN_EPS)
+    rm, rv = sd[f"{prefix}.running_mean"].detach().clone(), sd[f"{prefix}.running_var"].detach().clone()
+    out = F.batch_norm(y, rm, rv, sd[f"{prefix}.weight"], sd[f"{prefix}.bias"], training=True, momentum=0.1, eps=BN_EPS)
+    upd = train.setdefault("bn", {})
+    upd[f"{prefix}.running_mean"], upd[f"{prefix}.running_var"] = rm, rv
+    upd[f"{prefix}.num_batches_tracked"] = sd[f"{prefix}.num_batches_tracked"] + 1
+    return out
+
+
+def _conv_bn_relu(sd: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor, train: Optional[dict] = None) -> torch.Tensor:
+    """nn.Sequential(Conv2d(6,256,1), BatchNorm2d(256), ReLU) on (b,m,k,6) -> (b,256,m,k)."""
     y = F.conv2d(x.permute(0, 3, 1, 2), sd[f"{prefix}.0.weight"], sd[f"{prefix}.0.bias"])
-    y = F.batch_norm(y, sd[f"{prefix}.1.running_mean"], sd[f"{prefix}.1.running_var"], sd[f"{prefix}.1.weight"],
-                     sd[f"{prefix}.1.bias"], training=False, eps=BN_EPS)
-    return F.relu(y)
+    return F.relu(_batch_norm(sd, f"{prefix}.1", y, train))
 
 
-def offset_network(sd, centre, cluster, prefix="get_deformable_cluster.get_offsets"):
+def offset_network(sd, centre, cluster, prefix="get_deformable_cluster.get_offsets", train=None):
     """:87-107 -> raw offsets (b,m,3) (before tanh*4)."""
-    y = _conv_bn_relu(sd, f"{prefix}.mlp", _cluster_features(centre, cluster))
+    y = _conv_bn_relu(sd, f"{prefix}.mlp", _cluster_features(centre, cluster), train)
     z = y.mean(dim=-1)                                       # (b,256,m), padded slots included
     return F.conv1d(z, sd[f"{prefix}.channel_mapper.weight"]).transpose(-2, -1)
 
 
-def deform_cluster(sd, P, gs, K, trace=None):
+def deform_cluster(sd, P, gs, K, trace=None, train=None):
     """:53-67 DeformablePointCluster.forward."""
     c0, mn, mx = grid_prior(P, gs)
     idx1, knn1 = ball_query(c0, P, K)
-    raw = offset_network(sd, c0, knn1)
+    raw = offset_network(sd, c0, knn1, train=train)
     off = raw.tanh() * MARGIN
     c1 = c0 + off
     cc = torch.max(torch.min(c1, mx), mn)
@@ -172,9 +193,9 @@ def cluster_dropout(cluster, centre, idx, ddr: float, trace=None):
 
 
 # ----------------------------------------------------------------------------- S6 point proxies
-def point_encoder(sd, centre, cluster, prefix="simple_encoder"):
+def point_encoder(sd, centre, cluster, prefix="simple_encoder", train=None):
     """:126-142 -> (b,n,256), max over K of ReLU(BN(conv))."""
-    y = _conv_bn_relu(sd, f"{prefix}.mlp", _cluster_features(centre, cluster))
+    y = _conv_bn_relu(sd, f"{prefix}.mlp", _cluster_features(centre, cluster), train)
     return y.permute(0, 2, 3, 1).max(dim=2)[0]
 
 
@@ -228,11 +249,10 @@ def branch(sd, stack, norm, n_blocks, pp, proxy, mask, num_heads, faithful_cost=
     return out
 
 
-def head(sd, lin, bn, g):
-    """:445-446 / :454-455 — Linear then BatchNorm1d(eval) over the channel dim."""
+def head(sd, lin, bn, g, train=None):
+    """:445-446 / :454-455 — Linear then BatchNorm1d over the channel dim."""
     y = F.linear(g, sd[f"{lin}.weight"], sd[f"{lin}.bias"])
-    return F.batch_norm(y.transpose(-2, -1), sd[f"{bn}.running_mean"], sd[f"{bn}.running_var"], sd[f"{bn}.weight"],
-                        sd[f"{bn}.bias"], training=False, eps=BN_EPS).transpose(-2, -1)
+    return _batch_norm(sd, bn, y.transpose(-2, -1), train).transpose(-2, -1)
 
 
 # ----------------------------------------------------------------------------- S9 image proxies
@@ -270,9 +290,7 @@ def affine(transform, translate, centre, cluster):
     return (T @ (cluster - tc).transpose(-2, -1)).transpose(-2, -1) + tc + translate.unsqueeze(-2)
 
 
-def scatter_last_writer_wins(P: torch.Tensor, idx: torch.Tensor, new: torch.Tensor) -> torch.Tensor:
-    """:472-498 with the pinned duplicate rule: numpy fancy assignment applies
-    repeated indices in order, so the largest flat (m,k) wins."""
+def _scatter_numpy(P: torch.Tensor, idx: torch.Tensor, new: torch.Tensor) -> torch.Tensor:
     out = P.clone().numpy()
     idx_np, new_np = idx.numpy(), new.numpy()
     for b in range(P.shape[0]):
@@ -280,6 +298,39 @@ def scatter_last_writer_wins(P: torch.Tensor, idx: torch.Tensor, new: torch.Tens
         valid = flat != -1
         out[b][flat[valid]] = new_np[b].reshape(-1, 3)[valid]
     return torch.from_numpy(out)
+
+
+class _ScatterTrain(torch.autograd.Function):
+    """Training-mode form of the scatter: forward = the pinned last-writer-wins result; backward = what autograd does for
+    the reference's ``p2[batch, idx] = cluster`` (:495, index_put_ without accumulate): EVERY valid source slot receives
+    the gradient of the destination it was written to — also the slots a later duplicate overwrote — and the overwritten
+    destinations of ``p2`` receive none."""
+
+    @staticmethod
+    def forward(ctx, P, idx, new):
+        ctx.save_for_backward(idx)
+        return _scatter_numpy(P.detach(), idx, new.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        B, M, K = idx.shape
+        flat = idx.reshape(B, M * K)
+        valid = flat != -1
+        src = torch.gather(g, 1, flat.clamp(min=0)[..., None].expand(-1, -1, 3))
+        g_new = src.masked_fill(~valid[..., None], 0.0).reshape(B, M, K, 3)
+        g_P = g.clone()
+        for b in range(B):
+            g_P[b, flat[b][valid[b]]] = 0.0
+        return g_P, None, g_new
+
+
+def scatter_last_writer_wins(P: torch.Tensor, idx: torch.Tensor, new: torch.Tensor) -> torch.Tensor:
+    """:472-498 with the pinned duplicate rule: numpy fancy assignment applies
+    repeated indices in order, so the largest flat (m,k) wins."""
+    if new.requires_grad or P.requires_grad:
+        return _ScatterTrain.apply(P, idx, new)
+    return _scatter_numpy(P, idx, new)
 
 
 def remove_points(P: torch.Tensor, drop_idx: torch.Tensor) -> List[torch.Tensor]:
@@ -332,20 +383,20 @@ def batch_sparse_collate(points: List[torch.Tensor], voxel_size: float, reciproc
 def forward(sd: Dict[str, torch.Tensor], points: List[torch.Tensor], text_dict, img_feat: Optional[torch.Tensor], *,
             grid_size: int, dynamic_drop_radio: float, text_blocks: int, img_blocks: int, num_sub: int = 30,
             num_heads: int = 8, img_proxy: Optional[torch.Tensor] = None, faithful_cost: bool = False,
-            trace: Optional[dict] = None) -> List[torch.Tensor]:
+            trace: Optional[dict] = None, train: Optional[dict] = None) -> List[torch.Tensor]:
     """:424-469.  ``img_proxy`` (B,V,256) may be given instead of ``img_feat`` to
-    time/check the core region."""
+    time/check the core region.  ``train`` (a dict): train() mode semantics, see the module docstring."""
     P = torch.stack([p.float() for p in points], 0)                                       # :426-427
-    centre, cluster, idx = deform_cluster(sd, P, grid_size, num_sub, trace)               # :430
+    centre, cluster, idx = deform_cluster(sd, P, grid_size, num_sub, trace, train)        # :430
     cluster, centre, idx, drop_idx = cluster_dropout(cluster, centre, idx, dynamic_drop_radio, trace)   # :433
-    pp = point_encoder(sd, centre, cluster)                                               # :437
+    pp = point_encoder(sd, centre, cluster, train=train)                                  # :437
     text, mask = tuple(text_dict.values())                                                # :332-333, :440
     tg = branch(sd, "textformer", "text_norm", text_blocks, pp, text.float(), mask, num_heads, faithful_cost)
-    translate = head(sd, "text_trans", "text_trans_norm", tg)                             # :445-446
+    translate = head(sd, "text_trans", "text_trans_norm", tg, train)                      # :445-446
     if img_proxy is None:
         img_proxy = image_proxies(sd, img_feat, num_heads, faithful_cost)                 # :449
     ig = branch(sd, "imgformer", "img_norm", img_blocks, pp, img_proxy, None, num_heads, faithful_cost)
-    transform = head(sd, "img_trans", "img_trans_norm", ig)                               # :454-455
+    transform = head(sd, "img_trans", "img_trans_norm", ig, train)                        # :454-455
     new = affine(transform, translate, centre, cluster)                                   # :459-462
     P2 = scatter_last_writer_wins(P, idx, new)                                            # :465
     out = remove_points(P2, drop_idx)                                                     # :467

@@ -70,3 +70,25 @@ def load_case(name: str):
 
 SMALL_CASES = [k for k, v in CASES.items() if v[5]]
 LARGE_CASES = [k for k, v in CASES.items() if not v[5]]
+
+
+# ---- training-mode pin (oracle side): tests/golden/make_golden_train.py -> c1_train.npz
+TRAIN_CASE = (C1.replace(name="C1-train", text_blocks=2, img_blocks=2, n_text=9, n_views=3), 2, 31, 12)   # cfg, batch, first scene, weight seed
+
+
+def train_loss_weights(counts):
+    """R_b of the fixed scalar loss L = sum_b <out_b, R_b>."""
+    return [torch.randn(int(n), 3, generator=torch.Generator().manual_seed(777 + b)) for b, n in enumerate(counts)]
+
+
+def FULL_GRAD_KEYS(cfg):
+    """Parameters whose full gradients are stored (the small ones); every other gradient is pinned by its norm."""
+    t, i = cfg.text_blocks - 1, cfg.img_blocks - 1
+    return {"text_trans.weight", "text_trans.bias", "img_trans.weight", "img_trans.bias", "text_trans_norm.weight",
+            "text_trans_norm.bias", "img_trans_norm.weight", "img_trans_norm.bias",
+            "get_deformable_cluster.get_offsets.channel_mapper.weight", "get_deformable_cluster.get_offsets.mlp.0.weight",
+            "get_deformable_cluster.get_offsets.mlp.1.weight", "get_deformable_cluster.get_offsets.mlp.1.bias",
+            "simple_encoder.mlp.0.weight", "simple_encoder.mlp.0.bias", "simple_encoder.mlp.1.weight",
+            f"textformer.{t}.norm1.weight", f"textformer.{t}.attn.pc_bias", f"imgformer.{i}.norm2.bias",
+            f"imgformer.{i}.attn.proxy_proj.bias", f"text_norm.{t}.weight", f"img_norm.{i}.bias", "norm_img.weight",
+            "channel_mapper.bias", "attn_pool2d.q_proj.bias"}
