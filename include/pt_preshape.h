@@ -135,6 +135,24 @@ int pt_proxy_attention_tc(const void* qk_split, long long qk_plane, int ldq, con
 int pt_heads(const float* guide, const float* lin_w, const float* lin_b, const float* bn_scale, const float* bn_shift,
              int rows, int c, int o, float* out, pt_stream_t stream);
 
+/* ---- training-mode BatchNorm statistics (forward only, no backward yet) ---------------
+ * In train() mode the BatchNorm2d of OffsetNetwork / SimplifiedPointNet (:72, :112) and the BatchNorm1d of the two heads
+ * (:326-330) normalise with batch statistics.  The fused stage kernels above take a per-channel (scale, shift), so a
+ * train-mode forward is: a statistics pass over the layer's pre-BN output (fp64 sums, sums[0..C) = sum, sums[C..2C) = sum
+ * of squares; the call zeroes them first), pt_bn_batch_affine, then the unchanged stage kernel.
+ *   pt_cluster_conv_bn_stats: pre-BN conv output of pt_offset_net_fused / pt_point_encoder_fused, count = B*M*K (padded
+ *                             slots included, as in the reference)
+ *   pt_linear_bn_stats:       pre-BN Linear output of pt_heads, count = rows
+ *   pt_bn_batch_affine:       scale = gamma / sqrt(var_biased + eps), shift = beta - mean * scale; when running_mean /
+ *                             running_var are given they become (1-momentum) * running + momentum * batch (unbiased
+ *                             variance), what nn.BatchNorm does in train() mode. */
+int pt_cluster_conv_bn_stats(const float* points, const int32_t* idx, const float* centres, const float* conv_w,
+                             const float* conv_b, int B, int M, int N, int K, int H, double* sums, pt_stream_t stream);
+int pt_linear_bn_stats(const float* guide, const float* lin_w, const float* lin_b, int rows, int c, int o, double* sums,
+                       pt_stream_t stream);
+int pt_bn_batch_affine(const double* sums, long long count, const float* gamma, const float* beta, float* running_mean,
+                       float* running_var, float momentum, float eps, int C, float* scale, float* shift, pt_stream_t stream);
+
 /* ---- S9 image proxies — get_img_proxy (:335-342) + AttentionPool2d.forward (:154-177) -----------------
  * Only token 0 of the 226-token attention is kept (:177), so the stage is evaluated in single-query form:
  * one pass for the per-channel spatial mean, folded q/k projections, one pass for scores -> softmax ->

@@ -59,6 +59,9 @@ _SIGNATURES = {
     "pt_proxy_block_fused": (c_int, [_P, _P, _P, POINTER(ProxyBlockParams), c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "pt_position_bias": (c_int, [_P, _P, _P, c_int, c_int, _P, _P]),
     "pt_heads": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "pt_cluster_conv_bn_stats": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "pt_linear_bn_stats": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P]),
+    "pt_bn_batch_affine": (c_int, [_P, ctypes.c_longlong, _P, _P, _P, _P, c_float, c_float, c_int, _P, _P, _P]),
     "pt_img_attnpool_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "pt_img_attnpool": (c_int, [_P, c_int, POINTER(ImgPoolParams), c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "pt_img_attnpool_stage": (c_int, [_P, c_int, POINTER(ImgPoolParams), c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, c_int, _P]),

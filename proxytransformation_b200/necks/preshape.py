@@ -4,8 +4,9 @@
 Same registry name, constructor signature, ``forward(points, text_dict, img_feat)`` contract and ``state_dict`` keys
 (released checkpoints load with ``strict=True``); the forward pass itself runs entirely in the sm_100a kernels behind
 ``include/pt_preshape.h`` — the sub-modules below are parameter containers that mirror the reference's key layout and
-are never called.  Eval/no-grad only: training mode (BN batch statistics, dropout, autograd through the gathers) is
-out of scope and raises.
+are never called.  Eval / no-grad is the supported mode; train() mode runs as a forward-only batch-statistics pass
+(BatchNorm batch statistics + running-statistics update) when every drop rate is 0 and autograd is off, and raises
+otherwise (no Dropout / DropPath, no backward pass).
 
 Algorithmic differences from the reference, all output-preserving:
   * only the LAST block of ``textformer`` / ``imgformer`` is evaluated — every block is fed ``point_proxy`` and only the
@@ -271,15 +272,27 @@ class ProxyTransformationNormReverse(nn.Module):
         return out
 
     # ------------------------------------------------------------------ forward (:424-469)
-    @torch.no_grad()
     def forward(self, points: Sequence[torch.Tensor], text_dict, img_feat: torch.Tensor, *, img_proxy: Optional[torch.Tensor] = None,
                 trace: Optional[dict] = None) -> List[torch.Tensor]:
         """points: list of B (N,3) fp32 tensors (equal N); text_dict: values() = (text_feats (B,L,c), mask (B,L) bool);
         img_feat: (B,V,input_dim,H,W) fp32 or bf16.  Returns the list of (N'_b,3) tensors on the inputs' device.
         Host tensors are accepted (pinned memory makes the copies asynchronous); results then come back on the host.
-        ``img_proxy`` (B,V,c) may replace ``img_feat`` (core region of the benchmark); ``trace`` collects intermediates."""
+        ``img_proxy`` (B,V,c) may replace ``img_feat`` (core region of the benchmark); ``trace`` collects intermediates.
+
+        train() mode is a FORWARD-ONLY mode: the four BatchNorm layers normalise with batch statistics and
+        update their running statistics as nn.BatchNorm does; it needs every drop rate at 0 (Dropout / DropPath are not
+        implemented) and a torch.no_grad() context (there is no backward pass) and raises otherwise."""
         if self.training:
-            raise NotImplementedError("ProxyTransformationNormReverse (B200): eval() only — training mode is out of scope")
+            if self.drop_rate or self.attn_drop_rate or self.drop_path_rate:
+                raise NotImplementedError("ProxyTransformationNormReverse (B200): train() mode needs drop_rate = attn_drop_rate = "
+                                          "drop_path_rate = 0 (Dropout / DropPath are not implemented)")
+            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                raise NotImplementedError("ProxyTransformationNormReverse (B200): no backward pass — train() mode is a "
+                                          "batch-statistics forward only; call it under torch.no_grad()")
+        with torch.no_grad():
+            return self._forward_impl(points, text_dict, img_feat, img_proxy, trace)
+
+    def _forward_impl(self, points, text_dict, img_feat, img_proxy, trace) -> List[torch.Tensor]:
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("ProxyTransformationNormReverse (B200) has no CPU path: move the module to a CUDA device")
@@ -309,7 +322,7 @@ class ProxyTransformationNormReverse(nn.Module):
         """Small batches are launch-latency bound (about 40 dependent kernels of a few microseconds each): replaying the whole
         forward as one CUDA graph removes the gaps.  The inputs have to be copied into the graph's static buffers, so the
         mode is limited to batches whose inputs are small (``cuda_graph_max_bytes``); off unless ``cuda_graphs`` is set."""
-        if not self.cuda_graphs or trace is not None or img_proxy is not None or torch.cuda.is_current_stream_capturing():
+        if not self.cuda_graphs or trace is not None or img_proxy is not None or torch.cuda.is_current_stream_capturing() or self.training:
             return False
         return P.numel() * 4 + img_feat.numel() * img_feat.element_size() <= self.cuda_graph_max_bytes
 
@@ -364,6 +377,8 @@ class ProxyTransformationNormReverse(nn.Module):
         host_out = torch.empty(B, N, 3, dtype=torch.float32, pin_memory=True)
         host_cnt = torch.empty(B, dtype=torch.int32, pin_memory=True)
         chunk = max(1, min(B, int(self.host_chunk_scenes)))
+        if self.training:
+            chunk = B                                 # batch statistics are over the whole batch
         traces = [] if trace is not None else None
         for s0 in range(0, B, chunk):
             s1 = min(B, s0 + chunk)
@@ -447,6 +462,7 @@ class ProxyTransformationNormReverse(nn.Module):
         (out (B,N,3) packed per scene, counts (B,) int32), no host synchronisation."""
         w = self._weights(P.device)
         K, n = self.num_sub, self.real_cluster_num
+        train = self.training                        # batch-statistics BatchNorm (forward only), see forward()
         # S9 image proxies (:449) depend on nothing but img_feat.  Their first half (pass over the features for the spatial
         # means + query-side projections) is HBM-bound and light on SM resources, the geometric stages S1-S6 are latency /
         # ALU bound and barely touch HBM: the two run concurrently on two streams.  The second half (the persistent pooling
@@ -464,16 +480,26 @@ class ProxyTransformationNormReverse(nn.Module):
         # S1-S4 deformable clustering (:53-67)
         mn, mx, c0 = ops.minmax_centres(P, self.grid_size, w["lin"])
         idx1, _ = ops.ball_query(c0, P, K)
-        centres = ops.offset_net(P, idx1, c0, mn, mx, w["offset"])
+        w_off = w["offset"]
+        if train:                                    # :72 BatchNorm2d over (B, M, K)
+            sc, sh = ops.bn_batch_affine_cluster_conv(P, idx1, c0, w_off, self.get_deformable_cluster.get_offsets.mlp[1])
+            w_off = dict(w_off, bn_scale=sc, bn_shift=sh)
+        centres = ops.offset_net(P, idx1, c0, mn, mx, w_off)
         idx2, _ = ops.ball_query(centres, P, K)
         # S5 dropout (:352-420)
         kept_src, kc, kidx, drop_idx, fps = ops.cluster_dropout(centres, idx2, self.keep1, n)
         # S6 point proxies (:437)
-        pp = ops.point_encoder(P, kidx, kc, w["encoder"])
+        w_enc = w["encoder"]
+        if train:                                    # :112 BatchNorm2d over (B, n, K)
+            sc, sh = ops.bn_batch_affine_cluster_conv(P, kidx, kc, w_enc, self.simple_encoder.mlp[1])
+            w_enc = dict(w_enc, bn_scale=sc, bn_shift=sh)
+        pp = ops.point_encoder(P, kidx, kc, w_enc)
         # S7/S8 text branch -> translate (:440-446)
         tg = ops.proxy_block(pp, text, mask, w["text"], self.num_heads, params=w["text_struct"])
         th = w["text_head"]
-        translate = ops.heads(tg, th["lin_w"], th["lin_b"], th["bn_scale"], th["bn_shift"])
+        t_sc, t_sh = (ops.bn_batch_affine_linear(tg, th["lin_w"], th["lin_b"], self.text_trans_norm) if train
+                      else (th["bn_scale"], th["bn_shift"]))                                # :328 BatchNorm1d over (B, n)
+        translate = ops.heads(tg, th["lin_w"], th["lin_b"], t_sc, t_sh)
         # S9 image proxies (:449) and image branch -> transform (:450-455)
         if side is not None:
             torch.cuda.current_stream(P.device).wait_stream(side)
@@ -483,7 +509,11 @@ class ProxyTransformationNormReverse(nn.Module):
             img_proxy = ops.img_attnpool(img_feat, w["img"], self.num_heads, params=w["img_struct"])
         ig = ops.proxy_block(pp, img_proxy, None, w["imgb"], self.num_heads, params=w["imgb_struct"])
         ih = w["img_head"]
-        transform = ops.heads(ig, ih["lin_w"], ih["lin_b"], ih["bn_scale"], ih["bn_shift"])
+        i_sc, i_sh = (ops.bn_batch_affine_linear(ig, ih["lin_w"], ih["lin_b"], self.img_trans_norm) if train
+                      else (ih["bn_scale"], ih["bn_shift"]))                                # :330 BatchNorm1d over (B, n)
+        transform = ops.heads(ig, ih["lin_w"], ih["lin_b"], i_sc, i_sh)
+        if train:
+            self._packed_key = None                  # running statistics changed behind torch's version counters: re-fold for eval
         # S10-S12 (:459-467)
         out, counts = ops.affine_scatter_compact(P, kidx, drop_idx, kc, transform, translate)
         if trace is not None:

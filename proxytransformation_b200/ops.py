@@ -122,6 +122,51 @@ def point_encoder(points, kept_idx, kept_centres, w: Dict[str, torch.Tensor]):
     return out
 
 
+def bn_batch_affine_cluster_conv(points, idx, centres, w: Dict[str, torch.Tensor], bn: "torch.nn.modules.batchnorm._BatchNorm"):
+    """Train-mode BatchNorm2d of OffsetNetwork / SimplifiedPointNet (:72, :112): batch statistics of the pre-BN conv output
+    over (B, M, K) -> (scale, shift) for the fused stage kernel; updates bn.running_mean / running_var in place (N4)."""
+    L = _lib.load()
+    B, M, K = idx.shape
+    H = w["conv_w"].shape[0]
+    f = torch.float32
+    sums = torch.empty(2 * H, dtype=torch.float64, device=points.device)
+    check(L.pt_cluster_conv_bn_stats(_chk(points, f, "points"), _chk(idx, torch.int32, "idx"), _chk(centres, f, "centres"),
+                                     _chk(w["conv_w"], f, "conv_w"), _chk(w["conv_b"], f, "conv_b"), B, M, points.shape[1], K, H,
+                                     sums.data_ptr(), _stream()), "pt_cluster_conv_bn_stats")
+    return _bn_batch_affine(sums, B * M * K, bn, H)
+
+
+def bn_batch_affine_linear(guide, lin_w, lin_b, bn: "torch.nn.modules.batchnorm._BatchNorm"):
+    """Train-mode BatchNorm1d of the heads (:326-330, :445-446, :454-455): batch statistics of the Linear output over the
+    rows -> (scale, shift) for pt_heads; updates the running statistics in place (N4)."""
+    L = _lib.load()
+    c = guide.shape[-1]
+    rows = guide.numel() // c
+    o = lin_w.shape[0]
+    f = torch.float32
+    sums = torch.empty(2 * o, dtype=torch.float64, device=guide.device)
+    check(L.pt_linear_bn_stats(_chk(guide, f, "guide"), _chk(lin_w, f, "lin_w"), _chk(lin_b, f, "lin_b"), rows, c, o,
+                               sums.data_ptr(), _stream()), "pt_linear_bn_stats")
+    return _bn_batch_affine(sums, rows, bn, o)
+
+
+def _bn_batch_affine(sums, count: int, bn, C: int):
+    L = _lib.load()
+    f = torch.float32
+    dev = sums.device
+    scale = torch.empty(C, dtype=f, device=dev)
+    shift = torch.empty(C, dtype=f, device=dev)
+    track = bn.track_running_stats and bn.running_mean is not None
+    momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+    check(L.pt_bn_batch_affine(sums.data_ptr(), count, _chk(bn.weight.detach(), f, "bn.weight"), _chk(bn.bias.detach(), f, "bn.bias"),
+                               _chk(bn.running_mean, f, "running_mean") if track else None,
+                               _chk(bn.running_var, f, "running_var") if track else None, momentum, float(bn.eps), C,
+                               scale.data_ptr(), shift.data_ptr(), _stream()), "pt_bn_batch_affine")
+    if track:
+        bn.num_batches_tracked += 1
+    return scale, shift
+
+
 _BLOCK_F32 = ("ln1_w", "ln1_b", "pos_bias", "qkv_w", "pp_w", "pp_b", "proj_w", "proj_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b",
               "fc2_w", "fc2_b", "lno_w", "lno_b")
 _BLOCK_SPLIT = ("qkv_w_split", "proj_w_split", "fc1_w_split", "fc2_w_split", "pp_w_split")

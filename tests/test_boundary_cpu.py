@@ -126,9 +126,16 @@ def test_no_cpu_path_and_no_training_mode():
     pts, td, img = syn.make_inputs(cfg, 1)
     with pytest.raises(RuntimeError, match="no CPU path"):
         m(pts, td, img)
+    # train() mode is a forward-only batch-statistics pass: it refuses non-zero drop rates (no Dropout / DropPath) and an
+    # autograd context (no backward pass) before anything else is looked at
     m.train()
-    with pytest.raises(NotImplementedError, match="eval"):
+    with pytest.raises(NotImplementedError, match="drop_rate"):
         m(pts, td, img)
+    m0 = ProxyTransformationNormReverse(**dict(cfg.module_kwargs(), drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.0)).train()
+    with pytest.raises(NotImplementedError, match="no backward pass"):
+        m0(pts, td, img)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU path"):
+        m0(pts, td, img)
 
 
 def test_oracle_is_not_imported_by_the_product_package():

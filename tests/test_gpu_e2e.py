@@ -240,3 +240,44 @@ def test_odd_shapes_against_oracle_chain(gs, ddr, N, V, L, B, dtype, box):
     for o, w in zip(out, want):
         assert o.shape == w.shape
         np.testing.assert_allclose(np_(o), w.numpy(), rtol=0, atol=1e-4)
+
+
+def test_train_mode_forward_uses_batch_statistics_like_the_reference():
+    """N4, forward only: train() mode with every drop rate at 0 under no_grad against the fixture captured from the
+    unmodified reference in train() mode (tests/golden/make_golden_train.py): outputs within the 1e-4 coordinate bar, the
+    four BatchNorm layers' running statistics after the step, and eval() afterwards folding the UPDATED statistics."""
+    import os
+    from tests.golden_cases import GOLDEN_DIR, TRAIN_CASE
+    cfg, batch, first, wseed = TRAIN_CASE
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "c1_train.npz"), allow_pickle=False))
+    sd = syn.make_state_dict(cfg, wseed)
+    pts, td, img = syn.make_inputs(cfg, batch, first)
+    from proxytransformation_b200 import ProxyTransformationNormReverse
+    m = ProxyTransformationNormReverse(**dict(cfg.module_kwargs(), drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.0))
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).train()
+    dpts, dtd, dimg = [cu(p) for p in pts], {k: v.to(DEV) for k, v in td.items()}, cu(img)
+    with pytest.raises(NotImplementedError, match="no backward pass"):
+        m(dpts, dtd, dimg)
+    with torch.no_grad():
+        out = m(dpts, dtd, dimg)
+    assert [o.shape[0] for o in out] == g["out_counts"].tolist()
+    for b, o in enumerate(out):
+        np.testing.assert_allclose(np_(o), g[f"out_{b}"], rtol=0, atol=1e-4)
+    got = m.state_dict()
+    for k in [k[3:] for k in g if k.startswith("bn/")]:
+        if k.endswith("num_batches_tracked"):
+            assert int(got[k]) == int(g["bn/" + k]), k
+        else:
+            np.testing.assert_allclose(np_(got[k]), g["bn/" + k], rtol=2e-5, atol=2e-6, err_msg=k)
+    # eval() after the step: the folded BatchNorm affine must come from the updated running statistics
+    m.eval()
+    sd2 = dict(sd)
+    for k in g:
+        if k.startswith("bn/"):
+            sd2[k[3:]] = torch.from_numpy(g[k])
+    want, _ = oracle_forward(cfg, sd2, pts, td, img)
+    got_eval = m(dpts, dtd, dimg)
+    assert [o.shape[0] for o in got_eval] == [o.shape[0] for o in want]
+    for a, b in zip(got_eval, want):
+        np.testing.assert_allclose(np_(a), b.numpy(), rtol=0, atol=1e-4)
