@@ -32,3 +32,12 @@ ext[:, :3, 3] = torch.rand(5, 3)
 agg = ops.aggregate_sample([v.cuda() for v in views], ext, torch.randint(0, sum(len(v) for v in views), (4096,)).cuda())
 torch.cuda.synchronize()
 print("ok", [tuple(o.shape) for o in outb], tuple(agg.shape))
+# train() mode as a batch-statistics forward (bnstats.cu: fp64 statistics kernels + running-statistics update)
+mt = ProxyTransformationNormReverse(**dict(syn.C1.module_kwargs(), drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.0))
+mt.load_state_dict(syn.make_state_dict(syn.C1, 2))
+mt = mt.cuda().train()
+ptst, tdt, imgt = syn.make_inputs(syn.C1, 2, first_scene=5)
+with torch.no_grad():
+    outt = mt([p.cuda() for p in ptst], {k: v.cuda() for k, v in tdt.items()}, imgt.cuda())
+torch.cuda.synchronize()
+print("ok", [tuple(o.shape) for o in outt], int(mt.text_trans_norm.num_batches_tracked))
