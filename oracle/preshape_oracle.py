@@ -22,9 +22,8 @@ stream and are not restated).  Pinned against the reference in ``train()`` mode 
 from __future__ import annotations
 
 import ctypes
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional
 
-import numpy as np
 import torch
 import torch.nn.functional as F
 

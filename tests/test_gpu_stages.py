@@ -7,7 +7,7 @@ import torch
 from oracle import preshape_oracle as po
 from proxytransformation_b200 import ops
 from proxytransformation_b200 import synthetic as syn
-from tests.golden_cases import CASES, LARGE_CASES, SMALL_CASES, load_case
+from tests.golden_cases import LARGE_CASES, SMALL_CASES, load_case
 from tests.gpu_util import DEV, build_module, conv_bn_weights, cu, np_
 
 pytestmark = pytest.mark.gpu

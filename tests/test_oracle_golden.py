@@ -2,15 +2,13 @@
 captured from the unmodified reference (tests/golden/make_golden.py), plus — when
 /root/reference is present (build container) — a live cross-check against the
 reference itself.  CPU only."""
-import hashlib
-
 import numpy as np
 import pytest
 import torch
 
 from oracle import preshape_oracle as po
 from oracle import ref_shim
-from tests.golden_cases import CASES, LARGE_CASES, SMALL_CASES, load_case
+from tests.golden_cases import LARGE_CASES, SMALL_CASES, load_case
 
 FLOAT_TOL = 2e-5   # oracle vs golden floats: same ops, possibly different CPU/oneDNN kernels
 
