@@ -1,7 +1,8 @@
 """Stage-level check of the image pool kernels (pass B of S9) against a float64 torch evaluation of the same algebra from
 the kernel's own inputs (w_eff planes, cterm, xbar in the workspace): scaled scores, probabilities, weighted sums.
 With a third argument it also times the BACK stage at bench size over a sweep of the producer's L2-prefetch distance (PT_POOL_PF).
-Usage (GPU box): python tools/pool_check.py [views_per_scene] [scenes] [time | comma-separated PT_POOL_PF values]"""
+Usage (GPU box): python tools/pool_check.py [views_per_scene] [scenes] [time | comma-separated PT_POOL_PF values] [single]
+(`single` also checks the experimental single-pass kernel, PT_POOL_SINGLE=1)"""
 import os, sys, torch, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("PT_POOL_DEBUG", "64")
@@ -37,7 +38,8 @@ score_ch = torch.tensor(128 * p_ + 64 * (e_ >> 1) + s_ + 16 * q_ + 8 * (e_ & 1),
 sl_, s2_, q2_, e2_ = j // 64, (j // 8) % 8, (j // 2) % 4, j % 2
 sum_ch = torch.tensor(64 * sl_ + s2_ + 16 * q2_ + 8 * e2_, device="cuda")
 
-def run():
+def run(single=False):
+    os.environ["PT_POOL_SINGLE"] = "1" if single else "0"      # experimental single-pass kernel (imgpool_tc.cu), off by default
     ws = torch.zeros(need + BV * DBG * 4, dtype=torch.uint8, device="cuda")
     out, ws = ops.img_attnpool(img, w["img"], HEADS, params=w["img_struct"], stages=1, ws=ws)
     out, ws = ops.img_attnpool(img, w["img"], HEADS, params=w["img_struct"], stages=2, out=out, ws=ws)
@@ -47,8 +49,9 @@ def run():
 def f32(ws, o, n): return ws[o:o + 4 * n].view(torch.float32)
 def bf(ws, o, n): return ws[o:o + 2 * n].view(torch.bfloat16)
 
-for _ in (0,):
-    out, ws = run()
+MODES = [False] + ([True] if "single" in sys.argv else [])
+for single in MODES:
+    out, ws = run(single)
     X = img.reshape(BV, C, HW).double()
     wpl = bf(ws, o_wpl, BV * 2 * WPLANE).double().reshape(BV, 2, HEADS, WPITCH)[..., :512].sum(1)      # (BV, 8, 512) score order
     weff = torch.zeros(BV, HEADS, C, dtype=torch.float64, device="cuda")
@@ -64,7 +67,7 @@ for _ in (0,):
     ya = bf(ws, o_ya, 2 * BV * HEADS * YA).double().reshape(2, BV, HEADS, YA).sum(0)
     P_k = ya[..., 512:512 + 226]
     Y_k = torch.zeros_like(Y); Y_k[:, :, sum_ch] = ya[..., :512]
-    name = "mma"
+    name = "single" if single else "mma"
     print(f"[{name}] scores max err {float((sv_k - sv).abs().max()):.3e}  probs max err {float((P_k - P).abs().max()):.3e}  "
           f"sums max rel err {float(((Y_k - Y).abs().max() / Y.abs().max())):.3e}")
     d = (sv_k - sv).abs()
@@ -73,7 +76,7 @@ for _ in (0,):
     dy = (Y_k - Y).abs().amax(dim=(0, 1)).reshape(8, 64)
     print(f"[{name}] sums err by slab:", [f"{float(dy[k].max()):.1e}" for k in range(8)])
 
-if len(sys.argv) > 3:                                             # timing: BACK stage (pool + value GEMMs + LayerNorm) at bench size
+if len(sys.argv) > 3 and sys.argv[3] != "single":                 # timing: BACK stage (pool + value GEMMs + LayerNorm) at bench size
     Bt, Vt = 64, 196
     imgs = [(torch.relu(torch.randn(Bt, Vt, C, 15, 15, device="cuda")) * 1.5).bfloat16() for _ in range(2)]   # 2 x 2.9 GB >> L2
     needt = _lib.load().pt_img_attnpool_ws_bytes(Bt * Vt, C, HW, EMB, HEADS)
