@@ -282,6 +282,12 @@ class ProxyTransformationNormReverse(nn.Module):
         train() mode is a FORWARD-ONLY mode: the four BatchNorm layers normalise with batch statistics and
         update their running statistics as nn.BatchNorm does; it needs every drop rate at 0 (Dropout / DropPath are not
         implemented) and a torch.no_grad() context (there is no backward pass) and raises otherwise."""
+        self._check_mode()
+        with torch.no_grad():
+            return self._forward_impl(points, text_dict, img_feat, img_proxy, trace)
+
+    def _check_mode(self):
+        """train() mode is supported as a forward-only batch-statistics pass (see forward()); everything else raises."""
         if self.training:
             if self.drop_rate or self.attn_drop_rate or self.drop_path_rate:
                 raise NotImplementedError("ProxyTransformationNormReverse (B200): train() mode needs drop_rate = attn_drop_rate = "
@@ -289,8 +295,6 @@ class ProxyTransformationNormReverse(nn.Module):
             if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
                 raise NotImplementedError("ProxyTransformationNormReverse (B200): no backward pass — train() mode is a "
                                           "batch-statistics forward only; call it under torch.no_grad()")
-        with torch.no_grad():
-            return self._forward_impl(points, text_dict, img_feat, img_proxy, trace)
 
     def _forward_impl(self, points, text_dict, img_feat, img_proxy, trace) -> List[torch.Tensor]:
         dev = next(self.parameters()).device
@@ -460,6 +464,7 @@ class ProxyTransformationNormReverse(nn.Module):
     def forward_packed(self, P, text, mask, img_feat, *, img_proxy=None, trace=None):
         """Device-resident form: P (B,N,3), text (B,L,c), mask (B,L) uint8|None, img_feat (B,V,C,H,W) ->
         (out (B,N,3) packed per scene, counts (B,) int32), no host synchronisation."""
+        self._check_mode()
         w = self._weights(P.device)
         K, n = self.num_sub, self.real_cluster_num
         train = self.training                        # batch-statistics BatchNorm (forward only), see forward()
