@@ -18,9 +18,11 @@ def _emu():
     return m
 
 
+@pytest.mark.parametrize("wch", [4, 8], ids=["64B-windows(kernel)", "128B-windows(next)"])
 @pytest.mark.parametrize("seed", [0, 7])
-def test_single_pass_schedule_matches_float64(seed):
+def test_single_pass_schedule_matches_float64(seed, wch):
     e = _emu()
+    e.set_shape(wch)
     rng = np.random.default_rng(seed)
     X = e.bf16_round(np.maximum(rng.standard_normal((e.C, e.HW)), 0) * 1.5)
     w_eff = (rng.standard_normal((e.HEADS, e.C)) * 0.08).astype(np.float32)
@@ -34,9 +36,11 @@ def test_single_pass_schedule_matches_float64(seed):
     np.testing.assert_allclose(probs.sum(1), 1.0, atol=1e-5)
 
 
-def test_window_loader_covers_every_token_exactly_once():
+@pytest.mark.parametrize("wch", [4, 8])
+def test_window_loader_covers_every_token_exactly_once(wch):
     """Every (channel, token) element appears at u = token + class in exactly one window chunk; chunks >= 29 are zero."""
     e = _emu()
+    e.set_shape(wch)
     view = np.zeros(e.C * e.HW + 64, np.float32)
     view[:e.C * e.HW] = np.arange(1, e.C * e.HW + 1, dtype=np.float32)      # unique non-zero tags
     seen = np.zeros(e.C * e.HW, np.int32)
@@ -48,8 +52,8 @@ def test_window_loader_covers_every_token_exactly_once():
             for ch in range(e.WCH):
                 vals = e.chunk_of(win, row, ch)
                 for k in range(8):
-                    t = 32 * w + 8 * ch + k - s
-                    if 0 <= t < e.HW and 4 * w + ch < e.NCHUNK:
+                    t = 8 * e.WCH * w + 8 * ch + k - s
+                    if 0 <= t < e.HW and e.WCH * w + ch < e.NCHUNK:
                         assert vals[k] == c * e.HW + t + 1
                         seen[c * e.HW + t] += 1
     assert (seen == 1).all()

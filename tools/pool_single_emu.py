@@ -6,16 +6,24 @@ evaluation of the same algebra.  It follows the planned kernel phase by phase an
 index formulas (class-major window rows, XOR-swizzled 16-byte chunks, two parity copies of the probabilities), so the
 formulas can be validated without a GPU.  It is NOT on any product path.
 
-    python tools/pool_single_emu.py [seed]
+    python tools/pool_single_emu.py [seed] [chunks per window: 4 (kernel as built) | 8 (128-byte pieces, the proposed next step)]
 """
 import sys
 
 import numpy as np
 
 C, HW, HEADS, HD = 512, 225, 8, 32
-NWIN, WCH = 8, 4                 # windows per view, 16-byte chunks (8 u-columns) per window
+NWIN, WCH = 8, 4                 # windows per view, 16-byte chunks (8 u-columns) per window: the kernel's shape (64-byte pieces)
 NCHUNK = 29                      # aligned chunks per channel row (232 >= 225 + 7)
 PP = 64                          # probability row pitch (elements): token slot i of the window sits at element i + 8 + copy
+
+
+def set_shape(wch):
+    """wch = 4: 64-byte pieces, 8 windows of 32 u-columns (img_pool_single_kernel); wch = 8: 128-byte pieces, 4 windows of 64."""
+    global NWIN, WCH, PP
+    WCH = wch
+    NWIN = -(-32 // wch)             # 29 chunks -> 8 windows of 4 or 4 windows of 8
+    PP = 8 * wch + 32                # slots + margins (8 + copy in front, >= 16 + 7 behind)
 
 
 def bf16_round(x):
@@ -32,8 +40,8 @@ def split(x):
 
 def load_window(view_bytes, w):
     """cp.async stage: window w of a view -> shared-memory image [512 rows][4 chunks][8 elements] (physical order).
-    Row of channel c = 8 r + s is s*64 + r; chunk ch of the window (u = 32 w + 8 ch ..) lands at position ch ^ ((row >> 1) & 3);
-    source address = 448 s + 3600 r + 16 (4 w + ch), zero fill for chunks >= 29."""
+    Row of channel c = 8 r + s is s*64 + r; chunk ch of the window (u = 8 WCH w + 8 ch ..) lands at position
+    ch ^ ((row >> 1) & (WCH - 1)); source address = 448 s + 3600 r + 16 (WCH w + ch), zero fill for chunks >= 29."""
     win = np.zeros((C, WCH, 8), np.float32)
     for row in range(C):
         s, r = row >> 6, row & 63
@@ -42,12 +50,12 @@ def load_window(view_bytes, w):
             if gch >= NCHUNK:
                 continue
             off = 448 * s + 3600 * r + 16 * gch
-            win[row, ch ^ ((row >> 1) & 3)] = view_bytes[off // 2: off // 2 + 8]
+            win[row, ch ^ ((row >> 1) & (WCH - 1))] = view_bytes[off // 2: off // 2 + 8]
     return win
 
 
 def chunk_of(win, row, ch):
-    return win[row, ch ^ ((row >> 1) & 3)]
+    return win[row, ch ^ ((row >> 1) & (WCH - 1))]
 
 
 def emulate_view(X, w_eff, cterm, xbar, scale):
@@ -62,14 +70,15 @@ def emulate_view(X, w_eff, cterm, xbar, scale):
         m[h], l[h] = sv0[h], 1.0
     svbuf = np.full((HEADS, 232), -np.inf, np.float32)  # raw scaled scores of the spatial tokens
     Y = np.zeros((2, HEADS, C), np.float32)             # accumulators: [hi part | lo part of the probabilities][head][channel]
-    part = np.zeros((2, 8, HEADS, 32), np.float32)      # [window parity][class][head][u_local]
+    W = 8 * WCH                                         # u-columns (= token slots) per window
+    part = np.zeros((2, 8, HEADS, W), np.float32)       # [window parity][class][head][u_local]
     wins = {}
     for w in range(NWIN):
         wins[w] = load_window(view, w)
         win = wins[w]
         # ---- step 1: scores, warp = (class s, chunk pair cp); k-step j covers class rows r = 16 j .. 16 j + 15
         for s in range(8):
-            for cp in range(2):
+            for cp in range(WCH // 2):
                 acc = np.zeros((16, 16), np.float64)                     # rows: 8 heads hi, 8 heads lo; cols: 2 chunks x 8
                 for j in range(4):
                     rows = s * 64 + 16 * j + np.arange(16)
@@ -78,19 +87,19 @@ def emulate_view(X, w_eff, cterm, xbar, scale):
                     B = np.stack([np.concatenate([chunk_of(win, row, 2 * cp), chunk_of(win, row, 2 * cp + 1)]) for row in rows])
                     acc += A @ B.astype(np.float64)
                 part[w & 1, s, :, 16 * cp:16 * cp + 16] = (acc[:8] + acc[8:]).astype(np.float32)
-        # ---- step 2: softmax step, warp = head, lane i = token slot: t = 32 w - 7 + i
-        P = np.zeros((HEADS, 32), np.float32)
+        # ---- step 2: softmax step, warp(s) = head, lane i = token slot: t = W w - 7 + i
+        P = np.zeros((HEADS, W), np.float32)
         alpha = np.ones(HEADS, np.float32)
         for h in range(HEADS):
-            sv = np.full(32, -np.inf, np.float32)
-            for i in range(32):
-                t = 32 * w - 7 + i
+            sv = np.full(W, -np.inf, np.float32)
+            for i in range(W):
+                t = W * w - 7 + i
                 if t < 0 or t >= HW:
                     continue
                 acc = np.float32(0.0)
                 for s in range(8):                                        # fixed order: bit-reproducible
                     ul = i - 7 + s                                        # u_local of class s for this token
-                    acc = np.float32(acc + (part[(w - 1) & 1, s, h, ul + 32] if ul < 0 else part[w & 1, s, h, ul]))
+                    acc = np.float32(acc + (part[(w - 1) & 1, s, h, ul + W] if ul < 0 else part[w & 1, s, h, ul]))
                 sv[i] = scale * (acc + cterm[h, t + 1])
                 svbuf[h, t] = sv[i]
             m_new = max(m[h], sv.max())
@@ -102,14 +111,14 @@ def emulate_view(X, w_eff, cterm, xbar, scale):
         # shared-memory image of the probabilities: [copy][hi|lo][head][PP], slot i at element i + 8 + copy, zero margins
         pbuf = np.zeros((2, 2, HEADS, PP), np.float32)
         for cpy in range(2):
-            pbuf[cpy, 0, :, 8 + cpy:40 + cpy] = p_hi
-            pbuf[cpy, 1, :, 8 + cpy:40 + cpy] = p_lo
-        # ---- step 3: weighted sums, warp = (class s, channel half hf); chunks -1 .. 3 (+ one zero chunk), 3 k-steps of 16 u
+            pbuf[cpy, 0, :, 8 + cpy:8 + W + cpy] = p_hi
+            pbuf[cpy, 1, :, 8 + cpy:8 + W + cpy] = p_lo
+        # ---- step 3: weighted sums, warp = (class s, channel half hf); chunks -1 .. WCH-1 (+ one zero chunk), k-steps of 16 u
         Y *= alpha[None, :, None]
         for s in range(8):
             cpy = (s + 1) & 1
             for hf in range(2):
-                for ks in range(3):
+                for ks in range(WCH // 2 + 1):
                     # A fragment: u_local = 8 (2 ks - 1) + kk, token slot i = u_local + 7 - s, element = i + 8 + cpy (pairs aligned)
                     base = 16 * ks - 8 + 7 - s + 8 + cpy
                     assert base % 2 == 0 and base >= 0 and base + 16 <= PP
@@ -119,8 +128,8 @@ def emulate_view(X, w_eff, cterm, xbar, scale):
                         Bt = []
                         for row in rows:                                   # B^T rows = channels, 16 k = two chunks
                             lo_ch, hi_ch = 2 * ks - 1, 2 * ks
-                            c_lo = chunk_of(wins[w - 1], row, 3) if lo_ch < 0 and w > 0 else chunk_of(win, row, max(lo_ch, 0))
-                            c_hi = chunk_of(win, row, min(hi_ch, 3))       # chunk "4" does not exist: probabilities are zero there
+                            c_lo = chunk_of(wins[w - 1], row, WCH - 1) if lo_ch < 0 and w > 0 else chunk_of(win, row, max(lo_ch, 0))
+                            c_hi = chunk_of(win, row, min(hi_ch, WCH - 1))  # the chunk past the window: probabilities are zero there
                             Bt.append(np.concatenate([c_lo, c_hi]))
                         D = A @ np.stack(Bt).astype(np.float64).T          # (16, 8)
                         chan = 8 * (32 * hf + 8 * nt + np.arange(8)) + s
@@ -146,6 +155,7 @@ def reference_view(X, w_eff, cterm, xbar, scale):
 
 def main():
     rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
+    set_shape(int(sys.argv[2]) if len(sys.argv) > 2 else 4)
     X = bf16_round(np.maximum(rng.standard_normal((C, HW)), 0) * 1.5)
     w_eff = (rng.standard_normal((HEADS, C)) * 0.08).astype(np.float32)
     cterm = (rng.standard_normal((HEADS, HW + 1)) * 0.5).astype(np.float32)
