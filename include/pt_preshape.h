@@ -180,7 +180,14 @@ typedef struct pt_img_pool_params {
      *   score_order[((p*8 + s)*4 + q)*4 + e] = 128 p + 64 (e >> 1) + s + 16 q + 8 (e & 1)      p<4, s<8, q<4, e<4
      *   sum_order[((sl*8 + s)*4 + q)*2 + e]  = 64 sl + s + 16 q + 8 e                          sl<8, s<8, q<4, e<2 */
     const void *w_qc_split, *wk_pad_split, *gk_pad_split, *wv_cat_split, *cproj_split;
+    /* Which pooling kernel the two channel orders above were folded for:
+     *   PT_POOL_VARIANT_MMA  (0) img_pool_mma_kernel (mma.sync + ldmatrix on the raw rows), orders as stated above
+     *   PT_POOL_VARIANT_UMMA (1) img_pool_umma_kernel (tcgen05 / TMEM, TMA-fed; csrc/imgpool_umma.cu):
+     *                            score_order[64 s + r] = sum_order[64 s + r] = s + 8 r   (residue class s, row r of the class) */
+    int variant;
 } pt_img_pool_params;
+#define PT_POOL_VARIANT_MMA 0
+#define PT_POOL_VARIANT_UMMA 1
 
 size_t pt_img_attnpool_ws_bytes(int BV, int C, int HW, int c, int heads);
 int pt_img_attnpool(const void* img_feat, int img_dtype, const pt_img_pool_params* p, int BV, int C, int HW, int c,

@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libptpreshape.so")
 
 PT_DTYPE_F32, PT_DTYPE_BF16 = 0, 1
+PT_POOL_VARIANT_MMA, PT_POOL_VARIANT_UMMA = 0, 1
 
 
 class PtError(RuntimeError):
@@ -36,7 +37,8 @@ class GemmTcDesc(Structure):
 
 class ImgPoolParams(Structure):
     _fields_ = [(n, c_void_p) for n in ("w_qc", "q0", "w_kc", "g_k", "w_vc", "h_v", "cproj_w", "cproj_b", "ln_w", "ln_b",
-                                        "w_qc_split", "wk_pad_split", "gk_pad_split", "wv_cat_split", "cproj_split")]
+                                        "w_qc_split", "wk_pad_split", "gk_pad_split", "wv_cat_split", "cproj_split")] + \
+               [("variant", c_int)]
 
 
 _P = c_void_p

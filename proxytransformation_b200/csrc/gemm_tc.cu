@@ -349,6 +349,22 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
     return PT_OK;
 }
 
+int encode_tensor_map_16bit(CUtensorMap* map, const void* base, int rank, const unsigned long long* dims,
+                            const unsigned long long* strides_bytes, const unsigned* box, bool fp16) {
+    EncodeTiledFn fn = encode_fn();
+    PT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+    PT_REQUIRE(rank >= 1 && rank <= 5, "tensor map rank %d", rank);
+    cuuint64_t gdim[5], gstride[4];
+    cuuint32_t bx[5], estr[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstride[i] = strides_bytes[i];
+    CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                    const_cast<void*>(base), gdim, gstride, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rank %d, inner dim %llu, box %u)", (int)r, rank, dims[0], box[0]);
+    return PT_OK;
+}
+
 bool gemm_tc_supported(int M, int N, int K) { return M >= 1 && N >= 4 && N % 4 == 0 && K % TC_BK == 0 && K >= TC_BK; }
 
 size_t gemm_tc_ws_bytes(int M, int N, int K) {

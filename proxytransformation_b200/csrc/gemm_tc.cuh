@@ -1,5 +1,6 @@
 // Internal interface of the tcgen05 3xBF16 GEMM (gemm_tc.cu).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -34,6 +35,12 @@ struct GemmTc {
     long long ct_ld = 0, ct_plane = 0;
     int bn = 0;                           // tile width override (32/64/128/256), 0 = auto
 };
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda): 16-bit elements (bf16, or fp16 when
+// `fp16`), rank <= 5, dims / box in elements (innermost first), strides in bytes for dims 1..rank-1, SWIZZLE_128B,
+// zero fill outside the tensor.
+int encode_tensor_map_16bit(CUtensorMap* map, const void* base, int rank, const unsigned long long* dims,
+                            const unsigned long long* strides_bytes, const unsigned* box, bool fp16);
 
 bool gemm_tc_supported(int M, int N, int K);
 size_t gemm_tc_ws_bytes(int M, int N, int K);

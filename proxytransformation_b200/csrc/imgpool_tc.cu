@@ -29,6 +29,8 @@ namespace pt {
 
 int launch_layernorm(const float* x, const float* w, const float* b, const float* add, int add_rows, int rows, int c,
                      float* out, cudaStream_t s);
+int launch_img_pool_umma(const void* img_feat, const __nv_bfloat16* wpl, const float* cterm, const float* xbar, __nv_bfloat16* ya_hi,
+                         long long ya_plane, int BV, float* dbg, cudaStream_t s);      // imgpool_umma.cu
 
 namespace ip {
 constexpr int C = 512, HW = 225, HEADS = 8, HD = 32, EMB = 256;
@@ -917,6 +919,7 @@ int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, in
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int rc;
+    const bool umma = p->variant == PT_POOL_VARIANT_UMMA;
     if (stages & PT_IMG_STAGE_FRONT) {
     {   // pass A
         const long long groups = (long long)BV * (C / 8);
@@ -944,7 +947,9 @@ int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, in
         gp.M = BV; gp.N = C; gp.K = 64; gp.batch = HEADS;
         gp.a_split = w.q_split; gp.a_rows = BV; gp.a_cols = EMB; gp.lda = EMB; gp.a_koff_z = HD;
         gp.w_split = p->wk_pad_split; gp.w_rows = HEADS * C; gp.ldw = 64; gp.w_row_z = C;
-        gp.c_split = w.wpl; gp.cs_plane = WPLANE; gp.ldcs = 2 * WPLANE; gp.cs_off_z = WPITCH;
+        // (the tcgen05 pool kernel reads the planes through a tensor map: unpadded rows of 512)
+        const int wpitch = umma ? C : WPITCH;
+        gp.c_split = w.wpl; gp.cs_plane = HEADS * wpitch; gp.ldcs = 2 * HEADS * wpitch; gp.cs_off_z = wpitch;
         if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
     }
     {   // G3: cterm[:, h, t] = q[:, 32h:32h+32] . g_k[t, 32h:32h+32]
@@ -957,7 +962,11 @@ int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, in
     }
     }
     if (!(stages & PT_IMG_STAGE_BACK)) return PT_OK;
-    {   // pass B
+    if (umma) {   // pass B on tcgen05 tensor cores, TMA-fed (imgpool_umma.cu)
+        const char* dbg = getenv("PT_POOL_DEBUG");
+        float* dump = dbg && (atoi(dbg) & 64) && ws_bytes >= w.total + (size_t)BV * DBG_PER_VIEW * 4 ? reinterpret_cast<float*>((char*)ws + w.total) : nullptr;
+        if ((rc = launch_img_pool_umma(img_feat, w.wpl, w.cterm, w.xbar, w.ya_split, (long long)BV * HEADS * YA, BV, dump, s))) return rc;
+    } else {   // pass B, mma.sync form
         static bool attr_set[PT_MAX_DEVICES] = {};
         if (first_use_on_current_device(attr_set))
             PT_CUDA_OK(cudaFuncSetAttribute(img_pool_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES + POOL_EV_SMEM));

@@ -170,25 +170,41 @@ class ProxyTransformationNormReverse(nn.Module):
         return text_dict.values()
 
     def get_img_proxy(self, img_feat: torch.Tensor) -> torch.Tensor:
-        w = self._weights(img_feat.device)
-        return ops.img_attnpool(img_feat.contiguous(), w["img"], self.num_heads, params=w["img_struct"])
+        with torch.cuda.device(img_feat.device):
+            w = self._weights(img_feat.device)
+            return ops.img_attnpool(self._img_feat_dtype(img_feat).contiguous(), w["img"], self.num_heads, params=w["img_struct"])
 
     def get_point_proxy(self, center, cluster_idx, points):
-        w = self._weights(points.device)
-        return ops.point_encoder(points, cluster_idx, center, w["encoder"])
+        with torch.cuda.device(points.device):
+            w = self._weights(points.device)
+            return ops.point_encoder(points, cluster_idx, center, w["encoder"])
+
+    @staticmethod
+    def _img_feat_dtype(img_feat: torch.Tensor) -> torch.Tensor:
+        """fp32, bf16 and fp16 feature maps are consumed as they are; anything else is converted to fp32."""
+        return img_feat if img_feat.dtype in ops.IMG_FEAT_DTYPES else img_feat.float()
 
     # ------------------------------------------------------------------ weight packing
     def _weight_key(self, device):
-        return (str(device), self.use_tensor_cores) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        return (str(device), self.use_tensor_cores, ops.img_pool_variant()) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
     def refresh_weights(self):
         """Force re-packing (folded BN, position-bias tables, folded image-pool projections) on the next forward."""
         self._packed = None
+        self._graphs.clear()          # captured graphs hold pointers into the packed weights
 
     def _weights(self, device) -> dict:
         key = self._weight_key(device)
         if self._packed is not None and self._packed_key == key:
             return self._packed
+        self._graphs.clear()          # captured graphs hold pointers into the packed weights that are replaced below
+        with torch.cuda.device(device):
+            return self._pack_weights(device, key)
+
+    def _pack_weights(self, device, key) -> dict:
+        for name, mod in self.named_modules():
+            if isinstance(mod, nn.LayerNorm) and abs(mod.eps - 1e-5) > 1e-12:
+                raise NotImplementedError(f"{name}: LayerNorm eps {mod.eps} (the kernels implement the reference's default 1e-5)")
         f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
         with torch.no_grad():
             def conv_bn(seq):
@@ -258,7 +274,8 @@ class ProxyTransformationNormReverse(nn.Module):
             TPc = 228
             # the pool kernel walks the channels residue class by residue class (channel mod 8, csrc/imgpool_tc.cu): w_eff
             # columns and weighted-sum columns come in the orders below, absorbed here into the GEMM weights
-            score_order, sum_order = ops.img_pool_channel_orders(device)
+            variant = ops.img_pool_variant()
+            score_order, sum_order = ops.img_pool_channel_orders(device, variant)
             wk_pad = torch.zeros(heads * C, 64, dtype=torch.float64, device=device)
             wk_pad[:, :hd] = w_kc[:, score_order, :].reshape(heads * C, hd)
             gk_pad = torch.zeros(heads, TPc, 64, dtype=torch.float64, device=device)
@@ -268,7 +285,7 @@ class ProxyTransformationNormReverse(nn.Module):
             wv_cat[:, C:C + T] = (posb @ Wv.T + bv).T
             out.update(w_qc_split=ops.split_bf16(out["w_qc"]), wk_pad_split=ops.split_bf16(f(wk_pad)),
                        gk_pad_split=ops.split_bf16(f(gk_pad.reshape(heads * TPc, 64))), wv_cat_split=ops.split_bf16(f(wv_cat)),
-                       cproj_split=ops.split_bf16(out["cproj_w"]))
+                       cproj_split=ops.split_bf16(out["cproj_w"]), variant=variant)
         return out
 
     # ------------------------------------------------------------------ forward (:424-469)
@@ -288,6 +305,13 @@ class ProxyTransformationNormReverse(nn.Module):
 
     def _check_mode(self):
         """train() mode is supported as a forward-only batch-statistics pass (see forward()); everything else raises."""
+        if not self.training and torch.is_grad_enabled() and not getattr(self, "_warned_no_grad", False) and \
+                any(p.requires_grad for p in self.parameters()):
+            import warnings
+            self._warned_no_grad = True
+            warnings.warn("ProxyTransformationNormReverse (B200) is inference-only: forward() runs under torch.no_grad() and its "
+                          "outputs carry no gradient into the parameters or the image / text backbones (the reference neck is "
+                          "differentiable); wrap the call in torch.no_grad() to silence this warning", stacklevel=3)
         if self.training:
             if self.drop_rate or self.attn_drop_rate or self.drop_path_rate:
                 raise NotImplementedError("ProxyTransformationNormReverse (B200): train() mode needs drop_rate = attn_drop_rate = "
@@ -309,9 +333,7 @@ class ProxyTransformationNormReverse(nn.Module):
         mask = mask.to(dev, non_blocking=True).to(torch.uint8).contiguous() if mask is not None else None
         if img_proxy is None:
             img_feat = img_feat.to(dev, non_blocking=True)
-            if img_feat.dtype not in (torch.float32, torch.bfloat16):
-                img_feat = img_feat.float()
-            img_feat = img_feat.contiguous()
+            img_feat = self._img_feat_dtype(img_feat).contiguous()
         else:
             img_proxy = img_proxy.to(dev, torch.float32, non_blocking=True).contiguous()
         if self._use_graph(P, img_feat, img_proxy, trace):
@@ -372,8 +394,8 @@ class ProxyTransformationNormReverse(nn.Module):
             if p.shape[0] != N:
                 raise RuntimeError(f"all scenes must have the same number of points (got {p.shape[0]} vs {N})")
         text, mask = tuple(self.get_text_proxy(text_dict))                                      # :440
-        if img_proxy is None and img_feat.dtype not in (torch.float32, torch.bfloat16):
-            img_feat = img_feat.float()
+        if img_proxy is None:
+            img_feat = self._img_feat_dtype(img_feat)
         cur = torch.cuda.current_stream(dev)
         h2d, d2h = self._side_stream(dev, "h2d"), self._side_stream(dev, "d2h")
         h2d.wait_stream(cur)
@@ -434,9 +456,7 @@ class ProxyTransformationNormReverse(nn.Module):
         text = text.to(dev, torch.float32).contiguous()
         mask = mask.to(dev).to(torch.uint8).contiguous() if mask is not None else None
         img_feat = img_feat.to(dev)
-        if img_feat.dtype not in (torch.float32, torch.bfloat16):
-            img_feat = img_feat.float()
-        out, counts = self.forward_packed(P, text, mask, img_feat.contiguous())
+        out, counts = self.forward_packed(P, text, mask, self._img_feat_dtype(img_feat).contiguous())
         coords, feats, total = ops.sparse_collate(out, counts, voxel_size, reciprocal=reciprocal, floor=floor)
         t = int(total.item())                                                                    # the one D2H sync
         return coords[:t], feats[:t]
@@ -463,7 +483,12 @@ class ProxyTransformationNormReverse(nn.Module):
 
     def forward_packed(self, P, text, mask, img_feat, *, img_proxy=None, trace=None):
         """Device-resident form: P (B,N,3), text (B,L,c), mask (B,L) uint8|None, img_feat (B,V,C,H,W) ->
-        (out (B,N,3) packed per scene, counts (B,) int32), no host synchronisation."""
+        (out (B,N,3) packed per scene, counts (B,) int32), no host synchronisation.  Runs on P's device and that device's
+        current stream whatever the calling thread's current device is."""
+        with torch.cuda.device(P.device):
+            return self._forward_packed(P, text, mask, img_feat, img_proxy, trace)
+
+    def _forward_packed(self, P, text, mask, img_feat, img_proxy, trace):
         self._check_mode()
         w = self._weights(P.device)
         K, n = self.num_sub, self.real_cluster_num

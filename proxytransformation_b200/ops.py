@@ -14,6 +14,8 @@ import torch
 from . import _lib
 from ._lib import ImgPoolParams, ProxyBlockParams, check
 
+# image feature dtypes consumed without conversion (fp16 is what the reference's --amp backbone emits, tools/train.py:93-105)
+IMG_FEAT_DTYPES = (torch.float32, torch.bfloat16)
 RADIUS = 3.0   # DeformablePointCluster(radius=3)  (:23)
 MARGIN = 4.0   # DeformablePointCluster(margin=4)  (:23)
 
@@ -156,8 +158,11 @@ def _bn_batch_affine(sums, count: int, bn, C: int):
     dev = sums.device
     scale = torch.empty(C, dtype=f, device=dev)
     shift = torch.empty(C, dtype=f, device=dev)
+    if count <= 1:
+        raise ValueError(f"Expected more than 1 value per channel when training, got {count}")     # as nn.BatchNorm raises
     track = bn.track_running_stats and bn.running_mean is not None
-    momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+    # momentum=None is torch's cumulative moving average: factor 1 / num_batches_tracked AFTER this step's increment
+    momentum = 1.0 / float(int(bn.num_batches_tracked) + 1) if bn.momentum is None and track else float(bn.momentum or 0.0)
     check(L.pt_bn_batch_affine(sums.data_ptr(), count, _chk(bn.weight.detach(), f, "bn.weight"), _chk(bn.bias.detach(), f, "bn.bias"),
                                _chk(bn.running_mean, f, "running_mean") if track else None,
                                _chk(bn.running_var, f, "running_var") if track else None, momentum, float(bn.eps), C,
@@ -239,13 +244,28 @@ def make_img_params(w: Dict[str, torch.Tensor]) -> ImgPoolParams:
     for k in _IMG_SPLIT_KEYS:      # tensor-core fast path operands (all or none)
         t = w.get(k)
         setattr(p, k, _chk(t, torch.bfloat16, k) if t is not None else None)
+    p.variant = int(w.get("variant", _lib.PT_POOL_VARIANT_MMA))
     return p
 
 
-def img_pool_channel_orders(device=None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Channel orders of the bf16 image-pool kernel (C=512), see csrc/imgpool_tc.cu and include/pt_preshape.h:
+def img_pool_variant() -> int:
+    """Pooling kernel of the 16-bit image path: tcgen05 / TMA (csrc/imgpool_umma.cu) unless PT_POOL_KERNEL=mma selects the
+    mma.sync kernel (csrc/imgpool_tc.cu).  Read when the weights are packed (the folded channel orders depend on it)."""
+    import os
+    return _lib.PT_POOL_VARIANT_MMA if os.environ.get("PT_POOL_KERNEL", "umma") == "mma" else _lib.PT_POOL_VARIANT_UMMA
+
+
+def img_pool_channel_orders(device=None, variant: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Channel orders of the 16-bit image-pool kernels (C=512), see include/pt_preshape.h.
+    variant 1 (tcgen05 kernel, csrc/imgpool_umma.cu): position 64 s + r <-> channel s + 8 r for both.
+    variant 0 (mma.sync kernel, csrc/imgpool_tc.cu):
     score_order[((p*8 + s)*4 + q)*4 + e] = 128 p + 64 (e >> 1) + s + 16 q + 8 (e & 1)   (w_eff columns)
     sum_order[((sl*8 + s)*4 + q)*2 + e]  = 64 sl + s + 16 q + 8 e                       (weighted-sum columns)."""
+    if variant == _lib.PT_POOL_VARIANT_UMMA:
+        j = torch.arange(512)
+        order = (j >> 6) + 8 * (j & 63)
+        assert sorted(order.tolist()) == list(range(512))
+        return order.to(device), order.clone().to(device)
     p, s, q, e = torch.meshgrid(torch.arange(4), torch.arange(8), torch.arange(4), torch.arange(4), indexing="ij")
     score = (128 * p + 64 * (e >> 1) + s + 16 * q + 8 * (e & 1)).reshape(-1)
     sl, s, q, e = torch.meshgrid(torch.arange(8), torch.arange(8), torch.arange(4), torch.arange(2), indexing="ij")

@@ -281,3 +281,26 @@ def test_train_mode_forward_uses_batch_statistics_like_the_reference():
     assert [o.shape[0] for o in got_eval] == [o.shape[0] for o in want]
     for a, b in zip(got_eval, want):
         np.testing.assert_allclose(np_(a), b.numpy(), rtol=0, atol=1e-4)
+
+
+def test_headline_config_full_forward_against_oracle():
+    """BASELINE config 2 exactly as bench.py times it — C2-wide, 100 000 points, 256 kept clusters, 64 text tokens, V = 196
+    bf16 views, B = 4 scenes (784 views: every CTA of the persistent image-pool kernel loops over 5-6 views) — through the
+    public forward() against the oracle on identically rounded inputs: cluster indices bit-exact, image proxies within 6e-5,
+    transformed coordinates within 1e-4 (north_star)."""
+    cfg = syn.C2_WIDE
+    B = 4
+    sd = syn.make_state_dict(cfg, 0, bf16_round=True)
+    pts, text_dict, img = syn.make_inputs(cfg, B, first_scene=500, img_dtype=torch.bfloat16)
+    want, wtr = oracle_forward(cfg, sd, pts, text_dict, img.float())
+    m = build_module(cfg, sd)
+    tr = {}
+    out = m([p.to(DEV) for p in pts], {k: v.to(DEV) for k, v in text_dict.items()}, img.to(DEV), trace=tr)
+    assert np.array_equal(np_(tr["idx2"]), wtr["idx2"].numpy())
+    assert np.array_equal(np_(tr["kept_idx"]), wtr["kept_idx"].numpy())
+    assert np.array_equal(np_(tr["drop_idx"]), wtr["drop_idx"].numpy())
+    np.testing.assert_allclose(np_(tr["img_proxy"]), wtr["img_proxy"].numpy(), rtol=0, atol=6e-5)
+    np.testing.assert_allclose(np_(tr["transform"]).reshape(B, -1, 9), wtr["transform"].reshape(B, -1, 9).numpy(), rtol=0, atol=5e-5)
+    for o, w in zip(out, want):
+        assert o.shape == w.shape
+        np.testing.assert_allclose(np_(o), w.numpy(), rtol=0, atol=1e-4)

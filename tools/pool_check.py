@@ -2,7 +2,8 @@
 the kernel's own inputs (w_eff planes, cterm, xbar in the workspace): scaled scores, probabilities, weighted sums.
 With a third argument it also times the BACK stage at bench size over a sweep of the producer's L2-prefetch distance (PT_POOL_PF).
 Usage (GPU box): python tools/pool_check.py [views_per_scene] [scenes] [time | comma-separated PT_POOL_PF values] [single]
-(`single` also checks the experimental single-pass kernel, PT_POOL_SINGLE=1)"""
+(`single` also checks the experimental single-pass kernel, PT_POOL_SINGLE=1; `umma` / `mma` in the arguments restrict the
+check to the tcgen05 or the mma.sync pool kernel, default both)"""
 import os, sys, torch, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("PT_POOL_DEBUG", "64")
@@ -19,7 +20,6 @@ m.load_state_dict(syn.make_state_dict(cfg, 0, bf16_round=True))
 m = m.cuda()
 torch.manual_seed(1)
 img = (torch.relu(torch.randn(B, V, C, 15, 15, device="cuda")) * 1.5).bfloat16()
-w = m._weights(img.device)
 BV = B * V
 need = _lib.load().pt_img_attnpool_ws_bytes(BV, C, HW, EMB, HEADS)
 al = lambda x: (x + 255) // 256 * 256
@@ -31,12 +31,14 @@ o_xbar = take(BV * C * 4); o_xs = take(2 * BV * C * 2); o_q = take(2 * BV * EMB 
 o_ct = take(BV * HEADS * TP * 4); o_ya = take(2 * BV * HEADS * YA * 2); o_z = take(2 * BV * EMB * 2); o_o = take(BV * EMB * 4)
 assert off == need, (off, need)
 
-# channel orders (imgpool_tc.cu)
-j = np.arange(512)
-p_, s_, q_, e_ = j // 128, (j // 16) % 8, (j // 4) % 4, j % 4
-score_ch = torch.tensor(128 * p_ + 64 * (e_ >> 1) + s_ + 16 * q_ + 8 * (e_ & 1), device="cuda")
-sl_, s2_, q2_, e2_ = j // 64, (j // 8) % 8, (j // 2) % 4, j % 2
-sum_ch = torch.tensor(64 * sl_ + s2_ + 16 * q2_ + 8 * e2_, device="cuda")
+def setup(kernel):
+    """weights folded for `kernel` ('mma' | 'umma'), its channel orders and w_eff plane pitch"""
+    global w, score_ch, sum_ch, WPITCH, WPLANE
+    os.environ["PT_POOL_KERNEL"] = kernel
+    w = m._weights(img.device)
+    score_ch, sum_ch = ops.img_pool_channel_orders(img.device, w["img"]["variant"])
+    WPITCH = 512 if kernel == "umma" else 528
+    WPLANE = HEADS * WPITCH
 
 def run(single=False):
     os.environ["PT_POOL_SINGLE"] = "1" if single else "0"      # experimental single-pass kernel (imgpool_tc.cu), off by default
@@ -49,9 +51,13 @@ def run(single=False):
 def f32(ws, o, n): return ws[o:o + 4 * n].view(torch.float32)
 def bf(ws, o, n): return ws[o:o + 2 * n].view(torch.bfloat16)
 
-MODES = [False] + ([True] if "single" in sys.argv else [])
-for single in MODES:
+KERNELS = [k for k in ("mma", "umma") if k in sys.argv] or ["mma", "umma"]
+MODES = [(k, False) for k in KERNELS] + ([("mma", True)] if "single" in sys.argv else [])
+finals = {}
+for kernel, single in MODES:
+    setup(kernel)
     out, ws = run(single)
+    finals["single" if single else kernel] = out.clone()
     X = img.reshape(BV, C, HW).double()
     wpl = bf(ws, o_wpl, BV * 2 * WPLANE).double().reshape(BV, 2, HEADS, WPITCH)[..., :512].sum(1)      # (BV, 8, 512) score order
     weff = torch.zeros(BV, HEADS, C, dtype=torch.float64, device="cuda")
@@ -67,7 +73,7 @@ for single in MODES:
     ya = bf(ws, o_ya, 2 * BV * HEADS * YA).double().reshape(2, BV, HEADS, YA).sum(0)
     P_k = ya[..., 512:512 + 226]
     Y_k = torch.zeros_like(Y); Y_k[:, :, sum_ch] = ya[..., :512]
-    name = "single" if single else "mma"
+    name = "single" if single else kernel
     print(f"[{name}] scores max err {float((sv_k - sv).abs().max()):.3e}  probs max err {float((P_k - P).abs().max()):.3e}  "
           f"sums max rel err {float(((Y_k - Y).abs().max() / Y.abs().max())):.3e}")
     d = (sv_k - sv).abs()
@@ -76,7 +82,11 @@ for single in MODES:
     dy = (Y_k - Y).abs().amax(dim=(0, 1)).reshape(8, 64)
     print(f"[{name}] sums err by slab:", [f"{float(dy[k].max()):.1e}" for k in range(8)])
 
-if len(sys.argv) > 3 and sys.argv[3] != "single":                 # timing: BACK stage (pool + value GEMMs + LayerNorm) at bench size
+if len(finals) > 1:
+    ks = list(finals)
+    print("final image proxies, max |%s - %s| = %.3e" % (ks[0], ks[-1], float((finals[ks[0]] - finals[ks[-1]]).abs().max())))
+
+if len(sys.argv) > 3 and sys.argv[3] not in ("single", "mma", "umma"):                 # timing: BACK stage (pool + value GEMMs + LayerNorm) at bench size
     Bt, Vt = 64, 196
     imgs = [(torch.relu(torch.randn(Bt, Vt, C, 15, 15, device="cuda")) * 1.5).bfloat16() for _ in range(2)]   # 2 x 2.9 GB >> L2
     needt = _lib.load().pt_img_attnpool_ws_bytes(Bt * Vt, C, HW, EMB, HEADS)
@@ -84,6 +94,7 @@ if len(sys.argv) > 3 and sys.argv[3] != "single":                 # timing: BACK
     outs_t = [ops.img_attnpool(imgs[k], w["img"], HEADS, params=w["img_struct"], stages=1, ws=wss[k])[0] for k in range(2)]
     for pf in ([int(x) for x in sys.argv[3].split(',')] if sys.argv[3][0].isdigit() else (4, 0, 2, 6, 8, 10, 4)):
         os.environ["PT_POOL_PF"] = str(pf)
+        setup("mma")
         for k in range(4):
             ops.img_attnpool(imgs[k & 1], w["img"], HEADS, params=w["img_struct"], stages=2, out=outs_t[k & 1], ws=wss[k & 1])
         torch.cuda.synchronize()
