@@ -1,14 +1,15 @@
-// S9 image proxies, pass B (scores -> softmax -> attention-weighted feature sums) on tcgen05 tensor cores, fed by TMA:
+// S9 image proxies, pass B (scores -> softmax -> attention-weighted feature sums) on tcgen05 tensor cores:
 // get_img_proxy (:335-342) + AttentionPool2d.forward (:154-177) in single-query form (algebra in imgpool.cu), shipped
 // geometry C = 512 channels, 15 x 15 = 225 positions, 8 heads of 32, 16-bit features (bf16).
 //
-// The feature map of a view is [512 channels][225 tokens] with a 450-byte row pitch, which no tensor map can describe
-// (strides must be multiples of 16 bytes).  But 225 = 1 (mod 8): the rows of one residue CLASS s = channel mod 8, channels
-// s + 8r, r = 0..63, are 3600 bytes apart and start 448 s + 2 s bytes into the view.  In the coordinate u = token + s a class is
-// therefore the 16-byte-aligned tensor (u: 232, r: 64, view) at base + 448 s with strides (3600, 230400) bytes, and because
-// TMA box origins are element-granular, the box at u0 = t0 + s lands tokens t0..t0+63 of all 64 class rows in shared memory
-// at the SAME alignment for every class: TMA does the realignment the mma.sync kernel needed ldmatrix tricks for.
-// One 8 KB SWIZZLE_128B tile [64 class rows][64 tokens] serves both contractions without any copy:
+// The feature map of a view is [512 channels][225 tokens] with a 450-byte row pitch.  UMMA shared-memory descriptors (and TMA
+// tensor maps) need 16-byte aligned rows, so the rows have to be REALIGNED on their way into shared memory.  225 = 1 (mod 8):
+// the rows of one residue CLASS s = channel mod 8 (channels s + 8r, r = 0..63) are 3600 bytes apart and all start 2 s bytes
+// after a 16-byte boundary, so a class is realigned by ONE shift of s elements.  TMA cannot do it (box origins must be 16-byte
+// aligned in global memory — measured: the first box with an odd origin raises "illegal instruction"), so loader warps do:
+// coalesced 16-byte loads of the aligned chunks, a funnel shift by s elements across neighbouring chunks (shuffles), and
+// 16-byte stores into the SWIZZLE_128B tile layout the tensor core reads.
+// One 8 KB tile [64 class rows][64 tokens] serves both contractions without any copy:
 //   scores  D1[token][n]   += X^T W^T : A = the tile read MN-major (M = 64 tokens, K = 16 class rows per MMA),
 //                                       B = w_eff rows n = (hi|lo, head) of this class, K-major           (tcgen05.mma M64 N16 K16)
 //   sums    D2[channel][n] += X  P^T : A = two class tiles read K-major (M = 128 channel rows, K = 16 tokens per MMA),
@@ -17,16 +18,18 @@
 // the accumulation is fp32 in TMEM (same numerics as the 3xBF16 GEMMs: ~2^-17 relative).
 //
 // One persistent CTA per SM, a view is streamed ONCE as 4 token windows of 64 (flash-attention structure, one query per head):
-//   warp 0      TMA producer: per view 8 w_eff boxes (2 KB each) and per window 4 class-pair slots of 2 boxes (8 KB each)
-//               into a 10-slot ring (160 KB)
-//   warp 1      MMA issuer (one elected thread): scores of window g+1 interleaved with the sums of window g; every slot is
-//               handed back to the producer by tcgen05.commit when the sums that read it have completed
-//   warps 4-7   softmax: tcgen05.ld the 64 x 16 score tile (lane = token), + position term, exp relative to a per-view
-//               reference maximum (established by window 0, raised FA-style by rescaling the accumulators in TMEM only when
-//               a later window exceeds it by more than TAU — never on ordinary data), bf16 hi/lo probability tile -> shared
-//               memory (the B operand of the sums), running sum in registers; end of view: final probabilities -> global
-//   warps 8-11  epilogue: mean-token score s0 = w_eff . xbar (CUDA cores, from L2), then per view Y = (D2 f + p0 xbar) / L
-//               from TMEM -> bf16 hi/lo planes for the value-side GEMM (same output format as the mma.sync kernel)
+//   warp 0       TMA producer of the per-view w_eff planes (8 boxes of 2 KB, SWIZZLE_128B)
+//   warp 1       MMA issuer (one elected thread): scores of window g+1 interleaved with the sums of window g; every ring slot is
+//                handed back to the loaders by tcgen05.commit when the sums that read it have completed
+//   warps 4-7    softmax: tcgen05.ld the 64 x 16 score tile (lane = token), + position term, exp relative to a per-view
+//                reference maximum (established by window 0, raised FA-style by rescaling the accumulators in TMEM only when
+//                a later window exceeds it by more than TAU — never on ordinary data), bf16 hi/lo probability tile -> shared
+//                memory (the B operand of the sums), running sum in registers; end of view: final probabilities -> global
+//   warps 8-11   epilogue: mean-token score s0 = w_eff . xbar (CUDA cores, from L2), then per view Y = (D2 f + p0 xbar) / L
+//                from TMEM -> bf16 hi/lo planes for the value-side GEMM (same output format as the mma.sync kernel)
+//   warps 12-19  loaders: warp l owns rows 8 l .. 8 l + 7 of every class tile; per window it issues its 20 loads (16 x 4 rows x
+//                8 chunks + the 9th chunk of its 64 rows) before it touches the ring, so 80 KB of loads are in flight per SM
+//                while earlier windows are consumed; 10-slot ring of class-pair slots (160 KB)
 // Channel order of w_eff columns and of the weighted sums: position 64 s + r  <->  channel s + 8 r (absorbed into the folded
 // GEMM weights on the host, pt_img_pool_params variant 1).
 #include "common.cuh"
@@ -58,7 +61,9 @@ constexpr int OFF_BAR = OFF_MISC + 1024;
 constexpr int NBAR = 2 * RING + 6 + 2 * PBUF + 8;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;      // + slack for the 1024-byte alignment of the swizzled tiles
-constexpr int THREADS = 32 * 12;
+// warp roles: 0 = MMA issuer + w_eff TMA + TMEM allocation, 1-4 softmax, 5-8 epilogue (TMEM lane quarter = warp mod 4), 9-16 loaders
+constexpr int SOFTMAX_WARP0 = 1, EPI_WARP0 = 5, LOADER_WARP0 = 9, LOADER_WARPS = 8;
+constexpr int THREADS = 32 * (LOADER_WARP0 + LOADER_WARPS);
 constexpr int TMEM_COLS = 256;               // D1: 2 x 16 columns at 0 ; D2: 2 x 64 columns at 64
 constexpr int D2_COL = 64;
 constexpr float TAU = 16.0f;                 // the reference maximum is raised when a score exceeds it by more than this
@@ -171,11 +176,50 @@ __device__ __forceinline__ float iu_bf(uint32_t packed, int k) {      // element
 }
 
 struct UmmaPoolMaps {
-    CUtensorMap x[8];      // class s: (u 232, r 64, view BV) over img + 448 s, strides (3600, 230400), box (64, 64, 1)
     CUtensorMap w;         // w_eff planes as (512 columns, BV*16 rows (view, hi|lo, head)), box (64, 16)
 };
 
+__device__ __forceinline__ uint4 iu_ldg_stream(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// One 16-byte output chunk of a class-S row: elements [8 j + S, 8 j + S + 8) of the row in u = token + S coordinates, i.e. the
+// tail of aligned chunk j (this lane's `a`) and the head of chunk j + 1 (the next lane's `a`; for j == 7 the 9th chunk of the
+// row, which lane `tail_lane` holds in `t`), stored at chunk j of tile row `row` (SWIZZLE_128B: chunk index XOR row mod 8).
+template <int S>
+__device__ __forceinline__ void iu_shift_store(uint8_t* tile, int row, int j, const uint4& a, const uint4& t, int tail_lane) {
+    constexpr int Q = S >> 1, ODD = S & 1, NB = Q + ODD;
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, tw[4] = {t.x, t.y, t.z, t.w};
+    uint32_t A[9] = {a.x, a.y, a.z, a.w, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        const uint32_t nxt = __shfl_down_sync(FULL, aw[i], 1);
+        const uint32_t tl = __shfl_sync(FULL, tw[i], tail_lane);
+        A[4 + i] = j == 7 ? tl : nxt;
+    }
+    uint4 o;
+    if (ODD) {
+        o.x = __funnelshift_r(A[Q], A[Q + 1], 16); o.y = __funnelshift_r(A[Q + 1], A[Q + 2], 16);
+        o.z = __funnelshift_r(A[Q + 2], A[Q + 3], 16); o.w = __funnelshift_r(A[Q + 3], A[Q + 4], 16);
+    } else {
+        o.x = A[Q]; o.y = A[Q + 1]; o.z = A[Q + 2]; o.w = A[Q + 3];
+    }
+    *reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4)) = o;
+}
+
+// Class pair P of one window: both tiles of ring slot `tile0`, this warp's 8 rows of each (two groups of 4 rows x 8 chunks).
+template <int P>
+__device__ __forceinline__ void iu_store_pair(uint8_t* tile0, int row0, int rr, int j, const uint4 (&am)[2][2], const uint4& at) {
+    iu_shift_store<2 * P>(tile0, row0 + rr, j, am[0][0], at, rr);
+    iu_shift_store<2 * P>(tile0, row0 + 4 + rr, j, am[0][1], at, 4 + rr);
+    iu_shift_store<2 * P + 1>(tile0 + ipu::TILE_BYTES, row0 + rr, j, am[1][0], at, 8 + rr);
+    iu_shift_store<2 * P + 1>(tile0 + ipu::TILE_BYTES, row0 + 4 + rr, j, am[1][1], at, 12 + rr);
+}
+
 struct UmmaPoolArgs {
+    const uint8_t* img;          // (BV, 512, 225) 16-bit features
     const __nv_bfloat16* wpl;    // (BV, 2, 8, 512) bf16 hi / lo planes of w_eff, columns 64 s + r
     const float* cterm;          // (BV, 8, TP)
     const float* xbar;           // (BV, 512) natural channel order
@@ -184,6 +228,8 @@ struct UmmaPoolArgs {
     int BV;
     float scale;
     float* dbg;                  // optional (PT_POOL_DEBUG bit 64): [BV][8][256] scaled scores, attention tokens 0..225
+    int debug;                   // PT_UMMA_DEBUG bring-up switches (garbage results): 1 no score MMAs, 2 no sum MMAs, 4 score MMAs with a
+                                 // K-major A descriptor, 8 score MMAs with M = 128
 };
 
 __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __grid_constant__ UmmaPoolMaps maps, const UmmaPoolArgs a) {
@@ -211,18 +257,16 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < RING; ++i) { iu_mbar_init(full + i, 1); iu_mbar_init(empty + i, 1); }
+        for (int i = 0; i < RING; ++i) { iu_mbar_init(full + i, LOADER_WARPS); iu_mbar_init(empty + i, 1); }
         for (int i = 0; i < 2; ++i) {
             iu_mbar_init(wfull + i, 1); iu_mbar_init(wempty + i, 1); iu_mbar_init(d1_full + i, 1);
             iu_mbar_init(d2_full + i, 1); iu_mbar_init(d2_empty + i, 4); iu_mbar_init(s0_full + i, 1); iu_mbar_init(l_full + i, 1);
         }
         for (int i = 0; i < PBUF; ++i) { iu_mbar_init(p_full + i, 4); iu_mbar_init(p_empty + i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#pragma unroll
-        for (int s = 0; s < 8; ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x[s]) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
     }
-    if (warp == 2) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(iu_smem(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -232,34 +276,45 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
     const uint32_t tmem = *tmem_slot;
     const int nviews = (int)blockIdx.x < a.BV ? (a.BV - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-    if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            unsigned it = 0;
-            for (int vi = 0; vi < nviews; ++vi) {
-                const int bv = blockIdx.x + vi * gridDim.x;
-                const int wb = vi & 1;
-                iu_wait(wempty + wb, ((vi >> 1) & 1) ^ 1);
-                iu_expect_tx(wfull + wb, W_BYTES);
+    if (warp >= LOADER_WARP0) {
+        // ===== loaders: global -> registers -> (shift by the class) -> swizzled tiles =====
+        const int row0 = 8 * (warp - LOADER_WARP0), rr = lane >> 3, j = lane & 7;
+        unsigned it = 0;
+        for (int vi = 0; vi < nviews; ++vi) {
+            const int bv = blockIdx.x + vi * gridDim.x;
+            const uint8_t* view = a.img + (size_t)bv * (C * HW * 2);
+#pragma unroll 1
+            for (int w = 0; w < NWIN; ++w) {
+                uint4 am[4][2][2], at[4];
+                const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+                const int chunk = 8 * w + j;                               // aligned 16-byte chunk of the row; 29 chunks per row
 #pragma unroll
-                for (int s = 0; s < 8; ++s) iu_tma_2d(smem + OFF_W + wb * W_BYTES + s * WCLASS_BYTES, &maps.w, 64 * s, 16 * bv, wfull + wb);
+                for (int p = 0; p < 4; ++p) {
 #pragma unroll
-                for (int w = 0; w < NWIN; ++w) {
+                    for (int e = 0; e < 2; ++e)
 #pragma unroll
-                    for (int p = 0; p < 4; ++p, ++it) {
-                        const unsigned slot = it % RING;
-                        iu_wait(empty + slot, ((it / RING) & 1) ^ 1);
-                        iu_expect_tx(full + slot, SLOT_BYTES);
-                        uint8_t* dst = smem + OFF_RING + slot * SLOT_BYTES;
-                        // box origin u0 = token0 + class: the class rows land aligned on token0 (see header)
-                        iu_tma_3d(dst, &maps.x[2 * p], WTOK * w + 2 * p, 0, bv, full + slot);
-                        iu_tma_3d(dst + TILE_BYTES, &maps.x[2 * p + 1], WTOK * w + 2 * p + 1, 0, bv, full + slot);
-                    }
+                        for (int hf = 0; hf < 2; ++hf)
+                            am[p][e][hf] = chunk <= 28 ? iu_ldg_stream(view + 448 * (2 * p + e) + 3600 * (row0 + 4 * hf + rr) + 16 * chunk) : zero;
+                    // 9th chunk of this warp's 16 rows of the pair: lanes 0-7 class 2p, lanes 8-15 class 2p + 1
+                    at[p] = (lane < 16 && 8 * w + 8 <= 28) ? iu_ldg_stream(view + 448 * (2 * p + (lane >> 3)) + 3600 * (row0 + (lane & 7)) + 16 * (8 * w + 8)) : zero;
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p, ++it) {
+                    const unsigned slot = it % RING;
+                    iu_wait(empty + slot, ((it / RING) & 1) ^ 1);
+                    uint8_t* tile0 = smem + OFF_RING + slot * SLOT_BYTES;
+                    if (p == 0) iu_store_pair<0>(tile0, row0, rr, j, am[0], at[0]);
+                    else if (p == 1) iu_store_pair<1>(tile0, row0, rr, j, am[1], at[1]);
+                    else if (p == 2) iu_store_pair<2>(tile0, row0, rr, j, am[2], at[2]);
+                    else iu_store_pair<3>(tile0, row0, rr, j, am[3], at[3]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) iu_arrive(full + slot);
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
+    } else if (warp == 0) {
+        // ===== MMA issuer (+ TMA of the per-view w_eff planes, one view ahead) =====
         if (lane == 0) {
             constexpr uint32_t IDESC1 = iu_idesc(64, 16, true), IDESC2 = iu_idesc(128, 16, false);
             const uint32_t ring = iu_smem(smem + OFF_RING), wbase = iu_smem(smem + OFF_W), pbase = iu_smem(smem + OFF_P);
@@ -277,7 +332,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 const uint32_t d2 = tmem + D2_COL + (vp & 1) * 64 + 16 * p;
                 const int nk = wp == 3 ? 3 : 4;                                      // tokens 240..255 do not exist
                 for (int j = 0; j < nk; ++j)
-                    iu_mma(d2, iu_desc(sa + 32 * j, 0), iu_desc(sp + 32 * j, 0), IDESC2, (wp | j) != 0 ? 1u : 0u);
+                    if (!(a.debug & 2)) iu_mma(d2, iu_desc(sa + 32 * j, 0), iu_desc(sp + 32 * j, 0), IDESC2, (wp | j) != 0 ? 1u : 0u);
                 iu_commit(empty + slot);                                             // slot back to the producer once read
                 ++it2;
                 if (p == 3) {
@@ -285,8 +340,18 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     if (wp == 3) iu_commit(d2_full + (vp & 1));
                 }
             };
+            auto load_w = [&](int vi) {            // w_eff planes of this CTA's view vi -> buffer vi & 1 (free once the scores of view vi - 2 are done)
+                if (vi >= nviews) return;
+                const int bv = blockIdx.x + vi * gridDim.x, wb = vi & 1;
+                iu_wait(wempty + wb, ((vi >> 1) & 1) ^ 1);
+                iu_expect_tx(wfull + wb, W_BYTES);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) iu_tma_2d(smem + OFF_W + wb * W_BYTES + s * WCLASS_BYTES, &maps.w, 64 * s, 16 * bv, wfull + wb);
+            };
+            load_w(0);
             for (int vi = 0; vi < nviews; ++vi) {
                 const int wb = vi & 1;
+                load_w(vi + 1);
                 iu_wait(wfull + wb, (vi >> 1) & 1);
                 iu_fence_after();
                 for (int w = 0; w < NWIN; ++w, ++g) {
@@ -300,9 +365,12 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                         for (int e = 0; e < 2; ++e) {
                             const uint32_t sw = wbase + wb * W_BYTES + (2 * p + e) * WCLASS_BYTES;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                iu_mma(d1, iu_desc(sa + e * TILE_BYTES + 2048 * j, TILE_BYTES), iu_desc(sw + 32 * j, 0), IDESC1,
+                            for (int j = 0; j < 4; ++j) {
+                                if (a.debug & 1) continue;
+                                const uint32_t idesc = (a.debug & 4) ? iu_idesc(64, 16, false) : (a.debug & 8) ? iu_idesc(128, 16, true) : IDESC1;
+                                iu_mma(d1, iu_desc(sa + e * TILE_BYTES + 2048 * j, TILE_BYTES), iu_desc(sw + 32 * j, 0), idesc,
                                        (p | e | j) != 0 ? 1u : 0u);
+                            }
                         }
                         ++it1;
                         if (p == 3) {
@@ -316,7 +384,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
             if (g > 0)
                 for (int p = 0; p < 4; ++p) sums(g - 1, p);
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= SOFTMAX_WARP0 && warp < EPI_WARP0) {
         // ===== softmax: lane < 16 of warp q owns token 16 q + lane of every window (TMEM lanes of an M = 64 accumulator) =====
         const int q = warp & 3;
         const bool act = lane < 16;
@@ -438,7 +506,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 fin[h] = f * inv;
                 p0n[h] = p0 * inv;
             }
-            if (warp == 4 && lane == 0) {
+            if (warp == SOFTMAX_WARP0 && lane == 0) {
 #pragma unroll
                 for (int h = 0; h < 8; ++h) { stat_l[(vi & 1) * 8 + h] = lt[h]; stat_m[(vi & 1) * 8 + h] = mref[h]; }
                 iu_arrive(l_full + (vi & 1));
@@ -470,9 +538,9 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 }
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= EPI_WARP0 && warp < LOADER_WARP0) {
         // ===== epilogue: mean-token score, then Y = (D2 f + p0 xbar) / L -> bf16 hi/lo planes =====
-        const int q = warp & 3, et = threadIdx.x - 256, row = 32 * q + lane;
+        const int q = warp & 3, et = threadIdx.x - 32 * EPI_WARP0, row = 32 * q + lane;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         for (int vi = 0; vi < nviews; ++vi) {
             const int bv = blockIdx.x + vi * gridDim.x;
@@ -544,7 +612,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
     }
     iu_fence_before();
     __syncthreads();
-    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------- host
@@ -556,12 +624,6 @@ int launch_img_pool_umma(const void* img_feat, const __nv_bfloat16* wpl, const f
     PT_REQUIRE(((uintptr_t)img_feat & 15) == 0 && ((uintptr_t)wpl & 15) == 0, "pt_img_attnpool: img_feat / workspace must be 16-byte aligned");
     UmmaPoolMaps maps;
     int rc;
-    for (int cls = 0; cls < 8; ++cls) {
-        const unsigned long long dims[3] = {232ull, 64ull, (unsigned long long)BV};
-        const unsigned long long strides[2] = {3600ull, (unsigned long long)C * HW * 2};
-        const unsigned box[3] = {64u, 64u, 1u};
-        if ((rc = encode_tensor_map_16bit(&maps.x[cls], (const uint8_t*)img_feat + 448 * cls, 3, dims, strides, box, false))) return rc;
-    }
     {
         const unsigned long long dims[2] = {(unsigned long long)C, (unsigned long long)BV * 16};
         const unsigned long long strides[1] = {(unsigned long long)C * 2};
@@ -574,9 +636,11 @@ int launch_img_pool_umma(const void* img_feat, const __nv_bfloat16* wpl, const f
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     UmmaPoolArgs a;
-    a.wpl = wpl; a.cterm = cterm; a.xbar = xbar; a.ya_hi = ya_hi; a.ya_plane = ya_plane; a.BV = BV;
+    a.img = (const uint8_t*)img_feat; a.wpl = wpl; a.cterm = cterm; a.xbar = xbar; a.ya_hi = ya_hi; a.ya_plane = ya_plane; a.BV = BV;
     a.scale = (float)(1.0 / sqrt(32.0));
     a.dbg = dbg;
+    const char* dbe = getenv("PT_UMMA_DEBUG");
+    a.debug = dbe ? atoi(dbe) : 0;
     const int grid = BV < sms ? BV : sms;
     { ProfScope prof_(PROF_IMG_POOL, s); img_pool_umma_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(maps, a); }
     PT_LAUNCH_CHECK();
