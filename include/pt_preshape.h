@@ -211,9 +211,6 @@ int pt_debug_pool_trace(unsigned long long* out8, int reset);
 /* Debug only (PT_POOL_DEBUG bit 32): (id, SM clock) event pairs logged by CTA 0 for views 40..43; returns the count and
  * clears the log.  Decoded by tools/pool_events.py. */
 int pt_debug_pool_events(long long* out, int max_events);
-/* Debug only (PT_UMMA_DEBUG bit 16): SM-clock cycles CTA 0 of the tcgen05 image-pool kernel spends per role and phase (slot
- * table in csrc/imgpool_umma.cu). */
-int pt_debug_umma_trace(unsigned long long* out32, int reset);
 
 /* ---- S10-S12 affine (:459-462) + pt_replace (:472-498) + remove_points_by_index (:501-525) ------------
  * new = (T[m] @ (p - centre[m]) + centre[m]) + t[m] for every valid (m,k); duplicate destinations resolved by the

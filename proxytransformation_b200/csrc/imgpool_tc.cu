@@ -598,266 +598,6 @@ __global__ void __launch_bounds__(ip::THREADS, 1) img_pool_mma_kernel(const Pool
 
 
 
-// ------------------------------------------------------------------------------------------------ pass B, single-pass form
-// EXPERIMENTAL (PT_POOL_SINGLE=1, off by default) — first version of the schedule of DESIGN.md §7a, transcribed from its
-// executable specification tools/pool_single_emu.py.  Same inputs, outputs and channel orders as img_pool_mma_kernel.
-// Status at the end of round 1: CORRECT on a B200 (tools/pool_check.py 50 8 single: scores 3.3e-7, probabilities 1.1e-7, sums
-// 5.2e-6 relative against float64 over 400 views — the same errors as the shipped kernel) but 2.7 x SLOWER (0.51 ms against
-// 0.19 ms per 16 scenes, tools/pool_time_quick.py): the three phases of a window run strictly one after the other behind
-// block-wide barriers and only 8 of the 16 warps work in the softmax step.  Not profiled yet.
-//
-// One persistent CTA per SM, 16 warps, no producer warp.  A view is streamed ONCE as 8 token windows of 32 u-columns
-// (u = token + residue class): a window is a 64-byte piece of every channel row (16-byte cp.async copies of the aligned
-// chunks, zero fill past chunk 28), stored class-major (row of channel 8 r + s = 64 s + r) with the chunk position
-// XOR-swizzled by the row so that every ldmatrix below is conflict-free; 5 slots, 3 windows in flight.  Per window w:
-//   (1) scores    warp = (class s, chunk pair): S_s[h][u] for its 16 u-columns over the 64 class-s channels (4 k-steps), A
-//                 fragments = the view's w_eff rows held in registers; partials -> part[w & 1][s][h][32]
-//   (2) softmax   warp = head (8 warps), lane = token slot: window w completes the tokens t in [32 w - 7, 32 w + 25); score =
-//                 fixed-order sum of the 8 class partials at u = t + s (window w or w - 1) + position term; running max / sum,
-//                 alpha = exp(m_old - m_new), probabilities of the slot as bf16 hi/lo (two parity copies, zero margins)
-//   (3) sums      warp = (class s, channel half): Y (4 column tiles in registers for the whole view) *= alpha, then 3 k-steps
-//                 over the chunks -1 .. 3 of the window (chunk -1 = last chunk of window w - 1) with the probabilities shifted
-//                 by s as A fragments
-// and at the end of the view: Y / l + p0 * xbar, hi/lo split; final probabilities exp(score - m) / l from the raw scores.
-namespace ip3 {
-using namespace ip;
-constexpr int NWIN = 8, WIN_BYTES = C * 64, SLOTS = 5, AHEAD = SLOTS - 2;   // windows in flight besides the one in use and w - 1
-constexpr int THREADS3 = 512;
-constexpr int OFF_WIN = 0;
-constexpr int OFF_W = OFF_WIN + SLOTS * WIN_BYTES;                          // w_eff planes, double-buffered by view parity
-constexpr int OFF_PART = OFF_W + 2 * WBYTES;                                // float [2][8 classes][8 heads][32]
-constexpr int OFF_PB = OFF_PART + 2 * 8 * HEADS * 32 * 4;                   // bf16 [2 copies][hi|lo][8 heads][64]: slot i at i + 8 + copy
-constexpr int OFF_SV = OFF_PB + 2 * 2 * HEADS * 64 * 2;                     // float [8 heads][232] scaled scores of the spatial tokens
-constexpr int OFF_ST = OFF_SV + HEADS * 232 * 4;                            // float m[8], l[8], alpha[8], sv0[8], s0part[8 classes][8]
-constexpr int SMEM3_BYTES = OFF_ST + (32 + 64) * 4;
-static_assert(SMEM3_BYTES <= 227 * 1024 && OFF_W % 16 == 0 && OFF_PART % 16 == 0 && OFF_PB % 16 == 0, "shared memory budget (single pass)");
-}  // namespace ip3
-
-__device__ __forceinline__ void ip_cp16_zfill(void* dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ip_smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
-}
-
-__global__ void __launch_bounds__(ip3::THREADS3, 1) img_pool_single_kernel(const PoolArgs a) {
-    using namespace ip3;
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, q = lane & 3, mi = lane >> 3, r8 = lane & 7;
-    const int s = warp & 7, half = warp >> 3;                              // class ; chunk pair (scores) / channel half (sums)
-    float* part = reinterpret_cast<float*>(smem + OFF_PART);
-    float* svbuf = reinterpret_cast<float*>(smem + OFF_SV);
-    float* st_m = reinterpret_cast<float*>(smem + OFF_ST);
-    float* st_l = st_m + 8;
-    float* st_alpha = st_l + 8;
-    float* st_sv0 = st_alpha + 8;
-    float* s0part = st_sv0 + 8;                                            // [8 classes][8 heads]
-    for (int i = tid; i < (2 * 2 * HEADS * 64 * 2) / 4; i += THREADS3) reinterpret_cast<uint32_t*>(smem + OFF_PB)[i] = 0u;   // margins stay zero
-
-    const int nviews = blockIdx.x < a.BV ? (a.BV - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int total = nviews * NWIN;
-    // one commit group per global window index gw (empty past the end): the window's 2048 chunks, plus the w_eff planes of the
-    // view with its window 0
-    auto issue = [&](int gw) {
-        if (gw < total) {
-            const int j = gw >> 3, w = gw & 7;
-            const int bv = blockIdx.x + j * gridDim.x;
-            const uint8_t* view = a.img + (size_t)bv * C * HW * 2;
-            uint8_t* dst = smem + OFF_WIN + (gw % SLOTS) * WIN_BYTES;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int e = tid + THREADS3 * i, row = e >> 2, ch = e & 3;
-                const int gch = 4 * w + ch;
-                const bool live = gch < NCHUNK;
-                const uint8_t* src = view + (live ? 448 * (row >> 6) + 3600 * (row & 63) + 16 * gch : 0);
-                ip_cp16_zfill(dst + 64 * row + 16 * (ch ^ ((row >> 1) & 3)), src, live ? 16u : 0u);
-            }
-            if (w == 0) {
-                const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpl + (size_t)bv * 2 * WPLANE);
-                uint8_t* wdst = smem + OFF_W + (j & 1) * WBYTES;
-                for (int i = tid; i < WBYTES / 16; i += THREADS3) ip_cp16_zfill(wdst + 16 * i, wsrc + 16 * i, 16u);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-#pragma unroll 1
-    for (int gw = 0; gw < AHEAD; ++gw) issue(gw);
-
-    uint32_t Aw[4][4];                                                     // w_eff fragments of the view (scores)
-    float Y[4][4];                                                         // weighted-sum accumulators of the view
-    float sv0 = 0.f, m_run = 0.f, l_run = 0.f;                             // softmax warps (warp < 8, head = warp): replicated per lane
-    const uint32_t win0 = ip_smem_u32(smem + OFF_WIN);
-
-#pragma unroll 1
-    for (int gw = 0; gw < total; ++gw) {
-        const int j = gw >> 3, w = gw & 7;
-        const int bv = blockIdx.x + j * gridDim.x;
-        asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD - 1) : "memory");   // this thread's copies of window gw have landed
-        __syncthreads();                                                   // ... everybody's; and every warp is done with window gw - 1
-        issue(gw + AHEAD);                                                 // into the slot window gw - 2 occupied
-        const uint32_t wbase = win0 + (gw % SLOTS) * WIN_BYTES;
-        const uint32_t pbase = win0 + ((gw + SLOTS - 1) % SLOTS) * WIN_BYTES;   // window gw - 1
-        // position term of the token this lane completes in this window (softmax warps); in flight during the score MMAs
-        const int tok = 32 * w - 7 + lane;
-        const bool tok_ok = tok >= 0 && tok < HW;
-        float ct = 0.f;
-        if (warp < HEADS && tok_ok) ct = __ldg(a.cterm + ((size_t)bv * HEADS + warp) * TP + tok + 1);
-
-        if (w == 0) {
-            // ---- view start: w_eff fragments, mean-token score partials, accumulators
-            const uint8_t* wbuf = smem + OFF_W + (j & 1) * WBYTES;
-            const float* xb = a.xbar + (size_t)bv * C;
-            float dotp = 0.f;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int col = ((k * 8 + s) * 4 + q) * 4;
-                const uint2 ah = *reinterpret_cast<const uint2*>(wbuf + (g * WPITCH + col) * 2);
-                const uint2 al = *reinterpret_cast<const uint2*>(wbuf + (WPLANE + g * WPITCH + col) * 2);
-                Aw[k][0] = ah.x; Aw[k][1] = al.x; Aw[k][2] = ah.y; Aw[k][3] = al.y;
-                if (half == 1) {
-                    const int ch = 128 * k + s + 16 * q;
-                    const float w0 = __uint_as_float(ah.x << 16) + __uint_as_float(al.x << 16), w1 = __uint_as_float(ah.x & 0xffff0000u) + __uint_as_float(al.x & 0xffff0000u);
-                    const float w2 = __uint_as_float(ah.y << 16) + __uint_as_float(al.y << 16), w3 = __uint_as_float(ah.y & 0xffff0000u) + __uint_as_float(al.y & 0xffff0000u);
-                    dotp = fmaf(w0, __ldg(xb + ch), dotp); dotp = fmaf(w1, __ldg(xb + ch + 8), dotp);
-                    dotp = fmaf(w2, __ldg(xb + ch + 64), dotp); dotp = fmaf(w3, __ldg(xb + ch + 72), dotp);
-                }
-            }
-            if (half == 1) {
-                dotp += __shfl_xor_sync(FULL, dotp, 1);
-                dotp += __shfl_xor_sync(FULL, dotp, 2);
-                if (q == 0) s0part[s * 8 + g] = dotp;
-            }
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) Y[nt][e] = 0.f;
-        }
-
-        // ---- (1) scores of this window: 2 chunks x 4 k-steps
-        {
-            float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int row = s * 64 + 16 * k + 8 * (mi & 1) + r8, ch = 2 * half + (mi >> 1);
-                uint32_t bf[4];
-                ldsm_x4_t(bf, wbase + 64 * row + 16 * (ch ^ ((row >> 1) & 3)));
-                mma_bf16_16816(acc[0], Aw[k], bf[0], bf[1]);
-                mma_bf16_16816(acc[1], Aw[k], bf[2], bf[3]);
-            }
-            float* dst = part + (((w & 1) * 8 + s) * HEADS + g) * 32 + 16 * half + 2 * q;
-            *reinterpret_cast<float2*>(dst) = make_float2(acc[0][0] + acc[0][2], acc[0][1] + acc[0][3]);
-            *reinterpret_cast<float2*>(dst + 8) = make_float2(acc[1][0] + acc[1][2], acc[1][1] + acc[1][3]);
-        }
-        __syncthreads();
-
-        // ---- (2) softmax step: head = warp, lane = token slot
-        if (warp < HEADS) {
-            const int h = warp;
-            if (w == 0) {                                                  // the mean token opens the running softmax
-                float s0 = 0.f;
-#pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) s0 += s0part[c8 * 8 + h];
-                sv0 = a.scale * (s0 + __ldg(a.cterm + ((size_t)bv * HEADS + h) * TP));
-                m_run = sv0; l_run = 1.0f;
-            }
-            float v = -INFINITY;
-            if (tok_ok) {
-                const float* pc = part + ((w & 1) * 8 * HEADS + h) * 32;           // + class * 8 * 32
-                const float* pp = part + (((w & 1) ^ 1) * 8 * HEADS + h) * 32;
-                float accs = 0.f;
-#pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) {
-                    const int ul = lane - 7 + c8;
-                    accs += ul < 0 ? pp[c8 * HEADS * 32 + ul + 32] : pc[c8 * HEADS * 32 + ul];
-                }
-                v = a.scale * (accs + ct);
-                svbuf[h * 232 + tok] = v;
-            }
-            const float m_new = fmaxf(m_run, warp_max(v));
-            const float alpha = expf(m_run - m_new);
-            const float pr = tok_ok ? expf(v - m_new) : 0.f;
-            l_run = l_run * alpha + warp_sum(pr);
-            m_run = m_new;
-            if (lane == 0) { st_alpha[h] = alpha; st_m[h] = m_run; st_l[h] = l_run; st_sv0[h] = sv0; }
-            uint32_t hi, lo;
-            split_hi_lo(pr, hi, lo);
-            unsigned short* pq = reinterpret_cast<unsigned short*>(smem + OFF_PB) + h * 64 + lane + 8;
-            pq[0] = (unsigned short)hi;                                    // copy 0, hi
-            pq[HEADS * 64] = (unsigned short)lo;                           // copy 0, lo
-            pq[2 * HEADS * 64 + 1] = (unsigned short)hi;                   // copy 1, hi
-            pq[3 * HEADS * 64 + 1] = (unsigned short)lo;                   // copy 1, lo
-        }
-        __syncthreads();
-
-        // ---- (3) weighted sums: Y *= alpha, then chunks -1 .. 3 (+ an empty one) as 3 k-steps
-        {
-            const float al = st_alpha[g];
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) Y[nt][e] *= al;
-            const int cpy = (s + 1) & 1;
-            const uint32_t* ph = reinterpret_cast<const uint32_t*>(smem + OFF_PB) + ((cpy * 2 + 0) * HEADS + g) * 32;
-            const uint32_t* pl = reinterpret_cast<const uint32_t*>(smem + OFF_PB) + ((cpy * 2 + 1) * HEADS + g) * 32;
-#pragma unroll
-            for (int ks = 0; ks < 3; ++ks) {
-                const int wd = (16 * ks + 7 - s + cpy) / 2 + q;            // element 16 ks - 8 + (7 - s) + 8 + cpy + 2 q, even
-                const uint32_t PA[4] = {ph[wd], pl[wd], ph[wd + 4], pl[wd + 4]};
-                const int clo = 2 * ks - 1, chi = 2 * ks;                  // chunks of k 0..7 / 8..15
-#pragma unroll
-                for (int np = 0; np < 2; ++np) {
-                    const int row = s * 64 + 32 * half + 8 * (2 * np + (mi >> 1)) + r8;
-                    uint32_t base;
-                    int ch;
-                    if (mi & 1) { base = wbase; ch = chi > 3 ? 3 : chi; }                       // the chunk past the window meets zero probabilities
-                    else if (clo < 0) { base = w > 0 ? pbase : wbase; ch = w > 0 ? 3 : 0; }    // chunk -1 = last chunk of window w - 1
-                    else { base = wbase; ch = clo; }
-                    uint32_t f[4];
-                    ldsm_x4(f, base + 64 * row + 16 * (ch ^ ((row >> 1) & 3)));
-                    mma_bf16_16816(Y[2 * np], PA, f[0], f[1]);
-                    mma_bf16_16816(Y[2 * np + 1], PA, f[2], f[3]);
-                }
-            }
-        }
-
-        if (w == NWIN - 1) {
-            // ---- end of the view (m, l, sv0 of step 2 are visible: the barrier after it)
-            const float inv = 1.0f / st_l[g];
-            const float p0g = expf(st_sv0[g] - st_m[g]) * inv;
-            const float* xb = a.xbar + (size_t)bv * C;
-            __nv_bfloat16* yrow = a.ya_hi + ((size_t)bv * HEADS + g) * YA;
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                const int sl = 4 * half + nt, ch = sl * SLAB_CH + s + 16 * q;
-                const float v0 = (Y[nt][0] + Y[nt][2]) * inv + p0g * __ldg(xb + ch);
-                const float v1 = (Y[nt][1] + Y[nt][3]) * inv + p0g * __ldg(xb + ch + 8);
-                uint32_t h0, l0, h1, l1;
-                split_hi_lo(v0, h0, l0);
-                split_hi_lo(v1, h1, l1);
-                const int col = ((sl * 8 + s) * 4 + q) * 2;
-                *reinterpret_cast<uint32_t*>(yrow + col) = h0 | (h1 << 16);
-                *reinterpret_cast<uint32_t*>(yrow + a.ya_plane + col) = l0 | (l1 << 16);
-            }
-            if (warp < HEADS) {                                            // final probabilities of head = warp (its own m_run / l_run)
-                const int h = warp;
-                const float invh = 1.0f / l_run;
-                __nv_bfloat16* ya = a.ya_hi + ((size_t)bv * HEADS + h) * YA + C;
-                float* dbg = ((a.debug_skip & 64) && a.dbg) ? a.dbg + (size_t)bv * DBG_PER_VIEW + h * 256 : nullptr;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int t = lane + 32 * i;                           // attention token (0 = mean token), >= 226: zero padding
-                    const float sc = t == 0 ? sv0 : (t < T ? svbuf[h * 232 + t - 1] : -INFINITY);
-                    const float pr = t < T ? expf(sc - m_run) * invh : 0.f;
-                    uint32_t hi, lo;
-                    split_hi_lo(pr, hi, lo);
-                    ya[t] = __ushort_as_bfloat16((unsigned short)hi);
-                    ya[a.ya_plane + t] = __ushort_as_bfloat16((unsigned short)lo);
-                    if (dbg) dbg[t] = sc;
-                }
-            }
-        }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-
 }  // namespace pt
 extern "C" int pt_debug_pool_events(long long* out, int max_events) {
     unsigned int n = 0;
@@ -980,15 +720,7 @@ int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, in
         const char* pf = getenv("PT_POOL_PF");
         a.pf_dist = pf ? atoi(pf) : PF_DIST;
         const int grid = BV < sms ? BV : sms;
-        const char* single = getenv("PT_POOL_SINGLE");                  // experimental single-pass kernel (correct, not yet faster)
-        if (single && atoi(single) != 0) {
-            static bool attr3[PT_MAX_DEVICES] = {};
-            if (first_use_on_current_device(attr3))
-                PT_CUDA_OK(cudaFuncSetAttribute(img_pool_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ip3::SMEM3_BYTES));
-            { ProfScope prof_(PROF_IMG_POOL, s); img_pool_single_kernel<<<grid, ip3::THREADS3, ip3::SMEM3_BYTES, s>>>(a); }
-        } else {
-            { ProfScope prof_(PROF_IMG_POOL, s); img_pool_mma_kernel<<<grid, THREADS, SMEM_BYTES + POOL_EV_SMEM, s>>>(a); }
-        }
+        { ProfScope prof_(PROF_IMG_POOL, s); img_pool_mma_kernel<<<grid, THREADS, SMEM_BYTES + POOL_EV_SMEM, s>>>(a); }
         PT_LAUNCH_CHECK();
     }
     {   // G4: z[:, 32h:32h+32] = [y_h | a_h] [W_vc_h | h_v_h]^T   -> split planes only

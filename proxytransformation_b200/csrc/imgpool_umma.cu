@@ -38,7 +38,6 @@
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
-#include <type_traits>
 
 namespace pt {
 
@@ -176,20 +175,6 @@ __device__ __forceinline__ float iu_bf(uint32_t packed, int k) {      // element
     return __uint_as_float(k ? (packed & 0xffff0000u) : (packed << 16));
 }
 
-// Bring-up timeline (PT_UMMA_DEBUG bit 16): SM-clock cycles CTA 0 spends in each wait / phase, by role (tools/pool_ab.py prints it):
-//  loader warp 0: [0] issue loads [1] wait empty slot [2] shift + store   MMA: [4] wait w_eff [5] wait full slot [6] wait p_full
-//  [7] wait d2_empty [8] issue   softmax warp 0: [10] wait d1_full [11] tmem ld + scores [12] max / raise [13] wait p_empty
-//  [14] exp + P store [15] end of view   epilogue warp 0: [20] s0 [21] wait l_full [22] wait d2_full [23] output   [30] views
-__device__ unsigned long long g_umma_trace[32];
-#define UTR(slot)                                                              \
-    do {                                                                       \
-        if (tr_on) {                                                           \
-            const long long now_ = clock64();                                  \
-            atomicAdd(&g_umma_trace[slot], (unsigned long long)(now_ - tr_t)); \
-            tr_t = now_;                                                       \
-        }                                                                      \
-    } while (0)
-
 struct UmmaPoolMaps {
     CUtensorMap w;         // w_eff planes as (512 columns, BV*16 rows (view, hi|lo, head)), box (64, 16)
 };
@@ -226,8 +211,7 @@ __device__ __forceinline__ void iu_shift_store(uint32_t tile, int row, int j, co
 
 // Class pair P of one window: both tiles of ring slot `tile0`, this warp's 8 rows of each (two groups of 4 rows x 8 chunks).
 template <int P>
-__device__ __forceinline__ void iu_store_pair(uint32_t tile0, int row0, int rr, int j, const uint4 (&am)[2][2], const uint4& at, bool on) {
-    if (!on) return;
+__device__ __forceinline__ void iu_store_pair(uint32_t tile0, int row0, int rr, int j, const uint4 (&am)[2][2], const uint4& at) {
     iu_shift_store<2 * P>(tile0, row0 + rr, j, am[0][0], at, rr);
     iu_shift_store<2 * P>(tile0, row0 + 4 + rr, j, am[0][1], at, 4 + rr);
     iu_shift_store<2 * P + 1>(tile0 + ipu::TILE_BYTES, row0 + rr, j, am[1][0], at, 8 + rr);
@@ -296,57 +280,38 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
         // ===== loaders: global -> registers -> (shift by the class) -> swizzled tiles =====
         const int row0 = 8 * (warp - LOADER_WARP0), rr = lane >> 3, j = lane & 7;
         unsigned it = 0;
-        const bool tr_on = (a.debug & 16) && blockIdx.x == 0 && warp == LOADER_WARP0 && lane == 0;
-        long long tr_t = clock64();
-        // Software pipeline over half windows (H = 0: class pairs 0, 1; H = 1: pairs 2, 3): while one half is shifted and
-        // stored, the loads of the other half and of the next window's first half are in flight.  All loads of a half hang
-        // off two base pointers with immediate offsets and are unconditional: chunks past the row's 29th (window 3 only) are
-        // clamped to chunk 28 — they only feed tokens >= 225, whose probabilities are zero and whose scores are never read.
-        uint4 am[2][2][2][2], at[2][2];                      // [half][pair in half][class in pair][row group], tails [half][pair]
-        const int total = nviews * NWIN;
-        auto issue = [&](int gw, auto HALF) {
-            constexpr int H = decltype(HALF)::value;
-            const int vi = gw >> 2, w = gw & 3;
-            const uint8_t* view = a.img + (size_t)(blockIdx.x + vi * gridDim.x) * (C * HW * 2);
-            const uint8_t* mb = view + 3600 * (row0 + rr) + 16 * min(8 * w + j, 28);
-            const uint8_t* tb = view + 448 * ((lane >> 3) & 1) + 3600 * (row0 + (lane & 7)) + 16 * min(8 * w + 8, 28);
-#pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e)
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) am[H][pp][e][hf] = iu_ldg_stream(mb + 448 * (2 * (2 * H + pp) + e) + 14400 * hf);
-                at[H][pp] = iu_ldg_stream(tb + 896 * (2 * H + pp));     // 9th chunk: lanes 0-7 class 2p, lanes 8-15 class 2p + 1 (other lanes: duplicates)
-            }
-        };
-        auto consume = [&](auto HALF) {
-            constexpr int H = decltype(HALF)::value;
-#pragma unroll
-            for (int pp = 0; pp < 2; ++pp, ++it) {
-                const unsigned slot = it % RING;
-                iu_wait(empty + slot, ((it / RING) & 1) ^ 1);
-                UTR(1);
-                const uint32_t tile0 = iu_smem(smem + OFF_RING) + slot * SLOT_BYTES;
-                iu_store_pair<2 * H + 0>(tile0, row0, rr, j, am[H][0], at[H][0], pp == 0);
-                iu_store_pair<2 * H + 1>(tile0, row0, rr, j, am[H][1], at[H][1], pp == 1);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) iu_arrive(full + slot);
-                UTR(2);
-            }
-        };
-        using H0 = std::integral_constant<int, 0>;
-        using H1 = std::integral_constant<int, 1>;
-        if (total > 0) { issue(0, H0{}); issue(0, H1{}); }
-        UTR(0);
+        for (int vi = 0; vi < nviews; ++vi) {
+            const int bv = blockIdx.x + vi * gridDim.x;
+            const uint8_t* view = a.img + (size_t)bv * (C * HW * 2);
 #pragma unroll 1
-        for (int gw = 0; gw < total; ++gw) {
-            consume(H0{});
-            if (gw + 1 < total) issue(gw + 1, H0{});
-            UTR(0);
-            consume(H1{});
-            if (gw + 1 < total) issue(gw + 1, H1{});
-            UTR(0);
+            for (int w = 0; w < NWIN; ++w) {
+                uint4 am[4][2][2], at[4];
+                const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+                const int chunk = 8 * w + j;                               // aligned 16-byte chunk of the row; 29 chunks per row
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf)
+                            am[p][e][hf] = chunk <= 28 ? iu_ldg_stream(view + 448 * (2 * p + e) + 3600 * (row0 + 4 * hf + rr) + 16 * chunk) : zero;
+                    // 9th chunk of this warp's 16 rows of the pair: lanes 0-7 class 2p, lanes 8-15 class 2p + 1
+                    at[p] = (lane < 16 && 8 * w + 8 <= 28) ? iu_ldg_stream(view + 448 * (2 * p + (lane >> 3)) + 3600 * (row0 + (lane & 7)) + 16 * (8 * w + 8)) : zero;
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p, ++it) {
+                    const unsigned slot = it % RING;
+                    iu_wait(empty + slot, ((it / RING) & 1) ^ 1);
+                    const uint32_t tile0 = iu_smem(smem + OFF_RING) + slot * SLOT_BYTES;
+                    if (p == 0) iu_store_pair<0>(tile0, row0, rr, j, am[0], at[0]);
+                    else if (p == 1) iu_store_pair<1>(tile0, row0, rr, j, am[1], at[1]);
+                    else if (p == 2) iu_store_pair<2>(tile0, row0, rr, j, am[2], at[2]);
+                    else iu_store_pair<3>(tile0, row0, rr, j, am[3], at[3]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) iu_arrive(full + slot);
+                }
+            }
         }
     } else if (warp == 0) {
         // ===== MMA issuer (+ TMA of the per-view w_eff planes, one view ahead) =====
@@ -354,17 +319,12 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
             constexpr uint32_t IDESC1 = iu_idesc(64, 16, true), IDESC2 = iu_idesc(128, 16, false);
             const uint32_t ring = iu_smem(smem + OFF_RING), wbase = iu_smem(smem + OFF_W), pbase = iu_smem(smem + OFF_P);
             unsigned it1 = 0, it2 = 0, g = 0;
-            const bool tr_on = (a.debug & 16) && blockIdx.x == 0;
-            long long tr_t = clock64();
             // sums of window gp (class pair p), interleaved below with the scores of window gp + 1
             auto sums = [&](unsigned gp, int p) {
                 const unsigned vp = gp >> 2, wp = gp & 3;
                 if (p == 0) {
-                    UTR(8);
                     iu_wait(p_full + wp, (gp >> 2) & 1);                            // probability tile of window gp is in shared memory
-                    UTR(6);
                     if (wp == 0) iu_wait(d2_empty + (vp & 1), ((vp >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator buffer
-                    UTR(7);
                     iu_fence_after();
                 }
                 const unsigned slot = it2 % RING;
@@ -392,17 +352,13 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
             for (int vi = 0; vi < nviews; ++vi) {
                 const int wb = vi & 1;
                 load_w(vi + 1);
-                UTR(8);
                 iu_wait(wfull + wb, (vi >> 1) & 1);
-                UTR(4);
                 iu_fence_after();
                 for (int w = 0; w < NWIN; ++w, ++g) {
                     const uint32_t d1 = tmem + (g & 1) * 16;
                     for (int p = 0; p < 4; ++p) {
                         const unsigned slot = it1 % RING;
-                        UTR(8);
                         iu_wait(full + slot, (it1 / RING) & 1);
-                        UTR(5);
                         iu_fence_after();
                         const uint32_t sa = ring + slot * SLOT_BYTES;
 #pragma unroll
@@ -436,8 +392,6 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         float mref[8], lsum[8], pr[NWIN][8];
         unsigned g = 0;
-        const bool tr_on = (a.debug & 16) && blockIdx.x == 0 && warp == SOFTMAX_WARP0 && lane == 0;
-        long long tr_t = clock64();
         for (int vi = 0; vi < nviews; ++vi) {
             const int bv = blockIdx.x + vi * gridDim.x;
 #pragma unroll
@@ -449,9 +403,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 float ct[8];
 #pragma unroll
                 for (int h = 0; h < 8; ++h) ct[h] = valid ? __ldg(a.cterm + ((size_t)bv * HEADS + h) * TP + 1 + t) : 0.f;
-                UTR(15);
                 iu_wait(d1_full + (g & 1), (g >> 1) & 1);
-                UTR(10);
                 iu_fence_after();
                 uint32_t v[16];
                 iu_tmem_ld16(trow + (g & 1) * 16, v);
@@ -463,7 +415,6 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
 #pragma unroll
                     for (int h = 0; h < 8; ++h) a.dbg[((size_t)bv * HEADS + h) * 256 + 1 + t] = s[h];
                 }
-                UTR(11);
                 bool raise = w == 0;
                 if (w > 0) {
                     bool ex = false;
@@ -512,7 +463,6 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                         }
                     }
                 }
-                UTR(12);
                 unsigned short ph[8], pl[8];
 #pragma unroll
                 for (int h = 0; h < 8; ++h) {
@@ -521,9 +471,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     pr[w][h] = p;
                     iu_split(p, ph[h], pl[h]);
                 }
-                UTR(14);
                 iu_wait(p_empty + w, ((g >> 2) & 1) ^ 1);           // the sums of the previous view's window w have read this buffer
-                UTR(13);
                 if (act) {
                     // K-major SWIZZLE_128B tile: row n (128 bytes = 64 tokens), 16-byte chunk index XOR (n mod 8)
                     const uint32_t pt = iu_smem(smem + OFF_P) + w * P_BYTES;
@@ -538,7 +486,6 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 iu_fence_before();
                 __syncwarp();
                 if (lane == 0) iu_arrive(p_full + w);
-                UTR(14);
             }
             // ---- end of the view: total of the running sums, the mean token, final probabilities
 #pragma unroll
@@ -595,11 +542,8 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
         // ===== epilogue: mean-token score, then Y = (D2 f + p0 xbar) / L -> bf16 hi/lo planes =====
         const int q = warp & 3, et = threadIdx.x - 32 * EPI_WARP0, row = 32 * q + lane;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-        const bool tr_on = (a.debug & 16) && blockIdx.x == 0 && warp == EPI_WARP0 && lane == 0;
-        long long tr_t = clock64();
         for (int vi = 0; vi < nviews; ++vi) {
             const int bv = blockIdx.x + vi * gridDim.x;
-            if (tr_on) atomicAdd(&g_umma_trace[30], 1ull);
             {   // s0[h] = scale (w_eff[h] . xbar + cterm[h][0]); this thread: columns 4 et .. 4 et + 3 (class et >> 4, rows 4 (et & 15)..)
                 const int c0 = 4 * et, cls = c0 >> 6, r0 = c0 & 63;
                 float xb[4];
@@ -632,9 +576,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     iu_arrive(s0_full + (vi & 1));
                 }
             }
-            UTR(20);
             iu_wait(l_full + (vi & 1), (vi >> 1) & 1);
-            UTR(21);
             float fin[8], p0n[8];
 #pragma unroll
             for (int h = 0; h < 8; ++h) {
@@ -646,7 +588,6 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 p0n[h] = p0 * inv;
             }
             iu_wait(d2_full + (vi & 1), (vi >> 1) & 1);
-            UTR(22);
             iu_fence_after();
 #pragma unroll 1
             for (int p = 0; p < 4; ++p) {
@@ -667,24 +608,12 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
             iu_fence_before();
             __syncwarp();
             if (lane == 0) iu_arrive(d2_empty + (vi & 1));
-            UTR(23);
         }
     }
     iu_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
-
-}  // namespace pt
-extern "C" int pt_debug_umma_trace(unsigned long long* out32, int reset) {
-    if (out32 && cudaMemcpyFromSymbol(out32, pt::g_umma_trace, sizeof(pt::g_umma_trace)) != cudaSuccess) return PT_ERR_CUDA;
-    if (reset) {
-        unsigned long long z[32] = {};
-        if (cudaMemcpyToSymbol(pt::g_umma_trace, z, sizeof(z)) != cudaSuccess) return PT_ERR_CUDA;
-    }
-    return PT_OK;
-}
-namespace pt {
 
 // ---------------------------------------------------------------------------------------------- host
 bool img_pool_umma_supported(int img_dtype) { return img_dtype == PT_DTYPE_BF16; }

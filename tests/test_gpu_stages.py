@@ -349,14 +349,17 @@ def test_aggregate_sample_input_side():
     np.testing.assert_allclose(np_(got), want.numpy(), rtol=0, atol=2e-5)      # fp32 LU solve vs fp64 inverse applied in fp32
 
 
-@pytest.mark.parametrize("B,V,dtype", [(3, 196, torch.bfloat16), (5, 61, torch.bfloat16), (2, 196, torch.float32)],
-                         ids=["bf16-588views", "bf16-305views", "f32-392views"])
-def test_image_proxies_many_views_per_cta(B, V, dtype):
+@pytest.mark.parametrize("B,V,dtype,kernel", [(3, 196, torch.bfloat16, "mma"), (5, 61, torch.bfloat16, "mma"), (2, 196, torch.float32, "mma"),
+                                              (3, 196, torch.bfloat16, "umma"), (5, 61, torch.bfloat16, "umma")],
+                         ids=["bf16-588views", "bf16-305views", "f32-392views", "bf16-588views-tcgen05", "bf16-305views-tcgen05"])
+def test_image_proxies_many_views_per_cta(B, V, dtype, kernel, monkeypatch):
     """The image-pool kernels are PERSISTENT (one CTA per SM, grid = min(views, SMs)): with B*V well above the SM count every
     CTA loops over several views, which is the path the benchmark times (12 544 views per step) and what production shapes
     hit (ring wrap-around, double-buffered per-view operands, barrier parities of the second and later views).  Compared
     against the oracle's reference formulation (:154-177, :335-342: conv + 226-token MHA, token 0) on identically rounded
-    features; V = 196 is the headline configuration's view count.  LayerNorm-ed outputs, tolerance 6e-5."""
+    features; V = 196 is the headline configuration's view count.  LayerNorm-ed outputs, tolerance 6e-5.  `kernel`: the shipped
+    mma.sync pool kernel and the opt-in tcgen05 / TMEM one (PT_POOL_KERNEL=umma, csrc/imgpool_umma.cu)."""
+    monkeypatch.setenv("PT_POOL_KERNEL", kernel)
     cfg = syn.C2_WIDE.replace(n_views=V)
     sd = syn.make_state_dict(cfg, 31, bf16_round=True)
     _, _, img = syn.make_inputs(cfg.replace(n_points=8), B, first_scene=300, img_dtype=dtype)
@@ -366,8 +369,36 @@ def test_image_proxies_many_views_per_cta(B, V, dtype):
     assert got.shape == (B, V, 256)
     err = np.abs(np_(got) - want.numpy()).reshape(B * V, -1).max(-1)
     assert err.max() <= 6e-5, f"views off by more than 6e-5: {np.nonzero(err > 6e-5)[0][:16].tolist()} (max {err.max():.3e})"
+    assert m._weights(torch.device(DEV))["img"].get("variant", 0) == (1 if kernel == "umma" else 0)
     # same call again on the same module: nothing may depend on leftover workspace / shared-memory state
     assert torch.equal(m.get_img_proxy(img.to(DEV)), got)
+
+
+def test_image_pool_tcgen05_kernel_raises_its_reference_maximum():
+    """The tcgen05 pool kernel exponentiates against a per-view reference maximum taken from the first 64 tokens and raises it
+    (rescaling the accumulators in TMEM) only when a later window exceeds it by more than 16: drive that path with views whose
+    late tokens score far above the early ones (features growing 40 x along the token axis) and compare with the oracle."""
+    import os
+    cfg = syn.C2_WIDE.replace(n_views=40)
+    sd = syn.make_state_dict(cfg, 33, bf16_round=True)
+    _, _, img = syn.make_inputs(cfg.replace(n_points=8), 5, first_scene=310, img_dtype=torch.float32)
+    ramp = torch.ones(225)
+    ramp[150:] = 40.0                                   # tokens of windows 2 and 3 dominate: scores ~40 x those of window 0
+    img = (img.reshape(5, 40, 512, 225) * ramp).reshape(5, 40, 512, 15, 15).to(torch.bfloat16)
+    want = po.image_proxies(sd, img.float(), cfg.num_heads)
+    old = os.environ.get("PT_POOL_KERNEL")
+    try:
+        got = {}
+        for kernel in ("umma", "mma"):
+            os.environ["PT_POOL_KERNEL"] = kernel
+            got[kernel] = build_module(cfg, sd).get_img_proxy(img.to(DEV))
+    finally:
+        if old is None:
+            os.environ.pop("PT_POOL_KERNEL", None)
+        else:
+            os.environ["PT_POOL_KERNEL"] = old
+    for kernel, g_ in got.items():
+        np.testing.assert_allclose(np_(g_), want.numpy(), rtol=0, atol=2e-4, err_msg=kernel)
 
 
 def _standalone_block_state(dim, n, hidden, seed):

@@ -31,17 +31,4 @@ for kern in kernels:
     _lib.profile_enable(False)
     pool_ms = prof["img_pool"][0] / prof["img_pool"][1]
     gbs = B * V * 230400 / pool_ms / 1e6
-    if kern == "umma" and int(os.environ.get("PT_UMMA_DEBUG", "0")) & 16:
-        import ctypes
-        buf = (ctypes.c_ulonglong * 32)()
-        L = _lib.load()
-        L.pt_debug_umma_trace(buf, 1)
-        ops.img_attnpool(imgs[0], w["img"], 8, params=w["img_struct"], stages=2, out=st[0][0], ws=st[0][1])
-        torch.cuda.synchronize()
-        L.pt_debug_umma_trace(buf, 0)
-        t = list(buf); nv = max(t[30], 1)
-        names = {0: "ld issue", 1: "ld wait empty", 2: "ld shift+store", 4: "mma wait w", 5: "mma wait full", 6: "mma wait p_full", 7: "mma wait d2_empty",
-                 8: "mma issue", 10: "sm wait d1", 11: "sm ld+score", 12: "sm max", 13: "sm wait p_empty", 14: "sm exp+store", 15: "sm view end",
-                 20: "ep s0", 21: "ep wait l", 22: "ep wait d2", 23: "ep output"}
-        print("  cycles per view of CTA 0 (%d views): " % nv + ", ".join(f"{names[k]} {t[k] / nv:.0f}" for k in sorted(names)), flush=True)
     print(f"{kern}: BACK stage {e0.elapsed_time(e1) / 20:.4f} ms, pool kernel {pool_ms:.4f} ms = {gbs:.0f} GB/s algorithmic, per {B} scenes", flush=True)

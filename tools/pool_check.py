@@ -1,9 +1,8 @@
 """Stage-level check of the image pool kernels (pass B of S9) against a float64 torch evaluation of the same algebra from
 the kernel's own inputs (w_eff planes, cterm, xbar in the workspace): scaled scores, probabilities, weighted sums.
 With a third argument it also times the BACK stage at bench size over a sweep of the producer's L2-prefetch distance (PT_POOL_PF).
-Usage (GPU box): python tools/pool_check.py [views_per_scene] [scenes] [time | comma-separated PT_POOL_PF values] [single]
-(`single` also checks the experimental single-pass kernel, PT_POOL_SINGLE=1; `umma` / `mma` in the arguments restrict the
-check to the tcgen05 or the mma.sync pool kernel, default both)"""
+Usage (GPU box): python tools/pool_check.py [views_per_scene] [scenes] [time | comma-separated PT_POOL_PF values] [mma | umma]
+(`umma` / `mma` restrict the check to the tcgen05 or the mma.sync pool kernel, default both)"""
 import os, sys, torch, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("PT_POOL_DEBUG", "64")
@@ -41,7 +40,6 @@ def setup(kernel):
     WPLANE = HEADS * WPITCH
 
 def run(single=False):
-    os.environ["PT_POOL_SINGLE"] = "1" if single else "0"      # experimental single-pass kernel (imgpool_tc.cu), off by default
     ws = torch.zeros(need + BV * DBG * 4, dtype=torch.uint8, device="cuda")
     out, ws = ops.img_attnpool(img, w["img"], HEADS, params=w["img_struct"], stages=1, ws=ws)
     out, ws = ops.img_attnpool(img, w["img"], HEADS, params=w["img_struct"], stages=2, out=out, ws=ws)
@@ -52,7 +50,7 @@ def f32(ws, o, n): return ws[o:o + 4 * n].view(torch.float32)
 def bf(ws, o, n): return ws[o:o + 2 * n].view(torch.bfloat16)
 
 KERNELS = [k for k in ("mma", "umma") if k in sys.argv] or ["mma", "umma"]
-MODES = [(k, False) for k in KERNELS] + ([("mma", True)] if "single" in sys.argv else [])
+MODES = [(k, False) for k in KERNELS]
 finals = {}
 for kernel, single in MODES:
     setup(kernel)
