@@ -8,11 +8,12 @@ proxies (config C2): one "step" = one forward of the module over 
   value     whole-job scenes/s, inputs resident in HBM (CUDA events, max over ranks, barrier on both sides)
   e2e       same metric through the module's public forward() with HOST (pinned) inputs and host results: the H2D copy of
             points/text/mask/image features and the D2H read of the packed result are inside the timed region
-  roofline  the dominant kernel (image-feature pooling pass, HBM-bound) timed live with CUDA events on its stream
-  cpu_baseline / --impl reference   the reference's algorithm on the host cores: the oracle port (oracle/preshape_oracle.py
-            with faithful_cost=True: all blocks, all 226 attention queries, exactly the work the reference's PyTorch path
-            does).  The reference itself is pure Python that needs pytorch3d/timm/mmengine shims and lives only in the
-            build container, so it cannot travel to the GPU box; kind = "port".
+  roofline  the dominant kernel (largest total time in the live per-kernel profile; today the image-feature pooling pass,
+            HBM-bound) timed with CUDA events on its stream; image_stage_roofline: the whole image stage against one read
+  cpu_baseline / --impl reference   the reference's CPU path on the host cores: the reference's OWN module (kind "reference":
+            its bytecode is compiled from /root/reference into oracle/_ref/ by oracle/build.py and travels with the repo;
+            pytorch3d / timm / registry come from the oracle's shims) or, when that file is absent, the oracle port with
+            faithful_cost=True (all blocks, all 226 attention queries; kind "port").
 Multi-GPU: scenes are independent, so each rank processes its own shard with no data-path collective (weak scaling,
 `--batch` scenes per GPU); one all_gather of a small per-rank metric tensor at the end.
 """
@@ -51,7 +52,20 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--core", action="store_true", help="core region: image proxies precomputed (diagnostic)")
+    ap.add_argument("--no-checks", action="store_true", help="skip the oracle check of the timed batch")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C1 / C3 / strong-scaling side measurements")
     return ap.parse_args()
+
+
+def config_dict(cfg, args, world: int, batch: int) -> dict:
+    """The `config` object of the JSON line — identical for both arms (the driver compares them key by key)."""
+    esz = 2 if args.img_dtype == "bf16" else 4
+    tile_bytes = cfg.input_dim * cfg.img_spacial_dim ** 2 * esz
+    return {"workload": cfg.name, "n_points": cfg.n_points, "clusters": cfg.real_cluster_num, "embed_dim": cfg.embed_dim,
+            "text_tokens": cfg.n_text, "image_views": cfg.n_views, "img_feat_dtype": args.img_dtype,
+            "region": "core" if args.core else "full", "scenes_per_gpu_per_step": batch, "box_m": list(cfg.box),
+            "l2": "two alternating input sets per rank, each %.1f GB >> 126 MB L2" % (batch * cfg.n_views * tile_bytes / 1e9),
+            "sharding": f"{world} x {batch} independent scenes, no data-path collective"}
 
 
 def workload(args):
@@ -117,27 +131,50 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU (reference arm)
-def cpu_reference_rate(cfg, n_scenes: int, per_call: int = 8, warm: int = 1, img_dtype=torch.float32):
-    """Oracle port, faithful cost, all host threads, `per_call` scenes per forward (the reference takes a batch as well);
-    returns (scenes/s, cores, seconds)."""
+def cpu_forward(cfg):
+    """-> (forward(points, text_dict, img_feat), kind, description): the reference's OWN module when its bytecode travelled
+    with the repo (oracle/_ref, built by oracle/build.py::build_ref from /root/reference; pytorch3d's two CPU loops come from
+    the C restatement, timm / registry from shims), else the oracle port with faithful cost."""
+    from proxytransformation_b200 import synthetic as syn
+    sd = syn.make_state_dict(cfg, 0, bf16_round=True)
+    try:
+        from oracle import ref_shim
+        if ref_shim.available():
+            net = ref_shim.build_module(cfg.module_kwargs(), sd, pinned=False)
+            ref_shim.use_native_fps(True)
+
+            def fwd(p, t, im):
+                with torch.no_grad():
+                    return net(p, t, im)
+            return fwd, "reference", ("the reference's own ProxyTransformationNormReverse.forward (unmodified module, eval, all blocks, "
+                                      "full 226-token attention pool; pytorch3d ball query / FPS = C restatement of its CPU loops)")
+    except Exception as e:      # pragma: no cover - fall back to the port, say why
+        sys.stderr.write(f"reference module unavailable ({e!r}); timing the oracle port\n")
     from oracle import preshape_oracle as po
+    kw = dict(grid_size=cfg.grid_size, dynamic_drop_radio=cfg.dynamic_drop_radio, text_blocks=cfg.text_blocks,
+              img_blocks=cfg.img_blocks, num_sub=cfg.num_sub, num_heads=cfg.num_heads, faithful_cost=True)
+    return (lambda p, t, im: po.forward(sd, p, t, im, **kw)), "port", ("oracle port of the reference's PyTorch path (all blocks, "
+                                                                        "full 226-token attention pool)")
+
+
+def cpu_reference_rate(cfg, n_scenes: int, per_call: int = 8, warm: int = 1, img_dtype=torch.float32):
+    """The reference's CPU path on all host threads, `per_call` scenes per forward (the reference takes a batch as well);
+    returns (scenes/s, cores, seconds, kind, description)."""
     from proxytransformation_b200 import synthetic as syn
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = syn.make_state_dict(cfg, 0, bf16_round=True)
-    kw = dict(grid_size=cfg.grid_size, dynamic_drop_radio=cfg.dynamic_drop_radio, text_blocks=cfg.text_blocks,
-              img_blocks=cfg.img_blocks, num_sub=cfg.num_sub, num_heads=cfg.num_heads, faithful_cost=True)
+    fwd, kind, desc = cpu_forward(cfg)
     per_call = max(1, min(per_call, n_scenes))
     calls = max(1, n_scenes // per_call)
     pool = [syn.make_inputs(cfg, per_call, first_scene=1000 + 16 * i, img_dtype=img_dtype) for i in range(2)]
     pool = [(p, t, im.float()) for p, t, im in pool]
     for i in range(warm):
-        po.forward(sd, *pool[i % 2], **kw)
+        fwd(*pool[i % 2])
     t0 = time.perf_counter()
-    for i in range(calls):                          # two distinct seeded batches, alternated: the oracle keeps no state
-        po.forward(sd, *pool[i % 2], **kw)
+    for i in range(calls):                          # two distinct seeded batches, alternated: no state is kept
+        fwd(*pool[i % 2])
     dt = time.perf_counter() - t0
-    return calls * per_call / dt, cores, dt
+    return calls * per_call / dt, cores, dt, kind, desc
 
 
 def run_reference(args):
@@ -146,34 +183,27 @@ def run_reference(args):
         return
     cfg = workload(args)
     per_step = max(1, args.ref_scenes_per_step)
-    rates, t_all = [], 0.0
-    from oracle import preshape_oracle as po
     from proxytransformation_b200 import synthetic as syn
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = syn.make_state_dict(cfg, 0, bf16_round=True)
-    kw = dict(grid_size=cfg.grid_size, dynamic_drop_radio=cfg.dynamic_drop_radio, text_blocks=cfg.text_blocks,
-              img_blocks=cfg.img_blocks, num_sub=cfg.num_sub, num_heads=cfg.num_heads, faithful_cost=True)
+    fwd, kind, desc = cpu_forward(cfg)
     dt_img = torch.bfloat16 if args.img_dtype == "bf16" else torch.float32
     data = [syn.make_inputs(cfg, per_step, first_scene=2000 + i, img_dtype=dt_img) for i in range(2)]
     data = [(p, t, im.float()) for p, t, im in data]
     for i in range(args.warmup):
-        p, t, im = data[i % 2]
-        po.forward(sd, p, t, im, **kw)
+        fwd(*data[i % 2])
     t0 = time.perf_counter()
     for i in range(args.steps):
-        p, t, im = data[i % 2]
-        po.forward(sd, p, t, im, **kw)
+        fwd(*data[i % 2])
     dt = time.perf_counter() - t0
     v = args.steps * per_step / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg.name, "n_points": cfg.n_points, "clusters": cfg.real_cluster_num, "embed_dim": cfg.embed_dim,
-                       "text_tokens": cfg.n_text, "image_views": cfg.n_views, "region": "full", "scenes_per_step": per_step},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps x {per_step} scene(s), oracle port of the reference's PyTorch path "
-                                       "(all blocks, full 226-token attention pool), fp32, all host threads"},
+            # same workload description as the B200 arm (the CPU arm's step is a bounded sample of it: see cpu_baseline.sample)
+            "config": config_dict(cfg, args, args.gpus, args.batch),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{args.steps} steps x {per_step} scene(s) of the workload, {desc}, fp32, all host threads"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -186,6 +216,59 @@ def measured_traffic(kernel: str, batch: int):
         return t["dram_bytes_per_launch"] * batch / t["batch"]
     except Exception:
         return None
+
+
+def forward_latency(cfg, batch: int, dev, img_dtype, iters: int = 20, graph: bool = False):
+    """GPU ms per forward() (device-resident inputs, CUDA events, one D2H of the counts inside) of another BASELINE.json
+    workload: two alternating input sets, 4 warm-up calls."""
+    from proxytransformation_b200 import ProxyTransformationNormReverse
+    from proxytransformation_b200 import synthetic as syn
+    m = ProxyTransformationNormReverse(**cfg.module_kwargs()).eval()
+    m.load_state_dict(syn.make_state_dict(cfg, 0, bf16_round=True), strict=True)
+    m = m.to(dev)
+    m.cuda_graphs = graph
+    sets = []
+    for k in range(2):
+        pts, td, img = syn.make_inputs(cfg, batch, first_scene=100 * k, img_dtype=img_dtype)
+        sets.append(([p.to(dev) for p in pts], {n: v.to(dev) for n, v in td.items()}, img.to(dev)))
+    with torch.no_grad():
+        for k in range(4):
+            m(*sets[k % 2])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(iters):
+            m(*sets[k % 2])
+        e1.record()
+        torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def oracle_checks(m, cfg, sets, B: int) -> dict:
+    """Parity of the TIMED inputs: scene 0 of input set 0 through the same forward_packed call the timed region makes,
+    against the oracle (CPU) on identical inputs — cluster indices bit-exact, image proxies, transformed coordinates."""
+    import numpy as np
+    from oracle import preshape_oracle as po
+    from proxytransformation_b200 import synthetic as syn
+    P, text, mask, img = sets[0]
+    tr = {}
+    out, counts = m.forward_packed(P, text, mask, img, trace=tr)
+    torch.cuda.synchronize()
+    sd = syn.make_state_dict(cfg, 0, bf16_round=True)
+    otr = {}
+    want = po.forward(sd, [P[0].cpu()], {"text_feats": text[:1].cpu(), "text_token_mask": mask[:1].bool().cpu()}, img[:1].float().cpu(),
+                      grid_size=cfg.grid_size, dynamic_drop_radio=cfg.dynamic_drop_radio, text_blocks=cfg.text_blocks,
+                      img_blocks=cfg.img_blocks, num_sub=cfg.num_sub, num_heads=cfg.num_heads, trace=otr)[0]
+    n0 = int(counts[0].item())
+    got = out[0, :n0].cpu()
+    idx_equal = bool(np.array_equal(tr["kept_idx"][0].cpu().numpy(), otr["kept_idx"][0].numpy()) and
+                     np.array_equal(tr["drop_idx"][0].cpu().numpy(), otr["drop_idx"][0].numpy()) and
+                     np.array_equal(tr["idx2"][0].cpu().numpy(), otr["idx2"][0].numpy()))
+    return {"scene": "scene 0 of the timed input set 0 vs the oracle on identical inputs",
+            "idx_equal": idx_equal, "count_equal": bool(n0 == want.shape[0]),
+            "max_coord_err": float((got - want).abs().max()) if n0 == want.shape[0] else None,
+            "img_proxy_max_err": float((tr["img_proxy"][0].cpu() - otr["img_proxy"][0]).abs().max()),
+            "img_proxy_views_checked": int(cfg.n_views), "coord_tolerance": 1e-4, "img_proxy_tolerance": 6e-5}
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -335,6 +418,31 @@ def run_b200(args):
                "timer": "host perf_counter around forward() incl. copies, max over ranks",
                "pipeline": f"{m.host_chunk_scenes}-scene chunks over H2D / compute / D2H streams, one host sync per call"}
 
+    # ---- BASELINE config 4 as worded: 64 scenes in total, sharded over the ranks (strong scaling: 64 / N scenes per rank).
+    # Latency-bound at 8 scenes per rank — reported beside the weak-scaling headline, same timing rules.
+    c4 = None
+    if not args.core and not args.no_extra:
+        b4 = max(1, min(B, 64 // world))
+        sub = [tuple(t[:b4] for t in s_) for s_ in sets]
+        for i in range(3):
+            m.forward_packed(*sub[i % 2])
+        sync_all()
+        s0_, s1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0_.record()
+        for i in range(args.steps):
+            m.forward_packed(*sub[i % 2])
+        s1_.record()
+        torch.cuda.synchronize()
+        c4_ms = s0_.elapsed_time(s1_)
+        if world > 1:
+            t = torch.tensor([c4_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            c4_ms = t.item()
+        c4 = {"scenes_total": b4 * world, "scenes_per_rank": b4, "ms_per_step": c4_ms / args.steps, "unit": UNIT,
+              "value": b4 * world * args.steps / (c4_ms / 1e3), "scaling": "strong", "l2": "%.2f GB of image features per rank per step" %
+              (b4 * cfg.n_views * cfg.input_dim * cfg.img_spacial_dim ** 2 * (2 if img_dtype == torch.bfloat16 else 4) / 1e9)}
+        del sub
+
     # ---- the one collective of the path: all_gather of per-rank metric tensors (sharding.py)
     from proxytransformation_b200 import sharding
     cnt_host = counts.cpu().tolist()
@@ -362,18 +470,42 @@ def run_b200(args):
         "img_pool": B * cfg.n_views * tile_bytes, "img_mean": B * cfg.n_views * tile_bytes,
         "scatter_compact": B * cfg.n_points * 24, "minmax_partial": B * cfg.n_points * 12,
     }
+    # dominant kernel = the profile tag with the largest total time in the timed steps (picked live, not hard-coded)
+    bf16_peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    c, hid, n_, Lt, V_ = cfg.embed_dim, 4 * cfg.embed_dim, cfg.real_cluster_num, cfg.n_text, cfg.n_views
+    blk_flops = lambda l: 2.0 * B * (n_ * c * 3 * c + l * c * c + n_ * c * c + 2 * n_ * c * hid)      # useful FLOPs of one live block's GEMMs
+    tensor_flops = {"gemm_tc_3xbf16": 3.0 * (blk_flops(Lt) + blk_flops(V_))}                            # x3: hi*hi + lo*hi + hi*lo products
     roof = None
-    dom = "img_pool" if ("img_pool" in prof and not args.core) else (top[0] if top else None)
+    dom = top[0] if top else None
     if dom in prof and dom in alg_bytes:
         t_ms, n = prof[dom]
         ach = alg_bytes[dom] / (t_ms / n / 1e3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                 "traffic": measured_traffic(dom, B), "peak_source": peak_src, "avg_launch_ms": t_ms / n,
                 "algorithmic_bytes_per_launch": alg_bytes[dom]}
+    elif dom in prof and dom in tensor_flops:
+        t_ms, n = prof[dom]
+        ach = tensor_flops[dom] / (t_ms / args.steps / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
+                "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)", "avg_launch_ms": t_ms / n,
+                "note": "all launches of the tag per step; issued FLOPs = 3 x useful (3xBF16 split)"}
     elif dom in prof:
         t_ms, n = prof[dom]
         roof = {"bound": "latency", "kernel": dom, "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,
                 "traffic": None, "avg_launch_ms": t_ms / n}
+    # the image stage as a whole (mean pass + query-side projections + pooling pass + value-side projections) against ONE
+    # algorithmic read of the feature maps
+    stage = None
+    if not args.core and "img_pool" in prof:
+        st_ms = sum(prof[k][0] for k in ("img_mean", "img_pool", "gemm_img_3xbf16") if k in prof) / args.steps
+        st_alg = B * cfg.n_views * tile_bytes
+        st_traffic = None
+        if all(measured_traffic(k, B) is not None for k in ("img_mean", "img_pool")):
+            st_traffic = measured_traffic("img_mean", B) + measured_traffic("img_pool", B) + (measured_traffic("gemm_img_3xbf16", B) or 0.0)
+        stage = {"kernels": [k for k in ("img_mean", "gemm_img_3xbf16", "img_pool") if k in prof], "ms_per_step": st_ms,
+                 "algorithmic_bytes_per_step": st_alg, "achieved": st_alg / (st_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                 "frac": st_alg / (st_ms / 1e3) / 1e9 / hbm_peak, "traffic": st_traffic,
+                 "note": "the query of the attention pool depends on the spatial mean of the whole view, so the stage reads the features twice"}
     # whole-path HBM roofline: algorithmic bytes per scene / measured copy bandwidth
     path_bytes = 24 * cfg.n_points + 2 * cfg.embed_dim * (cfg.n_text + cfg.n_views) + cfg.n_text + (0 if args.core else cfg.n_views * tile_bytes)
     path_bound = hbm_peak * 1e9 / path_bytes
@@ -382,25 +514,37 @@ def run_b200(args):
 
     cpu = None
     if not args.no_cpu_baseline:
-        v, cores, dt = cpu_reference_rate(cfg, args.cpu_scenes, per_call=args.ref_scenes_per_step, img_dtype=img_dtype)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+        v, cores, dt, kind, desc = cpu_reference_rate(cfg, args.cpu_scenes, per_call=args.ref_scenes_per_step, img_dtype=img_dtype)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"{args.cpu_scenes} scenes of the same workload in batches of {min(args.ref_scenes_per_step, args.cpu_scenes)} ({dt:.1f} s), "
-                         "oracle port of the reference's PyTorch path (all blocks, full 226-token attention pool), fp32, all host threads"}
+                         f"{desc}, fp32, all host threads"}
 
+    checks = {"survivors_per_scene": allm[0, 1].item() / B}
+    if not args.core and not args.no_checks:
+        checks.update(oracle_checks(m, cfg, sets, B))
+    extra = {}
+    if not args.core and not args.no_extra:
+        # the other BASELINE.json configurations, single GPU forward latency (rank 0): C1 (4 096 points / 16 clusters, one scene),
+        # C3 (the shipped grounding config gs=12 / ddr=0.6 -> 691 clusters, batch 4, 50 views, 32 text tokens), eager and CUDA graph
+        del sets
+        torch.cuda.empty_cache()
+        for key, c_, b_ in (("c1", syn.C1, 1), ("c3", syn.C3, 4), ("c3_wide", syn.C3_WIDE, 4)):
+            ms_e = forward_latency(c_, b_, dev, img_dtype)
+            ms_g = forward_latency(c_, b_, dev, img_dtype, graph=True)
+            extra[key] = {"workload": c_.name, "batch": b_, "clusters": c_.real_cluster_num, "views": c_.n_views, "ms_per_forward": ms_e,
+                          "ms_per_forward_cuda_graph": ms_g, "scenes_per_s": b_ / (min(ms_e, ms_g) / 1e3)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (3xBF16 tensor-core dense layers, bf16 image features)" if img_dtype == torch.bfloat16 else "f32",
             "data": "synthetic",
-            "config": {"workload": cfg.name, "n_points": cfg.n_points, "clusters": cfg.real_cluster_num, "embed_dim": cfg.embed_dim,
-                       "text_tokens": cfg.n_text, "image_views": cfg.n_views, "img_feat_dtype": args.img_dtype,
-                       "region": "core" if args.core else "full", "scenes_per_gpu_per_step": B, "box_m": list(cfg.box),
-                       "l2": "two alternating input sets per rank, each %.1f GB >> 126 MB L2" % (B * cfg.n_views * tile_bytes / 1e9),
-                       "sharding": f"{world} x {B} independent scenes, no data-path collective"},
+            "config": config_dict(cfg, args, world, B),
             "e2e": e2e, "gpu_launches": int(allm[:, 4].sum().item()), "clocks": clocks, "roofline": roof,
             "path_roofline": {"algorithmic_bytes_per_scene": path_bytes, "hbm_bound_scenes_per_s_per_gpu": path_bound,
                               "frac": value / world / path_bound},
+            "image_stage_roofline": stage, "c4_strong": c4,
             "core_region": core, "kernel_breakdown": breakdown, "profiled_pass_ms_per_step": prof_ms / args.steps, "cpu_baseline": cpu,
-            "checks": {"survivors_per_scene": allm[0, 1].item() / B}}
+            "checks": checks}
+    line.update(extra)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

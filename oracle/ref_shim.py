@@ -1,11 +1,11 @@
 """ORACLE — TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
-Imports the reference's hot-path file UNMODIFIED from ``/root/reference`` under
-three import shims (SURVEY.md §8c recipe) so the restatement in
-``preshape_oracle.py`` can be pinned against the reference itself and golden
-vectors can be generated.  ``/root/reference`` exists only in the build
-container: nothing that runs on the GPU box (``-m gpu`` tests, ``smoke()``,
-``bench.py``) may call into this file.
+Imports the reference's hot-path file UNMODIFIED under three import shims (SURVEY.md §8c recipe) so the restatement
+in ``preshape_oracle.py`` can be pinned against the reference itself and golden vectors can be generated.  The module is
+loaded from ``/root/reference`` in the build container, or — on the GPU box, where that tree does not exist — from the
+bytecode ``oracle/build.py::build_ref`` compiled from it into ``oracle/_ref/`` (git-ignored; travels like a built .so).
+Nothing in the ``-m gpu`` tests or ``smoke()`` depends on it; ``bench.py`` uses it for the CPU arm only
+(``cpu_baseline.kind = "reference"``) and falls back to the restatement (``"port"``) when it is absent.
 
 Shims (none of these packages is installed here, and ``import embodiedscan``
 proper fails as shipped — ``embodiedscan/utils/__init__.py:2`` needs a file that
@@ -22,6 +22,7 @@ reference module's namespace (:378) and single-threaded ``index_put_`` (:495).
 from __future__ import annotations
 
 import collections
+import importlib.machinery
 import importlib.util
 import os
 import sys
@@ -34,8 +35,11 @@ REF_ROOT = "/root/reference"
 REF_FILE = os.path.join(REF_ROOT, "embodiedscan/models/necks/preshape_norm_reverse_drop.py")
 
 
+REF_PYC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "preshape_norm_reverse_drop.pyc")
+
+
 def available() -> bool:
-    return os.path.exists(REF_FILE)
+    return os.path.exists(REF_FILE) or os.path.exists(REF_PYC)
 
 
 class _Registry:
@@ -89,7 +93,7 @@ def load():
     if _module is not None:
         return _module
     if not available():
-        raise FileNotFoundError(REF_FILE)
+        raise FileNotFoundError(f"{REF_FILE} (or the bytecode {REF_PYC} built from it by oracle/build.py)")
     from . import preshape_oracle as po
 
     def mod(name):
@@ -114,7 +118,11 @@ def load():
 
     ops.ball_query = ball_query
     ops.sample_farthest_points = None   # replaced below with the in-tree naive copy
-    spec = importlib.util.spec_from_file_location("_ref_preshape_norm_reverse_drop", REF_FILE)
+    if os.path.exists(REF_FILE):
+        spec = importlib.util.spec_from_file_location("_ref_preshape_norm_reverse_drop", REF_FILE)
+    else:
+        spec = importlib.util.spec_from_loader("_ref_preshape_norm_reverse_drop",
+                                               importlib.machinery.SourcelessFileLoader("_ref_preshape_norm_reverse_drop", REF_PYC))
     m = importlib.util.module_from_spec(spec)
     try:
         spec.loader.exec_module(m)
@@ -140,6 +148,21 @@ class _PinnedTorch:
 
     def argsort(self, x, dim=-1, descending=False, stable=False):
         return torch.argsort(x, dim=dim, descending=descending, stable=True)
+
+
+def use_native_fps(on: bool = True):
+    """Timing mode: ``sample_farthest_points`` -> the C restatement of pytorch3d's CPU loop (what the reference executes in
+    production) instead of the reference's in-tree pure-Python copy (:527-625), which is what the parity pins use."""
+    m = load()
+    if on:
+        from . import preshape_oracle as po
+
+        def sample_farthest_points(points, lengths=None, K=50, random_start_point=False):
+            idx = po.farthest_point_indices(points, int(K))
+            return torch.gather(points, 1, idx[..., None].expand(-1, -1, points.shape[-1])), idx
+        m.sample_farthest_points = sample_farthest_points
+    else:
+        m.sample_farthest_points = m.sample_farthest_points_naive
 
 
 def build_module(cfg_kwargs: dict, state_dict=None, pinned: bool = True):

@@ -26,7 +26,7 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static const char* const g_prof_names[PROF_NTAGS] = {
     "minmax_partial", "centres", "ball_query", "offset_net", "cluster_dropout", "point_encoder", "layernorm", "gemm_f32",
     "gemm_tc_3xbf16", "split_bf16", "proxy_attention", "heads", "img_mean", "img_pool", "scatter_mark", "scatter_count",
-    "scatter_compact", "misc"};
+    "scatter_compact", "misc", "gemm_img_3xbf16"};
 struct ProfRec { int tag; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;

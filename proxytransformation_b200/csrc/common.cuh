@@ -16,7 +16,7 @@ void count_launch(int n = 1);
 enum ProfTag {
     PROF_MINMAX = 0, PROF_CENTRES, PROF_BALL_QUERY, PROF_OFFSET_NET, PROF_DROPOUT, PROF_ENCODER, PROF_LAYERNORM,
     PROF_GEMM_F32, PROF_GEMM_TC, PROF_SPLIT, PROF_ATTENTION, PROF_HEADS, PROF_IMG_MEAN, PROF_IMG_POOL, PROF_MARK,
-    PROF_COUNT, PROF_COMPACT, PROF_MISC, PROF_NTAGS
+    PROF_COUNT, PROF_COMPACT, PROF_MISC, PROF_GEMM_IMG, PROF_NTAGS
 };
 struct ProfScope {
     int slot;

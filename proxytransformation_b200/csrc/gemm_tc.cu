@@ -365,6 +365,10 @@ int encode_tensor_map_16bit(CUtensorMap* map, const void* base, int rank, const 
     return PT_OK;
 }
 
+static thread_local int t_gemm_prof_tag = PROF_GEMM_TC;
+GemmProfTagScope::GemmProfTagScope(int tag) : saved(t_gemm_prof_tag) { t_gemm_prof_tag = tag; }
+GemmProfTagScope::~GemmProfTagScope() { t_gemm_prof_tag = saved; }
+
 bool gemm_tc_supported(int M, int N, int K) { return M >= 1 && N >= 4 && N % 4 == 0 && K % TC_BK == 0 && K >= TC_BK; }
 
 size_t gemm_tc_ws_bytes(int M, int N, int K) {
@@ -399,7 +403,7 @@ static int launch_variant(const CUtensorMap& mapA, const CUtensorMap& mapW, TcKe
     k.tiles_n = ceil_div(k.N, BN);
     const int total = k.tiles_m * k.tiles_n * k.batch;
     const int grid = total < num_sms() ? total : num_sms();
-    { ProfScope prof_(PROF_GEMM_TC, s); gemm_tc_kernel<BN, ACT, SPLIT><<<grid, TC_THREADS, smem, s>>>(mapA, mapW, k); }
+    { ProfScope prof_(t_gemm_prof_tag, s); gemm_tc_kernel<BN, ACT, SPLIT><<<grid, TC_THREADS, smem, s>>>(mapA, mapW, k); }
     PT_LAUNCH_CHECK();
     return PT_OK;
 }

@@ -42,6 +42,14 @@ struct GemmTc {
 int encode_tensor_map_16bit(CUtensorMap* map, const void* base, int rank, const unsigned long long* dims,
                             const unsigned long long* strides_bytes, const unsigned* box, bool fp16);
 
+// Profiling tag of the GEMMs launched by the calling thread while the scope lives (the image stage books its projections
+// under PROF_GEMM_IMG so that bench.py can report a roofline for the whole stage).
+struct GemmProfTagScope {
+    int saved;
+    explicit GemmProfTagScope(int tag);
+    ~GemmProfTagScope();
+};
+
 bool gemm_tc_supported(int M, int N, int K);
 size_t gemm_tc_ws_bytes(int M, int N, int K);
 int launch_gemm_tc_ex(const GemmTc& p, cudaStream_t s);

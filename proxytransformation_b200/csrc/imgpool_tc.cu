@@ -659,6 +659,7 @@ int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, in
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int rc;
+    GemmProfTagScope img_gemms(PROF_GEMM_IMG);
     const bool umma = p->variant == PT_POOL_VARIANT_UMMA;
     if (stages & PT_IMG_STAGE_FRONT) {
     {   // pass A
