@@ -377,7 +377,9 @@ def test_image_proxies_many_views_per_cta(B, V, dtype, kernel, monkeypatch):
 def test_image_pool_tcgen05_kernel_raises_its_reference_maximum():
     """The tcgen05 pool kernel exponentiates against a per-view reference maximum taken from the first 64 tokens and raises it
     (rescaling the accumulators in TMEM) only when a later window exceeds it by more than 16: drive that path with views whose
-    late tokens score far above the early ones (features growing 40 x along the token axis) and compare with the oracle."""
+    late tokens score far above the early ones (features growing 40 x along the token axis).  With features of that size both
+    kernels sit 9e-4 from the oracle's reference formulation (the error of the folded fp32 projections scales with the feature
+    magnitude), so the bar is: the tcgen05 kernel within 1e-4 of the mma.sync kernel, both within 2e-3 of the oracle, no NaN."""
     import os
     cfg = syn.C2_WIDE.replace(n_views=40)
     sd = syn.make_state_dict(cfg, 33, bf16_round=True)
@@ -398,7 +400,9 @@ def test_image_pool_tcgen05_kernel_raises_its_reference_maximum():
         else:
             os.environ["PT_POOL_KERNEL"] = old
     for kernel, g_ in got.items():
-        np.testing.assert_allclose(np_(g_), want.numpy(), rtol=0, atol=2e-4, err_msg=kernel)
+        assert torch.isfinite(g_).all(), kernel
+        np.testing.assert_allclose(np_(g_), want.numpy(), rtol=0, atol=2e-3, err_msg=kernel)
+    np.testing.assert_allclose(np_(got["umma"]), np_(got["mma"]), rtol=0, atol=1e-4)
 
 
 def _standalone_block_state(dim, n, hidden, seed):
