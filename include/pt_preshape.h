@@ -205,6 +205,8 @@ int pt_img_attnpool_stage(const void* img_feat, int img_dtype, const pt_img_pool
 /* Debug only: per-phase SM-clock cycles of CTA 0 of the bf16 image-pool kernel, accumulated while PT_POOL_DEBUG has bit 8
  * set: [0] view barrier, [1] operand wait, [2] score MMAs, [3] score exchange + softmax, [4] weighted sums. */
 int pt_debug_pool_trace(unsigned long long* out8, int reset);
+/* Per-role SM-clock trace of CTA 0 of img_pool_umma_kernel (PT_UMMA_DEBUG bit 16; slots in csrc/imgpool_umma.cu). */
+int pt_debug_umma_trace(unsigned long long* out16, int reset);
 /* Debug only (PT_POOL_DEBUG bit 64): when the workspace handed to pt_img_attnpool[_stage] is at least
  * pt_img_attnpool_ws_bytes() + BV * 8 * 256 * 4 bytes, the bf16 pool kernel also writes the scaled scores [BV][8 heads][256]
  * (fp32, tokens 0..225) behind the regular workspace; tools/pool_check.py compares them with a float64 evaluation. */

@@ -68,6 +68,7 @@ _SIGNATURES = {
     "pt_img_attnpool": (c_int, [_P, c_int, POINTER(ImgPoolParams), c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "pt_img_attnpool_stage": (c_int, [_P, c_int, POINTER(ImgPoolParams), c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, c_int, _P]),
     "pt_debug_pool_trace": (c_int, [POINTER(ctypes.c_ulonglong), c_int]),
+    "pt_debug_umma_trace": (c_int, [POINTER(ctypes.c_ulonglong), c_int]),
     "pt_debug_pool_events": (c_int, [POINTER(ctypes.c_longlong), c_int]),
     "pt_scatter_ws_bytes": (c_size_t, [c_int, c_int]),
     "pt_affine_scatter_compact": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),

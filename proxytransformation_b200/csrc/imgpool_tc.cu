@@ -720,7 +720,8 @@ int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, in
         a.dbg = ws_bytes >= w.total + (size_t)BV * DBG_PER_VIEW * 4 ? reinterpret_cast<float*>((char*)ws + w.total) : nullptr;
         const char* pf = getenv("PT_POOL_PF");
         a.pf_dist = pf ? atoi(pf) : PF_DIST;
-        const int grid = BV < sms ? BV : sms;
+        int grid = BV < sms ? BV : sms;
+        if (const char* ge = getenv("PT_POOL_GRID")) { const int gv = atoi(ge); if (gv >= 1 && gv < grid) grid = gv; }   // probes: fewer persistent CTAs
         { ProfScope prof_(PROF_IMG_POOL, s); img_pool_mma_kernel<<<grid, THREADS, SMEM_BYTES + POOL_EV_SMEM, s>>>(a); }
         PT_LAUNCH_CHECK();
     }

@@ -1,35 +1,39 @@
-// S9 image proxies, pass B (scores -> softmax -> attention-weighted feature sums) on tcgen05 tensor cores:
+// S9 image proxies, pass B (scores -> softmax -> attention-weighted feature sums) on tcgen05 tensor cores, TMA-fed:
 // get_img_proxy (:335-342) + AttentionPool2d.forward (:154-177) in single-query form (algebra in imgpool.cu), shipped
 // geometry C = 512 channels, 15 x 15 = 225 positions, 8 heads of 32, 16-bit features (bf16).
 //
-// The feature map of a view is [512 channels][225 tokens] with a 450-byte row pitch.  UMMA shared-memory descriptors (and TMA
-// tensor maps) need 16-byte aligned rows, so the rows have to be REALIGNED on their way into shared memory.  225 = 1 (mod 8):
-// the rows of one residue CLASS s = channel mod 8 (channels s + 8r, r = 0..63) are 3600 bytes apart and all start 2 s bytes
-// after a 16-byte boundary, so a class is realigned by ONE shift of s elements.  TMA cannot do it (box origins must be 16-byte
-// aligned in global memory — measured: the first box with an odd origin raises "illegal instruction"), so loader warps do:
-// coalesced 16-byte loads of the aligned chunks, a funnel shift by s elements across neighbouring chunks (shuffles), and
-// 16-byte stores into the SWIZZLE_128B tile layout the tensor core reads.
-// One 8 KB tile [64 class rows][64 tokens] serves both contractions without any copy:
-//   scores  D1[token][n]   += X^T W^T : A = the tile read MN-major (M = 64 tokens, K = 16 class rows per MMA),
-//                                       B = w_eff rows n = (hi|lo, head) of this class, K-major           (tcgen05.mma M64 N16 K16)
-//   sums    D2[channel][n] += X  P^T : A = two class tiles read K-major (M = 128 channel rows, K = 16 tokens per MMA),
-//                                       B = probabilities n = (hi|lo, head), K-major over the tokens      (tcgen05.mma M128 N16 K16)
+// The feature map of a view is [512 channels][225 tokens] with a 450-byte row pitch: the rows are not 16-byte aligned, which
+// TMA boxes and UMMA shared-memory descriptors need.  225 = 1 (mod 8): the rows of one residue CLASS s = channel mod 8
+// (channels s + 8 r, r = 0..63) are 3600 bytes apart and start 2 s bytes after a 16-byte boundary.  In the coordinate
+// u = token + s every class is a regular, 16-byte aligned matrix X_s[r][u] at byte 3600 r + 448 s + 2 u of the view (columns
+// u < s and u >= s + 225 belong to the neighbouring channels).  So one 4-D tensor map (u, r, s, view) lets TMA deliver
+// SWIZZLE_128B tiles [64 class rows][64 u] straight from the raw NCHW tensor: no register staging, no realignment.  The price
+// is that the token axis of class s is shifted by s:
+//   scores  D1_s[u][n]    = sum_r X_s[r][u] w_eff[n][s + 8 r]      one accumulator per class (tcgen05.mma M64 N16 K16, A = the
+//                           tile read MN-major, B = the class's w_eff rows n = (hi|lo, head), K-major); the score of token t
+//                           is sum_s D1_s[t + s]: the softmax warps add the eight classes with lane shifts (shuffles + a small
+//                           shared-memory halo for the rows of the neighbouring warp / previous window);
+//   sums    D2_s[r][n]   += sum_u X_s[r][u] P[u - s][n]            (tcgen05.mma M64 N16 K16, A = the tile read K-major,
+//                           B = the probabilities as an MN-major, unswizzled operand [token][8 (hi|lo) heads x 2 B]: a row
+//                           shift of s tokens is a 16 s-byte shift of the descriptor start address, so ONE copy of the
+//                           probabilities serves all classes).
 // The fp32 operands (w_eff, probabilities) enter as bf16 hi + lo halves in separate N columns, so every product is exact and
 // the accumulation is fp32 in TMEM (same numerics as the 3xBF16 GEMMs: ~2^-17 relative).
 //
-// One persistent CTA per SM, a view is streamed ONCE as 4 token windows of 64 (flash-attention structure, one query per head):
-//   warp 0       TMA producer of the per-view w_eff planes (8 boxes of 2 KB, SWIZZLE_128B)
-//   warp 1       MMA issuer (one elected thread): scores of window g+1 interleaved with the sums of window g; every ring slot is
-//                handed back to the loaders by tcgen05.commit when the sums that read it have completed
-//   warps 4-7    softmax: tcgen05.ld the 64 x 16 score tile (lane = token), + position term, exp relative to a per-view
-//                reference maximum (established by window 0, raised FA-style by rescaling the accumulators in TMEM only when
-//                a later window exceeds it by more than TAU — never on ordinary data), bf16 hi/lo probability tile -> shared
-//                memory (the B operand of the sums), running sum in registers; end of view: final probabilities -> global
-//   warps 8-11   epilogue: mean-token score s0 = w_eff . xbar (CUDA cores, from L2), then per view Y = (D2 f + p0 xbar) / L
+// One persistent CTA per SM; a view is streamed ONCE as 4 windows of 64 u-columns (flash-attention structure, one query per
+// head).  Window w completes the scores of the token SET w = [64 w - 7, 64 w + 57) (the last 7 u-columns of a window wait for
+// the next one); the sums of set w read window w and the last 16 u-columns of window w-1 (5 k-steps of 16):
+//   warp 0       MMA issuer (one elected thread) + TMA of the per-view w_eff planes: scores of window g+1 interleaved with the
+//                sums of set g; a ring slot goes back to the producer (tcgen05.commit) when the tail k-step of the NEXT set
+//                has read it
+//   warps 1-4    softmax: tcgen05.ld of the eight 64 x 16 class score tiles (lane = u), class exchange, + position term, exp
+//                relative to a per-view reference maximum (established by window 0, raised FA-style by rescaling the
+//                accumulators in TMEM only when a later window exceeds it by more than TAU — never on ordinary data),
+//                bf16 hi/lo probability rows -> shared memory (16-byte stores), running sum in registers; end of view: final
+//                probabilities -> global
+//   warps 5-8    epilogue: mean-token score s0 = w_eff . xbar (CUDA cores, from L2), then per view Y = (D2 f + p0 xbar) / L
 //                from TMEM -> bf16 hi/lo planes for the value-side GEMM (same output format as the mma.sync kernel)
-//   warps 12-19  loaders: warp l owns rows 8 l .. 8 l + 7 of every class tile; per window it issues its 20 loads (16 x 4 rows x
-//                8 chunks + the 9th chunk of its 64 rows) before it touches the ring, so 80 KB of loads are in flight per SM
-//                while earlier windows are consumed; 10-slot ring of class-pair slots (160 KB)
+//   warp 9       TMA producer of the feature tiles: one 16 KB box (64 u x 64 rows x 2 classes) per ring slot, 10 slots
 // Channel order of w_eff columns and of the weighted sums: position 64 s + r  <->  channel s + 8 r (absorbed into the folded
 // GEMM weights on the host, pt_img_pool_params variant 1).
 #include "common.cuh"
@@ -45,31 +49,40 @@ namespace ipu {
 constexpr int C = 512, HW = 225, HEADS = 8;
 constexpr int TP = 228;                      // cterm row pitch (floats)
 constexpr int YA = 768;                      // output row: 512 weighted sums + 256 probabilities
-constexpr int NWIN = 4, WTOK = 64;           // token windows per view
-constexpr int TILE_BYTES = 64 * 128;         // [64 class rows][64 tokens] bf16
-constexpr int SLOT_BYTES = 2 * TILE_BYTES;   // a class pair: rows 0-63 class 2p, rows 64-127 class 2p+1
+constexpr int NWIN = 4, WTOK = 64;           // u-windows per view (u = token + class, 232 columns -> 4 x 64, zero filled)
+constexpr int UCOLS = 232;                   // valid u range of the tensor map: 225 tokens + 7 class shifts
+constexpr int TILE_BYTES = 64 * 128;         // [64 class rows][64 u] bf16, SWIZZLE_128B
+constexpr int SLOT_BYTES = 2 * TILE_BYTES;   // a class pair: rows 0-63 class 2p, rows 64-127 class 2p+1 (one TMA box)
 constexpr int RING = 10;
 constexpr int WCLASS_BYTES = 16 * 128;       // w_eff rows (hi|lo, head) x 64 class channels
 constexpr int W_BYTES = 8 * WCLASS_BYTES;
-constexpr int P_BYTES = 16 * 128, PBUF = 4;  // probability tile [16 rows (hi|lo, head)][64 tokens]; buffer = window index
+// Probabilities of token set w as the MN-major, unswizzled B operand of the sums: two planes (hi, lo), each [P_ROWS][8 heads]
+// bf16 = 16 bytes per token row; row 16 + i holds token 64 w - 7 + i; rows [0,16) and [80,88) stay zero (tokens of the
+// neighbouring sets that the shifted 16-row k-steps of a class reach).
+constexpr int P_ROWS = 88, P_PLANE = P_ROWS * 16, P_BYTES = 2 * P_PLANE, PBUF = 4;
+// class-exchange halo: [window parity][softmax warp][28 (class, row) entries][8 heads] fp32
+constexpr int HALO_ENTRIES = 28, HALO_BYTES = 2 * 4 * HALO_ENTRIES * 32;
 constexpr int OFF_RING = 0;
 constexpr int OFF_W = OFF_RING + RING * SLOT_BYTES;
 constexpr int OFF_P = OFF_W + 2 * W_BYTES;
-constexpr int OFF_MISC = OFF_P + PBUF * P_BYTES;      // floats: smax[32] sred[32] ered[32] s0[16] stat_l[16] stat_m[16]
+constexpr int OFF_HALO = OFF_P + PBUF * P_BYTES;
+constexpr int OFF_MISC = OFF_HALO + HALO_BYTES;       // floats: smax[32] sred[32] ered[32] s0[16] stat_l[16] stat_m[16]
 constexpr int OFF_BAR = OFF_MISC + 1024;
 // mbarriers: full[RING] empty[RING] wfull[2] wempty[2] d1_full[2] p_full[PBUF] p_empty[PBUF] d2_full[2] d2_empty[2] s0_full[2] l_full[2]
 constexpr int NBAR = 2 * RING + 6 + 2 * PBUF + 8;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;      // + slack for the 1024-byte alignment of the swizzled tiles
-// warp roles: 0 = MMA issuer + w_eff TMA + TMEM allocation, 1-4 softmax, 5-8 epilogue (TMEM lane quarter = warp mod 4), 9-16 loaders
-constexpr int SOFTMAX_WARP0 = 1, EPI_WARP0 = 5, LOADER_WARP0 = 9, LOADER_WARPS = 8;
-constexpr int THREADS = 32 * (LOADER_WARP0 + LOADER_WARPS);
-constexpr int TMEM_COLS = 256;               // D1: 2 x 16 columns at 0 ; D2: 2 x 64 columns at 64
-constexpr int D2_COL = 64;
+// warp roles: 0 = MMA issuer + w_eff TMA + TMEM allocation, 1-4 softmax, 5-8 epilogue (TMEM lane quarter = warp mod 4), 9 = TMA producer
+constexpr int SOFTMAX_WARP0 = 1, EPI_WARP0 = 5, PRODUCER_WARP = 9;
+constexpr int THREADS = 32 * (PRODUCER_WARP + 1);
+// TMEM: D1 (scores) 2 window buffers x 8 classes x 16 columns at 0 ; D2 (sums) 2 view buffers x 8 classes x 16 columns at 256.
+// Both are M = 64 accumulators: row r lives in lane 32 (r / 16) + r % 16.
+constexpr int TMEM_COLS = 512;
+constexpr int D1_BUF_COLS = 128, D2_COL = 256, D2_BUF_COLS = 128;
 constexpr float TAU = 16.0f;                 // the reference maximum is raised when a score exceeds it by more than this
 constexpr float LOG2E = 1.4426950408889634f;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(OFF_W % 1024 == 0 && OFF_P % 1024 == 0 && SLOT_BYTES % 1024 == 0, "swizzled tiles need 1024-byte alignment");
+static_assert(OFF_W % 1024 == 0 && SLOT_BYTES % 1024 == 0 && OFF_P % 16 == 0 && OFF_HALO % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
 }  // namespace ipu
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -104,6 +117,11 @@ __device__ __forceinline__ void iu_tma_3d(void* dst, const CUtensorMap* map, int
                  "l"(map), "r"(iu_smem(bar)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+__device__ __forceinline__ void iu_tma_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(iu_smem(dst)),
+                 "l"(map), "r"(iu_smem(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void iu_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void iu_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void iu_commit(uint64_t* bar) {
@@ -131,9 +149,22 @@ __device__ __forceinline__ uint64_t iu_desc(uint32_t saddr, uint32_t lbo_bytes) 
     d |= (uint64_t)2 << 61;
     return d;
 }
-// kind::f16 instruction descriptor: D = f32, A = B = bf16; bit 15 = A is MN-major; N >> 3 at bit 17, M >> 4 at bit 24.
-__host__ __device__ constexpr uint32_t iu_idesc(int m, int n, bool a_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major ? (1u << 15) : 0u) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// MN-major operand WITHOUT swizzle (canonical layout ((8,1,m),(8,k)):((1,8,SBO),(8,LBO)) in elements): 16-byte rows of 8
+// MN elements, 8 consecutive K rows form a 128-byte core matrix, LBO = distance between K blocks of 8 rows, SBO = distance
+// between MN blocks of 8 elements.  The start address only needs 16-byte alignment: a K shift of one row is 16 bytes.
+__device__ __forceinline__ uint64_t iu_desc_mn_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16; bit 15 = A is MN-major, bit 16 = B is MN-major; N >> 3 at bit 17,
+// M >> 4 at bit 24.
+__host__ __device__ constexpr uint32_t iu_idesc(int m, int n, bool a_mn_major, bool b_mn_major = false) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major ? (1u << 15) : 0u) | (b_mn_major ? (1u << 16) : 0u) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void iu_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -177,49 +208,10 @@ __device__ __forceinline__ float iu_bf(uint32_t packed, int k) {      // element
 
 struct UmmaPoolMaps {
     CUtensorMap w;         // w_eff planes as (512 columns, BV*16 rows (view, hi|lo, head)), box (64, 16)
+    CUtensorMap x;         // features as (u 232, class row 64, class 8, view BV) with strides (3600, 448, 230400) bytes, box (64, 64, 2, 1)
 };
 
-__device__ __forceinline__ uint4 iu_ldg_stream(const void* p) {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-
-// One 16-byte output chunk of a class-S row: elements [8 j + S, 8 j + S + 8) of the row in u = token + S coordinates, i.e. the
-// tail of aligned chunk j (this lane's `a`) and the head of chunk j + 1 (the next lane's `a`; for j == 7 the 9th chunk of the
-// row, which lane `tail_lane` holds in `t`), stored at chunk j of tile row `row` (SWIZZLE_128B: chunk index XOR row mod 8).
-template <int S>
-__device__ __forceinline__ void iu_shift_store(uint32_t tile, int row, int j, const uint4& a, const uint4& t, int tail_lane) {
-    constexpr int Q = S >> 1, ODD = S & 1, NB = Q + ODD;
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, tw[4] = {t.x, t.y, t.z, t.w};
-    uint32_t A[9] = {a.x, a.y, a.z, a.w, 0u, 0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        const uint32_t nxt = __shfl_down_sync(FULL, aw[i], 1);
-        const uint32_t tl = __shfl_sync(FULL, tw[i], tail_lane);
-        A[4 + i] = j == 7 ? tl : nxt;
-    }
-    uint4 o;
-    if (ODD) {
-        o.x = __funnelshift_r(A[Q], A[Q + 1], 16); o.y = __funnelshift_r(A[Q + 1], A[Q + 2], 16);
-        o.z = __funnelshift_r(A[Q + 2], A[Q + 3], 16); o.w = __funnelshift_r(A[Q + 3], A[Q + 4], 16);
-    } else {
-        o.x = A[Q]; o.y = A[Q + 1]; o.z = A[Q + 2]; o.w = A[Q + 3];
-    }
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(tile + row * 128 + ((j ^ (row & 7)) << 4)), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
-}
-
-// Class pair P of one window: both tiles of ring slot `tile0`, this warp's 8 rows of each (two groups of 4 rows x 8 chunks).
-template <int P>
-__device__ __forceinline__ void iu_store_pair(uint32_t tile0, int row0, int rr, int j, const uint4 (&am)[2][2], const uint4& at) {
-    iu_shift_store<2 * P>(tile0, row0 + rr, j, am[0][0], at, rr);
-    iu_shift_store<2 * P>(tile0, row0 + 4 + rr, j, am[0][1], at, 4 + rr);
-    iu_shift_store<2 * P + 1>(tile0 + ipu::TILE_BYTES, row0 + rr, j, am[1][0], at, 8 + rr);
-    iu_shift_store<2 * P + 1>(tile0 + ipu::TILE_BYTES, row0 + 4 + rr, j, am[1][1], at, 12 + rr);
-}
-
 struct UmmaPoolArgs {
-    const uint8_t* img;          // (BV, 512, 225) 16-bit features
     const __nv_bfloat16* wpl;    // (BV, 2, 8, 512) bf16 hi / lo planes of w_eff, columns 64 s + r
     const float* cterm;          // (BV, 8, TP)
     const float* xbar;           // (BV, 512) natural channel order
@@ -228,9 +220,20 @@ struct UmmaPoolArgs {
     int BV;
     float scale;
     float* dbg;                  // optional (PT_POOL_DEBUG bit 64): [BV][8][256] scaled scores, attention tokens 0..225
-    int debug;                   // PT_UMMA_DEBUG bring-up switches (garbage results): 1 no score MMAs, 2 no sum MMAs, 4 score MMAs with a
-                                 // K-major A descriptor, 8 score MMAs with M = 128
+    int debug;                   // PT_UMMA_DEBUG bring-up switches (garbage results): 1 no score MMAs, 2 no sum MMAs
 };
+
+// Per-role cycle trace of CTA 0 (PT_UMMA_DEBUG bit 16): SM clocks spent in each wait / work section, summed over its views;
+// read with pt_debug_umma_trace.  Slots: 0 producer wait empty | 1 issuer wait full, 2 wait p_full, 3 wait wfull, 4 wait d2_empty,
+// 5 issuer total | 6 softmax wait d1_full, 7 class exchange (tmem loads + shuffles + barrier), 8 wait p_empty, 9 softmax total,
+// 10 bar_or / raise | 11 epilogue s0, 12 wait l_full, 13 wait d2_full, 14 epilogue store, 15 epilogue total
+__device__ unsigned long long g_umma_trace[16];
+// (accumulated in registers, written once at the end of the role: a global read-modify-write per section would itself cost an
+// L2 round trip)
+#define UT(acc, stmt) do { const long long ut0_ = tracing ? clock64() : 0; stmt; if (tracing) acc += clock64() - ut0_; } while (0)
+
+// first halo entry of class s (classes 0..6 need 7 - s rows of the neighbouring warp)
+__host__ __device__ constexpr int iu_halo_off(int s) { return 7 * s - s * (s - 1) / 2; }
 
 __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __grid_constant__ UmmaPoolMaps maps, const UmmaPoolArgs a) {
     using namespace ipu;
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < RING; ++i) { iu_mbar_init(full + i, LOADER_WARPS); iu_mbar_init(empty + i, 1); }
+        for (int i = 0; i < RING; ++i) { iu_mbar_init(full + i, 1); iu_mbar_init(empty + i, 1); }
         for (int i = 0; i < 2; ++i) {
             iu_mbar_init(wfull + i, 1); iu_mbar_init(wempty + i, 1); iu_mbar_init(d1_full + i, 1);
             iu_mbar_init(d2_full + i, 1); iu_mbar_init(d2_empty + i, 4); iu_mbar_init(s0_full + i, 1); iu_mbar_init(l_full + i, 1);
@@ -265,7 +268,11 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
         for (int i = 0; i < PBUF; ++i) { iu_mbar_init(p_full + i, 4); iu_mbar_init(p_empty + i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x) : "memory");
     }
+    // the zero margins of the probability buffers are never written again
+    for (int i = threadIdx.x; i < PBUF * P_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(smem + OFF_P)[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(iu_smem(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -275,66 +282,65 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
     iu_fence_after();
     const uint32_t tmem = *tmem_slot;
     const int nviews = (int)blockIdx.x < a.BV ? (a.BV - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const bool tracing = (a.debug & 16) && blockIdx.x == 0 && (lane == 0);
 
-    if (warp >= LOADER_WARP0) {
-        // ===== loaders: global -> registers -> (shift by the class) -> swizzled tiles =====
-        const int row0 = 8 * (warp - LOADER_WARP0), rr = lane >> 3, j = lane & 7;
-        unsigned it = 0;
-        for (int vi = 0; vi < nviews; ++vi) {
-            const int bv = blockIdx.x + vi * gridDim.x;
-            const uint8_t* view = a.img + (size_t)bv * (C * HW * 2);
-#pragma unroll 1
-            for (int w = 0; w < NWIN; ++w) {
-                uint4 am[4][2][2], at[4];
-                const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-                const int chunk = 8 * w + j;                               // aligned 16-byte chunk of the row; 29 chunks per row
-#pragma unroll
-                for (int p = 0; p < 4; ++p) {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e)
-#pragma unroll
-                        for (int hf = 0; hf < 2; ++hf)
-                            am[p][e][hf] = chunk <= 28 ? iu_ldg_stream(view + 448 * (2 * p + e) + 3600 * (row0 + 4 * hf + rr) + 16 * chunk) : zero;
-                    // 9th chunk of this warp's 16 rows of the pair: lanes 0-7 class 2p, lanes 8-15 class 2p + 1
-                    at[p] = (lane < 16 && 8 * w + 8 <= 28) ? iu_ldg_stream(view + 448 * (2 * p + (lane >> 3)) + 3600 * (row0 + (lane & 7)) + 16 * (8 * w + 8)) : zero;
-                }
-#pragma unroll
-                for (int p = 0; p < 4; ++p, ++it) {
-                    const unsigned slot = it % RING;
-                    iu_wait(empty + slot, ((it / RING) & 1) ^ 1);
-                    const uint32_t tile0 = iu_smem(smem + OFF_RING) + slot * SLOT_BYTES;
-                    if (p == 0) iu_store_pair<0>(tile0, row0, rr, j, am[0], at[0]);
-                    else if (p == 1) iu_store_pair<1>(tile0, row0, rr, j, am[1], at[1]);
-                    else if (p == 2) iu_store_pair<2>(tile0, row0, rr, j, am[2], at[2]);
-                    else iu_store_pair<3>(tile0, row0, rr, j, am[3], at[3]);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) iu_arrive(full + slot);
-                }
+    if (warp == PRODUCER_WARP) {
+        // ===== TMA producer: window w, class pair p of the view -> ring slot (4 g + p) mod RING =====
+        if (lane == 0) {
+            unsigned it = 0;
+            long long tw0 = 0;
+            for (int vi = 0; vi < nviews; ++vi) {
+                const int bv = blockIdx.x + vi * gridDim.x;
+                for (int w = 0; w < NWIN; ++w)
+                    for (int p = 0; p < 4; ++p, ++it) {
+                        const unsigned slot = it % RING;
+                        UT(tw0, iu_wait(empty + slot, ((it / RING) & 1) ^ 1));
+                        iu_expect_tx(full + slot, SLOT_BYTES);
+                        iu_tma_4d(smem + OFF_RING + slot * SLOT_BYTES, &maps.x, WTOK * w, 0, 2 * p, bv, full + slot);
+                    }
             }
+            if (tracing) g_umma_trace[0] += (unsigned long long)tw0;
         }
     } else if (warp == 0) {
         // ===== MMA issuer (+ TMA of the per-view w_eff planes, one view ahead) =====
         if (lane == 0) {
-            constexpr uint32_t IDESC1 = iu_idesc(64, 16, true), IDESC2 = iu_idesc(128, 16, false);
+            constexpr uint32_t IDESC1 = iu_idesc(64, 16, true, false), IDESC2 = iu_idesc(64, 16, false, true);
             const uint32_t ring = iu_smem(smem + OFF_RING), wbase = iu_smem(smem + OFF_W), pbase = iu_smem(smem + OFF_P);
-            unsigned it1 = 0, it2 = 0, g = 0;
-            // sums of window gp (class pair p), interleaved below with the scores of window gp + 1
+            unsigned g = 0;
+            long long tw1 = 0, tw2 = 0, tw3 = 0, tw4 = 0;
+            // sums of token set gp (class pair p), interleaved below with the scores of window gp + 1
             auto sums = [&](unsigned gp, int p) {
                 const unsigned vp = gp >> 2, wp = gp & 3;
                 if (p == 0) {
-                    iu_wait(p_full + wp, (gp >> 2) & 1);                            // probability tile of window gp is in shared memory
-                    if (wp == 0) iu_wait(d2_empty + (vp & 1), ((vp >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator buffer
+                    UT(tw2, iu_wait(p_full + wp, (gp >> 2) & 1));                     // probabilities of set gp are in shared memory
+                    if (wp == 0) UT(tw4, iu_wait(d2_empty + (vp & 1), ((vp >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator buffer
                     iu_fence_after();
                 }
-                const unsigned slot = it2 % RING;
-                const uint32_t sa = ring + slot * SLOT_BYTES, sp = pbase + wp * P_BYTES;
-                const uint32_t d2 = tmem + D2_COL + (vp & 1) * 64 + 16 * p;
-                const int nk = wp == 3 ? 3 : 4;                                      // tokens 240..255 do not exist
-                for (int j = 0; j < nk; ++j)
-                    if (!(a.debug & 2)) iu_mma(d2, iu_desc(sa + 32 * j, 0), iu_desc(sp + 32 * j, 0), IDESC2, (wp | j) != 0 ? 1u : 0u);
-                iu_commit(empty + slot);                                             // slot back to the producer once read
-                ++it2;
+                const unsigned slot_cur = (4 * gp + p) % RING;
+                const uint32_t sa = ring + slot_cur * SLOT_BYTES, pb = pbase + wp * P_BYTES;
+                const uint32_t d2 = tmem + D2_COL + (vp & 1) * D2_BUF_COLS;
+                if (wp > 0) {
+                    // tail k-step: u in [64 wp - 16, 64 wp) lives in the previous window's tile (columns 48..63 = byte 96 of the row);
+                    // it is the last reader of that slot
+                    const unsigned slot_prev = (4 * (gp - 1) + p) % RING;
+                    const uint32_t sp = ring + slot_prev * SLOT_BYTES;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int s = 2 * p + e;
+                        if (!(a.debug & 2)) iu_mma(d2 + 16 * s, iu_desc(sp + e * TILE_BYTES + 96, 0), iu_desc_mn_noswz(pb + 16 * (7 - s), 128, P_PLANE), IDESC2, 1u);
+                    }
+                    iu_commit(empty + slot_prev);
+                }
+                const int nk = wp == 3 ? 3 : 4;                                      // u in [240, 256) does not exist
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int s = 2 * p + e;
+                    for (int j = 1; j <= nk; ++j)
+                        if (!(a.debug & 2))
+                            iu_mma(d2 + 16 * s, iu_desc(sa + e * TILE_BYTES + 32 * (j - 1), 0), iu_desc_mn_noswz(pb + 16 * (7 + 16 * j - s), 128, P_PLANE),
+                                   IDESC2, (wp > 0 || j > 1) ? 1u : 0u);
+                }
+                if (wp == 3) iu_commit(empty + slot_cur);                            // no next set in this view
                 if (p == 3) {
                     iu_commit(p_empty + wp);
                     if (wp == 3) iu_commit(d2_full + (vp & 1));
@@ -348,31 +354,30 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
 #pragma unroll
                 for (int s = 0; s < 8; ++s) iu_tma_2d(smem + OFF_W + wb * W_BYTES + s * WCLASS_BYTES, &maps.w, 64 * s, 16 * bv, wfull + wb);
             };
+            const long long ti0 = tracing ? clock64() : 0;
             load_w(0);
             for (int vi = 0; vi < nviews; ++vi) {
                 const int wb = vi & 1;
                 load_w(vi + 1);
-                iu_wait(wfull + wb, (vi >> 1) & 1);
+                UT(tw3, iu_wait(wfull + wb, (vi >> 1) & 1));
                 iu_fence_after();
                 for (int w = 0; w < NWIN; ++w, ++g) {
-                    const uint32_t d1 = tmem + (g & 1) * 16;
+                    const uint32_t d1 = tmem + (g & 1) * D1_BUF_COLS;
                     for (int p = 0; p < 4; ++p) {
-                        const unsigned slot = it1 % RING;
-                        iu_wait(full + slot, (it1 / RING) & 1);
+                        const unsigned it1 = 4 * g + p, slot = it1 % RING;
+                        UT(tw1, iu_wait(full + slot, (it1 / RING) & 1));
                         iu_fence_after();
                         const uint32_t sa = ring + slot * SLOT_BYTES;
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            const uint32_t sw = wbase + wb * W_BYTES + (2 * p + e) * WCLASS_BYTES;
+                            const int s = 2 * p + e;
+                            const uint32_t sw = wbase + wb * W_BYTES + s * WCLASS_BYTES;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 if (a.debug & 1) continue;
-                                const uint32_t idesc = (a.debug & 4) ? iu_idesc(64, 16, false) : (a.debug & 8) ? iu_idesc(128, 16, true) : IDESC1;
-                                iu_mma(d1, iu_desc(sa + e * TILE_BYTES + 2048 * j, TILE_BYTES), iu_desc(sw + 32 * j, 0), idesc,
-                                       (p | e | j) != 0 ? 1u : 0u);
+                                iu_mma(d1 + 16 * s, iu_desc(sa + e * TILE_BYTES + 2048 * j, TILE_BYTES), iu_desc(sw + 32 * j, 0), IDESC1, j != 0 ? 1u : 0u);
                             }
                         }
-                        ++it1;
                         if (p == 3) {
                             iu_commit(d1_full + (g & 1));
                             if (w == 3) iu_commit(wempty + wb);
@@ -383,38 +388,92 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
             }
             if (g > 0)
                 for (int p = 0; p < 4; ++p) sums(g - 1, p);
+            if (tracing) {
+                g_umma_trace[5] += (unsigned long long)(clock64() - ti0);
+                g_umma_trace[1] += (unsigned long long)tw1; g_umma_trace[2] += (unsigned long long)tw2;
+                g_umma_trace[3] += (unsigned long long)tw3; g_umma_trace[4] += (unsigned long long)tw4;
+            }
         }
     } else if (warp >= SOFTMAX_WARP0 && warp < EPI_WARP0) {
-        // ===== softmax: lane < 16 of warp q owns token 16 q + lane of every window (TMEM lanes of an M = 64 accumulator) =====
-        const int q = warp & 3;
+        // ===== softmax: lane < 16 of warp q owns row r = 16 q + lane of every M = 64 score tile and token 64 w - 7 + r of set w =====
+        const int q = warp & 3, l16 = lane & 15;
         const bool act = lane < 16;
-        const int tl = 16 * q + (lane & 15);
+        const int r = 16 * q + l16;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        float* halo = reinterpret_cast<float*>(smem + OFF_HALO);
         float mref[8], lsum[8], pr[NWIN][8];
         unsigned g = 0;
+        const bool tr_s = tracing && warp == SOFTMAX_WARP0;
+        const long long ts0 = tr_s ? clock64() : 0;
+        long long ta6 = 0, ta7 = 0, ta8 = 0, ta10 = 0;
         for (int vi = 0; vi < nviews; ++vi) {
             const int bv = blockIdx.x + vi * gridDim.x;
 #pragma unroll
             for (int h = 0; h < 8; ++h) { lsum[h] = 0.f; mref[h] = 0.f; }
 #pragma unroll
             for (int w = 0; w < NWIN; ++w, ++g) {
-                const int t = WTOK * w + tl;
-                const bool valid = act && t < HW;
+                const int t = WTOK * w - 7 + r;
+                const bool valid = act && t >= 0 && t < HW;
                 float ct[8];
 #pragma unroll
                 for (int h = 0; h < 8; ++h) ct[h] = valid ? __ldg(a.cterm + ((size_t)bv * HEADS + h) * TP + 1 + t) : 0.f;
-                iu_wait(d1_full + (g & 1), (g >> 1) & 1);
+                { const long long c0_ = tr_s ? clock64() : 0; iu_wait(d1_full + (g & 1), (g >> 1) & 1); if (tr_s) ta6 += clock64() - c0_; }
                 iu_fence_after();
-                uint32_t v[16];
-                iu_tmem_ld16(trow + (g & 1) * 16, v);
+                const long long cx0 = tr_s ? clock64() : 0;
+                // class exchange: token t needs row r - (7 - s) of class s: a lane shift inside the warp, the halo for the first
+                // 7 - s lanes (rows of the previous warp; for warp 0 rows 57..63 of the previous window)
+                float acc[8];
+#pragma unroll
+                for (int h = 0; h < 8; ++h) acc[h] = 0.f;
+                float* hw = halo + (((g & 1) * 4 + q) * HALO_ENTRIES) * 8;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    uint32_t v[16];
+                    iu_tmem_ld16(trow + (g & 1) * D1_BUF_COLS + 16 * s, v);
+                    float xs[8];
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) xs[h] = __uint_as_float(v[h]) + __uint_as_float(v[8 + h]);
+                    const int delta = 7 - s;
+                    if (delta == 0) {
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) acc[h] += xs[h];
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) {
+                            const float y = __shfl_up_sync(FULL, xs[h], delta);
+                            acc[h] += l16 >= delta ? y : 0.f;
+                        }
+                        if (act && l16 >= 16 - delta) {
+                            float4* dst = reinterpret_cast<float4*>(hw + (iu_halo_off(s) + l16 - (16 - delta)) * 8);
+                            dst[0] = make_float4(xs[0], xs[1], xs[2], xs[3]);
+                            dst[1] = make_float4(xs[4], xs[5], xs[6], xs[7]);
+                        }
+                    }
+                }
+                iu_bar_sync(1);
+                if (act && l16 < 7 && !(w == 0 && q == 0)) {
+                    const int qsrc = (q + 3) & 3;
+                    const unsigned hb = q == 0 ? ((g - 1) & 1) : (g & 1);
+                    const float* hr = halo + ((hb * 4 + qsrc) * HALO_ENTRIES) * 8;
+#pragma unroll
+                    for (int s = 0; s < 7; ++s) {
+                        if (l16 < 7 - s) {
+                            const float4* src = reinterpret_cast<const float4*>(hr + (iu_halo_off(s) + l16) * 8);
+                            const float4 x0 = src[0], x1 = src[1];
+                            acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w;
+                            acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
+                        }
+                    }
+                }
+                if (tr_s) ta7 += clock64() - cx0;
                 float s[8];
 #pragma unroll
-                for (int h = 0; h < 8; ++h)
-                    s[h] = valid ? a.scale * ((__uint_as_float(v[h]) + __uint_as_float(v[8 + h])) + ct[h]) : -INFINITY;
+                for (int h = 0; h < 8; ++h) s[h] = valid ? a.scale * (acc[h] + ct[h]) : -INFINITY;
                 if (a.dbg != nullptr && valid) {
 #pragma unroll
                     for (int h = 0; h < 8; ++h) a.dbg[((size_t)bv * HEADS + h) * 256 + 1 + t] = s[h];
                 }
+                const long long cr0 = tr_s ? clock64() : 0;
                 bool raise = w == 0;
                 if (w > 0) {
                     bool ex = false;
@@ -440,14 +499,14 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     }
                     if (w > 0) {
                         // everything accumulated so far is relative to the old reference: rescale the weighted sums in TMEM
-                        // (the sums of window g-1 must have completed; those of window g are not issued before this warp's
+                        // (the sums of set g-1 must have completed; those of set g are not issued before this warp's
                         // arrival on p_full), the running sums and the probabilities kept for the final output
                         iu_wait(p_empty + ((g - 1) & 3), ((g - 1) >> 2) & 1);
                         iu_fence_after();
 #pragma unroll 1
-                        for (int p = 0; p < 4; ++p) {
+                        for (int c8 = 0; c8 < 8; ++c8) {
                             uint32_t y[16];
-                            const uint32_t ta = trow + D2_COL + (vi & 1) * 64 + 16 * p;
+                            const uint32_t ta = trow + D2_COL + (vi & 1) * D2_BUF_COLS + 16 * c8;
                             iu_tmem_ld16(ta, y);
 #pragma unroll
                             for (int n = 0; n < 16; ++n) y[n] = __float_as_uint(__uint_as_float(y[n]) * fc[n & 7]);
@@ -463,6 +522,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                         }
                     }
                 }
+                if (tr_s) ta10 += clock64() - cr0;
                 unsigned short ph[8], pl[8];
 #pragma unroll
                 for (int h = 0; h < 8; ++h) {
@@ -471,16 +531,16 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     pr[w][h] = p;
                     iu_split(p, ph[h], pl[h]);
                 }
-                iu_wait(p_empty + w, ((g >> 2) & 1) ^ 1);           // the sums of the previous view's window w have read this buffer
+                { const long long c0_ = tr_s ? clock64() : 0; iu_wait(p_empty + w, ((g >> 2) & 1) ^ 1); if (tr_s) ta8 += clock64() - c0_; }   // the sums of the previous view's set w have read this buffer
                 if (act) {
-                    // K-major SWIZZLE_128B tile: row n (128 bytes = 64 tokens), 16-byte chunk index XOR (n mod 8)
-                    const uint32_t pt = iu_smem(smem + OFF_P) + w * P_BYTES;
-#pragma unroll
-                    for (int h = 0; h < 8; ++h) {
-                        const uint32_t off = pt + h * 128 + (((tl >> 3) ^ h) << 4) + ((tl & 7) << 1);
-                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(off), "h"(ph[h]) : "memory");
-                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(off + 1024), "h"(pl[h]) : "memory");
-                    }
+                    // row 16 + r of both planes: 8 heads x bf16 = one 16-byte store each
+                    const uint32_t pt = iu_smem(smem + OFF_P) + w * P_BYTES + (16 + r) * 16;
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(pt), "r"((uint32_t)ph[0] | ((uint32_t)ph[1] << 16)),
+                                 "r"((uint32_t)ph[2] | ((uint32_t)ph[3] << 16)), "r"((uint32_t)ph[4] | ((uint32_t)ph[5] << 16)),
+                                 "r"((uint32_t)ph[6] | ((uint32_t)ph[7] << 16)) : "memory");
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(pt + P_PLANE), "r"((uint32_t)pl[0] | ((uint32_t)pl[1] << 16)),
+                                 "r"((uint32_t)pl[2] | ((uint32_t)pl[3] << 16)), "r"((uint32_t)pl[4] | ((uint32_t)pl[5] << 16)),
+                                 "r"((uint32_t)pl[6] | ((uint32_t)pl[7] << 16)) : "memory");
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 iu_fence_before();
@@ -514,8 +574,8 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
             if (act) {
 #pragma unroll
                 for (int w = 0; w < NWIN; ++w) {
-                    const int t = WTOK * w + tl;
-                    if (1 + t < 256) {
+                    const int t = WTOK * w - 7 + r;
+                    if (t >= 0 && 1 + t < 256) {
 #pragma unroll
                         for (int h = 0; h < 8; ++h) {
                             unsigned short hi, lo;
@@ -526,7 +586,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                         }
                     }
                 }
-                if (tl == 0) {
+                if (r == 0) {
 #pragma unroll
                     for (int h = 0; h < 8; ++h) {
                         unsigned short hi, lo;
@@ -537,13 +597,24 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     }
                 }
             }
+            iu_bar_sync(1);                                         // sred is rewritten by the next view
         }
-    } else if (warp >= EPI_WARP0 && warp < LOADER_WARP0) {
+        if (tr_s) {
+            g_umma_trace[9] += (unsigned long long)(clock64() - ts0);
+            g_umma_trace[6] += (unsigned long long)ta6; g_umma_trace[7] += (unsigned long long)ta7;
+            g_umma_trace[8] += (unsigned long long)ta8; g_umma_trace[10] += (unsigned long long)ta10;
+        }
+    } else if (warp >= EPI_WARP0 && warp < PRODUCER_WARP) {
         // ===== epilogue: mean-token score, then Y = (D2 f + p0 xbar) / L -> bf16 hi/lo planes =====
-        const int q = warp & 3, et = threadIdx.x - 32 * EPI_WARP0, row = 32 * q + lane;
+        const int q = warp & 3, et = threadIdx.x - 32 * EPI_WARP0, l16 = lane & 15, row = 16 * q + l16;
+        const bool act = lane < 16;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        const bool tr_e = tracing && warp == EPI_WARP0;
+        const long long te0 = tr_e ? clock64() : 0;
+        long long ta11 = 0, ta12 = 0, ta13 = 0, ta14 = 0;
         for (int vi = 0; vi < nviews; ++vi) {
             const int bv = blockIdx.x + vi * gridDim.x;
+            const long long ce0 = tr_e ? clock64() : 0;
             {   // s0[h] = scale (w_eff[h] . xbar + cterm[h][0]); this thread: columns 4 et .. 4 et + 3 (class et >> 4, rows 4 (et & 15)..)
                 const int c0 = 4 * et, cls = c0 >> 6, r0 = c0 & 63;
                 float xb[4];
@@ -576,7 +647,9 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     iu_arrive(s0_full + (vi & 1));
                 }
             }
+            const long long ce1 = tr_e ? clock64() : 0;
             iu_wait(l_full + (vi & 1), (vi >> 1) & 1);
+            const long long ce2 = tr_e ? clock64() : 0;
             float fin[8], p0n[8];
 #pragma unroll
             for (int h = 0; h < 8; ++h) {
@@ -588,26 +661,39 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 p0n[h] = p0 * inv;
             }
             iu_wait(d2_full + (vi & 1), (vi >> 1) & 1);
+            const long long ce3 = tr_e ? clock64() : 0;
             iu_fence_after();
 #pragma unroll 1
-            for (int p = 0; p < 4; ++p) {
+            for (int s = 0; s < 8; ++s) {
                 uint32_t y[16];
-                iu_tmem_ld16(trow + D2_COL + (vi & 1) * 64 + 16 * p, y);
-                const int cp = 128 * p + row;                           // output column 64 s + r of channel s + 8 r
-                const float xb = __ldg(a.xbar + (size_t)bv * C + (cp >> 6) + 8 * (cp & 63));
+                iu_tmem_ld16(trow + D2_COL + (vi & 1) * D2_BUF_COLS + 16 * s, y);
+                if (act) {
+                    const int cp = 64 * s + row;                            // output column 64 s + r of channel s + 8 r
+                    const float xb = __ldg(a.xbar + (size_t)bv * C + s + 8 * row);
 #pragma unroll
-                for (int h = 0; h < 8; ++h) {
-                    const float val = (__uint_as_float(y[h]) + __uint_as_float(y[8 + h])) * fin[h] + p0n[h] * xb;
-                    unsigned short hi, lo;
-                    iu_split(val, hi, lo);
-                    __nv_bfloat16* dst = a.ya_hi + ((size_t)bv * HEADS + h) * YA + cp;
-                    dst[0] = __ushort_as_bfloat16(hi);
-                    dst[a.ya_plane] = __ushort_as_bfloat16(lo);
+                    for (int h = 0; h < 8; ++h) {
+                        const float val = (__uint_as_float(y[h]) + __uint_as_float(y[8 + h])) * fin[h] + p0n[h] * xb;
+                        unsigned short hi, lo;
+                        iu_split(val, hi, lo);
+                        __nv_bfloat16* dst = a.ya_hi + ((size_t)bv * HEADS + h) * YA + cp;
+                        dst[0] = __ushort_as_bfloat16(hi);
+                        dst[a.ya_plane] = __ushort_as_bfloat16(lo);
+                    }
                 }
             }
             iu_fence_before();
             __syncwarp();
             if (lane == 0) iu_arrive(d2_empty + (vi & 1));
+            if (tr_e) {
+                const long long ce4 = clock64();
+                ta11 += ce1 - ce0; ta12 += ce2 - ce1; ta13 += ce3 - ce2; ta14 += ce4 - ce3;
+            }
+            iu_bar_sync(2);                                         // ered / sm_s0 of view vi + 2 reuse this parity: keep the warps together
+        }
+        if (tr_e) {
+            g_umma_trace[15] += (unsigned long long)(clock64() - te0);
+            g_umma_trace[11] += (unsigned long long)ta11; g_umma_trace[12] += (unsigned long long)ta12;
+            g_umma_trace[13] += (unsigned long long)ta13; g_umma_trace[14] += (unsigned long long)ta14;
         }
     }
     iu_fence_before();
@@ -616,6 +702,16 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
 }
 
 // ---------------------------------------------------------------------------------------------- host
+}  // namespace pt
+extern "C" int pt_debug_umma_trace(unsigned long long* out16, int reset) {
+    if (out16 && cudaMemcpyFromSymbol(out16, pt::g_umma_trace, sizeof(pt::g_umma_trace)) != cudaSuccess) return PT_ERR_CUDA;
+    if (reset) {
+        unsigned long long z[16] = {};
+        if (cudaMemcpyToSymbol(pt::g_umma_trace, z, sizeof(z)) != cudaSuccess) return PT_ERR_CUDA;
+    }
+    return PT_OK;
+}
+namespace pt {
 bool img_pool_umma_supported(int img_dtype) { return img_dtype == PT_DTYPE_BF16; }
 
 int launch_img_pool_umma(const void* img_feat, const __nv_bfloat16* wpl, const float* cterm, const float* xbar, __nv_bfloat16* ya_hi,
@@ -630,18 +726,25 @@ int launch_img_pool_umma(const void* img_feat, const __nv_bfloat16* wpl, const f
         const unsigned box[2] = {64u, 16u};
         if ((rc = encode_tensor_map_16bit(&maps.w, wpl, 2, dims, strides, box, false))) return rc;
     }
+    {   // class-aligned view of the raw (BV, 512, 225) features: element (u, r, s, v) at byte 2 u + 3600 r + 448 s + 230400 v
+        const unsigned long long dims[4] = {(unsigned long long)UCOLS, 64ull, 8ull, (unsigned long long)BV};
+        const unsigned long long strides[3] = {3600ull, 448ull, (unsigned long long)C * HW * 2};
+        const unsigned box[4] = {64u, 64u, 2u, 1u};
+        if ((rc = encode_tensor_map_16bit(&maps.x, img_feat, 4, dims, strides, box, false))) return rc;
+    }
     static bool attr_set[PT_MAX_DEVICES] = {};
     if (first_use_on_current_device(attr_set))
         PT_CUDA_OK(cudaFuncSetAttribute(img_pool_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     UmmaPoolArgs a;
-    a.img = (const uint8_t*)img_feat; a.wpl = wpl; a.cterm = cterm; a.xbar = xbar; a.ya_hi = ya_hi; a.ya_plane = ya_plane; a.BV = BV;
+    a.wpl = wpl; a.cterm = cterm; a.xbar = xbar; a.ya_hi = ya_hi; a.ya_plane = ya_plane; a.BV = BV;
     a.scale = (float)(1.0 / sqrt(32.0));
     a.dbg = dbg;
     const char* dbe = getenv("PT_UMMA_DEBUG");
     a.debug = dbe ? atoi(dbe) : 0;
-    const int grid = BV < sms ? BV : sms;
+    int grid = BV < sms ? BV : sms;
+    if (const char* ge = getenv("PT_POOL_GRID")) { const int gv = atoi(ge); if (gv >= 1 && gv < grid) grid = gv; }   // probes: fewer persistent CTAs
     { ProfScope prof_(PROF_IMG_POOL, s); img_pool_umma_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(maps, a); }
     PT_LAUNCH_CHECK();
     return PT_OK;
