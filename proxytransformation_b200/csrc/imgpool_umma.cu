@@ -20,20 +20,22 @@
 // The fp32 operands (w_eff, probabilities) enter as bf16 hi + lo halves in separate N columns, so every product is exact and
 // the accumulation is fp32 in TMEM (same numerics as the 3xBF16 GEMMs: ~2^-17 relative).
 //
-// One persistent CTA per SM; a view is streamed ONCE as 4 windows of 64 u-columns (flash-attention structure, one query per
-// head).  Window w completes the scores of the token SET w = [64 w - 7, 64 w + 57) (the last 7 u-columns of a window wait for
-// the next one); the sums of set w read window w and the last 16 u-columns of window w-1 (5 k-steps of 16):
-//   warp 0       MMA issuer (one elected thread) + TMA of the per-view w_eff planes: scores of window g+1 interleaved with the
-//                sums of set g; a ring slot goes back to the producer (tcgen05.commit) when the tail k-step of the NEXT set
-//                has read it
-//   warps 1-4    softmax: tcgen05.ld of the eight 64 x 16 class score tiles (lane = u), class exchange, + position term, exp
+// One persistent CTA per SM; a view is streamed as 5 OVERLAPPING windows of 64 u-columns that advance by 48 (flash-attention
+// structure, one query per head).  The score of token t needs u = t .. t + 7 and its weighted sum touches the same columns, so
+// window g = [48 g, 48 g + 64) is self-contained for the token SET g = [48 g + 9, 48 g + 56] (set 0: [0, 56]): scores and sums of
+// a set read the SAME tiles and no slot outlives its window (the 16 re-read columns per window are L2 hits: 1.25 x the bytes
+// through TMA, 1 x from HBM).
+//   warps 0-3    MMA issuers, one per class pair p (ring slots 4 g + p, accumulators of classes 2p, 2p+1); the warp stays
+//                converged and lane 0 issues: scores of window g+1 are issued before the sums of set g; a ring slot goes back to
+//                the producer (tcgen05.commit) when the sums that read it have completed.  Warp 0 also fetches the w_eff planes
+//   warps 4-7    softmax: tcgen05.ld of the eight 64 x 16 class score tiles (lane = u), class exchange, + position term, exp
 //                relative to a per-view reference maximum (established by window 0, raised FA-style by rescaling the
 //                accumulators in TMEM only when a later window exceeds it by more than TAU — never on ordinary data),
 //                bf16 hi/lo probability rows -> shared memory (16-byte stores), running sum in registers; end of view: final
 //                probabilities -> global
-//   warps 5-8    epilogue: mean-token score s0 = w_eff . xbar (CUDA cores, from L2), then per view Y = (D2 f + p0 xbar) / L
+//   warps 8-11   epilogue: mean-token score s0 = w_eff . xbar (CUDA cores, from L2), then per view Y = (D2 f + p0 xbar) / L
 //                from TMEM -> bf16 hi/lo planes for the value-side GEMM (same output format as the mma.sync kernel)
-//   warp 9       TMA producer of the feature tiles: one 16 KB box (64 u x 64 rows x 2 classes) per ring slot, 10 slots
+//   warp 12      TMA producer of the feature tiles: one 16 KB box (64 u x 64 rows x 2 classes) per ring slot, 11 slots
 // Channel order of w_eff columns and of the weighted sums: position 64 s + r  <->  channel s + 8 r (absorbed into the folded
 // GEMM weights on the host, pt_img_pool_params variant 1).
 #include "common.cuh"
@@ -49,19 +51,19 @@ namespace ipu {
 constexpr int C = 512, HW = 225, HEADS = 8;
 constexpr int TP = 228;                      // cterm row pitch (floats)
 constexpr int YA = 768;                      // output row: 512 weighted sums + 256 probabilities
-constexpr int NWIN = 4, WTOK = 64;           // u-windows per view (u = token + class, 232 columns -> 4 x 64, zero filled)
+constexpr int NWIN = 5, WSTEP = 48;          // overlapping u-windows per view: [48 w, 48 w + 64), u = token + class in [0, 232)
 constexpr int UCOLS = 232;                   // valid u range of the tensor map: 225 tokens + 7 class shifts
 constexpr int TILE_BYTES = 64 * 128;         // [64 class rows][64 u] bf16, SWIZZLE_128B
 constexpr int SLOT_BYTES = 2 * TILE_BYTES;   // a class pair: rows 0-63 class 2p, rows 64-127 class 2p+1 (one TMA box)
-constexpr int RING = 10;
+constexpr int RING = 11;
 constexpr int WCLASS_BYTES = 16 * 128;       // w_eff rows (hi|lo, head) x 64 class channels
 constexpr int W_BYTES = 8 * WCLASS_BYTES;
-// Probabilities of token set w as the MN-major, unswizzled B operand of the sums: two planes (hi, lo), each [P_ROWS][8 heads]
-// bf16 = 16 bytes per token row; row 16 + i holds token 64 w - 7 + i; rows [0,16) and [80,88) stay zero (tokens of the
-// neighbouring sets that the shifted 16-row k-steps of a class reach).
-constexpr int P_ROWS = 88, P_PLANE = P_ROWS * 16, P_BYTES = 2 * P_PLANE, PBUF = 4;
-// class-exchange halo: [window parity][softmax warp][28 (class, row) entries][8 heads] fp32
-constexpr int HALO_ENTRIES = 28, HALO_BYTES = 2 * 4 * HALO_ENTRIES * 32;
+// Probabilities of a token set as the MN-major, unswizzled B operand of the sums: two planes (hi, lo), each [P_ROWS][8 heads]
+// bf16 = 16 bytes per row; row r holds token 48 w - 7 + r (zero if that token is not in the set); rows [64,72) stay zero (the
+// shifted 16-row k-steps of a class reach 7 rows further).  Buffer = window index mod PBUF.
+constexpr int P_ROWS = 72, P_PLANE = P_ROWS * 16, P_BYTES = 2 * P_PLANE, PBUF = 4;
+// class-exchange halo: [softmax warp][28 (class, row) entries][8 heads] fp32
+constexpr int HALO_ENTRIES = 28, HALO_BYTES = 4 * HALO_ENTRIES * 32;
 constexpr int OFF_RING = 0;
 constexpr int OFF_W = OFF_RING + RING * SLOT_BYTES;
 constexpr int OFF_P = OFF_W + 2 * W_BYTES;
@@ -72,8 +74,9 @@ constexpr int OFF_BAR = OFF_MISC + 1024;
 constexpr int NBAR = 2 * RING + 6 + 2 * PBUF + 8;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;      // + slack for the 1024-byte alignment of the swizzled tiles
-// warp roles: 0 = MMA issuer + w_eff TMA + TMEM allocation, 1-4 softmax, 5-8 epilogue (TMEM lane quarter = warp mod 4), 9 = TMA producer
-constexpr int SOFTMAX_WARP0 = 1, EPI_WARP0 = 5, PRODUCER_WARP = 9;
+// warp roles: 0-3 = MMA issuers (one per class pair; warp 0 also TMA of w_eff + TMEM allocation), 4-7 softmax, 8-11 epilogue
+// (TMEM lane quarter = warp mod 4), 12 = TMA producer
+constexpr int ISSUE_WARPS = 4, SOFTMAX_WARP0 = 4, EPI_WARP0 = 8, PRODUCER_WARP = 12;
 constexpr int THREADS = 32 * (PRODUCER_WARP + 1);
 // TMEM: D1 (scores) 2 window buffers x 8 classes x 16 columns at 0 ; D2 (sums) 2 view buffers x 8 classes x 16 columns at 256.
 // Both are M = 64 accumulators: row r lives in lane 32 (r / 16) + r % 16.
@@ -136,6 +139,31 @@ __device__ __forceinline__ void iu_mma(uint32_t tmem_d, uint64_t da, uint64_t db
         "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Issued by lane 0 of a CONVERGED warp (the whole warp runs the issue loop, so that addresses and descriptors stay warp-uniform;
+// a divergent `if (lane == 0)` region makes the compiler wrap every tcgen05.mma in an elect / R2UR.BROADCAST loop).
+__device__ __forceinline__ void iu_mma_l0(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, e;\n"
+        ".reg .u32 l;\n"
+        "mov.u32 l, %%laneid;\n"
+        "setp.eq.u32 e, l, 0;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void iu_commit_l0(uint64_t* bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred e;\n"
+        ".reg .u32 l;\n"
+        "mov.u32 l, %%laneid;\n"
+        "setp.eq.u32 e, l, 0;\n"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+        "}\n" ::"r"(iu_smem(bar)) : "memory");
+}
+__device__ __forceinline__ uint64_t iu_mk64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 // Shared-memory operand descriptors (sm_100 version 1, SWIZZLE_128B, 8-row groups 1024 bytes apart).
 //   K-major: rows = M/N index, 128-byte rows hold 64 K elements; a K = 16 step advances the start address by 32 bytes.
 //   MN-major: rows = K index, 128-byte rows hold 64 M elements; a K = 16 step advances by two 8-row groups (2048 bytes);
@@ -173,6 +201,20 @@ __device__ __forceinline__ void iu_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) 
           "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// the same load without the wait: issue several, then iu_tmem_wait_ld(), then iu_tmem_use16 on each register set (ties the
+// registers to a point after the wait so that no consumer is scheduled above it)
+__device__ __forceinline__ void iu_tmem_ld16_async(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void iu_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void iu_tmem_use16(uint32_t (&v)[16]) {
+    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                      "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
 }
 __device__ __forceinline__ void iu_tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
     asm volatile(
@@ -262,10 +304,10 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
     if (threadIdx.x == 0) {
         for (int i = 0; i < RING; ++i) { iu_mbar_init(full + i, 1); iu_mbar_init(empty + i, 1); }
         for (int i = 0; i < 2; ++i) {
-            iu_mbar_init(wfull + i, 1); iu_mbar_init(wempty + i, 1); iu_mbar_init(d1_full + i, 1);
-            iu_mbar_init(d2_full + i, 1); iu_mbar_init(d2_empty + i, 4); iu_mbar_init(s0_full + i, 1); iu_mbar_init(l_full + i, 1);
+            iu_mbar_init(wfull + i, 1); iu_mbar_init(wempty + i, ISSUE_WARPS); iu_mbar_init(d1_full + i, ISSUE_WARPS);
+            iu_mbar_init(d2_full + i, ISSUE_WARPS); iu_mbar_init(d2_empty + i, 4); iu_mbar_init(s0_full + i, 1); iu_mbar_init(l_full + i, 1);
         }
-        for (int i = 0; i < PBUF; ++i) { iu_mbar_init(p_full + i, 4); iu_mbar_init(p_empty + i, 1); }
+        for (int i = 0; i < PBUF; ++i) { iu_mbar_init(p_full + i, 4); iu_mbar_init(p_empty + i, ISSUE_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x) : "memory");
@@ -296,106 +338,92 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                         const unsigned slot = it % RING;
                         UT(tw0, iu_wait(empty + slot, ((it / RING) & 1) ^ 1));
                         iu_expect_tx(full + slot, SLOT_BYTES);
-                        iu_tma_4d(smem + OFF_RING + slot * SLOT_BYTES, &maps.x, WTOK * w, 0, 2 * p, bv, full + slot);
+                        iu_tma_4d(smem + OFF_RING + slot * SLOT_BYTES, &maps.x, WSTEP * w, 0, 2 * p, bv, full + slot);
                     }
             }
             if (tracing) g_umma_trace[0] += (unsigned long long)tw0;
         }
-    } else if (warp == 0) {
-        // ===== MMA issuer (+ TMA of the per-view w_eff planes, one view ahead) =====
-        if (lane == 0) {
-            constexpr uint32_t IDESC1 = iu_idesc(64, 16, true, false), IDESC2 = iu_idesc(64, 16, false, true);
-            const uint32_t ring = iu_smem(smem + OFF_RING), wbase = iu_smem(smem + OFF_W), pbase = iu_smem(smem + OFF_P);
-            unsigned g = 0;
-            long long tw1 = 0, tw2 = 0, tw3 = 0, tw4 = 0;
-            // sums of token set gp (class pair p), interleaved below with the scores of window gp + 1
-            auto sums = [&](unsigned gp, int p) {
-                const unsigned vp = gp >> 2, wp = gp & 3;
-                if (p == 0) {
-                    UT(tw2, iu_wait(p_full + wp, (gp >> 2) & 1));                     // probabilities of set gp are in shared memory
-                    if (wp == 0) UT(tw4, iu_wait(d2_empty + (vp & 1), ((vp >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator buffer
-                    iu_fence_after();
-                }
-                const unsigned slot_cur = (4 * gp + p) % RING;
-                const uint32_t sa = ring + slot_cur * SLOT_BYTES, pb = pbase + wp * P_BYTES;
-                const uint32_t d2 = tmem + D2_COL + (vp & 1) * D2_BUF_COLS;
-                if (wp > 0) {
-                    // tail k-step: u in [64 wp - 16, 64 wp) lives in the previous window's tile (columns 48..63 = byte 96 of the row);
-                    // it is the last reader of that slot
-                    const unsigned slot_prev = (4 * (gp - 1) + p) % RING;
-                    const uint32_t sp = ring + slot_prev * SLOT_BYTES;
+    } else if (warp < ISSUE_WARPS) {
+        // ===== MMA issuers: warp p owns class pair p (ring slots 4 g + p, D1 / D2 columns of classes 2p, 2p+1); the warp stays
+        // converged, lane 0 issues.  Warp 0 also fetches the per-view w_eff planes one view ahead. =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");     // the softmax warpgroup needs the registers
+        const int p = warp;
+        constexpr uint32_t IDESC1 = iu_idesc(64, 16, true, false), IDESC2 = iu_idesc(64, 16, false, true);
+        // descriptor words (addresses in 16-byte units): SWIZZLE_128B tiles (SBO 1024, version 1, layout 2) and the unswizzled
+        // MN-major probability planes (LBO 128 between K blocks, SBO P_PLANE between the hi / lo planes, version 1)
+        constexpr uint32_t HI_SW = (1024u >> 4) | (1u << 14) | (2u << 29), HI_P = ((uint32_t)P_PLANE >> 4) | (1u << 14);
+        constexpr uint32_t LBO_TILE = ((uint32_t)TILE_BYTES >> 4) << 16, LBO_P = (128u >> 4) << 16;
+        const uint32_t ring = iu_smem(smem + OFF_RING) >> 4, wbase = iu_smem(smem + OFF_W) >> 4, pbase = iu_smem(smem + OFF_P) >> 4;
+        unsigned g = 0;
+        long long tw1 = 0, tw2 = 0, tw3 = 0, tw4 = 0;
+        // sums of token set gp (window wp of view vp), issued after the scores of the next window
+        auto sums = [&](unsigned gp, unsigned vp, int wp) {
+            const unsigned pbi = gp & (PBUF - 1);
+            UT(tw2, iu_wait(p_full + pbi, (gp / PBUF) & 1));                        // probabilities of set gp are in shared memory
+            if (wp == 0) UT(tw4, iu_wait(d2_empty + (vp & 1), ((vp >> 1) & 1) ^ 1));  // the epilogue has drained this accumulator buffer
+            iu_fence_after();
+            const unsigned slot = (4 * gp + p) % RING;
+            const uint32_t sa = ring + slot * (SLOT_BYTES >> 4), pb = pbase + pbi * (P_BYTES >> 4) + 7 - 2 * p;
+            const uint32_t d2 = tmem + D2_COL + (vp & 1) * D2_BUF_COLS + 32 * p;
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int s = 2 * p + e;
-                        if (!(a.debug & 2)) iu_mma(d2 + 16 * s, iu_desc(sp + e * TILE_BYTES + 96, 0), iu_desc_mn_noswz(pb + 16 * (7 - s), 128, P_PLANE), IDESC2, 1u);
-                    }
-                    iu_commit(empty + slot_prev);
-                }
-                const int nk = wp == 3 ? 3 : 4;                                      // u in [240, 256) does not exist
+            for (int e = 0; e < 2; ++e) {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int s = 2 * p + e;
-                    for (int j = 1; j <= nk; ++j)
-                        if (!(a.debug & 2))
-                            iu_mma(d2 + 16 * s, iu_desc(sa + e * TILE_BYTES + 32 * (j - 1), 0), iu_desc_mn_noswz(pb + 16 * (7 + 16 * j - s), 128, P_PLANE),
-                                   IDESC2, (wp > 0 || j > 1) ? 1u : 0u);
-                }
-                if (wp == 3) iu_commit(empty + slot_cur);                            // no next set in this view
-                if (p == 3) {
-                    iu_commit(p_empty + wp);
-                    if (wp == 3) iu_commit(d2_full + (vp & 1));
-                }
-            };
-            auto load_w = [&](int vi) {            // w_eff planes of this CTA's view vi -> buffer vi & 1 (free once the scores of view vi - 2 are done)
-                if (vi >= nviews) return;
-                const int bv = blockIdx.x + vi * gridDim.x, wb = vi & 1;
-                iu_wait(wempty + wb, ((vi >> 1) & 1) ^ 1);
+                for (int j = 0; j < 4; ++j)
+                    if ((j < 3 || wp < NWIN - 1) && !(a.debug & 2))                  // u in [240, 256) does not exist
+                        iu_mma_l0(d2 + 16 * e, iu_mk64(sa + e * (TILE_BYTES >> 4) + 2 * j, HI_SW), iu_mk64((pb - e + 16 * j) | LBO_P, HI_P),
+                                  IDESC2, (wp > 0 || j > 0) ? 1u : 0u);
+            }
+            iu_commit_l0(empty + slot);                                              // slot back to the producer once read
+            iu_commit_l0(p_empty + pbi);
+            if (wp == NWIN - 1) iu_commit_l0(d2_full + (vp & 1));
+        };
+        auto load_w = [&](int vi) {            // w_eff planes of this CTA's view vi -> buffer vi & 1 (free once the scores of view vi - 2 are done)
+            if (vi >= nviews || p != 0) return;
+            const int bv = blockIdx.x + vi * gridDim.x, wb = vi & 1;
+            iu_wait(wempty + wb, ((vi >> 1) & 1) ^ 1);
+            if (lane == 0) {
                 iu_expect_tx(wfull + wb, W_BYTES);
 #pragma unroll
                 for (int s = 0; s < 8; ++s) iu_tma_2d(smem + OFF_W + wb * W_BYTES + s * WCLASS_BYTES, &maps.w, 64 * s, 16 * bv, wfull + wb);
-            };
-            const long long ti0 = tracing ? clock64() : 0;
-            load_w(0);
-            for (int vi = 0; vi < nviews; ++vi) {
-                const int wb = vi & 1;
-                load_w(vi + 1);
-                UT(tw3, iu_wait(wfull + wb, (vi >> 1) & 1));
-                iu_fence_after();
-                for (int w = 0; w < NWIN; ++w, ++g) {
-                    const uint32_t d1 = tmem + (g & 1) * D1_BUF_COLS;
-                    for (int p = 0; p < 4; ++p) {
-                        const unsigned it1 = 4 * g + p, slot = it1 % RING;
-                        UT(tw1, iu_wait(full + slot, (it1 / RING) & 1));
-                        iu_fence_after();
-                        const uint32_t sa = ring + slot * SLOT_BYTES;
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int s = 2 * p + e;
-                            const uint32_t sw = wbase + wb * W_BYTES + s * WCLASS_BYTES;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                if (a.debug & 1) continue;
-                                iu_mma(d1 + 16 * s, iu_desc(sa + e * TILE_BYTES + 2048 * j, TILE_BYTES), iu_desc(sw + 32 * j, 0), IDESC1, j != 0 ? 1u : 0u);
-                            }
-                        }
-                        if (p == 3) {
-                            iu_commit(d1_full + (g & 1));
-                            if (w == 3) iu_commit(wempty + wb);
-                        }
-                        if (g > 0) sums(g - 1, p);
-                    }
-                }
             }
-            if (g > 0)
-                for (int p = 0; p < 4; ++p) sums(g - 1, p);
-            if (tracing) {
-                g_umma_trace[5] += (unsigned long long)(clock64() - ti0);
-                g_umma_trace[1] += (unsigned long long)tw1; g_umma_trace[2] += (unsigned long long)tw2;
-                g_umma_trace[3] += (unsigned long long)tw3; g_umma_trace[4] += (unsigned long long)tw4;
+            __syncwarp();
+        };
+        const long long ti0 = tracing ? clock64() : 0;
+        load_w(0);
+        for (int vi = 0; vi < nviews; ++vi) {
+            const int wb = vi & 1;
+            load_w(vi + 1);
+            UT(tw3, iu_wait(wfull + wb, (vi >> 1) & 1));
+            iu_fence_after();
+            const uint32_t sw = wbase + wb * (W_BYTES >> 4) + 2 * p * (WCLASS_BYTES >> 4);
+            for (int w = 0; w < NWIN; ++w, ++g) {
+                const uint32_t d1 = tmem + (g & 1) * D1_BUF_COLS + 32 * p;
+                const unsigned it1 = 4 * g + p, slot = it1 % RING;
+                UT(tw1, iu_wait(full + slot, (it1 / RING) & 1));
+                iu_fence_after();
+                const uint32_t sa = ring + slot * (SLOT_BYTES >> 4);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (!(a.debug & 1))
+                            iu_mma_l0(d1 + 16 * e, iu_mk64((sa + e * (TILE_BYTES >> 4) + 128 * j) | LBO_TILE, HI_SW),
+                                      iu_mk64(sw + e * (WCLASS_BYTES >> 4) + 2 * j, HI_SW), IDESC1, j != 0 ? 1u : 0u);
+                }
+                iu_commit_l0(d1_full + (g & 1));
+                if (w == NWIN - 1) iu_commit_l0(wempty + wb);
+                if (g > 0) sums(g - 1, w == 0 ? vi - 1 : vi, w == 0 ? NWIN - 1 : w - 1);
             }
         }
+        if (g > 0) sums(g - 1, nviews - 1, NWIN - 1);
+        if (tracing && p == 0) {
+            g_umma_trace[5] += (unsigned long long)(clock64() - ti0);
+            g_umma_trace[1] += (unsigned long long)tw1; g_umma_trace[2] += (unsigned long long)tw2;
+            g_umma_trace[3] += (unsigned long long)tw3; g_umma_trace[4] += (unsigned long long)tw4;
+        }
     } else if (warp >= SOFTMAX_WARP0 && warp < EPI_WARP0) {
-        // ===== softmax: lane < 16 of warp q owns row r = 16 q + lane of every M = 64 score tile and token 64 w - 7 + r of set w =====
+        // ===== softmax: lane < 16 of warp q owns row r = 16 q + lane of every M = 64 score tile and token 48 w - 7 + r of set w =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 176;" ::: "memory");
         const int q = warp & 3, l16 = lane & 15;
         const bool act = lane < 16;
         const int r = 16 * q + l16;
@@ -406,55 +434,72 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
         const bool tr_s = tracing && warp == SOFTMAX_WARP0;
         const long long ts0 = tr_s ? clock64() : 0;
         long long ta6 = 0, ta7 = 0, ta8 = 0, ta10 = 0;
+        // token of this thread in window w of a view (-1: not in the set), and its position terms, fetched one window ahead
+        auto token_of = [&](int w) { const int t = WSTEP * w - 7 + r; return (act && r >= (w == 0 ? 7 : 16) && t < HW) ? t : -1; };
+        float ctn[8];
+        auto load_ct = [&](int vi2, int w2) {
+            const int t = token_of(w2);
+            const int bv2 = blockIdx.x + vi2 * gridDim.x;
+#pragma unroll
+            for (int h = 0; h < 8; ++h) ctn[h] = (t >= 0 && vi2 < nviews) ? __ldg(a.cterm + ((size_t)bv2 * HEADS + h) * TP + 1 + t) : 0.f;
+        };
+        load_ct(0, 0);
         for (int vi = 0; vi < nviews; ++vi) {
             const int bv = blockIdx.x + vi * gridDim.x;
 #pragma unroll
             for (int h = 0; h < 8; ++h) { lsum[h] = 0.f; mref[h] = 0.f; }
 #pragma unroll
             for (int w = 0; w < NWIN; ++w, ++g) {
-                const int t = WTOK * w - 7 + r;
-                const bool valid = act && t >= 0 && t < HW;
+                const int t = token_of(w);
+                const bool valid = t >= 0;
                 float ct[8];
 #pragma unroll
-                for (int h = 0; h < 8; ++h) ct[h] = valid ? __ldg(a.cterm + ((size_t)bv * HEADS + h) * TP + 1 + t) : 0.f;
+                for (int h = 0; h < 8; ++h) ct[h] = ctn[h];
+                if (w + 1 < NWIN) load_ct(vi, w + 1); else load_ct(vi + 1, 0);
                 { const long long c0_ = tr_s ? clock64() : 0; iu_wait(d1_full + (g & 1), (g >> 1) & 1); if (tr_s) ta6 += clock64() - c0_; }
                 iu_fence_after();
                 const long long cx0 = tr_s ? clock64() : 0;
                 // class exchange: token t needs row r - (7 - s) of class s: a lane shift inside the warp, the halo for the first
-                // 7 - s lanes (rows of the previous warp; for warp 0 rows 57..63 of the previous window)
+                // 7 - s lanes (rows of the previous warp; the rows of warp 0 that would need one are never tokens of the set)
                 float acc[8];
 #pragma unroll
                 for (int h = 0; h < 8; ++h) acc[h] = 0.f;
-                float* hw = halo + (((g & 1) * 4 + q) * HALO_ENTRIES) * 8;
+                float* hw = halo + (q * HALO_ENTRIES) * 8;
 #pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    uint32_t v[16];
-                    iu_tmem_ld16(trow + (g & 1) * D1_BUF_COLS + 16 * s, v);
-                    float xs[8];
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[4][16];
 #pragma unroll
-                    for (int h = 0; h < 8; ++h) xs[h] = __uint_as_float(v[h]) + __uint_as_float(v[8 + h]);
-                    const int delta = 7 - s;
-                    if (delta == 0) {
+                    for (int k = 0; k < 4; ++k) iu_tmem_ld16_async(trow + (g & 1) * D1_BUF_COLS + 16 * (4 * half + k), v[k]);
+                    iu_tmem_wait_ld();
 #pragma unroll
-                        for (int h = 0; h < 8; ++h) acc[h] += xs[h];
-                    } else {
+                    for (int k = 0; k < 4; ++k) iu_tmem_use16(v[k]);
 #pragma unroll
-                        for (int h = 0; h < 8; ++h) {
-                            const float y = __shfl_up_sync(FULL, xs[h], delta);
-                            acc[h] += l16 >= delta ? y : 0.f;
-                        }
-                        if (act && l16 >= 16 - delta) {
-                            float4* dst = reinterpret_cast<float4*>(hw + (iu_halo_off(s) + l16 - (16 - delta)) * 8);
-                            dst[0] = make_float4(xs[0], xs[1], xs[2], xs[3]);
-                            dst[1] = make_float4(xs[4], xs[5], xs[6], xs[7]);
+                    for (int k = 0; k < 4; ++k) {
+                        const int s = 4 * half + k;
+                        float xs[8];
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) xs[h] = __uint_as_float(v[k][h]) + __uint_as_float(v[k][8 + h]);
+                        const int delta = 7 - s;
+                        if (delta == 0) {
+#pragma unroll
+                            for (int h = 0; h < 8; ++h) acc[h] += xs[h];
+                        } else {
+#pragma unroll
+                            for (int h = 0; h < 8; ++h) {
+                                const float y = __shfl_up_sync(FULL, xs[h], delta);
+                                acc[h] += l16 >= delta ? y : 0.f;
+                            }
+                            if (act && l16 >= 16 - delta) {
+                                float4* dst = reinterpret_cast<float4*>(hw + (iu_halo_off(s) + l16 - (16 - delta)) * 8);
+                                dst[0] = make_float4(xs[0], xs[1], xs[2], xs[3]);
+                                dst[1] = make_float4(xs[4], xs[5], xs[6], xs[7]);
+                            }
                         }
                     }
                 }
                 iu_bar_sync(1);
-                if (act && l16 < 7 && !(w == 0 && q == 0)) {
-                    const int qsrc = (q + 3) & 3;
-                    const unsigned hb = q == 0 ? ((g - 1) & 1) : (g & 1);
-                    const float* hr = halo + ((hb * 4 + qsrc) * HALO_ENTRIES) * 8;
+                if (act && l16 < 7 && q > 0) {
+                    const float* hr = halo + ((q - 1) * HALO_ENTRIES) * 8;
 #pragma unroll
                     for (int s = 0; s < 7; ++s) {
                         if (l16 < 7 - s) {
@@ -479,7 +524,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     bool ex = false;
 #pragma unroll
                     for (int h = 0; h < 8; ++h) ex = ex || (s[h] > mref[h] + TAU);
-                    raise = iu_bar_or(1, ex);
+                    raise = iu_bar_or(1, ex);                       // (also orders the halo reads before the next window's writes)
                 }
                 if (raise) {
                     // window 0 establishes the reference maximum; a later window raises it only in the (rare) case above
@@ -501,7 +546,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                         // everything accumulated so far is relative to the old reference: rescale the weighted sums in TMEM
                         // (the sums of set g-1 must have completed; those of set g are not issued before this warp's
                         // arrival on p_full), the running sums and the probabilities kept for the final output
-                        iu_wait(p_empty + ((g - 1) & 3), ((g - 1) >> 2) & 1);
+                        iu_wait(p_empty + ((g - 1) & (PBUF - 1)), ((g - 1) / PBUF) & 1);
                         iu_fence_after();
 #pragma unroll 1
                         for (int c8 = 0; c8 < 8; ++c8) {
@@ -521,6 +566,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                                 if (w2 < w) pr[w2][h] *= fc[h];
                         }
                     }
+                    iu_bar_sync(1);                                 // smax is rewritten by the next raise
                 }
                 if (tr_s) ta10 += clock64() - cr0;
                 unsigned short ph[8], pl[8];
@@ -531,10 +577,11 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     pr[w][h] = p;
                     iu_split(p, ph[h], pl[h]);
                 }
-                { const long long c0_ = tr_s ? clock64() : 0; iu_wait(p_empty + w, ((g >> 2) & 1) ^ 1); if (tr_s) ta8 += clock64() - c0_; }   // the sums of the previous view's set w have read this buffer
+                const unsigned pbi = g & (PBUF - 1);
+                { const long long c0_ = tr_s ? clock64() : 0; iu_wait(p_empty + pbi, ((g / PBUF) & 1) ^ 1); if (tr_s) ta8 += clock64() - c0_; }   // the sums that read this buffer last have completed
                 if (act) {
-                    // row 16 + r of both planes: 8 heads x bf16 = one 16-byte store each
-                    const uint32_t pt = iu_smem(smem + OFF_P) + w * P_BYTES + (16 + r) * 16;
+                    // row r of both planes: 8 heads x bf16 = one 16-byte store each
+                    const uint32_t pt = iu_smem(smem + OFF_P) + pbi * P_BYTES + r * 16;
                     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(pt), "r"((uint32_t)ph[0] | ((uint32_t)ph[1] << 16)),
                                  "r"((uint32_t)ph[2] | ((uint32_t)ph[3] << 16)), "r"((uint32_t)ph[4] | ((uint32_t)ph[5] << 16)),
                                  "r"((uint32_t)ph[6] | ((uint32_t)ph[7] << 16)) : "memory");
@@ -545,7 +592,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 iu_fence_before();
                 __syncwarp();
-                if (lane == 0) iu_arrive(p_full + w);
+                if (lane == 0) iu_arrive(p_full + pbi);
             }
             // ---- end of the view: total of the running sums, the mean token, final probabilities
 #pragma unroll
@@ -574,16 +621,24 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
             if (act) {
 #pragma unroll
                 for (int w = 0; w < NWIN; ++w) {
-                    const int t = WTOK * w - 7 + r;
-                    if (t >= 0 && 1 + t < 256) {
+                    const int t = token_of(w);
+                    if (t >= 0) {
 #pragma unroll
                         for (int h = 0; h < 8; ++h) {
                             unsigned short hi, lo;
-                            iu_split(t < HW ? pr[w][h] * fin[h] : 0.f, hi, lo);
+                            iu_split(pr[w][h] * fin[h], hi, lo);
                             __nv_bfloat16* dst = a.ya_hi + ((size_t)bv * HEADS + h) * YA + C + 1 + t;
                             dst[0] = __ushort_as_bfloat16(hi);
                             dst[a.ya_plane] = __ushort_as_bfloat16(lo);
                         }
+                    }
+                }
+                if (r < 256 - (HW + 1)) {                               // zero padding of the probability block (the value GEMM reads 256 columns)
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) {
+                        __nv_bfloat16* dst = a.ya_hi + ((size_t)bv * HEADS + h) * YA + C + HW + 1 + r;
+                        dst[0] = __ushort_as_bfloat16((unsigned short)0);
+                        dst[a.ya_plane] = __ushort_as_bfloat16((unsigned short)0);
                     }
                 }
                 if (r == 0) {
