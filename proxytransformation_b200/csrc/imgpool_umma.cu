@@ -9,14 +9,14 @@
 // u < s and u >= s + 225 belong to the neighbouring channels).  So one 4-D tensor map (u, r, s, view) lets TMA deliver
 // SWIZZLE_128B tiles [64 class rows][64 u] straight from the raw NCHW tensor: no register staging, no realignment.  The price
 // is that the token axis of class s is shifted by s:
-//   scores  D1_s[u][n]    = sum_r X_s[r][u] w_eff[n][s + 8 r]      one accumulator per class (tcgen05.mma M64 N16 K16, A = the
-//                           tile read MN-major, B = the class's w_eff rows n = (hi|lo, head), K-major); the score of token t
-//                           is sum_s D1_s[t + s]: the softmax warps add the eight classes with lane shifts (shuffles + a small
-//                           shared-memory halo for the rows of the neighbouring warp / previous window);
-//   sums    D2_s[r][n]   += sum_u X_s[r][u] P[u - s][n]            (tcgen05.mma M64 N16 K16, A = the tile read K-major,
-//                           B = the probabilities as an MN-major, unswizzled operand [token][8 (hi|lo) heads x 2 B]: a row
-//                           shift of s tokens is a 16 s-byte shift of the descriptor start address, so ONE copy of the
-//                           probabilities serves all classes).
+//   scores  D1_s[u][n]    = sum_r X_s[r][u] w_eff[n][s + 8 r]      one accumulator per class; the two classes of a pair share one
+//                           tcgen05.mma M128 N32 K16 (A = both tiles read MN-major, rows 0-63 / 64-127; B = the w_eff rows
+//                           n = (hi|lo, head) of both classes, K-major); the score of token t is sum_s D1_s[t + s]: the softmax
+//                           warps add the eight classes with lane shifts (shuffles + a small shared-memory exchange);
+//   sums    D2_s[r][n]   += sum_u X_s[r][u] P[u - s][n]            (tcgen05.mma M128 N32 K16, A = both tiles read K-major,
+//                           B = the probabilities as an MN-major, unswizzled operand [token][8 heads x 2 B] per (hi|lo) plane:
+//                           a shift of s tokens is a 16 s-byte shift of the descriptor start address, so one copy of the
+//                           probabilities (plus a one-row-shifted copy for the odd class of a pair) serves all classes).
 // The fp32 operands (w_eff, probabilities) enter as bf16 hi + lo halves in separate N columns, so every product is exact and
 // the accumulation is fp32 in TMEM (same numerics as the 3xBF16 GEMMs: ~2^-17 relative).
 //
@@ -58,17 +58,21 @@ constexpr int SLOT_BYTES = 2 * TILE_BYTES;   // a class pair: rows 0-63 class 2p
 constexpr int RING = 11;
 constexpr int WCLASS_BYTES = 16 * 128;       // w_eff rows (hi|lo, head) x 64 class channels
 constexpr int W_BYTES = 8 * WCLASS_BYTES;
-// Probabilities of a token set as the MN-major, unswizzled B operand of the sums: two planes (hi, lo), each [P_ROWS][8 heads]
-// bf16 = 16 bytes per row; row r holds token 48 w - 7 + r (zero if that token is not in the set); rows [64,72) stay zero (the
-// shifted 16-row k-steps of a class reach 7 rows further).  Buffer = window index mod PBUF.
-constexpr int P_ROWS = 72, P_PLANE = P_ROWS * 16, P_BYTES = 2 * P_PLANE, PBUF = 4;
-// class-exchange halo: [softmax warp][28 (class, row) entries][8 heads] fp32
-constexpr int HALO_ENTRIES = 28, HALO_BYTES = 4 * HALO_ENTRIES * 32;
+// Probabilities of a token set as the MN-major, unswizzled B operand of the sums (N = 32: both classes of a pair in one MMA):
+// four planes of [P_ROWS][8 heads] bf16 = 16 bytes per row: hi, lo, and a copy of each stored ONE ROW LATER, so that the same
+// start address reads the copies shifted by one more token (class 2p+1 next to class 2p; the four 8-column blocks of the operand
+// have to be equidistant).  Row r holds token 48 w - 7 + r (zero if that token is not in the set); the rows above 63 stay zero
+// (the shifted 16-row k-steps of a class reach 7 rows further).  Buffer = window index mod PBUF.
+constexpr int P_ROWS = 73, P_PLANE = P_ROWS * 16, P_BYTES = 4 * P_PLANE, PBUF = 2;
+// class exchange: halo [half (class parity)][28 (class, row) entries][8 heads] fp32 (rows of the lower warp that the upper warp's first
+// lanes need), xch [half][64 rows][4 heads] fp32 (the partial sums over the classes of one parity for the heads the other thread keeps)
+constexpr int HALO_ENTRIES = 28, HALO_BYTES = 2 * HALO_ENTRIES * 32, XCH_BYTES = 2 * 64 * 16;
 constexpr int OFF_RING = 0;
 constexpr int OFF_W = OFF_RING + RING * SLOT_BYTES;
 constexpr int OFF_P = OFF_W + 2 * W_BYTES;
 constexpr int OFF_HALO = OFF_P + PBUF * P_BYTES;
-constexpr int OFF_MISC = OFF_HALO + HALO_BYTES;       // floats: smax[32] sred[32] ered[32] s0[16] stat_l[16] stat_m[16]
+constexpr int OFF_XCH = OFF_HALO + HALO_BYTES;
+constexpr int OFF_MISC = OFF_XCH + XCH_BYTES;         // floats: smax[32] sred[32] ered[32] s0[16] stat_l[16] stat_m[16] fcs[8]
 constexpr int OFF_BAR = OFF_MISC + 1024;
 // mbarriers: full[RING] empty[RING] wfull[2] wempty[2] d1_full[2] p_full[PBUF] p_empty[PBUF] d2_full[2] d2_empty[2] s0_full[2] l_full[2]
 constexpr int NBAR = 2 * RING + 6 + 2 * PBUF + 8;
@@ -78,14 +82,15 @@ constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;      // + slack for the 1024-by
 // (TMEM lane quarter = warp mod 4), 12 = TMA producer
 constexpr int ISSUE_WARPS = 4, SOFTMAX_WARP0 = 4, EPI_WARP0 = 8, PRODUCER_WARP = 12;
 constexpr int THREADS = 32 * (PRODUCER_WARP + 1);
-// TMEM: D1 (scores) 2 window buffers x 8 classes x 16 columns at 0 ; D2 (sums) 2 view buffers x 8 classes x 16 columns at 256.
-// Both are M = 64 accumulators: row r lives in lane 32 (r / 16) + r % 16.
+// TMEM: D1 (scores) 2 window buffers x 4 class pairs x 32 columns at 0 ; D2 (sums) 2 view buffers x 4 class pairs x 32 columns at
+// 256.  Both are M = 128 accumulators (row = lane): rows 0-63 belong to class 2p and are valid in columns 0-15 (hi | lo heads) of
+// the pair's block, rows 64-127 to class 2p+1, valid in columns 16-31; the other two quadrants hold cross products nobody reads.
 constexpr int TMEM_COLS = 512;
 constexpr int D1_BUF_COLS = 128, D2_COL = 256, D2_BUF_COLS = 128;
 constexpr float TAU = 16.0f;                 // the reference maximum is raised when a score exceeds it by more than this
 constexpr float LOG2E = 1.4426950408889634f;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(OFF_W % 1024 == 0 && SLOT_BYTES % 1024 == 0 && OFF_P % 16 == 0 && OFF_HALO % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
+static_assert(OFF_W % 1024 == 0 && SLOT_BYTES % 1024 == 0 && OFF_P % 16 == 0 && OFF_HALO % 16 == 0 && OFF_XCH % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
 }  // namespace ipu
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -299,13 +304,14 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
     float* sm_s0 = ered + 32;                                    // [2][8]
     float* stat_l = sm_s0 + 16;                                  // [2][8]
     float* stat_m = stat_l + 16;                                 // [2][8]
+    float* fcs = stat_m + 16;                                    // [8]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < RING; ++i) { iu_mbar_init(full + i, 1); iu_mbar_init(empty + i, 1); }
         for (int i = 0; i < 2; ++i) {
             iu_mbar_init(wfull + i, 1); iu_mbar_init(wempty + i, ISSUE_WARPS); iu_mbar_init(d1_full + i, ISSUE_WARPS);
-            iu_mbar_init(d2_full + i, ISSUE_WARPS); iu_mbar_init(d2_empty + i, 4); iu_mbar_init(s0_full + i, 1); iu_mbar_init(l_full + i, 1);
+            iu_mbar_init(d2_full + i, ISSUE_WARPS); iu_mbar_init(d2_empty + i, 4); iu_mbar_init(s0_full + i, 1); iu_mbar_init(l_full + i, 2);
         }
         for (int i = 0; i < PBUF; ++i) { iu_mbar_init(p_full + i, 4); iu_mbar_init(p_empty + i, ISSUE_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -346,9 +352,9 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
     } else if (warp < ISSUE_WARPS) {
         // ===== MMA issuers: warp p owns class pair p (ring slots 4 g + p, D1 / D2 columns of classes 2p, 2p+1); the warp stays
         // converged, lane 0 issues.  Warp 0 also fetches the per-view w_eff planes one view ahead. =====
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");     // the softmax warpgroup needs the registers
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");     // the softmax warpgroup takes the registers
         const int p = warp;
-        constexpr uint32_t IDESC1 = iu_idesc(64, 16, true, false), IDESC2 = iu_idesc(64, 16, false, true);
+        constexpr uint32_t IDESC1 = iu_idesc(128, 32, true, false), IDESC2 = iu_idesc(128, 32, false, true);
         // descriptor words (addresses in 16-byte units): SWIZZLE_128B tiles (SBO 1024, version 1, layout 2) and the unswizzled
         // MN-major probability planes (LBO 128 between K blocks, SBO P_PLANE between the hi / lo planes, version 1)
         constexpr uint32_t HI_SW = (1024u >> 4) | (1u << 14) | (2u << 29), HI_P = ((uint32_t)P_PLANE >> 4) | (1u << 14);
@@ -366,13 +372,9 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
             const uint32_t sa = ring + slot * (SLOT_BYTES >> 4), pb = pbase + pbi * (P_BYTES >> 4) + 7 - 2 * p;
             const uint32_t d2 = tmem + D2_COL + (vp & 1) * D2_BUF_COLS + 32 * p;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if ((j < 3 || wp < NWIN - 1) && !(a.debug & 2))                  // u in [240, 256) does not exist
-                        iu_mma_l0(d2 + 16 * e, iu_mk64(sa + e * (TILE_BYTES >> 4) + 2 * j, HI_SW), iu_mk64((pb - e + 16 * j) | LBO_P, HI_P),
-                                  IDESC2, (wp > 0 || j > 0) ? 1u : 0u);
-            }
+            for (int j = 0; j < 4; ++j)
+                if ((j < 3 || wp < NWIN - 1) && !(a.debug & 2))                      // u in [240, 256) does not exist
+                    iu_mma_l0(d2, iu_mk64(sa + 2 * j, HI_SW), iu_mk64((pb + 16 * j) | LBO_P, HI_P), IDESC2, (wp > 0 || j > 0) ? 1u : 0u);
             iu_commit_l0(empty + slot);                                              // slot back to the producer once read
             iu_commit_l0(p_empty + pbi);
             if (wp == NWIN - 1) iu_commit_l0(d2_full + (vp & 1));
@@ -403,13 +405,8 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 iu_fence_after();
                 const uint32_t sa = ring + slot * (SLOT_BYTES >> 4);
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (!(a.debug & 1))
-                            iu_mma_l0(d1 + 16 * e, iu_mk64((sa + e * (TILE_BYTES >> 4) + 128 * j) | LBO_TILE, HI_SW),
-                                      iu_mk64(sw + e * (WCLASS_BYTES >> 4) + 2 * j, HI_SW), IDESC1, j != 0 ? 1u : 0u);
-                }
+                for (int j = 0; j < 4; ++j)
+                    if (!(a.debug & 1)) iu_mma_l0(d1, iu_mk64((sa + 128 * j) | LBO_TILE, HI_SW), iu_mk64(sw + 2 * j, HI_SW), IDESC1, j != 0 ? 1u : 0u);
                 iu_commit_l0(d1_full + (g & 1));
                 if (w == NWIN - 1) iu_commit_l0(wempty + wb);
                 if (g > 0) sums(g - 1, w == 0 ? vi - 1 : vi, w == 0 ? NWIN - 1 : w - 1);
@@ -422,172 +419,177 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
             g_umma_trace[3] += (unsigned long long)tw3; g_umma_trace[4] += (unsigned long long)tw4;
         }
     } else if (warp >= SOFTMAX_WARP0 && warp < EPI_WARP0) {
-        // ===== softmax: lane < 16 of warp q owns row r = 16 q + lane of every M = 64 score tile and token 48 w - 7 + r of set w =====
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 176;" ::: "memory");
-        const int q = warp & 3, l16 = lane & 15;
-        const bool act = lane < 16;
-        const int r = 16 * q + l16;
+        // ===== softmax: thread (half, r) reads row r of the class-(2p + half) score tiles (TMEM lane 64 half + r) and keeps heads
+        // 4 half .. 4 half + 3 of token 48 w - 7 + r =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 160;" ::: "memory");
+        const int q = warp & 3, half = q >> 1, qq = q & 1;
+        const int r = 32 * qq + lane, hb = 4 * half;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         float* halo = reinterpret_cast<float*>(smem + OFF_HALO);
-        float mref[8], lsum[8], pr[NWIN][8];
+        float* xch = reinterpret_cast<float*>(smem + OFF_XCH);
+        float mref[4], lsum[4], pr[NWIN][4];
         unsigned g = 0;
         const bool tr_s = tracing && warp == SOFTMAX_WARP0;
         const long long ts0 = tr_s ? clock64() : 0;
         long long ta6 = 0, ta7 = 0, ta8 = 0, ta10 = 0;
         // token of this thread in window w of a view (-1: not in the set), and its position terms, fetched one window ahead
-        auto token_of = [&](int w) { const int t = WSTEP * w - 7 + r; return (act && r >= (w == 0 ? 7 : 16) && t < HW) ? t : -1; };
-        float ctn[8];
+        auto token_of = [&](int w) { const int t = WSTEP * w - 7 + r; return (r >= (w == 0 ? 7 : 16) && t < HW) ? t : -1; };
+        float ctn[4];
         auto load_ct = [&](int vi2, int w2) {
             const int t = token_of(w2);
             const int bv2 = blockIdx.x + vi2 * gridDim.x;
 #pragma unroll
-            for (int h = 0; h < 8; ++h) ctn[h] = (t >= 0 && vi2 < nviews) ? __ldg(a.cterm + ((size_t)bv2 * HEADS + h) * TP + 1 + t) : 0.f;
+            for (int k = 0; k < 4; ++k) ctn[k] = (t >= 0 && vi2 < nviews) ? __ldg(a.cterm + ((size_t)bv2 * HEADS + hb + k) * TP + 1 + t) : 0.f;
         };
         load_ct(0, 0);
         for (int vi = 0; vi < nviews; ++vi) {
             const int bv = blockIdx.x + vi * gridDim.x;
 #pragma unroll
-            for (int h = 0; h < 8; ++h) { lsum[h] = 0.f; mref[h] = 0.f; }
+            for (int k = 0; k < 4; ++k) { lsum[k] = 0.f; mref[k] = 0.f; }
 #pragma unroll
             for (int w = 0; w < NWIN; ++w, ++g) {
                 const int t = token_of(w);
                 const bool valid = t >= 0;
-                float ct[8];
+                float ct[4];
 #pragma unroll
-                for (int h = 0; h < 8; ++h) ct[h] = ctn[h];
+                for (int k = 0; k < 4; ++k) ct[k] = ctn[k];
                 if (w + 1 < NWIN) load_ct(vi, w + 1); else load_ct(vi + 1, 0);
                 { const long long c0_ = tr_s ? clock64() : 0; iu_wait(d1_full + (g & 1), (g >> 1) & 1); if (tr_s) ta6 += clock64() - c0_; }
                 iu_fence_after();
                 const long long cx0 = tr_s ? clock64() : 0;
-                // class exchange: token t needs row r - (7 - s) of class s: a lane shift inside the warp, the halo for the first
-                // 7 - s lanes (rows of the previous warp; the rows of warp 0 that would need one are never tokens of the set)
-                float acc[8];
+                // class exchange: token t needs row r - (7 - s) of class s.  Partial sums over this thread's four classes for all 8
+                // heads: lane shifts inside the warp; the first 7 - s lanes of the upper warp take the lower warp's rows from the halo
+                uint32_t v[4][16];
 #pragma unroll
-                for (int h = 0; h < 8; ++h) acc[h] = 0.f;
-                float* hw = halo + (q * HALO_ENTRIES) * 8;
+                for (int p = 0; p < 4; ++p) iu_tmem_ld16_async(trow + (g & 1) * D1_BUF_COLS + 32 * p + 16 * half, v[p]);
+                iu_tmem_wait_ld();
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[4][16];
+                for (int p = 0; p < 4; ++p) iu_tmem_use16(v[p]);
+                float part[8];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) iu_tmem_ld16_async(trow + (g & 1) * D1_BUF_COLS + 16 * (4 * half + k), v[k]);
-                    iu_tmem_wait_ld();
+                for (int h = 0; h < 8; ++h) part[h] = 0.f;
+                float* hw = halo + (half * HALO_ENTRIES) * 8;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) iu_tmem_use16(v[k]);
+                for (int p = 0; p < 4; ++p) {
+                    const int s = 2 * p + half, delta = 7 - s;
+                    float xs[8];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int s = 4 * half + k;
-                        float xs[8];
+                    for (int h = 0; h < 8; ++h) xs[h] = __uint_as_float(v[p][h]) + __uint_as_float(v[p][8 + h]);
 #pragma unroll
-                        for (int h = 0; h < 8; ++h) xs[h] = __uint_as_float(v[k][h]) + __uint_as_float(v[k][8 + h]);
-                        const int delta = 7 - s;
-                        if (delta == 0) {
-#pragma unroll
-                            for (int h = 0; h < 8; ++h) acc[h] += xs[h];
-                        } else {
-#pragma unroll
-                            for (int h = 0; h < 8; ++h) {
-                                const float y = __shfl_up_sync(FULL, xs[h], delta);
-                                acc[h] += l16 >= delta ? y : 0.f;
-                            }
-                            if (act && l16 >= 16 - delta) {
-                                float4* dst = reinterpret_cast<float4*>(hw + (iu_halo_off(s) + l16 - (16 - delta)) * 8);
-                                dst[0] = make_float4(xs[0], xs[1], xs[2], xs[3]);
-                                dst[1] = make_float4(xs[4], xs[5], xs[6], xs[7]);
-                            }
-                        }
+                    for (int h = 0; h < 8; ++h) {
+                        const float y = __shfl_up_sync(FULL, xs[h], delta);      // delta == 0: the value itself
+                        part[h] += lane >= delta ? y : 0.f;
+                    }
+                    if (qq == 0 && lane >= 32 - delta) {
+                        float4* dst = reinterpret_cast<float4*>(hw + (iu_halo_off(s) + lane - (32 - delta)) * 8);
+                        dst[0] = make_float4(xs[0], xs[1], xs[2], xs[3]);
+                        dst[1] = make_float4(xs[4], xs[5], xs[6], xs[7]);
                     }
                 }
+                // the partial sums of the heads the other thread of this row keeps
+                *reinterpret_cast<float4*>(xch + (half * 64 + r) * 4) =
+                    half ? make_float4(part[0], part[1], part[2], part[3]) : make_float4(part[4], part[5], part[6], part[7]);
                 iu_bar_sync(1);
-                if (act && l16 < 7 && q > 0) {
-                    const float* hr = halo + ((q - 1) * HALO_ENTRIES) * 8;
+                float tot[4];
+                {
+                    const float4 o = *reinterpret_cast<const float4*>(xch + ((half ^ 1) * 64 + r) * 4);
+                    tot[0] = part[hb + 0] + o.x; tot[1] = part[hb + 1] + o.y; tot[2] = part[hb + 2] + o.z; tot[3] = part[hb + 3] + o.w;
+                }
+                if (qq == 1 && lane < 7) {
 #pragma unroll
                     for (int s = 0; s < 7; ++s) {
-                        if (l16 < 7 - s) {
-                            const float4* src = reinterpret_cast<const float4*>(hr + (iu_halo_off(s) + l16) * 8);
-                            const float4 x0 = src[0], x1 = src[1];
-                            acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w;
-                            acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
+                        if (lane < 7 - s) {
+                            const float4 x = *reinterpret_cast<const float4*>(halo + (((s & 1) * HALO_ENTRIES) + iu_halo_off(s) + lane) * 8 + hb);
+                            tot[0] += x.x; tot[1] += x.y; tot[2] += x.z; tot[3] += x.w;
                         }
                     }
                 }
                 if (tr_s) ta7 += clock64() - cx0;
-                float s[8];
+                float sc[4];
 #pragma unroll
-                for (int h = 0; h < 8; ++h) s[h] = valid ? a.scale * (acc[h] + ct[h]) : -INFINITY;
+                for (int k = 0; k < 4; ++k) sc[k] = valid ? a.scale * (tot[k] + ct[k]) : -INFINITY;
                 if (a.dbg != nullptr && valid) {
 #pragma unroll
-                    for (int h = 0; h < 8; ++h) a.dbg[((size_t)bv * HEADS + h) * 256 + 1 + t] = s[h];
+                    for (int k = 0; k < 4; ++k) a.dbg[((size_t)bv * HEADS + hb + k) * 256 + 1 + t] = sc[k];
                 }
                 const long long cr0 = tr_s ? clock64() : 0;
                 bool raise = w == 0;
                 if (w > 0) {
                     bool ex = false;
 #pragma unroll
-                    for (int h = 0; h < 8; ++h) ex = ex || (s[h] > mref[h] + TAU);
-                    raise = iu_bar_or(1, ex);                       // (also orders the halo reads before the next window's writes)
+                    for (int k = 0; k < 4; ++k) ex = ex || (sc[k] > mref[k] + TAU);
+                    raise = iu_bar_or(1, ex);                       // (also orders the exchange reads before the next window's writes)
                 }
                 if (raise) {
                     // window 0 establishes the reference maximum; a later window raises it only in the (rare) case above
 #pragma unroll
-                    for (int h = 0; h < 8; ++h) {
-                        const float x = warp_max(s[h]);
-                        if (lane == 0) smax[q * 8 + h] = x;
+                    for (int k = 0; k < 4; ++k) {
+                        const float x = warp_max(sc[k]);
+                        if (lane == 0) smax[q * 4 + k] = x;
                     }
                     iu_bar_sync(1);
-                    float fc[8];
+                    float fc[4];
 #pragma unroll
-                    for (int h = 0; h < 8; ++h) {
-                        const float wm = fmaxf(fmaxf(smax[h], smax[8 + h]), fmaxf(smax[16 + h], smax[24 + h]));
-                        const float mn = w == 0 ? wm : fmaxf(mref[h], wm);
-                        fc[h] = w == 0 ? 1.f : exp2f((mref[h] - mn) * LOG2E);
-                        mref[h] = mn;
+                    for (int k = 0; k < 4; ++k) {
+                        const float wm = fmaxf(smax[(2 * half) * 4 + k], smax[(2 * half + 1) * 4 + k]);
+                        const float mn = w == 0 ? wm : fmaxf(mref[k], wm);
+                        fc[k] = w == 0 ? 1.f : exp2f((mref[k] - mn) * LOG2E);
+                        mref[k] = mn;
                     }
                     if (w > 0) {
                         // everything accumulated so far is relative to the old reference: rescale the weighted sums in TMEM
                         // (the sums of set g-1 must have completed; those of set g are not issued before this warp's
                         // arrival on p_full), the running sums and the probabilities kept for the final output
+                        if (qq == 0 && lane == 0) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) fcs[hb + k] = fc[k];
+                        }
+                        iu_bar_sync(1);
+                        float fc8[8];
+#pragma unroll
+                        for (int h = 0; h < 8; ++h) fc8[h] = fcs[h];
                         iu_wait(p_empty + ((g - 1) & (PBUF - 1)), ((g - 1) / PBUF) & 1);
                         iu_fence_after();
 #pragma unroll 1
-                        for (int c8 = 0; c8 < 8; ++c8) {
+                        for (int c16 = 0; c16 < 8; ++c16) {
                             uint32_t y[16];
-                            const uint32_t ta = trow + D2_COL + (vi & 1) * D2_BUF_COLS + 16 * c8;
+                            const uint32_t ta = trow + D2_COL + (vi & 1) * D2_BUF_COLS + 16 * c16;
                             iu_tmem_ld16(ta, y);
 #pragma unroll
-                            for (int n = 0; n < 16; ++n) y[n] = __float_as_uint(__uint_as_float(y[n]) * fc[n & 7]);
+                            for (int n = 0; n < 16; ++n) y[n] = __float_as_uint(__uint_as_float(y[n]) * fc8[n & 7]);
                             iu_tmem_st16(ta, y);
                         }
                         iu_fence_before();
 #pragma unroll
-                        for (int h = 0; h < 8; ++h) {
-                            lsum[h] *= fc[h];
+                        for (int k = 0; k < 4; ++k) {
+                            lsum[k] *= fc[k];
 #pragma unroll
                             for (int w2 = 0; w2 < NWIN; ++w2)
-                                if (w2 < w) pr[w2][h] *= fc[h];
+                                if (w2 < w) pr[w2][k] *= fc[k];
                         }
                     }
-                    iu_bar_sync(1);                                 // smax is rewritten by the next raise
+                    iu_bar_sync(1);                                 // smax / fcs are rewritten by the next raise
                 }
                 if (tr_s) ta10 += clock64() - cr0;
-                unsigned short ph[8], pl[8];
+                unsigned short ph[4], pl[4];
 #pragma unroll
-                for (int h = 0; h < 8; ++h) {
-                    const float p = valid ? exp2f((s[h] - mref[h]) * LOG2E) : 0.f;
-                    lsum[h] += p;
-                    pr[w][h] = p;
-                    iu_split(p, ph[h], pl[h]);
+                for (int k = 0; k < 4; ++k) {
+                    const float p = valid ? exp2f((sc[k] - mref[k]) * LOG2E) : 0.f;
+                    lsum[k] += p;
+                    pr[w][k] = p;
+                    iu_split(p, ph[k], pl[k]);
                 }
                 const unsigned pbi = g & (PBUF - 1);
                 { const long long c0_ = tr_s ? clock64() : 0; iu_wait(p_empty + pbi, ((g / PBUF) & 1) ^ 1); if (tr_s) ta8 += clock64() - c0_; }   // the sums that read this buffer last have completed
-                if (act) {
-                    // row r of both planes: 8 heads x bf16 = one 16-byte store each
-                    const uint32_t pt = iu_smem(smem + OFF_P) + pbi * P_BYTES + r * 16;
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(pt), "r"((uint32_t)ph[0] | ((uint32_t)ph[1] << 16)),
-                                 "r"((uint32_t)ph[2] | ((uint32_t)ph[3] << 16)), "r"((uint32_t)ph[4] | ((uint32_t)ph[5] << 16)),
-                                 "r"((uint32_t)ph[6] | ((uint32_t)ph[7] << 16)) : "memory");
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(pt + P_PLANE), "r"((uint32_t)pl[0] | ((uint32_t)pl[1] << 16)),
-                                 "r"((uint32_t)pl[2] | ((uint32_t)pl[3] << 16)), "r"((uint32_t)pl[4] | ((uint32_t)pl[5] << 16)),
-                                 "r"((uint32_t)pl[6] | ((uint32_t)pl[7] << 16)) : "memory");
+                {
+                    // row r of the hi / lo planes and row r + 1 of their copies: this thread's 4 heads = 8 bytes each
+                    const uint32_t pt = iu_smem(smem + OFF_P) + pbi * P_BYTES + r * 16 + 8 * half;
+                    const uint32_t h01 = (uint32_t)ph[0] | ((uint32_t)ph[1] << 16), h23 = (uint32_t)ph[2] | ((uint32_t)ph[3] << 16);
+                    const uint32_t l01 = (uint32_t)pl[0] | ((uint32_t)pl[1] << 16), l23 = (uint32_t)pl[2] | ((uint32_t)pl[3] << 16);
+                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(pt), "r"(h01), "r"(h23) : "memory");
+                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(pt + P_PLANE), "r"(l01), "r"(l23) : "memory");
+                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(pt + 2 * P_PLANE + 16), "r"(h01), "r"(h23) : "memory");
+                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(pt + 3 * P_PLANE + 16), "r"(l01), "r"(l23) : "memory");
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 iu_fence_before();
@@ -596,60 +598,58 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
             }
             // ---- end of the view: total of the running sums, the mean token, final probabilities
 #pragma unroll
-            for (int h = 0; h < 8; ++h) {
-                const float x = warp_sum(lsum[h]);
-                if (lane == 0) sred[q * 8 + h] = x;
+            for (int k = 0; k < 4; ++k) {
+                const float x = warp_sum(lsum[k]);
+                if (lane == 0) sred[q * 4 + k] = x;
             }
             iu_bar_sync(1);
             iu_wait(s0_full + (vi & 1), (vi >> 1) & 1);
-            float fin[8], p0n[8], lt[8];
+            float fin[4], p0n[4], lt[4];
 #pragma unroll
-            for (int h = 0; h < 8; ++h) {
-                lt[h] = (sred[h] + sred[8 + h]) + (sred[16 + h] + sred[24 + h]);
-                const float s0 = sm_s0[(vi & 1) * 8 + h];
-                const float mf = fmaxf(mref[h], s0);
-                const float f = exp2f((mref[h] - mf) * LOG2E), p0 = exp2f((s0 - mf) * LOG2E);
-                const float inv = 1.0f / (lt[h] * f + p0);
-                fin[h] = f * inv;
-                p0n[h] = p0 * inv;
+            for (int k = 0; k < 4; ++k) {
+                lt[k] = sred[(2 * half) * 4 + k] + sred[(2 * half + 1) * 4 + k];
+                const float s0 = sm_s0[(vi & 1) * 8 + hb + k];
+                const float mf = fmaxf(mref[k], s0);
+                const float f = exp2f((mref[k] - mf) * LOG2E), p0 = exp2f((s0 - mf) * LOG2E);
+                const float inv = 1.0f / (lt[k] * f + p0);
+                fin[k] = f * inv;
+                p0n[k] = p0 * inv;
             }
-            if (warp == SOFTMAX_WARP0 && lane == 0) {
+            if (qq == 0 && lane == 0) {
 #pragma unroll
-                for (int h = 0; h < 8; ++h) { stat_l[(vi & 1) * 8 + h] = lt[h]; stat_m[(vi & 1) * 8 + h] = mref[h]; }
+                for (int k = 0; k < 4; ++k) { stat_l[(vi & 1) * 8 + hb + k] = lt[k]; stat_m[(vi & 1) * 8 + hb + k] = mref[k]; }
                 iu_arrive(l_full + (vi & 1));
             }
-            if (act) {
 #pragma unroll
-                for (int w = 0; w < NWIN; ++w) {
-                    const int t = token_of(w);
-                    if (t >= 0) {
+            for (int w = 0; w < NWIN; ++w) {
+                const int t = token_of(w);
+                if (t >= 0) {
 #pragma unroll
-                        for (int h = 0; h < 8; ++h) {
-                            unsigned short hi, lo;
-                            iu_split(pr[w][h] * fin[h], hi, lo);
-                            __nv_bfloat16* dst = a.ya_hi + ((size_t)bv * HEADS + h) * YA + C + 1 + t;
-                            dst[0] = __ushort_as_bfloat16(hi);
-                            dst[a.ya_plane] = __ushort_as_bfloat16(lo);
-                        }
-                    }
-                }
-                if (r < 256 - (HW + 1)) {                               // zero padding of the probability block (the value GEMM reads 256 columns)
-#pragma unroll
-                    for (int h = 0; h < 8; ++h) {
-                        __nv_bfloat16* dst = a.ya_hi + ((size_t)bv * HEADS + h) * YA + C + HW + 1 + r;
-                        dst[0] = __ushort_as_bfloat16((unsigned short)0);
-                        dst[a.ya_plane] = __ushort_as_bfloat16((unsigned short)0);
-                    }
-                }
-                if (r == 0) {
-#pragma unroll
-                    for (int h = 0; h < 8; ++h) {
+                    for (int k = 0; k < 4; ++k) {
                         unsigned short hi, lo;
-                        iu_split(p0n[h], hi, lo);
-                        __nv_bfloat16* dst = a.ya_hi + ((size_t)bv * HEADS + h) * YA + C;
+                        iu_split(pr[w][k] * fin[k], hi, lo);
+                        __nv_bfloat16* dst = a.ya_hi + ((size_t)bv * HEADS + hb + k) * YA + C + 1 + t;
                         dst[0] = __ushort_as_bfloat16(hi);
                         dst[a.ya_plane] = __ushort_as_bfloat16(lo);
                     }
+                }
+            }
+            if (r < 256 - (HW + 1)) {                                   // zero padding of the probability block (the value GEMM reads 256 columns)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    __nv_bfloat16* dst = a.ya_hi + ((size_t)bv * HEADS + hb + k) * YA + C + HW + 1 + r;
+                    dst[0] = __ushort_as_bfloat16((unsigned short)0);
+                    dst[a.ya_plane] = __ushort_as_bfloat16((unsigned short)0);
+                }
+            }
+            if (r == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    unsigned short hi, lo;
+                    iu_split(p0n[k], hi, lo);
+                    __nv_bfloat16* dst = a.ya_hi + ((size_t)bv * HEADS + hb + k) * YA + C;
+                    dst[0] = __ushort_as_bfloat16(hi);
+                    dst[a.ya_plane] = __ushort_as_bfloat16(lo);
                 }
             }
             iu_bar_sync(1);                                         // sred is rewritten by the next view
@@ -661,8 +661,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
         }
     } else if (warp >= EPI_WARP0 && warp < PRODUCER_WARP) {
         // ===== epilogue: mean-token score, then Y = (D2 f + p0 xbar) / L -> bf16 hi/lo planes =====
-        const int q = warp & 3, et = threadIdx.x - 32 * EPI_WARP0, l16 = lane & 15, row = 16 * q + l16;
-        const bool act = lane < 16;
+        const int q = warp & 3, et = threadIdx.x - 32 * EPI_WARP0, half = q >> 1, row = 32 * (q & 1) + lane;   // class row of class 2p + half
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         const bool tr_e = tracing && warp == EPI_WARP0;
         const long long te0 = tr_e ? clock64() : 0;
@@ -719,21 +718,20 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
             const long long ce3 = tr_e ? clock64() : 0;
             iu_fence_after();
 #pragma unroll 1
-            for (int s = 0; s < 8; ++s) {
+            for (int p = 0; p < 4; ++p) {
                 uint32_t y[16];
-                iu_tmem_ld16(trow + D2_COL + (vi & 1) * D2_BUF_COLS + 16 * s, y);
-                if (act) {
-                    const int cp = 64 * s + row;                            // output column 64 s + r of channel s + 8 r
-                    const float xb = __ldg(a.xbar + (size_t)bv * C + s + 8 * row);
+                iu_tmem_ld16(trow + D2_COL + (vi & 1) * D2_BUF_COLS + 32 * p + 16 * half, y);
+                const int s = 2 * p + half;
+                const int cp = 64 * s + row;                                // output column 64 s + r of channel s + 8 r
+                const float xb = __ldg(a.xbar + (size_t)bv * C + s + 8 * row);
 #pragma unroll
-                    for (int h = 0; h < 8; ++h) {
-                        const float val = (__uint_as_float(y[h]) + __uint_as_float(y[8 + h])) * fin[h] + p0n[h] * xb;
-                        unsigned short hi, lo;
-                        iu_split(val, hi, lo);
-                        __nv_bfloat16* dst = a.ya_hi + ((size_t)bv * HEADS + h) * YA + cp;
-                        dst[0] = __ushort_as_bfloat16(hi);
-                        dst[a.ya_plane] = __ushort_as_bfloat16(lo);
-                    }
+                for (int h = 0; h < 8; ++h) {
+                    const float val = (__uint_as_float(y[h]) + __uint_as_float(y[8 + h])) * fin[h] + p0n[h] * xb;
+                    unsigned short hi, lo;
+                    iu_split(val, hi, lo);
+                    __nv_bfloat16* dst = a.ya_hi + ((size_t)bv * HEADS + h) * YA + cp;
+                    dst[0] = __ushort_as_bfloat16(hi);
+                    dst[a.ya_plane] = __ushort_as_bfloat16(lo);
                 }
             }
             iu_fence_before();
