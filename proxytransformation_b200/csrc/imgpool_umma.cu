@@ -20,22 +20,22 @@
 // The fp32 operands (w_eff, probabilities) enter as bf16 hi + lo halves in separate N columns, so every product is exact and
 // the accumulation is fp32 in TMEM (same numerics as the 3xBF16 GEMMs: ~2^-17 relative).
 //
-// One persistent CTA per SM; a view is streamed as 5 OVERLAPPING windows of 64 u-columns that advance by 48 (flash-attention
+// One persistent CTA per SM; a view is streamed as 4 OVERLAPPING windows of 64 u-columns that advance by 56 (flash-attention
 // structure, one query per head).  The score of token t needs u = t .. t + 7 and its weighted sum touches the same columns, so
-// window g = [48 g, 48 g + 64) is self-contained for the token SET g = [48 g + 9, 48 g + 56] (set 0: [0, 56]): scores and sums of
-// a set read the SAME tiles and no slot outlives its window (the 16 re-read columns per window are L2 hits: 1.25 x the bytes
-// through TMA, 1 x from HBM).
+// window g = [56 g, 56 g + 64) is self-contained for the token SET g = [56 g, 56 g + 55] (last set: up to token 224): scores and
+// sums of a set read the SAME tiles and no slot outlives its window (the 8 re-read columns per window are L2 hits).
 //   warps 0-3    MMA issuers, one per class pair p (ring slots 4 g + p, accumulators of classes 2p, 2p+1); the warp stays
 //                converged and lane 0 issues: scores of window g+1 are issued before the sums of set g; a ring slot goes back to
 //                the producer (tcgen05.commit) when the sums that read it have completed.  Warp 0 also fetches the w_eff planes
-//   warps 4-7    softmax: tcgen05.ld of the eight 64 x 16 class score tiles (lane = u), class exchange, + position term, exp
+//   warps 4-11   softmax (a row's work is split over 4 threads: class parity x pair group, 2 heads each): tcgen05.ld of the class
+//                score tiles (lane = u), class exchange, + position term, exp
 //                relative to a per-view reference maximum (established by window 0, raised FA-style by rescaling the
 //                accumulators in TMEM only when a later window exceeds it by more than TAU — never on ordinary data),
 //                bf16 hi/lo probability rows -> shared memory (16-byte stores), running sum in registers; end of view: final
 //                probabilities -> global
-//   warps 8-11   epilogue: mean-token score s0 = w_eff . xbar (CUDA cores, from L2), then per view Y = (D2 f + p0 xbar) / L
+//   warps 12-15  epilogue: mean-token score s0 = w_eff . xbar (CUDA cores, from L2), then per view Y = (D2 f + p0 xbar) / L
 //                from TMEM -> bf16 hi/lo planes for the value-side GEMM (same output format as the mma.sync kernel)
-//   warp 12      TMA producer of the feature tiles: one 16 KB box (64 u x 64 rows x 2 classes) per ring slot, 11 slots
+//   warp 16      TMA producer of the feature tiles: one 16 KB box (64 u x 64 rows x 2 classes) per ring slot, 10 slots
 // Channel order of w_eff columns and of the weighted sums: position 64 s + r  <->  channel s + 8 r (absorbed into the folded
 // GEMM weights on the host, pt_img_pool_params variant 1).
 #include "common.cuh"
@@ -51,22 +51,22 @@ namespace ipu {
 constexpr int C = 512, HW = 225, HEADS = 8;
 constexpr int TP = 228;                      // cterm row pitch (floats)
 constexpr int YA = 768;                      // output row: 512 weighted sums + 256 probabilities
-constexpr int NWIN = 5, WSTEP = 48;          // overlapping u-windows per view: [48 w, 48 w + 64), u = token + class in [0, 232)
+constexpr int NWIN = 4, WSTEP = 56;          // overlapping u-windows per view: [56 w, 56 w + 64), u = token + class in [0, 232)
 constexpr int UCOLS = 232;                   // valid u range of the tensor map: 225 tokens + 7 class shifts
 constexpr int TILE_BYTES = 64 * 128;         // [64 class rows][64 u] bf16, SWIZZLE_128B
 constexpr int SLOT_BYTES = 2 * TILE_BYTES;   // a class pair: rows 0-63 class 2p, rows 64-127 class 2p+1 (one TMA box)
-constexpr int RING = 11;
+constexpr int RING = 10;
 constexpr int WCLASS_BYTES = 16 * 128;       // w_eff rows (hi|lo, head) x 64 class channels
 constexpr int W_BYTES = 8 * WCLASS_BYTES;
 // Probabilities of a token set as the MN-major, unswizzled B operand of the sums (N = 32: both classes of a pair in one MMA):
 // four planes of [P_ROWS][8 heads] bf16 = 16 bytes per row: hi, lo, and a copy of each stored ONE ROW LATER, so that the same
 // start address reads the copies shifted by one more token (class 2p+1 next to class 2p; the four 8-column blocks of the operand
-// have to be equidistant).  Row r holds token 48 w - 7 + r (zero if that token is not in the set); the rows above 63 stay zero
+// have to be equidistant).  Row r holds token 56 w - 7 + r (zero if that token is not in the set); the rows above 63 stay zero
 // (the shifted 16-row k-steps of a class reach 7 rows further).  Buffer = window index mod PBUF.
 constexpr int P_ROWS = 73, P_PLANE = P_ROWS * 16, P_BYTES = 4 * P_PLANE, PBUF = 2;
 // class exchange: halo [half (class parity)][28 (class, row) entries][8 heads] fp32 (rows of the lower warp that the upper warp's first
-// lanes need), xch [half][64 rows][4 heads] fp32 (the partial sums over the classes of one parity for the heads the other thread keeps)
-constexpr int HALO_ENTRIES = 28, HALO_BYTES = 2 * HALO_ENTRIES * 32, XCH_BYTES = 2 * 64 * 16;
+// lanes need), xch [source thread of the row (half, pair group)][64 rows][8 heads] fp32 (partial sums over that thread's two classes)
+constexpr int HALO_ENTRIES = 28, HALO_BYTES = 2 * HALO_ENTRIES * 32, XCH_BYTES = 4 * 64 * 32;
 constexpr int OFF_RING = 0;
 constexpr int OFF_W = OFF_RING + RING * SLOT_BYTES;
 constexpr int OFF_P = OFF_W + 2 * W_BYTES;
@@ -78,9 +78,9 @@ constexpr int OFF_BAR = OFF_MISC + 1024;
 constexpr int NBAR = 2 * RING + 6 + 2 * PBUF + 8;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;      // + slack for the 1024-byte alignment of the swizzled tiles
-// warp roles: 0-3 = MMA issuers (one per class pair; warp 0 also TMA of w_eff + TMEM allocation), 4-7 softmax, 8-11 epilogue
-// (TMEM lane quarter = warp mod 4), 12 = TMA producer
-constexpr int ISSUE_WARPS = 4, SOFTMAX_WARP0 = 4, EPI_WARP0 = 8, PRODUCER_WARP = 12;
+// warp roles: 0-3 = MMA issuers (one per class pair; warp 0 also TMA of w_eff + TMEM allocation), 4-11 softmax, 12-15 epilogue
+// (TMEM lane quarter = warp mod 4), 16 = TMA producer
+constexpr int ISSUE_WARPS = 4, SOFTMAX_WARP0 = 4, SOFTMAX_WARPS = 8, EPI_WARP0 = 12, PRODUCER_WARP = 16;
 constexpr int THREADS = 32 * (PRODUCER_WARP + 1);
 // TMEM: D1 (scores) 2 window buffers x 4 class pairs x 32 columns at 0 ; D2 (sums) 2 view buffers x 4 class pairs x 32 columns at
 // 256.  Both are M = 128 accumulators (row = lane): rows 0-63 belong to class 2p and are valid in columns 0-15 (hi | lo heads) of
@@ -230,13 +230,14 @@ __device__ __forceinline__ void iu_tmem_st16(uint32_t taddr, const uint32_t (&v)
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void iu_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void iu_bar_sync256(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ bool iu_bar_or(int id, bool pred) {
     uint32_t r;
     asm volatile(
         "{\n"
         ".reg .pred p, q;\n"
         "setp.ne.b32 q, %2, 0;\n"
-        "bar.red.or.pred p, %1, 128, q;\n"
+        "bar.red.or.pred p, %1, 256, q;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(r)
@@ -311,9 +312,9 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
         for (int i = 0; i < RING; ++i) { iu_mbar_init(full + i, 1); iu_mbar_init(empty + i, 1); }
         for (int i = 0; i < 2; ++i) {
             iu_mbar_init(wfull + i, 1); iu_mbar_init(wempty + i, ISSUE_WARPS); iu_mbar_init(d1_full + i, ISSUE_WARPS);
-            iu_mbar_init(d2_full + i, ISSUE_WARPS); iu_mbar_init(d2_empty + i, 4); iu_mbar_init(s0_full + i, 1); iu_mbar_init(l_full + i, 2);
+            iu_mbar_init(d2_full + i, ISSUE_WARPS); iu_mbar_init(d2_empty + i, 4); iu_mbar_init(s0_full + i, 1); iu_mbar_init(l_full + i, 4);
         }
-        for (int i = 0; i < PBUF; ++i) { iu_mbar_init(p_full + i, 4); iu_mbar_init(p_empty + i, ISSUE_WARPS); }
+        for (int i = 0; i < PBUF; ++i) { iu_mbar_init(p_full + i, SOFTMAX_WARPS); iu_mbar_init(p_empty + i, ISSUE_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x) : "memory");
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
     } else if (warp < ISSUE_WARPS) {
         // ===== MMA issuers: warp p owns class pair p (ring slots 4 g + p, D1 / D2 columns of classes 2p, 2p+1); the warp stays
         // converged, lane 0 issues.  Warp 0 also fetches the per-view w_eff planes one view ahead. =====
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");     // the softmax warpgroup takes the registers
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");     // the softmax / epilogue warpgroups take the registers
         const int p = warp;
         constexpr uint32_t IDESC1 = iu_idesc(128, 32, true, false), IDESC2 = iu_idesc(128, 32, false, true);
         // descriptor words (addresses in 16-byte units): SWIZZLE_128B tiles (SBO 1024, version 1, layout 2) and the unswizzled
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
             const uint32_t d2 = tmem + D2_COL + (vp & 1) * D2_BUF_COLS + 32 * p;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if ((j < 3 || wp < NWIN - 1) && !(a.debug & 2))                      // u in [240, 256) does not exist
+                if (!(a.debug & 2))
                     iu_mma_l0(d2, iu_mk64(sa + 2 * j, HI_SW), iu_mk64((pb + 16 * j) | LBO_P, HI_P), IDESC2, (wp > 0 || j > 0) ? 1u : 0u);
             iu_commit_l0(empty + slot);                                              // slot back to the producer once read
             iu_commit_l0(p_empty + pbi);
@@ -419,62 +420,63 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
             g_umma_trace[3] += (unsigned long long)tw3; g_umma_trace[4] += (unsigned long long)tw4;
         }
     } else if (warp >= SOFTMAX_WARP0 && warp < EPI_WARP0) {
-        // ===== softmax: thread (half, r) reads row r of the class-(2p + half) score tiles (TMEM lane 64 half + r) and keeps heads
-        // 4 half .. 4 half + 3 of token 48 w - 7 + r =====
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 160;" ::: "memory");
-        const int q = warp & 3, half = q >> 1, qq = q & 1;
-        const int r = 32 * qq + lane, hb = 4 * half;
+        // ===== softmax: row r of a window is shared by 4 threads (half = class parity, pg = pair group): thread (half, pg, r) reads
+        // row r of the class-(2p + half) score tiles of pairs p = 2 pg, 2 pg + 1 (TMEM lane 64 half + r) and keeps heads
+        // 4 half + 2 pg, + 1 of token 56 w - 7 + r =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;" ::: "memory");
+        const int ws = warp - SOFTMAX_WARP0, q = warp & 3, half = q >> 1, qq = q & 1, pg = ws >> 2;
+        const int r = 32 * qq + lane, hb = 4 * half + 2 * pg, src = 2 * half + pg, wpair = 4 * pg + 2 * half;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         float* halo = reinterpret_cast<float*>(smem + OFF_HALO);
         float* xch = reinterpret_cast<float*>(smem + OFF_XCH);
-        float mref[4], lsum[4], pr[NWIN][4];
+        float mref[2], lsum[2], pr[NWIN][2];
         unsigned g = 0;
         const bool tr_s = tracing && warp == SOFTMAX_WARP0;
         const long long ts0 = tr_s ? clock64() : 0;
         long long ta6 = 0, ta7 = 0, ta8 = 0, ta10 = 0;
         // token of this thread in window w of a view (-1: not in the set), and its position terms, fetched one window ahead
-        auto token_of = [&](int w) { const int t = WSTEP * w - 7 + r; return (r >= (w == 0 ? 7 : 16) && t < HW) ? t : -1; };
-        float ctn[4];
+        auto token_of = [&](int w) { return (r >= 7 && r <= (w == NWIN - 1 ? 63 : 62)) ? WSTEP * w - 7 + r : -1; };
+        float ctn[2];
         auto load_ct = [&](int vi2, int w2) {
             const int t = token_of(w2);
             const int bv2 = blockIdx.x + vi2 * gridDim.x;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) ctn[k] = (t >= 0 && vi2 < nviews) ? __ldg(a.cterm + ((size_t)bv2 * HEADS + hb + k) * TP + 1 + t) : 0.f;
+            for (int k = 0; k < 2; ++k) ctn[k] = (t >= 0 && vi2 < nviews) ? __ldg(a.cterm + ((size_t)bv2 * HEADS + hb + k) * TP + 1 + t) : 0.f;
         };
         load_ct(0, 0);
         for (int vi = 0; vi < nviews; ++vi) {
             const int bv = blockIdx.x + vi * gridDim.x;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { lsum[k] = 0.f; mref[k] = 0.f; }
+            for (int k = 0; k < 2; ++k) { lsum[k] = 0.f; mref[k] = 0.f; }
 #pragma unroll
             for (int w = 0; w < NWIN; ++w, ++g) {
                 const int t = token_of(w);
                 const bool valid = t >= 0;
-                float ct[4];
+                float ct[2];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ct[k] = ctn[k];
+                for (int k = 0; k < 2; ++k) ct[k] = ctn[k];
                 if (w + 1 < NWIN) load_ct(vi, w + 1); else load_ct(vi + 1, 0);
                 { const long long c0_ = tr_s ? clock64() : 0; iu_wait(d1_full + (g & 1), (g >> 1) & 1); if (tr_s) ta6 += clock64() - c0_; }
                 iu_fence_after();
                 const long long cx0 = tr_s ? clock64() : 0;
-                // class exchange: token t needs row r - (7 - s) of class s.  Partial sums over this thread's four classes for all 8
+                // class exchange: token t needs row r - (7 - s) of class s.  Partial sums over this thread's two classes for all 8
                 // heads: lane shifts inside the warp; the first 7 - s lanes of the upper warp take the lower warp's rows from the halo
-                uint32_t v[4][16];
+                uint32_t v[2][16];
 #pragma unroll
-                for (int p = 0; p < 4; ++p) iu_tmem_ld16_async(trow + (g & 1) * D1_BUF_COLS + 32 * p + 16 * half, v[p]);
+                for (int i = 0; i < 2; ++i) iu_tmem_ld16_async(trow + (g & 1) * D1_BUF_COLS + 32 * (2 * pg + i) + 16 * half, v[i]);
                 iu_tmem_wait_ld();
 #pragma unroll
-                for (int p = 0; p < 4; ++p) iu_tmem_use16(v[p]);
+                for (int i = 0; i < 2; ++i) iu_tmem_use16(v[i]);
                 float part[8];
 #pragma unroll
                 for (int h = 0; h < 8; ++h) part[h] = 0.f;
                 float* hw = halo + (half * HALO_ENTRIES) * 8;
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    const int s = 2 * p + half, delta = 7 - s;
+                for (int i = 0; i < 2; ++i) {
+                    const int s = 2 * (2 * pg + i) + half, delta = 7 - s;
                     float xs[8];
 #pragma unroll
-                    for (int h = 0; h < 8; ++h) xs[h] = __uint_as_float(v[p][h]) + __uint_as_float(v[p][8 + h]);
+                    for (int h = 0; h < 8; ++h) xs[h] = __uint_as_float(v[i][h]) + __uint_as_float(v[i][8 + h]);
 #pragma unroll
                     for (int h = 0; h < 8; ++h) {
                         const float y = __shfl_up_sync(FULL, xs[h], delta);      // delta == 0: the value itself
@@ -486,52 +488,55 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                         dst[1] = make_float4(xs[4], xs[5], xs[6], xs[7]);
                     }
                 }
-                // the partial sums of the heads the other thread of this row keeps
-                *reinterpret_cast<float4*>(xch + (half * 64 + r) * 4) =
-                    half ? make_float4(part[0], part[1], part[2], part[3]) : make_float4(part[4], part[5], part[6], part[7]);
-                iu_bar_sync(1);
-                float tot[4];
                 {
-                    const float4 o = *reinterpret_cast<const float4*>(xch + ((half ^ 1) * 64 + r) * 4);
-                    tot[0] = part[hb + 0] + o.x; tot[1] = part[hb + 1] + o.y; tot[2] = part[hb + 2] + o.z; tot[3] = part[hb + 3] + o.w;
+                    float4* dst = reinterpret_cast<float4*>(xch + (src * 64 + r) * 8);
+                    dst[0] = make_float4(part[0], part[1], part[2], part[3]);
+                    dst[1] = make_float4(part[4], part[5], part[6], part[7]);
+                }
+                iu_bar_sync256(1);
+                float tot[2] = {0.f, 0.f};
+#pragma unroll
+                for (int sr = 0; sr < 4; ++sr) {                        // fixed order: the four threads of a row get identical sums
+                    const float2 o = *reinterpret_cast<const float2*>(xch + (sr * 64 + r) * 8 + hb);
+                    tot[0] += o.x; tot[1] += o.y;
                 }
                 if (qq == 1 && lane < 7) {
 #pragma unroll
                     for (int s = 0; s < 7; ++s) {
                         if (lane < 7 - s) {
-                            const float4 x = *reinterpret_cast<const float4*>(halo + (((s & 1) * HALO_ENTRIES) + iu_halo_off(s) + lane) * 8 + hb);
-                            tot[0] += x.x; tot[1] += x.y; tot[2] += x.z; tot[3] += x.w;
+                            const float2 x = *reinterpret_cast<const float2*>(halo + (((s & 1) * HALO_ENTRIES) + iu_halo_off(s) + lane) * 8 + hb);
+                            tot[0] += x.x; tot[1] += x.y;
                         }
                     }
                 }
                 if (tr_s) ta7 += clock64() - cx0;
-                float sc[4];
+                float sc[2];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) sc[k] = valid ? a.scale * (tot[k] + ct[k]) : -INFINITY;
+                for (int k = 0; k < 2; ++k) sc[k] = valid ? a.scale * (tot[k] + ct[k]) : -INFINITY;
                 if (a.dbg != nullptr && valid) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) a.dbg[((size_t)bv * HEADS + hb + k) * 256 + 1 + t] = sc[k];
+                    for (int k = 0; k < 2; ++k) a.dbg[((size_t)bv * HEADS + hb + k) * 256 + 1 + t] = sc[k];
                 }
                 const long long cr0 = tr_s ? clock64() : 0;
                 bool raise = w == 0;
                 if (w > 0) {
                     bool ex = false;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) ex = ex || (sc[k] > mref[k] + TAU);
+                    for (int k = 0; k < 2; ++k) ex = ex || (sc[k] > mref[k] + TAU);
                     raise = iu_bar_or(1, ex);                       // (also orders the exchange reads before the next window's writes)
                 }
                 if (raise) {
                     // window 0 establishes the reference maximum; a later window raises it only in the (rare) case above
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < 2; ++k) {
                         const float x = warp_max(sc[k]);
-                        if (lane == 0) smax[q * 4 + k] = x;
+                        if (lane == 0) smax[ws * 2 + k] = x;
                     }
-                    iu_bar_sync(1);
-                    float fc[4];
+                    iu_bar_sync256(1);
+                    float fc[2];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float wm = fmaxf(smax[(2 * half) * 4 + k], smax[(2 * half + 1) * 4 + k]);
+                    for (int k = 0; k < 2; ++k) {
+                        const float wm = fmaxf(smax[wpair * 2 + k], smax[(wpair + 1) * 2 + k]);
                         const float mn = w == 0 ? wm : fmaxf(mref[k], wm);
                         fc[k] = w == 0 ? 1.f : exp2f((mref[k] - mn) * LOG2E);
                         mref[k] = mn;
@@ -542,16 +547,16 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                         // arrival on p_full), the running sums and the probabilities kept for the final output
                         if (qq == 0 && lane == 0) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) fcs[hb + k] = fc[k];
+                            for (int k = 0; k < 2; ++k) fcs[hb + k] = fc[k];
                         }
-                        iu_bar_sync(1);
+                        iu_bar_sync256(1);
                         float fc8[8];
 #pragma unroll
                         for (int h = 0; h < 8; ++h) fc8[h] = fcs[h];
                         iu_wait(p_empty + ((g - 1) & (PBUF - 1)), ((g - 1) / PBUF) & 1);
                         iu_fence_after();
 #pragma unroll 1
-                        for (int c16 = 0; c16 < 8; ++c16) {
+                        for (int c16 = 4 * pg; c16 < 4 * pg + 4; ++c16) {
                             uint32_t y[16];
                             const uint32_t ta = trow + D2_COL + (vi & 1) * D2_BUF_COLS + 16 * c16;
                             iu_tmem_ld16(ta, y);
@@ -561,19 +566,19 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                         }
                         iu_fence_before();
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
+                        for (int k = 0; k < 2; ++k) {
                             lsum[k] *= fc[k];
 #pragma unroll
                             for (int w2 = 0; w2 < NWIN; ++w2)
                                 if (w2 < w) pr[w2][k] *= fc[k];
                         }
                     }
-                    iu_bar_sync(1);                                 // smax / fcs are rewritten by the next raise
+                    iu_bar_sync256(1);                              // smax / fcs are rewritten by the next raise
                 }
                 if (tr_s) ta10 += clock64() - cr0;
-                unsigned short ph[4], pl[4];
+                unsigned short ph[2], pl[2];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < 2; ++k) {
                     const float p = valid ? exp2f((sc[k] - mref[k]) * LOG2E) : 0.f;
                     lsum[k] += p;
                     pr[w][k] = p;
@@ -582,14 +587,13 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 const unsigned pbi = g & (PBUF - 1);
                 { const long long c0_ = tr_s ? clock64() : 0; iu_wait(p_empty + pbi, ((g / PBUF) & 1) ^ 1); if (tr_s) ta8 += clock64() - c0_; }   // the sums that read this buffer last have completed
                 {
-                    // row r of the hi / lo planes and row r + 1 of their copies: this thread's 4 heads = 8 bytes each
-                    const uint32_t pt = iu_smem(smem + OFF_P) + pbi * P_BYTES + r * 16 + 8 * half;
-                    const uint32_t h01 = (uint32_t)ph[0] | ((uint32_t)ph[1] << 16), h23 = (uint32_t)ph[2] | ((uint32_t)ph[3] << 16);
-                    const uint32_t l01 = (uint32_t)pl[0] | ((uint32_t)pl[1] << 16), l23 = (uint32_t)pl[2] | ((uint32_t)pl[3] << 16);
-                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(pt), "r"(h01), "r"(h23) : "memory");
-                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(pt + P_PLANE), "r"(l01), "r"(l23) : "memory");
-                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(pt + 2 * P_PLANE + 16), "r"(h01), "r"(h23) : "memory");
-                    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(pt + 3 * P_PLANE + 16), "r"(l01), "r"(l23) : "memory");
+                    // row r of the hi / lo planes and row r + 1 of their copies: this thread's 2 heads = 4 bytes each
+                    const uint32_t pt = iu_smem(smem + OFF_P) + pbi * P_BYTES + r * 16 + 2 * hb;
+                    const uint32_t h01 = (uint32_t)ph[0] | ((uint32_t)ph[1] << 16), l01 = (uint32_t)pl[0] | ((uint32_t)pl[1] << 16);
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(pt), "r"(h01) : "memory");
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(pt + P_PLANE), "r"(l01) : "memory");
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(pt + 2 * P_PLANE + 16), "r"(h01) : "memory");
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(pt + 3 * P_PLANE + 16), "r"(l01) : "memory");
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 iu_fence_before();
@@ -598,16 +602,16 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
             }
             // ---- end of the view: total of the running sums, the mean token, final probabilities
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 2; ++k) {
                 const float x = warp_sum(lsum[k]);
-                if (lane == 0) sred[q * 4 + k] = x;
+                if (lane == 0) sred[ws * 2 + k] = x;
             }
-            iu_bar_sync(1);
+            iu_bar_sync256(1);
             iu_wait(s0_full + (vi & 1), (vi >> 1) & 1);
-            float fin[4], p0n[4], lt[4];
+            float fin[2], p0n[2], lt[2];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                lt[k] = sred[(2 * half) * 4 + k] + sred[(2 * half + 1) * 4 + k];
+            for (int k = 0; k < 2; ++k) {
+                lt[k] = sred[wpair * 2 + k] + sred[(wpair + 1) * 2 + k];
                 const float s0 = sm_s0[(vi & 1) * 8 + hb + k];
                 const float mf = fmaxf(mref[k], s0);
                 const float f = exp2f((mref[k] - mf) * LOG2E), p0 = exp2f((s0 - mf) * LOG2E);
@@ -617,7 +621,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
             }
             if (qq == 0 && lane == 0) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { stat_l[(vi & 1) * 8 + hb + k] = lt[k]; stat_m[(vi & 1) * 8 + hb + k] = mref[k]; }
+                for (int k = 0; k < 2; ++k) { stat_l[(vi & 1) * 8 + hb + k] = lt[k]; stat_m[(vi & 1) * 8 + hb + k] = mref[k]; }
                 iu_arrive(l_full + (vi & 1));
             }
 #pragma unroll
@@ -625,7 +629,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 const int t = token_of(w);
                 if (t >= 0) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < 2; ++k) {
                         unsigned short hi, lo;
                         iu_split(pr[w][k] * fin[k], hi, lo);
                         __nv_bfloat16* dst = a.ya_hi + ((size_t)bv * HEADS + hb + k) * YA + C + 1 + t;
@@ -636,7 +640,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
             }
             if (r < 256 - (HW + 1)) {                                   // zero padding of the probability block (the value GEMM reads 256 columns)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < 2; ++k) {
                     __nv_bfloat16* dst = a.ya_hi + ((size_t)bv * HEADS + hb + k) * YA + C + HW + 1 + r;
                     dst[0] = __ushort_as_bfloat16((unsigned short)0);
                     dst[a.ya_plane] = __ushort_as_bfloat16((unsigned short)0);
@@ -644,7 +648,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
             }
             if (r == 0) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < 2; ++k) {
                     unsigned short hi, lo;
                     iu_split(p0n[k], hi, lo);
                     __nv_bfloat16* dst = a.ya_hi + ((size_t)bv * HEADS + hb + k) * YA + C;
@@ -652,7 +656,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     dst[a.ya_plane] = __ushort_as_bfloat16(lo);
                 }
             }
-            iu_bar_sync(1);                                         // sred is rewritten by the next view
+            iu_bar_sync256(1);                                      // sred is rewritten by the next view
         }
         if (tr_s) {
             g_umma_trace[9] += (unsigned long long)(clock64() - ts0);
@@ -661,6 +665,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
         }
     } else if (warp >= EPI_WARP0 && warp < PRODUCER_WARP) {
         // ===== epilogue: mean-token score, then Y = (D2 f + p0 xbar) / L -> bf16 hi/lo planes =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
         const int q = warp & 3, et = threadIdx.x - 32 * EPI_WARP0, half = q >> 1, row = 32 * (q & 1) + lane;   // class row of class 2p + half
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         const bool tr_e = tracing && warp == EPI_WARP0;
