@@ -18,6 +18,7 @@
 
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace pt {
 

@@ -35,7 +35,7 @@
 //                probabilities -> global
 //   warps 12-15  epilogue: mean-token score s0 = w_eff . xbar (CUDA cores, from L2), then per view Y = (D2 f + p0 xbar) / L
 //                from TMEM -> bf16 hi/lo planes for the value-side GEMM (same output format as the mma.sync kernel)
-//   warp 16      TMA producer of the feature tiles: one 16 KB box (64 u x 64 rows x 2 classes) per ring slot, 10 slots
+//   warp 16      TMA producer of the feature tiles: one 16 KB box (64 u x 64 rows x 2 classes) per ring slot, 11 slots
 // Channel order of w_eff columns and of the weighted sums: position 64 s + r  <->  channel s + 8 r (absorbed into the folded
 // GEMM weights on the host, pt_img_pool_params variant 1).
 #include "common.cuh"
@@ -55,7 +55,7 @@ constexpr int NWIN = 4, WSTEP = 56;          // overlapping u-windows per view: 
 constexpr int UCOLS = 232;                   // valid u range of the tensor map: 225 tokens + 7 class shifts
 constexpr int TILE_BYTES = 64 * 128;         // [64 class rows][64 u] bf16, SWIZZLE_128B
 constexpr int SLOT_BYTES = 2 * TILE_BYTES;   // a class pair: rows 0-63 class 2p, rows 64-127 class 2p+1 (one TMA box)
-constexpr int RING = 10;
+constexpr int RING = 11;
 constexpr int WCLASS_BYTES = 16 * 128;       // w_eff rows (hi|lo, head) x 64 class channels
 constexpr int W_BYTES = 8 * WCLASS_BYTES;
 // Probabilities of a token set as the MN-major, unswizzled B operand of the sums (N = 32: both classes of a pair in one MMA):
@@ -65,8 +65,9 @@ constexpr int W_BYTES = 8 * WCLASS_BYTES;
 // (the shifted 16-row k-steps of a class reach 7 rows further).  Buffer = window index mod PBUF.
 constexpr int P_ROWS = 73, P_PLANE = P_ROWS * 16, P_BYTES = 4 * P_PLANE, PBUF = 2;
 // class exchange: halo [half (class parity)][28 (class, row) entries][8 heads] fp32 (rows of the lower warp that the upper warp's first
-// lanes need), xch [source thread of the row (half, pair group)][64 rows][8 heads] fp32 (partial sums over that thread's two classes)
-constexpr int HALO_ENTRIES = 28, HALO_BYTES = 2 * HALO_ENTRIES * 32, XCH_BYTES = 4 * 64 * 32;
+// lanes need), xch [source thread of the row (half, pair group)][64 rows][6 heads] fp32 (partial sums over that thread's two classes
+// for the three head pairs the other threads of the row keep)
+constexpr int HALO_ENTRIES = 28, HALO_BYTES = 2 * HALO_ENTRIES * 32, XCH_BYTES = 4 * 64 * 24;
 constexpr int OFF_RING = 0;
 constexpr int OFF_W = OFF_RING + RING * SLOT_BYTES;
 constexpr int OFF_P = OFF_W + 2 * W_BYTES;
@@ -77,7 +78,7 @@ constexpr int OFF_BAR = OFF_MISC + 1024;
 // mbarriers: full[RING] empty[RING] wfull[2] wempty[2] d1_full[2] p_full[PBUF] p_empty[PBUF] d2_full[2] d2_empty[2] s0_full[2] l_full[2]
 constexpr int NBAR = 2 * RING + 6 + 2 * PBUF + 8;
 constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
-constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;      // + slack for the 1024-byte alignment of the swizzled tiles
+constexpr int SMEM_BYTES = OFF_TMEM + 16;             // no slack: the dynamic shared memory window itself is 1024-byte aligned (checked)
 // warp roles: 0-3 = MMA issuers (one per class pair; warp 0 also TMA of w_eff + TMEM allocation), 4-11 softmax, 12-15 epilogue
 // (TMEM lane quarter = warp mod 4), 16 = TMA producer
 constexpr int ISSUE_WARPS = 4, SOFTMAX_WARP0 = 4, SOFTMAX_WARPS = 8, EPI_WARP0 = 12, PRODUCER_WARP = 16;
@@ -268,14 +269,20 @@ struct UmmaPoolArgs {
     int BV;
     float scale;
     float* dbg;                  // optional (PT_POOL_DEBUG bit 64): [BV][8][256] scaled scores, attention tokens 0..225
-    int debug;                   // PT_UMMA_DEBUG bring-up switches (garbage results): 1 no score MMAs, 2 no sum MMAs
+    int debug;                   // PT_UMMA_DEBUG bring-up switches (garbage results): 1 no score MMAs, 2 no sum MMAs, 16 per-role trace (trace
+                                 // build), timing probes: 32 no halo reads, 64 no raise vote, 128 no final probability stores, 256 no s0, 512 no Y stores
 };
 
 // Per-role cycle trace of CTA 0 (PT_UMMA_DEBUG bit 16): SM clocks spent in each wait / work section, summed over its views;
 // read with pt_debug_umma_trace.  Slots: 0 producer wait empty | 1 issuer wait full, 2 wait p_full, 3 wait wfull, 4 wait d2_empty,
 // 5 issuer total | 6 softmax wait d1_full, 7 class exchange (tmem loads + shuffles + barrier), 8 wait p_empty, 9 softmax total,
 // 10 bar_or / raise | 11 epilogue s0, 12 wait l_full, 13 wait d2_full, 14 epilogue store, 15 epilogue total
-__device__ unsigned long long g_umma_trace[16];
+#ifdef PT_UMMA_TRACE
+#define PT_UMMA_TRACE_ON 1
+#else
+#define PT_UMMA_TRACE_ON 0      // build with PT_NVCC_DEFINES=-DPT_UMMA_TRACE (tools/umma_trace.py): the timers cost issue slots in every CTA
+#endif
+__device__ unsigned long long g_umma_trace[24];   // 16..23: softmax sub-sections (tmem load | shuffles + stores | barrier | gather | exp + split | stores + fences + arrive | end of view)
 // (accumulated in registers, written once at the end of the role: a global read-modify-write per section would itself cost an
 // L2 round trip)
 #define UT(acc, stmt) do { const long long ut0_ = tracing ? clock64() : 0; stmt; if (tracing) acc += clock64() - ut0_; } while (0)
@@ -285,8 +292,8 @@ __host__ __device__ constexpr int iu_halo_off(int s) { return 7 * s - s * (s - 1
 
 __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __grid_constant__ UmmaPoolMaps maps, const UmmaPoolArgs a) {
     using namespace ipu;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if (threadIdx.x == 0 && (iu_smem(smem) & 1023u) != 0u) __trap();      // SWIZZLE_128B tiles need a 1024-byte aligned base
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* empty = full + RING;
     uint64_t* wfull = empty + RING;
@@ -331,7 +338,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
     iu_fence_after();
     const uint32_t tmem = *tmem_slot;
     const int nviews = (int)blockIdx.x < a.BV ? (a.BV - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const bool tracing = (a.debug & 16) && blockIdx.x == 0 && (lane == 0);
+    const bool tracing = PT_UMMA_TRACE_ON && (a.debug & 16) && blockIdx.x == 0 && (lane == 0);
 
     if (warp == PRODUCER_WARP) {
         // ===== TMA producer: window w, class pair p of the view -> ring slot (4 g + p) mod RING =====
@@ -433,7 +440,9 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
         unsigned g = 0;
         const bool tr_s = tracing && warp == SOFTMAX_WARP0;
         const long long ts0 = tr_s ? clock64() : 0;
-        long long ta6 = 0, ta7 = 0, ta8 = 0, ta10 = 0;
+        long long ta6 = 0, ta7 = 0, ta8 = 0, ta10 = 0, tb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define TB(i) do { if (tr_s) { const long long n_ = clock64(); tb[i] += n_ - tbp; tbp = n_; } } while (0)
+        long long tbp = 0;
         // token of this thread in window w of a view (-1: not in the set), and its position terms, fetched one window ahead
         auto token_of = [&](int w) { return (r >= 7 && r <= (w == NWIN - 1 ? 63 : 62)) ? WSTEP * w - 7 + r : -1; };
         float ctn[2];
@@ -458,7 +467,16 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 if (w + 1 < NWIN) load_ct(vi, w + 1); else load_ct(vi + 1, 0);
                 { const long long c0_ = tr_s ? clock64() : 0; iu_wait(d1_full + (g & 1), (g >> 1) & 1); if (tr_s) ta6 += clock64() - c0_; }
                 iu_fence_after();
+                if (a.debug & 4096) {                                   // timing probe: no softmax work at all, the window is handed on at once
+                    const unsigned pbi0 = g & (PBUF - 1);
+                    iu_wait(p_empty + pbi0, ((g / PBUF) & 1) ^ 1);
+                    iu_fence_before();
+                    __syncwarp();
+                    if (lane == 0) iu_arrive(p_full + pbi0);
+                    continue;
+                }
                 const long long cx0 = tr_s ? clock64() : 0;
+                tbp = cx0;
                 // class exchange: token t needs row r - (7 - s) of class s.  Partial sums over this thread's two classes for all 8
                 // heads: lane shifts inside the warp; the first 7 - s lanes of the upper warp take the lower warp's rows from the halo
                 uint32_t v[2][16];
@@ -467,6 +485,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 iu_tmem_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 2; ++i) iu_tmem_use16(v[i]);
+                TB(0);
                 float part[8];
 #pragma unroll
                 for (int h = 0; h < 8; ++h) part[h] = 0.f;
@@ -489,27 +508,40 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     }
                 }
                 {
-                    float4* dst = reinterpret_cast<float4*>(xch + (src * 64 + r) * 8);
-                    dst[0] = make_float4(part[0], part[1], part[2], part[3]);
-                    dst[1] = make_float4(part[4], part[5], part[6], part[7]);
-                }
-                iu_bar_sync256(1);
-                float tot[2] = {0.f, 0.f};
+                    // this thread keeps head pair `src`; the other three pairs go to the row's three float2 slots (24-byte pitch:
+                    // 8-byte accesses of a warp spread over all banks)
+                    float* row = xch + (src * 64 + r) * 6;
 #pragma unroll
-                for (int sr = 0; sr < 4; ++sr) {                        // fixed order: the four threads of a row get identical sums
-                    const float2 o = *reinterpret_cast<const float2*>(xch + (sr * 64 + r) * 8 + hb);
-                    tot[0] += o.x; tot[1] += o.y;
+                    for (int j = 0; j < 4; ++j)
+                        if (j != src) *reinterpret_cast<float2*>(row + 2 * (j < src ? j : j - 1)) = make_float2(part[2 * j], part[2 * j + 1]);
                 }
-                if (qq == 1 && lane < 7) {
+                TB(1);
+                iu_bar_sync256(1);
+                TB(2);
+                float tot[2] = {0.f, 0.f};
+                {
+                    float2 o[4];
+#pragma unroll
+                    for (int sr = 0; sr < 4; ++sr)
+                        o[sr] = sr == src ? make_float2(part[2 * sr], part[2 * sr + 1])     // (static register index: sr is unrolled)
+                                          : *reinterpret_cast<const float2*>(xch + (sr * 64 + r) * 6 + 2 * (src < sr ? src : src - 1));
+#pragma unroll
+                    for (int sr = 0; sr < 4; ++sr) { tot[0] += o[sr].x; tot[1] += o[sr].y; }
+                }
+                if (qq == 1 && !(a.debug & 32)) {                       // rows 32..38 take the lower warp's rows of the classes with 7 - s > lane
+                    float2 x[7];
 #pragma unroll
                     for (int s = 0; s < 7; ++s) {
-                        if (lane < 7 - s) {
-                            const float2 x = *reinterpret_cast<const float2*>(halo + (((s & 1) * HALO_ENTRIES) + iu_halo_off(s) + lane) * 8 + hb);
-                            tot[0] += x.x; tot[1] += x.y;
-                        }
+                        const bool need = lane < 7 - s;
+                        const float2* src2 = reinterpret_cast<const float2*>(halo + (((s & 1) * HALO_ENTRIES) + iu_halo_off(s) + (need ? lane : 0)) * 8 + hb);
+                        x[s] = *src2;
+                        if (!need) x[s] = make_float2(0.f, 0.f);
                     }
+#pragma unroll
+                    for (int s = 0; s < 7; ++s) { tot[0] += x[s].x; tot[1] += x[s].y; }
                 }
                 if (tr_s) ta7 += clock64() - cx0;
+                TB(3);
                 float sc[2];
 #pragma unroll
                 for (int k = 0; k < 2; ++k) sc[k] = valid ? a.scale * (tot[k] + ct[k]) : -INFINITY;
@@ -523,7 +555,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     bool ex = false;
 #pragma unroll
                     for (int k = 0; k < 2; ++k) ex = ex || (sc[k] > mref[k] + TAU);
-                    raise = iu_bar_or(1, ex);                       // (also orders the exchange reads before the next window's writes)
+                    raise = (a.debug & 64) ? false : iu_bar_or(1, ex);   // (also orders the exchange reads before the next window's writes)
                 }
                 if (raise) {
                     // window 0 establishes the reference maximum; a later window raises it only in the (rare) case above
@@ -576,6 +608,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     iu_bar_sync256(1);                              // smax / fcs are rewritten by the next raise
                 }
                 if (tr_s) ta10 += clock64() - cr0;
+                if (tr_s) tbp = clock64();
                 unsigned short ph[2], pl[2];
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
@@ -585,7 +618,9 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     iu_split(p, ph[k], pl[k]);
                 }
                 const unsigned pbi = g & (PBUF - 1);
-                { const long long c0_ = tr_s ? clock64() : 0; iu_wait(p_empty + pbi, ((g / PBUF) & 1) ^ 1); if (tr_s) ta8 += clock64() - c0_; }   // the sums that read this buffer last have completed
+                TB(4);
+                { const long long c0_ = tr_s ? clock64() : 0; iu_wait(p_empty + pbi, ((g / PBUF) & 1) ^ 1); if (tr_s) ta8 += clock64() - c0_; }
+                if (tr_s) tbp = clock64();   // the sums that read this buffer last have completed
                 {
                     // row r of the hi / lo planes and row r + 1 of their copies: this thread's 2 heads = 4 bytes each
                     const uint32_t pt = iu_smem(smem + OFF_P) + pbi * P_BYTES + r * 16 + 2 * hb;
@@ -599,6 +634,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 iu_fence_before();
                 __syncwarp();
                 if (lane == 0) iu_arrive(p_full + pbi);
+                TB(5);
             }
             // ---- end of the view: total of the running sums, the mean token, final probabilities
 #pragma unroll
@@ -627,7 +663,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
 #pragma unroll
             for (int w = 0; w < NWIN; ++w) {
                 const int t = token_of(w);
-                if (t >= 0) {
+                if (t >= 0 && !(a.debug & 128)) {
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         unsigned short hi, lo;
@@ -657,11 +693,13 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 }
             }
             iu_bar_sync256(1);                                      // sred is rewritten by the next view
+            TB(6);
         }
         if (tr_s) {
             g_umma_trace[9] += (unsigned long long)(clock64() - ts0);
             g_umma_trace[6] += (unsigned long long)ta6; g_umma_trace[7] += (unsigned long long)ta7;
             g_umma_trace[8] += (unsigned long long)ta8; g_umma_trace[10] += (unsigned long long)ta10;
+            for (int i = 0; i < 8; ++i) g_umma_trace[16 + i] += (unsigned long long)tb[i];
         }
     } else if (warp >= EPI_WARP0 && warp < PRODUCER_WARP) {
         // ===== epilogue: mean-token score, then Y = (D2 f + p0 xbar) / L -> bf16 hi/lo planes =====
@@ -674,7 +712,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
         for (int vi = 0; vi < nviews; ++vi) {
             const int bv = blockIdx.x + vi * gridDim.x;
             const long long ce0 = tr_e ? clock64() : 0;
-            {   // s0[h] = scale (w_eff[h] . xbar + cterm[h][0]); this thread: columns 4 et .. 4 et + 3 (class et >> 4, rows 4 (et & 15)..)
+            if (!(a.debug & 256)) {   // s0[h] = scale (w_eff[h] . xbar + cterm[h][0]); this thread: columns 4 et .. 4 et + 3 (class et >> 4, rows 4 (et & 15)..)
                 const int c0 = 4 * et, cls = c0 >> 6, r0 = c0 & 63;
                 float xb[4];
 #pragma unroll
@@ -705,6 +743,9 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     }
                     iu_arrive(s0_full + (vi & 1));
                 }
+            } else if (et == 0) {
+                for (int h = 0; h < 8; ++h) sm_s0[(vi & 1) * 8 + h] = 0.f;
+                iu_arrive(s0_full + (vi & 1));
             }
             const long long ce1 = tr_e ? clock64() : 0;
             iu_wait(l_full + (vi & 1), (vi >> 1) & 1);
@@ -735,6 +776,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     unsigned short hi, lo;
                     iu_split(val, hi, lo);
                     __nv_bfloat16* dst = a.ya_hi + ((size_t)bv * HEADS + h) * YA + cp;
+                    if (a.debug & 512) continue;
                     dst[0] = __ushort_as_bfloat16(hi);
                     dst[a.ya_plane] = __ushort_as_bfloat16(lo);
                 }
@@ -761,10 +803,10 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
 
 // ---------------------------------------------------------------------------------------------- host
 }  // namespace pt
-extern "C" int pt_debug_umma_trace(unsigned long long* out16, int reset) {
+extern "C" int pt_debug_umma_trace(unsigned long long* out16, int reset) {   // 24 slots
     if (out16 && cudaMemcpyFromSymbol(out16, pt::g_umma_trace, sizeof(pt::g_umma_trace)) != cudaSuccess) return PT_ERR_CUDA;
     if (reset) {
-        unsigned long long z[16] = {};
+        unsigned long long z[24] = {};
         if (cudaMemcpyToSymbol(pt::g_umma_trace, z, sizeof(z)) != cudaSuccess) return PT_ERR_CUDA;
     }
     return PT_OK;

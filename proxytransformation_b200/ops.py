@@ -249,12 +249,12 @@ def make_img_params(w: Dict[str, torch.Tensor]) -> ImgPoolParams:
 
 
 def img_pool_variant() -> int:
-    """Pooling kernel of the 16-bit image path: the mma.sync kernel fed by bulk copies (csrc/imgpool_tc.cu, 0.72 ms per 64
-    scenes) unless PT_POOL_KERNEL=umma selects the tcgen05 / TMEM kernel (csrc/imgpool_umma.cu: correct, parity-tested, 1.6 x
-    slower — its loaders have to realign the 450-byte-pitch rows through registers).  Read when the weights
-    are packed (the folded channel orders depend on it)."""
+    """Pooling kernel of the 16-bit image path: the tcgen05 / TMEM kernel fed by TMA in class-aligned coordinates
+    (csrc/imgpool_umma.cu, 0.60 ms per 64 scenes at the benchmark shape) unless PT_POOL_KERNEL=mma selects the mma.sync kernel
+    fed by bulk copies (csrc/imgpool_tc.cu, 0.73 ms).  Both are parity-tested.  Read when the weights are packed (the folded
+    channel orders depend on it)."""
     import os
-    return _lib.PT_POOL_VARIANT_UMMA if os.environ.get("PT_POOL_KERNEL", "mma") == "umma" else _lib.PT_POOL_VARIANT_MMA
+    return _lib.PT_POOL_VARIANT_MMA if os.environ.get("PT_POOL_KERNEL", "umma") == "mma" else _lib.PT_POOL_VARIANT_UMMA
 
 
 def img_pool_channel_orders(device=None, variant: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:

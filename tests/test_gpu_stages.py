@@ -358,7 +358,7 @@ def test_image_proxies_many_views_per_cta(B, V, dtype, kernel, monkeypatch):
     hit (ring wrap-around, double-buffered per-view operands, barrier parities of the second and later views).  Compared
     against the oracle's reference formulation (:154-177, :335-342: conv + 226-token MHA, token 0) on identically rounded
     features; V = 196 is the headline configuration's view count.  LayerNorm-ed outputs, tolerance 6e-5.  `kernel`: the shipped
-    mma.sync pool kernel and the opt-in tcgen05 / TMEM one (PT_POOL_KERNEL=umma, csrc/imgpool_umma.cu)."""
+    tcgen05 / TMEM pool kernel (csrc/imgpool_umma.cu) and the mma.sync one (PT_POOL_KERNEL=mma, csrc/imgpool_tc.cu)."""
     monkeypatch.setenv("PT_POOL_KERNEL", kernel)
     cfg = syn.C2_WIDE.replace(n_views=V)
     sd = syn.make_state_dict(cfg, 31, bf16_round=True)
@@ -375,7 +375,7 @@ def test_image_proxies_many_views_per_cta(B, V, dtype, kernel, monkeypatch):
 
 
 def test_image_pool_tcgen05_kernel_raises_its_reference_maximum():
-    """The tcgen05 pool kernel exponentiates against a per-view reference maximum taken from the first 64 tokens and raises it
+    """The tcgen05 pool kernel exponentiates against a per-view reference maximum taken from its first window (57 tokens) and raises it
     (rescaling the accumulators in TMEM) only when a later window exceeds it by more than 16: drive that path with views whose
     late tokens score far above the early ones (features growing 40 x along the token axis).  With features of that size both
     kernels sit 9e-4 from the oracle's reference formulation (the error of the folded fp32 projections scales with the feature

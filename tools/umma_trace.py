@@ -14,14 +14,16 @@ m = m.cuda()
 img = (torch.relu(torch.randn(B, cfg.n_views, 512, 15, 15, device="cuda")) * 1.5).bfloat16()
 m.get_img_proxy(img); torch.cuda.synchronize()
 L = _lib.load()
-buf = (ctypes.c_ulonglong * 16)()
+buf = (ctypes.c_ulonglong * 24)()
 L.pt_debug_umma_trace(buf, 1)
 m.get_img_proxy(img); torch.cuda.synchronize()
 L.pt_debug_umma_trace(buf, 0)
 views = -(-B * cfg.n_views // 148)
 names = ["producer: wait empty", "issuer: wait full", "issuer: wait p_full", "issuer: wait wfull", "issuer: wait d2_empty", "issuer: total",
          "softmax: wait d1_full", "softmax: class exchange", "softmax: wait p_empty", "softmax: total", "softmax: bar_or/raise",
-         "epilogue: s0", "epilogue: wait l_full", "epilogue: wait d2_full", "epilogue: store", "epilogue: total"]
+         "epilogue: s0", "epilogue: wait l_full", "epilogue: wait d2_full", "epilogue: store", "epilogue: total",
+         "  softmax: tmem load", "  softmax: shuffles+stores", "  softmax: exchange barrier", "  softmax: gather", "  softmax: exp+split",
+         "  softmax: P stores+arrive", "  softmax: end of view", "-"]
 for n, v in zip(names, buf):
     print(f"{n:28s} {v / views:9.0f} cycles/view")
 _lib.profile_enable(True)
