@@ -35,6 +35,7 @@ extern "C" {
 
 #define PT_DTYPE_F32 0
 #define PT_DTYPE_BF16 1
+#define PT_DTYPE_F16 2   /* image features only: tensor-core pooling path (tcgen05 kernel), what the reference's --amp backbone emits */
 
 typedef void* pt_stream_t; /* cudaStream_t */
 

@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_size
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libptpreshape.so")
 
-PT_DTYPE_F32, PT_DTYPE_BF16 = 0, 1
+PT_DTYPE_F32, PT_DTYPE_BF16, PT_DTYPE_F16 = 0, 1, 2
 PT_POOL_VARIANT_MMA, PT_POOL_VARIANT_UMMA = 0, 1
 
 

@@ -17,6 +17,7 @@
 #include "gemm_tc.cuh"
 
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -100,6 +101,7 @@ struct TcKernelArgs {
     const float* residual;                 // same layout as C (ldc, c_off_z); may alias C
     float* C; int ldc; long long c_off_z;
     __nv_bfloat16* Cs; long long cs_plane; int ldcs; long long cs_off_z;     // optional bf16 hi/lo planes of the result
+    int cs_fp16; float cs_scale;                                             // ... as IEEE half planes of cs_scale * result
     __nv_bfloat16* Ct; int ct_col0; long long ct_ld, ct_plane;               // optional transposed planes for columns >= ct_col0
     int act;
     int tiles_m, tiles_n, stages;
@@ -276,11 +278,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                         if (g.C != nullptr) *reinterpret_cast<float4*>(g.C + coff) = make_float4(y[0], y[1], y[2], y[3]);
                         if (SPLIT) {
                             __nv_bfloat16* shi = g.Cs + (size_t)z * g.cs_off_z + (size_t)row * g.ldcs + n;
-                            __nv_bfloat16 h[4], l[4];
+                            if (g.cs_fp16) {
+                                __half h[4], l[4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) { h[e] = __float2bfloat16_rn(y[e]); l[e] = __float2bfloat16_rn(y[e] - __bfloat162float(h[e])); }
-                            *reinterpret_cast<uint2*>(shi) = *reinterpret_cast<const uint2*>(h);
-                            *reinterpret_cast<uint2*>(shi + g.cs_plane) = *reinterpret_cast<const uint2*>(l);
+                                for (int e = 0; e < 4; ++e) { const float v = y[e] * g.cs_scale; h[e] = __float2half_rn(v); l[e] = __float2half_rn(v - __half2float(h[e])); }
+                                *reinterpret_cast<uint2*>(shi) = *reinterpret_cast<const uint2*>(h);
+                                *reinterpret_cast<uint2*>(shi + g.cs_plane) = *reinterpret_cast<const uint2*>(l);
+                            } else {
+                                __nv_bfloat16 h[4], l[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) { h[e] = __float2bfloat16_rn(y[e]); l[e] = __float2bfloat16_rn(y[e] - __bfloat162float(h[e])); }
+                                *reinterpret_cast<uint2*>(shi) = *reinterpret_cast<const uint2*>(h);
+                                *reinterpret_cast<uint2*>(shi + g.cs_plane) = *reinterpret_cast<const uint2*>(l);
+                            }
                         }
                     }
                 }
@@ -442,6 +452,7 @@ int launch_gemm_tc_ex(const GemmTc& p, cudaStream_t s) {
     k.bias = p.bias; k.bias_off_z = p.bias_off_z; k.residual = p.residual;
     k.C = p.C; k.ldc = p.ldc; k.c_off_z = p.c_off_z;
     k.Cs = (__nv_bfloat16*)p.c_split; k.cs_plane = p.cs_plane; k.ldcs = p.ldcs; k.cs_off_z = p.cs_off_z;
+    k.cs_fp16 = p.cs_fp16 ? 1 : 0; k.cs_scale = p.cs_scale;
     k.act = p.act;
     k.Ct = (__nv_bfloat16*)p.ct_split; k.ct_col0 = p.ct_col0; k.ct_ld = p.ct_ld; k.ct_plane = p.ct_plane;
     k.tiles_m = ceil_div(p.M, TC_BM);

@@ -27,6 +27,10 @@ struct GemmTc {
     long long cs_plane = 0;
     int ldcs = 0;
     long long cs_off_z = 0;
+    // the split planes as IEEE half instead of bfloat16, of cs_scale * result (cs_scale a power of two that keeps the lo halves out of
+    // the half subnormals; the consumer folds 1 / cs_scale).  Used for the w_eff planes of fp16 image features.
+    bool cs_fp16 = false;
+    float cs_scale = 1.0f;
     // optional TRANSPOSED bf16 hi/lo planes for the output columns n >= ct_col0 (those columns are then written nowhere
     // else): element (row, n) goes to ct_split[(n - ct_col0) * ct_ld + row], lo plane ct_plane elements later.  No bias /
     // activation / residual on these columns.  Used for V^T, the K-major value operand of the tcgen05 attention.

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(PB_THREADS) img_pool_kernel(const void* __rest
 
 size_t img_attnpool_tc_ws_bytes(int BV);
 bool img_attnpool_tc_supported(int img_dtype, const pt_img_pool_params* p, int C, int HW, int c, int heads);
-int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, int BV, float* img_proxy, void* ws, size_t ws_bytes, int stages,
+int launch_img_attnpool_tc(const void* img_feat, int img_dtype, const pt_img_pool_params* p, int BV, float* img_proxy, void* ws, size_t ws_bytes, int stages,
                            cudaStream_t s);
 
 static size_t pool_smem_bytes(int HW, int Tp) {
@@ -247,10 +247,12 @@ extern "C" int pt_img_attnpool(const void* img_feat, int img_dtype, const pt_img
 extern "C" int pt_img_attnpool_stage(const void* img_feat, int img_dtype, const pt_img_pool_params* p, int BV, int C, int HW,
                                      int c, int heads, float* img_proxy, void* ws, size_t ws_bytes, int stages, pt_stream_t stream) {
     PT_REQUIRE(img_feat && p && img_proxy && ws, "pt_img_attnpool: null pointer");
-    PT_REQUIRE(img_dtype == PT_DTYPE_F32 || img_dtype == PT_DTYPE_BF16, "pt_img_attnpool: dtype %d", img_dtype);
+    PT_REQUIRE(img_dtype == PT_DTYPE_F32 || img_dtype == PT_DTYPE_BF16 || img_dtype == PT_DTYPE_F16, "pt_img_attnpool: dtype %d", img_dtype);
     PT_REQUIRE(stages >= 1 && stages <= 3, "pt_img_attnpool_stage: stages=%d", stages);
-    if (BV > 0 && img_attnpool_tc_supported(img_dtype, p, C, HW, c, heads))      // bf16 tensor-core fast path (imgpool_tc.cu)
-        return launch_img_attnpool_tc(img_feat, p, BV, img_proxy, ws, ws_bytes, stages, (cudaStream_t)stream);
+    if (BV > 0 && img_attnpool_tc_supported(img_dtype, p, C, HW, c, heads))      // 16-bit tensor-core fast path (imgpool_tc.cu)
+        return launch_img_attnpool_tc(img_feat, img_dtype, p, BV, img_proxy, ws, ws_bytes, stages, (cudaStream_t)stream);
+    PT_REQUIRE(img_dtype != PT_DTYPE_F16, "pt_img_attnpool: fp16 features need the tcgen05 pooling path (shipped geometry C=512, 15x15, c=256, 8 heads, "
+                                          "split weights, variant PT_POOL_VARIANT_UMMA); convert to fp32 otherwise");
     if (!(stages & PT_IMG_STAGE_BACK)) return PT_OK;                              // generic path: everything runs in the back stage
     PT_REQUIRE(heads == PB_HEADS, "pt_img_attnpool: heads=%d unsupported (8)", heads);
     PT_REQUIRE(BV > 0 && C % PB_CH == 0 && c % heads == 0 && HW >= 1 && HW <= PB_THREADS,

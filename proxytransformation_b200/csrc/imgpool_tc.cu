@@ -20,6 +20,7 @@
 //               (pt_img_pool_params: wk_pad_split rows, wv_cat_split columns).
 //   G4-G5   z_h = [y_h | a_h] [W_vc_h | h_v_h]^T ; o = W_c z + b_c ; LayerNorm                      (gemm_tc.cu, dense.cu)
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include "gemm_tc.cuh"
 
 #include <math.h>
@@ -29,7 +30,8 @@ namespace pt {
 
 int launch_layernorm(const float* x, const float* w, const float* b, const float* add, int add_rows, int rows, int c,
                      float* out, cudaStream_t s);
-int launch_img_pool_umma(const void* img_feat, const __nv_bfloat16* wpl, const float* cterm, const float* xbar, __nv_bfloat16* ya_hi,
+constexpr float UMMA_FP16_WSCALE = 16.0f;       // scale of the half w_eff planes (launch_img_attnpool_tc G2 <-> imgpool_umma.cu)
+int launch_img_pool_umma(const void* img_feat, bool fp16, float wscale, const __nv_bfloat16* wpl, const float* cterm, const float* xbar, __nv_bfloat16* ya_hi,
                          long long ya_plane, int BV, float* dbg, cudaStream_t s);      // imgpool_umma.cu
 
 namespace ip {
@@ -128,6 +130,8 @@ __device__ __forceinline__ void split_hi_lo(float x, uint32_t& hi, uint32_t& lo)
 // ------------------------------------------------------------------------------------------------ pass A
 // One warp per group of 8 channels (1800 bf16 = 225 uint4, 16-byte aligned).  Iteration i of a lane reads uint4
 // lane + 32 i, whose 8 elements belong to channel i or i+1 of the group only, so the 8 running sums are static registers.
+// FP16: the 16-bit elements are IEEE half instead of bfloat16 (features of an autocast backbone).
+template <bool FP16>
 __global__ void __launch_bounds__(256) img_mean_bf16_kernel(const uint4* __restrict__ img, long long groups,
                                                             float* __restrict__ xbar, __nv_bfloat16* __restrict__ xb_hi,
                                                             __nv_bfloat16* __restrict__ xb_lo) {
@@ -151,7 +155,14 @@ __global__ void __launch_bounds__(256) img_mean_bf16_kernel(const uint4* __restr
             const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
             float f[8];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { f[2 * e] = __uint_as_float(w[e] << 16); f[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
+            for (int e = 0; e < 4; ++e) {
+                if (FP16) {
+                    const float2 h2 = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
+                    f[2 * e] = h2.x; f[2 * e + 1] = h2.y;
+                } else {
+                    f[2 * e] = __uint_as_float(w[e] << 16); f[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+                }
+            }
             const float s_all = ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
             const int nlo = min(max(225 * (i + 1) - 8 * j, 0), 8);       // elements of this uint4 that belong to channel i
             if (nlo == 8) acc[i] += s_all;
@@ -646,12 +657,16 @@ static ImgTcWs carve_tc(void* ws, int BV) {
 size_t img_attnpool_tc_ws_bytes(int BV) { return carve_tc(nullptr, BV).total; }
 
 bool img_attnpool_tc_supported(int img_dtype, const pt_img_pool_params* p, int C, int HW, int c, int heads) {
-    return img_dtype == PT_DTYPE_BF16 && C == ip::C && HW == ip::HW && c == ip::EMB && heads == ip::HEADS && p->w_qc_split &&
+    // fp16 features: the tcgen05 kernel only (its feature tiles are the A operand of both contractions; kind::f16 takes an f16 A
+    // next to bf16 B operands), the mma.sync kernel is bf16 x bf16
+    const bool dtype_ok = img_dtype == PT_DTYPE_BF16 || (img_dtype == PT_DTYPE_F16 && p->variant == PT_POOL_VARIANT_UMMA);
+    return dtype_ok && C == ip::C && HW == ip::HW && c == ip::EMB && heads == ip::HEADS && p->w_qc_split &&
            p->wk_pad_split && p->gk_pad_split && p->wv_cat_split && p->cproj_split;
 }
 
-int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, int BV, float* img_proxy, void* ws, size_t ws_bytes,
+int launch_img_attnpool_tc(const void* img_feat, int img_dtype, const pt_img_pool_params* p, int BV, float* img_proxy, void* ws, size_t ws_bytes,
                            int stages, cudaStream_t s) {
+    const bool fp16 = img_dtype == PT_DTYPE_F16;
     using namespace ip;
     PT_REQUIRE(((uintptr_t)img_feat & 15) == 0, "pt_img_attnpool: img_feat must be 16-byte aligned");
     ImgTcWs w = carve_tc(ws, BV);
@@ -670,7 +685,8 @@ int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, in
         static const int per_sm = [] { const char* e = getenv("PT_MEAN_CTAS"); const int v = e ? atoi(e) : 8; return v >= 1 && v <= 8 ? v : 8; }();
         const int grid = (int)(blocks < (long long)sms * per_sm ? blocks : (long long)sms * per_sm);
         ProfScope prof_(PROF_IMG_MEAN, s);
-        img_mean_bf16_kernel<<<grid, 256, 0, s>>>((const uint4*)img_feat, groups, w.xbar, w.xbar_split, w.xbar_split + (size_t)BV * C);
+        if (fp16) img_mean_bf16_kernel<true><<<grid, 256, 0, s>>>((const uint4*)img_feat, groups, w.xbar, w.xbar_split, w.xbar_split + (size_t)BV * C);
+        else img_mean_bf16_kernel<false><<<grid, 256, 0, s>>>((const uint4*)img_feat, groups, w.xbar, w.xbar_split, w.xbar_split + (size_t)BV * C);
     }
     PT_LAUNCH_CHECK();
     {   // G1: q = xbar W_qc^T + q0  -> split planes only
@@ -691,6 +707,9 @@ int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, in
         // (the tcgen05 pool kernel reads the planes through a tensor map: unpadded rows of 512)
         const int wpitch = umma ? C : WPITCH;
         gp.c_split = w.wpl; gp.cs_plane = HEADS * wpitch; gp.ldcs = 2 * HEADS * wpitch; gp.cs_off_z = wpitch;
+        // fp16 features: kind::f16 wants both MMA operands in the same 16-bit format, so the planes are IEEE half (x 16: |w_eff| < 4094,
+        // lo halves clear of the half subnormals down to |w_eff| ~ 1e-2; the pool kernel folds the 1/16 into its score scale)
+        gp.cs_fp16 = fp16; gp.cs_scale = fp16 ? UMMA_FP16_WSCALE : 1.0f;
         if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
     }
     {   // G3: cterm[:, h, t] = q[:, 32h:32h+32] . g_k[t, 32h:32h+32]
@@ -706,7 +725,7 @@ int launch_img_attnpool_tc(const void* img_feat, const pt_img_pool_params* p, in
     if (umma) {   // pass B on tcgen05 tensor cores, TMA-fed (imgpool_umma.cu)
         const char* dbg = getenv("PT_POOL_DEBUG");
         float* dump = dbg && (atoi(dbg) & 64) && ws_bytes >= w.total + (size_t)BV * DBG_PER_VIEW * 4 ? reinterpret_cast<float*>((char*)ws + w.total) : nullptr;
-        if ((rc = launch_img_pool_umma(img_feat, w.wpl, w.cterm, w.xbar, w.ya_split, (long long)BV * HEADS * YA, BV, dump, s))) return rc;
+        if ((rc = launch_img_pool_umma(img_feat, fp16, fp16 ? UMMA_FP16_WSCALE : 1.0f, w.wpl, w.cterm, w.xbar, w.ya_split, (long long)BV * HEADS * YA, BV, dump, s))) return rc;
     } else {   // pass B, mma.sync form
         static bool attr_set[PT_MAX_DEVICES] = {};
         if (first_use_on_current_device(attr_set))

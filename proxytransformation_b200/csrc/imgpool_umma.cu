@@ -42,6 +42,7 @@
 #include "gemm_tc.cuh"
 
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -196,6 +197,9 @@ __device__ __forceinline__ uint64_t iu_desc_mn_noswz(uint32_t saddr, uint32_t lb
 }
 // kind::f16 instruction descriptor: D = f32, A = B = bf16; bit 15 = A is MN-major, bit 16 = B is MN-major; N >> 3 at bit 17,
 // M >> 4 at bit 24.
+// (A / B formats at bits 7 / 10: 1 = bf16 here; IU_AB_FP16 clears both: features, w_eff planes and probabilities are IEEE half —
+// the hardware rejects an f16 A next to a bf16 B ("illegal instruction"))
+constexpr uint32_t IU_AB_FP16 = ~((1u << 7) | (1u << 10));
 __host__ __device__ constexpr uint32_t iu_idesc(int m, int n, bool a_mn_major, bool b_mn_major = false) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major ? (1u << 15) : 0u) | (b_mn_major ? (1u << 16) : 0u) |
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -251,6 +255,11 @@ __device__ __forceinline__ void iu_split(float x, unsigned short& hi, unsigned s
     hi = __bfloat16_as_ushort(h);
     lo = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(h)));
 }
+__device__ __forceinline__ void iu_split_h(float x, unsigned short& hi, unsigned short& lo) {     // IEEE half hi + lo
+    const __half h = __float2half_rn(x);
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(__float2half_rn(x - __half2float(h)));
+}
 __device__ __forceinline__ float iu_bf(uint32_t packed, int k) {      // element k (0/1) of a packed bf16 pair
     return __uint_as_float(k ? (packed & 0xffff0000u) : (packed << 16));
 }
@@ -269,6 +278,9 @@ struct UmmaPoolArgs {
     int BV;
     float scale;
     float* dbg;                  // optional (PT_POOL_DEBUG bit 64): [BV][8][256] scaled scores, attention tokens 0..225
+    int fp16;                    // the features (and therefore the w_eff planes and the probability operand) are IEEE half, else bfloat16
+    float wscale_inv;            // 1 / scale of the w_eff planes (fp16: 1/16)
+    float tau;                   // raise threshold of the reference maximum (fp16: 10, so that exp(tau) fits a half)
     int debug;                   // PT_UMMA_DEBUG bring-up switches (garbage results): 1 no score MMAs, 2 no sum MMAs, 16 per-role trace (trace
                                  // build), timing probes: 32 no halo reads, 64 no raise vote, 128 no final probability stores, 256 no s0, 512 no Y stores
 };
@@ -362,7 +374,8 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
         // converged, lane 0 issues.  Warp 0 also fetches the per-view w_eff planes one view ahead. =====
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");     // the softmax / epilogue warpgroups take the registers
         const int p = warp;
-        constexpr uint32_t IDESC1 = iu_idesc(128, 32, true, false), IDESC2 = iu_idesc(128, 32, false, true);
+        const uint32_t amask = a.fp16 ? IU_AB_FP16 : 0xffffffffu;
+        const uint32_t IDESC1 = iu_idesc(128, 32, true, false) & amask, IDESC2 = iu_idesc(128, 32, false, true) & amask;
         // descriptor words (addresses in 16-byte units): SWIZZLE_128B tiles (SBO 1024, version 1, layout 2) and the unswizzled
         // MN-major probability planes (LBO 128 between K blocks, SBO P_PLANE between the hi / lo planes, version 1)
         constexpr uint32_t HI_SW = (1024u >> 4) | (1u << 14) | (2u << 29), HI_P = ((uint32_t)P_PLANE >> 4) | (1u << 14);
@@ -544,7 +557,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 TB(3);
                 float sc[2];
 #pragma unroll
-                for (int k = 0; k < 2; ++k) sc[k] = valid ? a.scale * (tot[k] + ct[k]) : -INFINITY;
+                for (int k = 0; k < 2; ++k) sc[k] = valid ? a.scale * (tot[k] * a.wscale_inv + ct[k]) : -INFINITY;
                 if (a.dbg != nullptr && valid) {
 #pragma unroll
                     for (int k = 0; k < 2; ++k) a.dbg[((size_t)bv * HEADS + hb + k) * 256 + 1 + t] = sc[k];
@@ -554,7 +567,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 if (w > 0) {
                     bool ex = false;
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) ex = ex || (sc[k] > mref[k] + TAU);
+                    for (int k = 0; k < 2; ++k) ex = ex || (sc[k] > mref[k] + a.tau);
                     raise = (a.debug & 64) ? false : iu_bar_or(1, ex);   // (also orders the exchange reads before the next window's writes)
                 }
                 if (raise) {
@@ -615,7 +628,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     const float p = valid ? exp2f((sc[k] - mref[k]) * LOG2E) : 0.f;
                     lsum[k] += p;
                     pr[w][k] = p;
-                    iu_split(p, ph[k], pl[k]);
+                    if (a.fp16) iu_split_h(p, ph[k], pl[k]); else iu_split(p, ph[k], pl[k]);
                 }
                 const unsigned pbi = g & (PBUF - 1);
                 TB(4);
@@ -722,10 +735,21 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 for (int h = 0; h < 8; ++h) {
                     const uint2 hi = __ldg(reinterpret_cast<const uint2*>(a.wpl + (((size_t)bv * 2 + 0) * HEADS + h) * C + c0));
                     const uint2 lo = __ldg(reinterpret_cast<const uint2*>(a.wpl + (((size_t)bv * 2 + 1) * HEADS + h) * C + c0));
-                    float d = (iu_bf(hi.x, 0) + iu_bf(lo.x, 0)) * xb[0];
-                    d = fmaf(iu_bf(hi.x, 1) + iu_bf(lo.x, 1), xb[1], d);
-                    d = fmaf(iu_bf(hi.y, 0) + iu_bf(lo.y, 0), xb[2], d);
-                    d = fmaf(iu_bf(hi.y, 1) + iu_bf(lo.y, 1), xb[3], d);
+                    float d;
+                    if (a.fp16) {
+                        const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
+                        const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&lo.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&lo.y));
+                        d = (h0.x + l0.x) * xb[0];
+                        d = fmaf(h0.y + l0.y, xb[1], d);
+                        d = fmaf(h1.x + l1.x, xb[2], d);
+                        d = fmaf(h1.y + l1.y, xb[3], d);
+                        d *= a.wscale_inv;
+                    } else {
+                        d = (iu_bf(hi.x, 0) + iu_bf(lo.x, 0)) * xb[0];
+                        d = fmaf(iu_bf(hi.x, 1) + iu_bf(lo.x, 1), xb[1], d);
+                        d = fmaf(iu_bf(hi.y, 0) + iu_bf(lo.y, 0), xb[2], d);
+                        d = fmaf(iu_bf(hi.y, 1) + iu_bf(lo.y, 1), xb[3], d);
+                    }
                     dot[h] = d;
                 }
 #pragma unroll
@@ -812,9 +836,9 @@ extern "C" int pt_debug_umma_trace(unsigned long long* out16, int reset) {   // 
     return PT_OK;
 }
 namespace pt {
-bool img_pool_umma_supported(int img_dtype) { return img_dtype == PT_DTYPE_BF16; }
+bool img_pool_umma_supported(int img_dtype) { return img_dtype == PT_DTYPE_BF16 || img_dtype == PT_DTYPE_F16; }
 
-int launch_img_pool_umma(const void* img_feat, const __nv_bfloat16* wpl, const float* cterm, const float* xbar, __nv_bfloat16* ya_hi,
+int launch_img_pool_umma(const void* img_feat, bool fp16, float wscale, const __nv_bfloat16* wpl, const float* cterm, const float* xbar, __nv_bfloat16* ya_hi,
                          long long ya_plane, int BV, float* dbg, cudaStream_t s) {
     using namespace ipu;
     PT_REQUIRE(((uintptr_t)img_feat & 15) == 0 && ((uintptr_t)wpl & 15) == 0, "pt_img_attnpool: img_feat / workspace must be 16-byte aligned");
@@ -824,13 +848,13 @@ int launch_img_pool_umma(const void* img_feat, const __nv_bfloat16* wpl, const f
         const unsigned long long dims[2] = {(unsigned long long)C, (unsigned long long)BV * 16};
         const unsigned long long strides[1] = {(unsigned long long)C * 2};
         const unsigned box[2] = {64u, 16u};
-        if ((rc = encode_tensor_map_16bit(&maps.w, wpl, 2, dims, strides, box, false))) return rc;
+        if ((rc = encode_tensor_map_16bit(&maps.w, wpl, 2, dims, strides, box, fp16))) return rc;
     }
     {   // class-aligned view of the raw (BV, 512, 225) features: element (u, r, s, v) at byte 2 u + 3600 r + 448 s + 230400 v
         const unsigned long long dims[4] = {(unsigned long long)UCOLS, 64ull, 8ull, (unsigned long long)BV};
         const unsigned long long strides[3] = {3600ull, 448ull, (unsigned long long)C * HW * 2};
         const unsigned box[4] = {64u, 64u, 2u, 1u};
-        if ((rc = encode_tensor_map_16bit(&maps.x, img_feat, 4, dims, strides, box, false))) return rc;
+        if ((rc = encode_tensor_map_16bit(&maps.x, img_feat, 4, dims, strides, box, fp16))) return rc;
     }
     static bool attr_set[PT_MAX_DEVICES] = {};
     if (first_use_on_current_device(attr_set))
@@ -841,6 +865,9 @@ int launch_img_pool_umma(const void* img_feat, const __nv_bfloat16* wpl, const f
     a.wpl = wpl; a.cterm = cterm; a.xbar = xbar; a.ya_hi = ya_hi; a.ya_plane = ya_plane; a.BV = BV;
     a.scale = (float)(1.0 / sqrt(32.0));
     a.dbg = dbg;
+    a.fp16 = fp16 ? 1 : 0;
+    a.wscale_inv = 1.0f / wscale;
+    a.tau = fp16 ? 10.0f : TAU;
     const char* dbe = getenv("PT_UMMA_DEBUG");
     a.debug = dbe ? atoi(dbe) : 0;
     int grid = BV < sms ? BV : sms;

@@ -14,8 +14,9 @@ import torch
 from . import _lib
 from ._lib import ImgPoolParams, ProxyBlockParams, check
 
-# image feature dtypes consumed without conversion (fp16 is what the reference's --amp backbone emits, tools/train.py:93-105)
-IMG_FEAT_DTYPES = (torch.float32, torch.bfloat16)
+# image feature dtypes consumed without conversion (fp16 is what the reference's --amp backbone emits, tools/train.py:93-105;
+# it needs the tcgen05 pooling kernel and the shipped geometry, see img_attnpool)
+IMG_FEAT_DTYPES = (torch.float32, torch.bfloat16, torch.float16)
 RADIUS = 3.0   # DeformablePointCluster(radius=3)  (:23)
 MARGIN = 4.0   # DeformablePointCluster(margin=4)  (:23)
 
@@ -292,9 +293,13 @@ def img_attnpool(img_feat, w: Dict[str, torch.Tensor], heads: int, ws: Optional[
         dt = _lib.PT_DTYPE_F32
     elif img_feat.dtype == torch.bfloat16:
         dt = _lib.PT_DTYPE_BF16
+    elif img_feat.dtype == torch.float16:
+        dt = _lib.PT_DTYPE_F16
     else:
-        raise ValueError(f"img_feat must be fp32 or bf16, got {img_feat.dtype}")
+        raise ValueError(f"img_feat must be fp32, bf16 or fp16, got {img_feat.dtype}")
     p = params if params is not None else make_img_params(w)
+    if dt == _lib.PT_DTYPE_F16 and not (p.variant == _lib.PT_POOL_VARIANT_UMMA and p.w_qc_split and (C, H * W, c, heads) == (512, 225, 256, 8)):
+        img_feat, dt = img_feat.float(), _lib.PT_DTYPE_F32      # no 16-bit tensor-core path for this geometry / kernel choice
     need = L.pt_img_attnpool_ws_bytes(B * V, C, H * W, c, heads)
     if ws is None or ws.numel() < need:
         ws = _ws(need, img_feat.device)

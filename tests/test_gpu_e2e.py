@@ -210,6 +210,8 @@ def test_cuda_graph_replay_equals_eager_forward():
     (6, 0.55, 6000, 2, 77, 1, torch.float32, 30.0),
     (7, 0.6, 9000, 5, 33, 2, torch.bfloat16, 40.0),          # n = 137 clusters: not a multiple of 8 -> mma.sync attention
     (4, 0.5, 2000, 9, 8, 5, torch.bfloat16, 9.0),
+    (5, 0.6, 4000, 7, 17, 2, torch.float16, 20.0),           # fp16 features (the reference's --amp backbone): tcgen05 pooling path
+    (4, 0.5, 3000, 40, 5, 5, torch.float16, 12.0),           # 200 views: several views per CTA
 ])
 def test_odd_shapes_against_oracle_chain(gs, ddr, N, V, L, B, dtype, box):
     """Shapes the fixtures do not cover (one view / one token, odd cluster counts, batches that are not powers of two):
@@ -229,7 +231,8 @@ def test_odd_shapes_against_oracle_chain(gs, ddr, N, V, L, B, dtype, box):
     pp = po.point_encoder(sd, kc, cl)
     np.testing.assert_allclose(np_(tr["point_proxy"]), pp.numpy(), rtol=0, atol=1e-5 + 2e-6 * pp.abs().max().item())
     ip = po.image_proxies(sd, img.float(), cfg.num_heads)
-    np.testing.assert_allclose(np_(tr["img_proxy"]), ip.numpy(), rtol=0, atol=3e-5)
+    # (fp16 cases run the tensor-core pooling path on weights that are NOT bf16-representable: the stage tolerance of 6e-5)
+    np.testing.assert_allclose(np_(tr["img_proxy"]), ip.numpy(), rtol=0, atol=6e-5 if dtype == torch.float16 else 3e-5)
     tg = po.branch(sd, "textformer", "text_norm", cfg.text_blocks, pp, text_dict["text_feats"], text_dict["text_token_mask"], cfg.num_heads)
     ig = po.branch(sd, "imgformer", "img_norm", cfg.img_blocks, pp, ip, None, cfg.num_heads)
     translate, transform = po.head(sd, "text_trans", "text_trans_norm", tg), po.head(sd, "img_trans", "img_trans_norm", ig)

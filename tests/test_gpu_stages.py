@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import preshape_oracle as po
-from proxytransformation_b200 import ops
+from proxytransformation_b200 import _lib, ops
 from proxytransformation_b200 import synthetic as syn
 from tests.golden_cases import LARGE_CASES, SMALL_CASES, load_case
 from tests.gpu_util import DEV, build_module, conv_bn_weights, cu, np_
@@ -350,8 +350,10 @@ def test_aggregate_sample_input_side():
 
 
 @pytest.mark.parametrize("B,V,dtype,kernel", [(3, 196, torch.bfloat16, "mma"), (5, 61, torch.bfloat16, "mma"), (2, 196, torch.float32, "mma"),
-                                              (3, 196, torch.bfloat16, "umma"), (5, 61, torch.bfloat16, "umma")],
-                         ids=["bf16-588views", "bf16-305views", "f32-392views", "bf16-588views-tcgen05", "bf16-305views-tcgen05"])
+                                              (3, 196, torch.bfloat16, "umma"), (5, 61, torch.bfloat16, "umma"),
+                                              (3, 196, torch.float16, "umma"), (2, 196, torch.float16, "mma")],
+                         ids=["bf16-588views", "bf16-305views", "f32-392views", "bf16-588views-tcgen05", "bf16-305views-tcgen05",
+                              "fp16-588views-tcgen05", "fp16-392views-no-16bit-path"])
 def test_image_proxies_many_views_per_cta(B, V, dtype, kernel, monkeypatch):
     """The image-pool kernels are PERSISTENT (one CTA per SM, grid = min(views, SMs)): with B*V well above the SM count every
     CTA loops over several views, which is the path the benchmark times (12 544 views per step) and what production shapes
@@ -370,6 +372,12 @@ def test_image_proxies_many_views_per_cta(B, V, dtype, kernel, monkeypatch):
     err = np.abs(np_(got) - want.numpy()).reshape(B * V, -1).max(-1)
     assert err.max() <= 6e-5, f"views off by more than 6e-5: {np.nonzero(err > 6e-5)[0][:16].tolist()} (max {err.max():.3e})"
     assert m._weights(torch.device(DEV))["img"].get("variant", 0) == (1 if kernel == "umma" else 0)
+    if dtype == torch.float16 and kernel == "umma":      # fp16 must really take the 16-bit tensor-core path (no fp32 materialisation)
+        _lib.profile_enable(True)
+        m.get_img_proxy(img.to(DEV)); torch.cuda.synchronize()
+        prof = _lib.profile_read()
+        _lib.profile_enable(False)
+        assert prof.get("img_pool", (0, 0))[1] == 1 and prof.get("gemm_img_3xbf16", (0, 0))[1] == 5, prof
     # same call again on the same module: nothing may depend on leftover workspace / shared-memory state
     assert torch.equal(m.get_img_proxy(img.to(DEV)), got)
 
