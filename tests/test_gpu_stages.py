@@ -329,6 +329,16 @@ def test_proxy_attention_tcgen05_core(B, n, l, masked):
     np.testing.assert_allclose(np_(got), want.numpy(), rtol=0, atol=6e-5)
 
 
+@pytest.mark.parametrize("name", ["xyz", "xyzrgb", "replace"])
+def test_aggregate_sample_against_the_reference_fixture(name):
+    """N3 on the GPU against the fixture generated from the reference's own transforms (tests/golden/make_golden_n3.py);
+    tolerance 2e-5 m: the reference solves the 4x4 system per view in fp32 (LU), the kernel applies the fp64 inverse in fp32."""
+    from tests.test_oracle_golden import load_n3_case
+    views, ext, choices, _, sampled = load_n3_case(name)
+    got = ops.aggregate_sample([p.to(DEV) for p in views], ext, choices.to(DEV))
+    np.testing.assert_allclose(np_(got), sampled[:, :3], rtol=0, atol=2e-5)
+
+
 def test_aggregate_sample_input_side():
     """N3: multi-view aggregation + PointSample gather on the device against the restatement of the reference's
     transforms (per-view torch.linalg.solve with the 4x4 extrinsic, concatenate, index with the sampled choices)."""

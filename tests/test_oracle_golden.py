@@ -2,6 +2,8 @@
 captured from the unmodified reference (tests/golden/make_golden.py), plus — when
 /root/reference is present (build container) — a live cross-check against the
 reference itself.  CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -166,3 +168,27 @@ def test_aggregate_sample_restatement_is_the_inverse_transform():
     choices = torch.tensor([149, 0, 75, 75, 3])
     got = po.aggregate_sample(ego, ext, choices)
     assert torch.allclose(got, torch.cat(glob)[choices], atol=1e-5)
+
+
+N3_CASES = ("xyz", "xyzrgb", "replace")
+
+
+def load_n3_case(name):
+    """tests/golden/n3_aggregate.npz (make_golden_n3.py: the UNMODIFIED reference transforms): views, extrinsics, choices, result."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "n3_aggregate.npz"))
+    sizes = z[f"{name}.sizes"].tolist()
+    views = list(torch.from_numpy(z[f"{name}.views"]).split(sizes))
+    return views, torch.from_numpy(z[f"{name}.extrinsics"]), torch.from_numpy(z[f"{name}.choices"]), z[f"{name}.aggregated"], z[f"{name}.sampled"]
+
+
+@pytest.mark.parametrize("name", N3_CASES)
+def test_aggregate_sample_pinned_to_the_reference_transforms(name):
+    """N3 pin: oracle.aggregate_sample against what the reference's own AggregateMultiViewPoints.transform
+    (datasets/transforms/multiview.py:224-251) + PointSample._points_random_sampling (points.py:373-419) produced on the same
+    views / extrinsics / np.random choices (xyz points, xyz+rgb points, sampling with replacement).  Same torch ops in the same
+    order: bit-exact."""
+    views, ext, choices, aggregated, sampled = load_n3_case(name)
+    got = po.aggregate_sample(views, ext, choices)
+    assert np.array_equal(got.numpy(), sampled[:, :3])
+    everything = po.aggregate_sample(views, ext, torch.arange(aggregated.shape[0]))
+    assert np.array_equal(everything.numpy(), aggregated[:, :3])
