@@ -19,7 +19,35 @@ __global__ void __launch_bounds__(MM_THREADS) minmax_partial_kernel(const float*
     const int p0 = blockIdx.x * MM_POINTS_PER_BLOCK;
     const int p1 = min(N, p0 + MM_POINTS_PER_BLOCK);
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int p = p0 + threadIdx.x; p < p1; p += MM_THREADS) {
+    int p_scalar = p0;
+    if ((reinterpret_cast<uintptr_t>(P) & 15) == 0) {           // 4 points = 3 x 16 bytes per thread and step
+        const int ngrp = (p1 - p0) >> 2;
+        const float4* P4 = reinterpret_cast<const float4*>(P + (size_t)p0 * 3);
+        auto fold = [&](const float4& a, const float4& b4, const float4& c) {
+            const float x[4] = {a.x, a.w, b4.z, c.y}, y[4] = {a.y, b4.x, b4.w, c.z}, z[4] = {a.z, b4.y, c.x, c.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                mn[0] = fminf(mn[0], x[i]); mx[0] = fmaxf(mx[0], x[i]);
+                mn[1] = fminf(mn[1], y[i]); mx[1] = fmaxf(mx[1], y[i]);
+                mn[2] = fminf(mn[2], z[i]); mx[2] = fmaxf(mx[2], z[i]);
+            }
+        };
+        if (ngrp == MM_POINTS_PER_BLOCK / 4) {                    // full block: all 12 loads of the thread in flight at once
+            constexpr int GPT = MM_POINTS_PER_BLOCK / 4 / MM_THREADS;
+            float4 v[GPT][3];
+#pragma unroll
+            for (int k = 0; k < GPT; ++k) {
+                const int gq = threadIdx.x + k * MM_THREADS;
+                v[k][0] = __ldg(P4 + 3 * gq); v[k][1] = __ldg(P4 + 3 * gq + 1); v[k][2] = __ldg(P4 + 3 * gq + 2);
+            }
+#pragma unroll
+            for (int k = 0; k < GPT; ++k) fold(v[k][0], v[k][1], v[k][2]);
+        } else {
+            for (int gq = threadIdx.x; gq < ngrp; gq += MM_THREADS) fold(__ldg(P4 + 3 * gq), __ldg(P4 + 3 * gq + 1), __ldg(P4 + 3 * gq + 2));
+        }
+        p_scalar = p0 + 4 * ngrp;
+    }
+    for (int p = p_scalar + threadIdx.x; p < p1; p += MM_THREADS) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
             float v = __ldg(P + (size_t)p * 3 + d);

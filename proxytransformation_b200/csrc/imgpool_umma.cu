@@ -90,6 +90,7 @@ constexpr int THREADS = 32 * (PRODUCER_WARP + 1);
 constexpr int TMEM_COLS = 512;
 constexpr int D1_BUF_COLS = 128, D2_COL = 256, D2_BUF_COLS = 128;
 constexpr float TAU = 16.0f;                 // the reference maximum is raised when a score exceeds it by more than this
+constexpr float TAU_FP16 = 10.0f;            // ... half probability operand: exp(TAU) has to fit a half
 constexpr float LOG2E = 1.4426950408889634f;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(OFF_W % 1024 == 0 && SLOT_BYTES % 1024 == 0 && OFF_P % 16 == 0 && OFF_HALO % 16 == 0 && OFF_XCH % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
@@ -278,9 +279,7 @@ struct UmmaPoolArgs {
     int BV;
     float scale;
     float* dbg;                  // optional (PT_POOL_DEBUG bit 64): [BV][8][256] scaled scores, attention tokens 0..225
-    int fp16;                    // the features (and therefore the w_eff planes and the probability operand) are IEEE half, else bfloat16
-    float wscale_inv;            // 1 / scale of the w_eff planes (fp16: 1/16)
-    float tau;                   // raise threshold of the reference maximum (fp16: 10, so that exp(tau) fits a half)
+    float wscale_inv;            // 1 / scale of the half w_eff planes (fp16 instantiation: 1/16)
     int debug;                   // PT_UMMA_DEBUG bring-up switches (garbage results): 1 no score MMAs, 2 no sum MMAs, 16 per-role trace (trace
                                  // build), timing probes: 32 no halo reads, 64 no raise vote, 128 no final probability stores, 256 no s0, 512 no Y stores
 };
@@ -302,6 +301,9 @@ __device__ unsigned long long g_umma_trace[24];   // 16..23: softmax sub-section
 // first halo entry of class s (classes 0..6 need 7 - s rows of the neighbouring warp)
 __host__ __device__ constexpr int iu_halo_off(int s) { return 7 * s - s * (s - 1) / 2; }
 
+// FP16: features, w_eff planes and the probability operand are IEEE half (compile-time: the bf16 instantiation is the round's
+// tuned kernel unchanged; run-time switches in the softmax chain cost 30 % of the kernel).
+template <bool FP16>
 __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __grid_constant__ UmmaPoolMaps maps, const UmmaPoolArgs a) {
     using namespace ipu;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -374,8 +376,8 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
         // converged, lane 0 issues.  Warp 0 also fetches the per-view w_eff planes one view ahead. =====
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");     // the softmax / epilogue warpgroups take the registers
         const int p = warp;
-        const uint32_t amask = a.fp16 ? IU_AB_FP16 : 0xffffffffu;
-        const uint32_t IDESC1 = iu_idesc(128, 32, true, false) & amask, IDESC2 = iu_idesc(128, 32, false, true) & amask;
+        constexpr uint32_t AMASK = FP16 ? IU_AB_FP16 : 0xffffffffu;
+        constexpr uint32_t IDESC1 = iu_idesc(128, 32, true, false) & AMASK, IDESC2 = iu_idesc(128, 32, false, true) & AMASK;
         // descriptor words (addresses in 16-byte units): SWIZZLE_128B tiles (SBO 1024, version 1, layout 2) and the unswizzled
         // MN-major probability planes (LBO 128 between K blocks, SBO P_PLANE between the hi / lo planes, version 1)
         constexpr uint32_t HI_SW = (1024u >> 4) | (1u << 14) | (2u << 29), HI_P = ((uint32_t)P_PLANE >> 4) | (1u << 14);
@@ -557,7 +559,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 TB(3);
                 float sc[2];
 #pragma unroll
-                for (int k = 0; k < 2; ++k) sc[k] = valid ? a.scale * (tot[k] * a.wscale_inv + ct[k]) : -INFINITY;
+                for (int k = 0; k < 2; ++k) sc[k] = valid ? a.scale * ((FP16 ? tot[k] * a.wscale_inv : tot[k]) + ct[k]) : -INFINITY;
                 if (a.dbg != nullptr && valid) {
 #pragma unroll
                     for (int k = 0; k < 2; ++k) a.dbg[((size_t)bv * HEADS + hb + k) * 256 + 1 + t] = sc[k];
@@ -567,7 +569,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 if (w > 0) {
                     bool ex = false;
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) ex = ex || (sc[k] > mref[k] + a.tau);
+                    for (int k = 0; k < 2; ++k) ex = ex || (sc[k] > mref[k] + (FP16 ? TAU_FP16 : TAU));
                     raise = (a.debug & 64) ? false : iu_bar_or(1, ex);   // (also orders the exchange reads before the next window's writes)
                 }
                 if (raise) {
@@ -628,7 +630,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     const float p = valid ? exp2f((sc[k] - mref[k]) * LOG2E) : 0.f;
                     lsum[k] += p;
                     pr[w][k] = p;
-                    if (a.fp16) iu_split_h(p, ph[k], pl[k]); else iu_split(p, ph[k], pl[k]);
+                    if (FP16) iu_split_h(p, ph[k], pl[k]); else iu_split(p, ph[k], pl[k]);
                 }
                 const unsigned pbi = g & (PBUF - 1);
                 TB(4);
@@ -736,7 +738,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                     const uint2 hi = __ldg(reinterpret_cast<const uint2*>(a.wpl + (((size_t)bv * 2 + 0) * HEADS + h) * C + c0));
                     const uint2 lo = __ldg(reinterpret_cast<const uint2*>(a.wpl + (((size_t)bv * 2 + 1) * HEADS + h) * C + c0));
                     float d;
-                    if (a.fp16) {
+                    if (FP16) {
                         const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
                         const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&lo.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&lo.y));
                         d = (h0.x + l0.x) * xb[0];
@@ -857,22 +859,26 @@ int launch_img_pool_umma(const void* img_feat, bool fp16, float wscale, const __
         if ((rc = encode_tensor_map_16bit(&maps.x, img_feat, 4, dims, strides, box, fp16))) return rc;
     }
     static bool attr_set[PT_MAX_DEVICES] = {};
-    if (first_use_on_current_device(attr_set))
-        PT_CUDA_OK(cudaFuncSetAttribute(img_pool_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    if (first_use_on_current_device(attr_set)) {
+        PT_CUDA_OK(cudaFuncSetAttribute(img_pool_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        PT_CUDA_OK(cudaFuncSetAttribute(img_pool_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    }
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     UmmaPoolArgs a;
     a.wpl = wpl; a.cterm = cterm; a.xbar = xbar; a.ya_hi = ya_hi; a.ya_plane = ya_plane; a.BV = BV;
     a.scale = (float)(1.0 / sqrt(32.0));
     a.dbg = dbg;
-    a.fp16 = fp16 ? 1 : 0;
     a.wscale_inv = 1.0f / wscale;
-    a.tau = fp16 ? 10.0f : TAU;
     const char* dbe = getenv("PT_UMMA_DEBUG");
     a.debug = dbe ? atoi(dbe) : 0;
     int grid = BV < sms ? BV : sms;
     if (const char* ge = getenv("PT_POOL_GRID")) { const int gv = atoi(ge); if (gv >= 1 && gv < grid) grid = gv; }   // probes: fewer persistent CTAs
-    { ProfScope prof_(PROF_IMG_POOL, s); img_pool_umma_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(maps, a); }
+    {
+        ProfScope prof_(PROF_IMG_POOL, s);
+        if (fp16) img_pool_umma_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>(maps, a);
+        else img_pool_umma_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(maps, a);
+    }
     PT_LAUNCH_CHECK();
     return PT_OK;
 }

@@ -10,8 +10,10 @@ namespace pt {
 constexpr int SC_DROP = 0x7fffffff;
 constexpr int SC_BLOCK = 1024;
 
+// `blockdrop[scene][block of SC_BLOCK points]` counts the DISTINCT dropped points of a block (the first SC_DROP mark of a point
+// is the one whose atomicMax returns something else), so the compaction needs no counting pass over the winner array.
 __global__ void mark_kernel(const int32_t* __restrict__ kept_idx, const int32_t* __restrict__ drop_idx, int B, int N, int nK,
-                            int n_drop_entries, int* __restrict__ winner) {
+                            int n_drop_entries, int nblk, int* __restrict__ winner, int* __restrict__ blockdrop) {
     const long long total_keep = (long long)B * nK, total = total_keep + (long long)B * n_drop_entries;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         if (i < total_keep) {
@@ -22,60 +24,88 @@ __global__ void mark_kernel(const int32_t* __restrict__ kept_idx, const int32_t*
             const long long k = i - total_keep;
             const int b = (int)(k / n_drop_entries);
             const int id = __ldg(drop_idx + k);
-            if (id >= 0) atomicMax(winner + (size_t)b * N + id, SC_DROP);
+            if (id >= 0 && atomicMax(winner + (size_t)b * N + id, SC_DROP) != SC_DROP) atomicAdd(blockdrop + (size_t)b * nblk + id / SC_BLOCK, 1);
         }
     }
 }
 
-__global__ void __launch_bounds__(SC_BLOCK) count_kernel(const int* __restrict__ winner, int N, int* __restrict__ blockcnt) {
-    const int b = blockIdx.y, i = blockIdx.x * SC_BLOCK + threadIdx.x;
-    const bool keep = i < N && winner[(size_t)b * N + i] != SC_DROP;
-    const int c = __syncthreads_count(keep);
-    if (threadIdx.x == 0) blockcnt[(size_t)b * gridDim.x + blockIdx.x] = c;
+// One CTA (SC_THREADS threads, 4 consecutive points each) per block of SC_BLOCK points of a scene: coordinates and winners come
+// in with 16-byte loads, the survivors (transformed where a cluster claimed them) are packed in shared memory and leave as one
+// contiguous, fully coalesced run at the scene's running output offset (prefix of the preceding blocks' survivor counts).
+constexpr int SC_THREADS = SC_BLOCK / 4;
+
+__device__ __forceinline__ void sc_affine(float& x, float& y, float& z, int w, int K, const float* __restrict__ centres,
+                                          const float* __restrict__ transform, const float* __restrict__ translate, size_t bn) {
+    const int m = w / K;
+    const float* T = transform + (bn + m) * 9;
+    const float* c = centres + (bn + m) * 3;
+    const float* t = translate + (bn + m) * 3;
+    const float cx = __ldg(c), cy = __ldg(c + 1), cz = __ldg(c + 2);
+    const float rx = __fsub_rn(x, cx), ry = __fsub_rn(y, cy), rz = __fsub_rn(z, cz);
+    // ((T @ rel) + centre) + translate (:462)
+    x = __fadd_rn(__fadd_rn(fmaf(__ldg(T + 2), rz, fmaf(__ldg(T + 1), ry, __fmul_rn(__ldg(T + 0), rx))), cx), __ldg(t));
+    y = __fadd_rn(__fadd_rn(fmaf(__ldg(T + 5), rz, fmaf(__ldg(T + 4), ry, __fmul_rn(__ldg(T + 3), rx))), cy), __ldg(t + 1));
+    z = __fadd_rn(__fadd_rn(fmaf(__ldg(T + 8), rz, fmaf(__ldg(T + 7), ry, __fmul_rn(__ldg(T + 6), rx))), cz), __ldg(t + 2));
 }
 
-__global__ void __launch_bounds__(SC_BLOCK) compact_kernel(const float* __restrict__ points, const int* __restrict__ winner,
-                                                           const int* __restrict__ blockcnt, const float* __restrict__ centres,
-                                                           const float* __restrict__ transform, const float* __restrict__ translate,
-                                                           int N, int n, int K, float* __restrict__ out, int32_t* __restrict__ counts) {
-    __shared__ int warp_tot[SC_BLOCK / 32];
+__global__ void __launch_bounds__(SC_THREADS) compact_kernel(const float* __restrict__ points, const int* __restrict__ winner,
+                                                             const int* __restrict__ blockdrop, const float* __restrict__ centres,
+                                                             const float* __restrict__ transform, const float* __restrict__ translate,
+                                                             int N, int n, int K, float* __restrict__ out, int32_t* __restrict__ counts) {
+    __shared__ float sout[3 * SC_BLOCK];
+    __shared__ int warp_tot[SC_THREADS / 32];
     __shared__ int base_s;
     const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (wid == 0) {                                   // exclusive prefix over the preceding blocks of this scene
+    const int i0 = blk * SC_BLOCK + 4 * tid;          // this thread's first point
+    if (wid == 0) {                                   // survivors of the preceding (full) blocks of this scene
         int s = 0;
-        for (int j = lane; j < blk; j += 32) s += blockcnt[(size_t)b * nblk + j];
+        for (int j = lane; j < blk; j += 32) s += SC_BLOCK - blockdrop[(size_t)b * nblk + j];
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
         if (lane == 0) base_s = s;
     }
-    const int i = blk * SC_BLOCK + tid;
-    int w = SC_DROP;
-    if (i < N) w = winner[(size_t)b * N + i];
-    const bool keep = w != SC_DROP;
-    const unsigned mask = __ballot_sync(FULL, keep);
-    if (lane == 0) warp_tot[wid] = __popc(mask);
-    __syncthreads();
-    int off = base_s;
-    for (int j = 0; j < wid; ++j) off += warp_tot[j];
-    if (keep) {
-        const float* p = points + ((size_t)b * N + i) * 3;
-        float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
-        if (w >= 0) {
-            const int m = w / K;
-            const float* T = transform + ((size_t)b * n + m) * 9;
-            const float* c = centres + ((size_t)b * n + m) * 3;
-            const float* t = translate + ((size_t)b * n + m) * 3;
-            const float cx = __ldg(c), cy = __ldg(c + 1), cz = __ldg(c + 2);
-            const float rx = __fsub_rn(x, cx), ry = __fsub_rn(y, cy), rz = __fsub_rn(z, cz);
-            // ((T @ rel) + centre) + translate (:462)
-            x = __fadd_rn(__fadd_rn(fmaf(__ldg(T + 2), rz, fmaf(__ldg(T + 1), ry, __fmul_rn(__ldg(T + 0), rx))), cx), __ldg(t));
-            y = __fadd_rn(__fadd_rn(fmaf(__ldg(T + 5), rz, fmaf(__ldg(T + 4), ry, __fmul_rn(__ldg(T + 3), rx))), cy), __ldg(t + 1));
-            z = __fadd_rn(__fadd_rn(fmaf(__ldg(T + 8), rz, fmaf(__ldg(T + 7), ry, __fmul_rn(__ldg(T + 6), rx))), cz), __ldg(t + 2));
+    const float* src = points + ((size_t)b * N + i0) * 3;
+    const int* wsrc = winner + (size_t)b * N + i0;
+    float x[4], y[4], z[4];
+    int w[4] = {SC_DROP, SC_DROP, SC_DROP, SC_DROP};
+    if (i0 + 3 < N && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(wsrc) & 15) == 0) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b4 = __ldg(reinterpret_cast<const float4*>(src) + 1),
+                     c = __ldg(reinterpret_cast<const float4*>(src) + 2);
+        x[0] = a.x; y[0] = a.y; z[0] = a.z; x[1] = a.w; y[1] = b4.x; z[1] = b4.y;
+        x[2] = b4.z; y[2] = b4.w; z[2] = c.x; x[3] = c.y; y[3] = c.z; z[3] = c.w;
+        const int4 w4 = *reinterpret_cast<const int4*>(wsrc);
+        w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            x[e] = y[e] = z[e] = 0.f;
+            if (i0 + e < N) { x[e] = __ldg(src + 3 * e); y[e] = __ldg(src + 3 * e + 1); z[e] = __ldg(src + 3 * e + 2); w[e] = wsrc[e]; }
         }
-        float* o = out + ((size_t)b * N + off + __popc(mask & ((1u << lane) - 1u))) * 3;
-        o[0] = x; o[1] = y; o[2] = z;
     }
-    if (blk == nblk - 1 && tid == SC_BLOCK - 1) counts[b] = off + __popc(mask);
+    int mine = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) mine += w[e] != SC_DROP;
+    int incl = mine;                                  // inclusive scan of the per-thread survivor counts within the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    int off = incl - mine, cnt = 0;
+#pragma unroll
+    for (int j = 0; j < SC_THREADS / 32; ++j) { const int t = warp_tot[j]; off += j < wid ? t : 0; cnt += t; }
+    const size_t bn = (size_t)b * n;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        if (w[e] != SC_DROP) {
+            if (w[e] >= 0) sc_affine(x[e], y[e], z[e], w[e], K, centres, transform, translate, bn);
+            sout[3 * off] = x[e]; sout[3 * off + 1] = y[e]; sout[3 * off + 2] = z[e];
+            ++off;
+        }
+    }
+    __syncthreads();
+    float* dst = out + ((size_t)b * N + base_s) * 3;
+    for (int j = tid; j < 3 * cnt; j += SC_THREADS) dst[j] = sout[j];
+    if (blk == nblk - 1 && tid == 0) counts[b] = base_s + cnt;
 }
 
 // N1 hand-off to the sparse backbone (detectors/sparse_featfusion_grounder_preshape.py:388-391):
@@ -185,16 +215,15 @@ extern "C" int pt_affine_scatter_compact(const float* points, const int32_t* kep
     cudaStream_t s = (cudaStream_t)stream;
     int* winner = (int*)ws;
     int* blockcnt = (int*)((char*)ws + align_up((size_t)B * N * sizeof(int), 256));
+    const int nblk = ceil_div(N, SC_BLOCK);
     PT_CUDA_OK(cudaMemsetAsync(winner, 0xff, (size_t)B * N * sizeof(int), s));   // -1 = untouched
+    PT_CUDA_OK(cudaMemsetAsync(blockcnt, 0, (size_t)B * nblk * sizeof(int), s));  // distinct dropped points per block
     const long long total = (long long)B * ((long long)n * K + n_drop_entries);
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    { ProfScope prof_(PROF_MARK, s); mark_kernel<<<grid, 256, 0, s>>>(kept_idx, drop_idx, B, N, n * K, n_drop_entries, winner); }
+    { ProfScope prof_(PROF_MARK, s); mark_kernel<<<grid, 256, 0, s>>>(kept_idx, drop_idx, B, N, n * K, n_drop_entries, nblk, winner, blockcnt); }
     PT_LAUNCH_CHECK();
-    const int nblk = ceil_div(N, SC_BLOCK);
-    { ProfScope prof_(PROF_COUNT, s); count_kernel<<<dim3(nblk, B), SC_BLOCK, 0, s>>>(winner, N, blockcnt); }
-    PT_LAUNCH_CHECK();
-    { ProfScope prof_(PROF_COMPACT, s); compact_kernel<<<dim3(nblk, B), SC_BLOCK, 0, s>>>(points, winner, blockcnt, kept_centres, transform, translate, N, n, K, out, counts); }
+    { ProfScope prof_(PROF_COMPACT, s); compact_kernel<<<dim3(nblk, B), SC_THREADS, 0, s>>>(points, winner, blockcnt, kept_centres, transform, translate, N, n, K, out, counts); }
     PT_LAUNCH_CHECK();
     return PT_OK;
 }
