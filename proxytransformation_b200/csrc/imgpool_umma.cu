@@ -12,7 +12,7 @@
 //   scores  D1_s[u][n]    = sum_r X_s[r][u] w_eff[n][s + 8 r]      one accumulator per class; the two classes of a pair share one
 //                           tcgen05.mma M128 N32 K16 (A = both tiles read MN-major, rows 0-63 / 64-127; B = the w_eff rows
 //                           n = (hi|lo, head) of both classes, K-major); the score of token t is sum_s D1_s[t + s]: the softmax
-//                           warps add the eight classes with lane shifts (shuffles + a small shared-memory exchange);
+//                           warps add the eight classes through a 16 KB shared-memory exchange (publish by row, gather shifted);
 //   sums    D2_s[r][n]   += sum_u X_s[r][u] P[u - s][n]            (tcgen05.mma M128 N32 K16, A = both tiles read K-major,
 //                           B = the probabilities as an MN-major, unswizzled operand [token][8 heads x 2 B] per (hi|lo) plane:
 //                           a shift of s tokens is a 16 s-byte shift of the descriptor start address, so one copy of the
@@ -35,7 +35,7 @@
 //                probabilities -> global
 //   warps 12-15  epilogue: mean-token score s0 = w_eff . xbar (CUDA cores, from L2), then per view Y = (D2 f + p0 xbar) / L
 //                from TMEM -> bf16 hi/lo planes for the value-side GEMM (same output format as the mma.sync kernel)
-//   warp 16      TMA producer of the feature tiles: one 16 KB box (64 u x 64 rows x 2 classes) per ring slot, 11 slots
+//   warp 16      TMA producer of the feature tiles: one 16 KB box (64 u x 64 rows x 2 classes) per ring slot, 10 slots
 // Channel order of w_eff columns and of the weighted sums: position 64 s + r  <->  channel s + 8 r (absorbed into the folded
 // GEMM weights on the host, pt_img_pool_params variant 1).
 #include "common.cuh"
@@ -56,7 +56,7 @@ constexpr int NWIN = 4, WSTEP = 56;          // overlapping u-windows per view: 
 constexpr int UCOLS = 232;                   // valid u range of the tensor map: 225 tokens + 7 class shifts
 constexpr int TILE_BYTES = 64 * 128;         // [64 class rows][64 u] bf16, SWIZZLE_128B
 constexpr int SLOT_BYTES = 2 * TILE_BYTES;   // a class pair: rows 0-63 class 2p, rows 64-127 class 2p+1 (one TMA box)
-constexpr int RING = 11;
+constexpr int RING = 10;
 constexpr int WCLASS_BYTES = 16 * 128;       // w_eff rows (hi|lo, head) x 64 class channels
 constexpr int W_BYTES = 8 * WCLASS_BYTES;
 // Probabilities of a token set as the MN-major, unswizzled B operand of the sums (N = 32: both classes of a pair in one MMA):
@@ -65,15 +65,13 @@ constexpr int W_BYTES = 8 * WCLASS_BYTES;
 // have to be equidistant).  Row r holds token 56 w - 7 + r (zero if that token is not in the set); the rows above 63 stay zero
 // (the shifted 16-row k-steps of a class reach 7 rows further).  Buffer = window index mod PBUF.
 constexpr int P_ROWS = 73, P_PLANE = P_ROWS * 16, P_BYTES = 4 * P_PLANE, PBUF = 2;
-// class exchange: halo [half (class parity)][28 (class, row) entries][8 heads] fp32 (rows of the lower warp that the upper warp's first
-// lanes need), xch [source thread of the row (half, pair group)][64 rows][6 heads] fp32 (partial sums over that thread's two classes
-// for the three head pairs the other threads of the row keep)
-constexpr int HALO_ENTRIES = 28, HALO_BYTES = 2 * HALO_ENTRIES * 32, XCH_BYTES = 4 * 64 * 24;
+// class exchange: [class][head pair][64 rows] float2 = the hi + lo score sums of a window, published by the thread that read them
+// from TMEM and gathered (shifted by 7 - class rows) by the thread that owns the token
+constexpr int XCH_BYTES = 8 * 4 * 64 * 8;
 constexpr int OFF_RING = 0;
 constexpr int OFF_W = OFF_RING + RING * SLOT_BYTES;
 constexpr int OFF_P = OFF_W + 2 * W_BYTES;
-constexpr int OFF_HALO = OFF_P + PBUF * P_BYTES;
-constexpr int OFF_XCH = OFF_HALO + HALO_BYTES;
+constexpr int OFF_XCH = OFF_P + PBUF * P_BYTES;
 constexpr int OFF_MISC = OFF_XCH + XCH_BYTES;         // floats: smax[32] sred[32] ered[32] s0[16] stat_l[16] stat_m[16] fcs[8]
 constexpr int OFF_BAR = OFF_MISC + 1024;
 // mbarriers: full[RING] empty[RING] wfull[2] wempty[2] d1_full[2] p_full[PBUF] p_empty[PBUF] d2_full[2] d2_empty[2] s0_full[2] l_full[2]
@@ -93,7 +91,7 @@ constexpr float TAU = 16.0f;                 // the reference maximum is raised 
 constexpr float TAU_FP16 = 10.0f;            // ... half probability operand: exp(TAU) has to fit a half
 constexpr float LOG2E = 1.4426950408889634f;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(OFF_W % 1024 == 0 && SLOT_BYTES % 1024 == 0 && OFF_P % 16 == 0 && OFF_HALO % 16 == 0 && OFF_XCH % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
+static_assert(OFF_W % 1024 == 0 && SLOT_BYTES % 1024 == 0 && OFF_P % 16 == 0 && OFF_XCH % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
 }  // namespace ipu
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -281,7 +279,7 @@ struct UmmaPoolArgs {
     float* dbg;                  // optional (PT_POOL_DEBUG bit 64): [BV][8][256] scaled scores, attention tokens 0..225
     float wscale_inv;            // 1 / scale of the half w_eff planes (fp16 instantiation: 1/16)
     int debug;                   // PT_UMMA_DEBUG bring-up switches (garbage results): 1 no score MMAs, 2 no sum MMAs, 16 per-role trace (trace
-                                 // build), timing probes: 32 no halo reads, 64 no raise vote, 128 no final probability stores, 256 no s0, 512 no Y stores
+                                 // build), timing probes: 64 no raise vote, 128 no final probability stores, 256 no s0, 512 no Y stores
 };
 
 // Per-role cycle trace of CTA 0 (PT_UMMA_DEBUG bit 16): SM clocks spent in each wait / work section, summed over its views;
@@ -297,9 +295,6 @@ __device__ unsigned long long g_umma_trace[24];   // 16..23: softmax sub-section
 // (accumulated in registers, written once at the end of the role: a global read-modify-write per section would itself cost an
 // L2 round trip)
 #define UT(acc, stmt) do { const long long ut0_ = tracing ? clock64() : 0; stmt; if (tracing) acc += clock64() - ut0_; } while (0)
-
-// first halo entry of class s (classes 0..6 need 7 - s rows of the neighbouring warp)
-__host__ __device__ constexpr int iu_halo_off(int s) { return 7 * s - s * (s - 1) / 2; }
 
 // FP16: features, w_eff planes and the probability operand are IEEE half (compile-time: the bf16 instantiation is the round's
 // tuned kernel unchanged; run-time switches in the softmax chain cost 30 % of the kernel).
@@ -449,8 +444,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
         const int ws = warp - SOFTMAX_WARP0, q = warp & 3, half = q >> 1, qq = q & 1, pg = ws >> 2;
         const int r = 32 * qq + lane, hb = 4 * half + 2 * pg, src = 2 * half + pg, wpair = 4 * pg + 2 * half;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-        float* halo = reinterpret_cast<float*>(smem + OFF_HALO);
-        float* xch = reinterpret_cast<float*>(smem + OFF_XCH);
+        float2* xch = reinterpret_cast<float2*>(smem + OFF_XCH);
         float mref[2], lsum[2], pr[NWIN][2];
         unsigned g = 0;
         const bool tr_s = tracing && warp == SOFTMAX_WARP0;
@@ -458,18 +452,26 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
         long long ta6 = 0, ta7 = 0, ta8 = 0, ta10 = 0, tb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define TB(i) do { if (tr_s) { const long long n_ = clock64(); tb[i] += n_ - tbp; tbp = n_; } } while (0)
         long long tbp = 0;
-        // token of this thread in window w of a view (-1: not in the set), and its position terms, fetched one window ahead
+        // token of this thread in window w of a view (-1: not in the set), and its position terms, fetched one VIEW ahead (a load
+        // issued one window ahead is still in flight when the window's fence.proxy.async drains the memory pipe)
         auto token_of = [&](int w) { return (r >= 7 && r <= (w == NWIN - 1 ? 63 : 62)) ? WSTEP * w - 7 + r : -1; };
-        float ctn[2];
-        auto load_ct = [&](int vi2, int w2) {
-            const int t = token_of(w2);
+        float ctn[NWIN][2];
+        auto load_ct = [&](int vi2) {
             const int bv2 = blockIdx.x + vi2 * gridDim.x;
 #pragma unroll
-            for (int k = 0; k < 2; ++k) ctn[k] = (t >= 0 && vi2 < nviews) ? __ldg(a.cterm + ((size_t)bv2 * HEADS + hb + k) * TP + 1 + t) : 0.f;
+            for (int w2 = 0; w2 < NWIN; ++w2) {
+                const int t = token_of(w2);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) ctn[w2][k] = (t >= 0 && vi2 < nviews) ? __ldg(a.cterm + ((size_t)bv2 * HEADS + hb + k) * TP + 1 + t) : 0.f;
+            }
         };
-        load_ct(0, 0);
+        load_ct(0);
         for (int vi = 0; vi < nviews; ++vi) {
             const int bv = blockIdx.x + vi * gridDim.x;
+            float ctv[NWIN][2];
+#pragma unroll
+            for (int w = 0; w < NWIN; ++w) { ctv[w][0] = ctn[w][0]; ctv[w][1] = ctn[w][1]; }
+            load_ct(vi + 1);
 #pragma unroll
             for (int k = 0; k < 2; ++k) { lsum[k] = 0.f; mref[k] = 0.f; }
 #pragma unroll
@@ -478,8 +480,7 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 const bool valid = t >= 0;
                 float ct[2];
 #pragma unroll
-                for (int k = 0; k < 2; ++k) ct[k] = ctn[k];
-                if (w + 1 < NWIN) load_ct(vi, w + 1); else load_ct(vi + 1, 0);
+                for (int k = 0; k < 2; ++k) ct[k] = ctv[w][k];
                 { const long long c0_ = tr_s ? clock64() : 0; iu_wait(d1_full + (g & 1), (g >> 1) & 1); if (tr_s) ta6 += clock64() - c0_; }
                 iu_fence_after();
                 if (a.debug & 4096) {                                   // timing probe: no softmax work at all, the window is handed on at once
@@ -492,8 +493,9 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
                 }
                 const long long cx0 = tr_s ? clock64() : 0;
                 tbp = cx0;
-                // class exchange: token t needs row r - (7 - s) of class s.  Partial sums over this thread's two classes for all 8
-                // heads: lane shifts inside the warp; the first 7 - s lanes of the upper warp take the lower warp's rows from the halo
+                // class exchange: token t needs row r - (7 - s) of class s.  Every thread publishes the hi + lo sums of its two classes
+                // (row r, all 8 heads) in shared memory as [class][head pair][row] float2 (consecutive rows = consecutive 8-byte
+                // slots: conflict-free both ways); after the barrier it gathers the eight shifted rows of its own head pair.
                 uint32_t v[2][16];
 #pragma unroll
                 for (int i = 0; i < 2; ++i) iu_tmem_ld16_async(trow + (g & 1) * D1_BUF_COLS + 32 * (2 * pg + i) + 16 * half, v[i]);
@@ -501,59 +503,25 @@ __global__ void __launch_bounds__(ipu::THREADS, 1) img_pool_umma_kernel(const __
 #pragma unroll
                 for (int i = 0; i < 2; ++i) iu_tmem_use16(v[i]);
                 TB(0);
-                float part[8];
-#pragma unroll
-                for (int h = 0; h < 8; ++h) part[h] = 0.f;
-                float* hw = halo + (half * HALO_ENTRIES) * 8;
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const int s = 2 * (2 * pg + i) + half, delta = 7 - s;
-                    float xs[8];
-#pragma unroll
-                    for (int h = 0; h < 8; ++h) xs[h] = __uint_as_float(v[i][h]) + __uint_as_float(v[i][8 + h]);
-#pragma unroll
-                    for (int h = 0; h < 8; ++h) {
-                        const float y = __shfl_up_sync(FULL, xs[h], delta);      // delta == 0: the value itself
-                        part[h] += lane >= delta ? y : 0.f;
-                    }
-                    if (qq == 0 && lane >= 32 - delta) {
-                        float4* dst = reinterpret_cast<float4*>(hw + (iu_halo_off(s) + lane - (32 - delta)) * 8);
-                        dst[0] = make_float4(xs[0], xs[1], xs[2], xs[3]);
-                        dst[1] = make_float4(xs[4], xs[5], xs[6], xs[7]);
-                    }
-                }
-                {
-                    // this thread keeps head pair `src`; the other three pairs go to the row's three float2 slots (24-byte pitch:
-                    // 8-byte accesses of a warp spread over all banks)
-                    float* row = xch + (src * 64 + r) * 6;
+                    const int s = 2 * (2 * pg + i) + half;
+                    float2* dst = xch + (s * 4) * 64 + r;
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if (j != src) *reinterpret_cast<float2*>(row + 2 * (j < src ? j : j - 1)) = make_float2(part[2 * j], part[2 * j + 1]);
+                        dst[j * 64] = make_float2(__uint_as_float(v[i][2 * j]) + __uint_as_float(v[i][8 + 2 * j]),
+                                                  __uint_as_float(v[i][2 * j + 1]) + __uint_as_float(v[i][8 + 2 * j + 1]));
                 }
                 TB(1);
                 iu_bar_sync256(1);
                 TB(2);
                 float tot[2] = {0.f, 0.f};
                 {
-                    float2 o[4];
+                    float2 o[8];
 #pragma unroll
-                    for (int sr = 0; sr < 4; ++sr)
-                        o[sr] = sr == src ? make_float2(part[2 * sr], part[2 * sr + 1])     // (static register index: sr is unrolled)
-                                          : *reinterpret_cast<const float2*>(xch + (sr * 64 + r) * 6 + 2 * (src < sr ? src : src - 1));
+                    for (int s = 0; s < 8; ++s) o[s] = xch[(s * 4 + src) * 64 + max(r - (7 - s), 0)];   // (rows below 7 are never tokens of a set)
 #pragma unroll
-                    for (int sr = 0; sr < 4; ++sr) { tot[0] += o[sr].x; tot[1] += o[sr].y; }
-                }
-                if (qq == 1 && !(a.debug & 32)) {                       // rows 32..38 take the lower warp's rows of the classes with 7 - s > lane
-                    float2 x[7];
-#pragma unroll
-                    for (int s = 0; s < 7; ++s) {
-                        const bool need = lane < 7 - s;
-                        const float2* src2 = reinterpret_cast<const float2*>(halo + (((s & 1) * HALO_ENTRIES) + iu_halo_off(s) + (need ? lane : 0)) * 8 + hb);
-                        x[s] = *src2;
-                        if (!need) x[s] = make_float2(0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int s = 0; s < 7; ++s) { tot[0] += x[s].x; tot[1] += x[s].y; }
+                    for (int s = 0; s < 8; ++s) { tot[0] += o[s].x; tot[1] += o[s].y; }
                 }
                 if (tr_s) ta7 += clock64() - cx0;
                 TB(3);
