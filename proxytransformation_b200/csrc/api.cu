@@ -58,7 +58,7 @@ bool proxy_attention_mma_supported(int n, int l, int c, int heads);
 int launch_proxy_attention_mma(const float* qkv, const float* pt_tok, const uint8_t* mask, int B, int n, int l, int c, int heads,
                                float* o, void* o_split, long long o_plane, cudaStream_t s);
 bool proxy_attention_tc_supported(int n, int l, int c, int heads);
-int launch_proxy_attention_tc(const void* qk_split, long long qk_plane, int ldq, const void* vt_split, long long vt_plane, long long ldv,
+int launch_proxy_attention_tc(const void* qk_split, long long qk_plane, int ldq, const void* vt_split, long long vt_plane, long long ldv, int vt_seg,
                               const void* pt_split, long long pt_plane, const uint8_t* mask, int B, int n, int l, int c, int heads,
                               float* o, void* o_split, long long o_plane, cudaStream_t s);
 int launch_gemm_f32(const float* A, const float* W, const float* bias, const float* residual, int act, int M, int N, int K,
@@ -86,7 +86,7 @@ static BlockWs carve_block(void* ws, int B, int n, int l, int c, int hidden) {
     auto take = [&](size_t bytes) { void* p = ws ? (void*)((char*)ws + off) : nullptr; off += align_up(bytes, 256); return p; };
     const size_t rows = (size_t)B * n;
     r.u = (float*)take(rows * c * 4);
-    r.qkv = (float*)take(rows * 3 * c * 4);
+    r.qkv = (float*)take(rows * 3 * c * 4 + (size_t)B * 8 * c * 4);      // (+ the per-scene padding of the V^T planes, see below)
     r.pt = (float*)take((size_t)B * l * c * 4);
     r.o = (float*)take(rows * c * 4);
     r.x1 = (float*)take(rows * c * 4);
@@ -174,7 +174,10 @@ extern "C" int pt_proxy_block_fused(const float* x, const float* proxy, const ui
         static const bool no_tc_attn = getenv("PT_ATTN_MMA") != nullptr;          // debug: force the mma.sync attention kernel
         if (!no_tc_attn && proxy_attention_tc_supported(n, l, c, heads)) {
             // tcgen05 / TMEM attention (attn_tc.cu): every operand is a bf16 hi/lo plane pair written by a projection GEMM.
-            // The fp32 qkv buffer (rows x 3c x 4 B) holds [Q|K] planes (2 x rows x 2c) followed by the V^T planes (2 x c x rows).
+            // The fp32 qkv buffer (rows x 3c x 4 B) holds [Q|K] planes (2 x rows x 2c) followed by the V^T planes (2 x c x B*npad8): every
+            // scene's columns start on a 16-byte boundary (n padded to a multiple of 8) whatever n is.
+            const int npad8 = (n + 7) & ~7;
+            const long long vt_cols = (long long)B * npad8;
             __nv_bfloat16* qk_s = (__nv_bfloat16*)w.qkv;
             __nv_bfloat16* vt_s = qk_s + (size_t)2 * rows * 2 * c;
             __nv_bfloat16* pt_s = (__nv_bfloat16*)w.pt;
@@ -186,7 +189,8 @@ extern "C" int pt_proxy_block_fused(const float* x, const float* proxy, const ui
                 gp.w_split = p->qkv_w_split; gp.w_rows = 3 * c; gp.ldw = c;
                 gp.bias = p->qkv_b;
                 gp.c_split = qk_s; gp.cs_plane = (long long)rows * 2 * c; gp.ldcs = 2 * c;
-                gp.ct_split = vt_s; gp.ct_col0 = 2 * c; gp.ct_ld = rows; gp.ct_plane = (long long)c * rows;
+                gp.ct_split = vt_s; gp.ct_col0 = 2 * c; gp.ct_ld = vt_cols; gp.ct_plane = (long long)c * vt_cols;
+                gp.ct_seg = n; gp.ct_seg_pad = npad8;
                 if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
             }
             // Pt = proxy Wp^T + bp                                     (:223)
@@ -201,7 +205,7 @@ extern "C" int pt_proxy_block_fused(const float* x, const float* proxy, const ui
                 if ((rc = launch_gemm_tc_ex(gp, s))) return rc;
             }
             // two-stage proxy attention                                (:225-252)
-            if ((rc = launch_proxy_attention_tc(qk_s, (long long)rows * 2 * c, 2 * c, vt_s, (long long)c * rows, rows, pt_s,
+            if ((rc = launch_proxy_attention_tc(qk_s, (long long)rows * 2 * c, 2 * c, vt_s, (long long)c * vt_cols, vt_cols, npad8, pt_s,
                                                 (long long)B * l * c, mask, B, n, l, c, heads, nullptr, w.o_s, (long long)rows * c, s)))
                 return rc;
         } else {

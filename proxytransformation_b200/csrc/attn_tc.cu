@@ -1,8 +1,10 @@
 // tcgen05 / TMEM form of the two-stage proxy attention core of ProxyAttention.forward (:225-252), one CTA per (scene, head):
 //   stage 1 (proxy as query, :232-238):  Pv = softmax_n((Pt*scale) K^T) V          (l x hd), unmasked
 //   stage 2 (proxy as key,   :241-250):  O  = softmax_l(mask((Q*scale) Pt^T)) Pv   (n x hd)
-// for heads of 32 channels, n <= 256 point proxies and l <= 256 text / image proxies (the benchmark shape; larger n fall
-// back to the mma.sync kernel in attn_mma.cu).
+// for heads of 32 channels, n <= 1024 point proxies (any n: the benchmark's 256, the shipped config's 691) and l <= 256 text / image
+// proxies.  The clusters are streamed: stage 1 walks the keys in tiles of 256 with an online softmax (running maximum / sum per
+// proxy row, accumulator rescaled in TMEM), stage 2 walks the cluster rows in tiles of 128; only one K / V^T tile and one Q tile
+// are resident at a time.  (Other head sizes / l > 256: the mma.sync kernel in attn_mma.cu.)
 //
 // Every contraction is a tcgen05.mma (cta_group::1, kind::f16, M = 128) with fp32 accumulation in TMEM and 3xBF16 operand
 // splitting (hi*hi + lo*hi + hi*lo), so scores and outputs keep ~2^-17 relative accuracy:
@@ -23,6 +25,7 @@ namespace pt {
 
 namespace at {
 constexpr int THREADS = 512, HD = 32, MAXR = 256;   // 16 warps: 4 per TMEM lane quarter, each takes every 4th 32-column chunk
+constexpr int MAXN = 1024;                            // clusters (streamed in key tiles of MAXR and row tiles of 128)
 constexpr int ROW_BYTES = 128;                        // [hi 32 | lo 32] bf16
 constexpr int TILE_BYTES = MAXR * ROW_BYTES;          // 32768: Q / K / Pt operand tiles (256 rows)
 constexpr int VT_TILE = HD * ROW_BYTES;               // 4096: one 64-key k-tile of V^T / Pv^T (32 rows)
@@ -30,8 +33,8 @@ constexpr int VT_PLANE = 4 * VT_TILE;                 // 16384: 256 keys
 constexpr int OFF_K = 0, OFF_Q = OFF_K + TILE_BYTES, OFF_P = OFF_Q + TILE_BYTES;
 constexpr int OFF_VT = OFF_P + TILE_BYTES;            // hi plane, then lo plane
 constexpr int OFF_PV = OFF_VT + 2 * VT_PLANE;         // hi plane, then lo plane
-constexpr int OFF_MISC = OFF_PV + 2 * VT_PLANE;       // rowmax [4][128], rowsum [4][128], keyflag [256] floats
-constexpr int OFF_BAR = OFF_MISC + (8 * 128 + 256) * 4;
+constexpr int OFF_MISC = OFF_PV + 2 * VT_PLANE;       // rowmax [4][128], rowsum [4][128], keyflag [256], runm [256], runl [256] floats
+constexpr int OFF_BAR = OFF_MISC + (8 * 128 + 3 * 256) * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 16 + 1024;       // + alignment slack
 constexpr int TMEM_COLS = 512, ACC_COL = 256;
 }  // namespace at
@@ -90,6 +93,11 @@ __device__ __forceinline__ void at_st16(uint32_t taddr, const uint32_t (&r)[16])
                  "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
                  : "memory");
 }
+__device__ __forceinline__ void at_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 __device__ __forceinline__ void at_ld8(uint32_t (&v)[8], uint32_t taddr) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -121,6 +129,7 @@ struct AtArgs {
     const __nv_bfloat16* vt;      // hi plane of V^T [c][ldv] (column = global row b*n + j); lo plane vt_plane later
     long long vt_plane;
     long long ldv;
+    int vt_seg;                   // columns per scene in V^T (>= n; a multiple of 8 keeps every scene on the 16-byte grid)
     const __nv_bfloat16* pt;      // hi plane of Pt [B*l][c]; lo plane pt_plane later
     long long pt_plane;
     const uint8_t* mask;          // (B,l) 1 = real token, or null
@@ -135,8 +144,11 @@ struct AtArgs {
 // (chunk j of 32 keys -> 16 hi columns, 16 lo columns).  nvalid = real keys; flag (smem) != 0 marks masked keys (-1e9).
 // Each of the 4 warps of a lane quarter (hh) takes every 4th chunk; the row maximum and the row sum meet in shared memory.
 // softmax(scale*s) is evaluated as 2^(s*c1 - max*c1) with c1 = scale*log2(e): one FFMA and one MUFU per element.
-__device__ __forceinline__ void at_softmax_tile(uint32_t tmem_row, int ncols, int nvalid, const float* __restrict__ flag, float scale,
-                                                int hh, float* __restrict__ rowmax, float* __restrict__ rowsum, int row) {
+// `m_old` (scaled running maximum of the row over the earlier key tiles, -inf for the first) makes it the step of an online softmax:
+// the probabilities are relative to max(m_old, tile maximum), which is returned for the caller's bookkeeping.
+__device__ __forceinline__ float at_softmax_tile(uint32_t tmem_row, int ncols, int nvalid, const float* __restrict__ flag, float scale,
+                                                 int hh, float* __restrict__ rowmax, float* __restrict__ rowsum, int row,
+                                                 float m_old = -INFINITY) {
     const int nch = (ncols + 31) >> 5;
     const float c1 = scale * 1.4426950408889634f;
     float mx = -INFINITY;                                      // maximum of the UNSCALED scores of the real, unmasked keys
@@ -164,6 +176,7 @@ __device__ __forceinline__ void at_softmax_tile(uint32_t tmem_row, int ncols, in
     rowmax[hh * 128 + row] = ms;
     __syncthreads();
     ms = fmaxf(fmaxf(rowmax[row], rowmax[128 + row]), fmaxf(rowmax[256 + row], rowmax[384 + row]));    // finite: key 0 is a real key
+    ms = fmaxf(ms, m_old);
     const float mc = ms * 1.4426950408889634f;
     const float pmask = at_ex2(-1e9f * 1.4426950408889634f - mc);      // probability weight of a masked key (1 if every key is masked)
     float sum = 0.f;
@@ -198,6 +211,7 @@ __device__ __forceinline__ void at_softmax_tile(uint32_t tmem_row, int ncols, in
     }
     rowsum[hh * 128 + row] = sum;
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    return ms;
 }
 
 __global__ void __launch_bounds__(at::THREADS, 1) proxy_attention_tc_kernel(const AtArgs a) {
@@ -223,31 +237,67 @@ __global__ void __launch_bounds__(at::THREADS, 1) proxy_attention_tc_kernel(cons
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
 
-    // ---- stage the operand tiles (K-major, SWIZZLE_128B: 16-byte chunk ch of row r sits at chunk ch ^ (r & 7))
+    // ---- operand tiles are K-major, SWIZZLE_128B: 16-byte chunk ch of row r sits at chunk ch ^ (r & 7); rows = [hi 32 | lo 32]
     const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < MAXR * 8; i += THREADS) {
-        const int r = i >> 3, ch = i & 7, half = ch >> 2, col = h * HD + 8 * (ch & 3);
-        const uint32_t dst = r * ROW_BYTES + ((ch ^ (r & 7)) << 4);
-        uint4 kq = z4, qq = z4, pp = z4;
-        if (r < n) {
-            const __nv_bfloat16* src = a.qk + (half ? a.qk_plane : 0) + ((size_t)b * n + r) * a.ldq + col;
-            qq = __ldg(reinterpret_cast<const uint4*>(src));
-            kq = __ldg(reinterpret_cast<const uint4*>(src + c));
+    float* runm = keyflag + 256;                                // running maximum (scaled) / sum of every proxy row over the key tiles
+    float* runl = runm + 256;
+    // [Q|K] rows r0.. (column col0 of the head) -> registers (RPT uint4 per thread) -> swizzled tile at `off`: the loads of the next
+    // tile are issued before the current tile's pass and land while it runs
+    auto load_rows = [&](uint4 (&reg)[4], int col0, int r0, int nrows_tile, int nrows_total) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = tid + k * THREADS, r = i >> 3, ch = i & 7, half = ch >> 2, col = col0 + 8 * (ch & 3);
+            reg[k] = z4;
+            if (i < nrows_tile * 8 && r0 + r < nrows_total)
+                reg[k] = __ldg(reinterpret_cast<const uint4*>(a.qk + (half ? a.qk_plane : 0) + ((size_t)b * n + r0 + r) * a.ldq + col));
         }
+    };
+    auto store_rows = [&](const uint4 (&reg)[4], int off, int nrows_tile) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = tid + k * THREADS, r = i >> 3, ch = i & 7;
+            if (i < nrows_tile * 8) *reinterpret_cast<uint4*>(smem + off + r * ROW_BYTES + ((ch ^ (r & 7)) << 4)) = reg[k];
+        }
+    };
+    auto stage_vt = [&](int k0) {                               // V^T planes of keys k0 .. k0 + 255 (zero past n)
+        const size_t key0 = (size_t)b * a.vt_seg + k0;
+        if ((key0 & 7) == 0 && (a.vt_seg & 7) == 0 && (a.ldv & 7) == 0 && (a.vt_plane & 7) == 0) {  // 16-byte chunks of 8 keys
+            for (int i = tid; i < 2 * HD * 32; i += THREADS) {
+                const int plane = i >> 10, e = (i >> 5) & 31, j8 = i & 31;
+                uint4 v = z4;
+                const int left = n - (k0 + 8 * j8);             // real keys in this chunk (the rest of a scene's last chunk is padding)
+                if (left > 0) {
+                    v = __ldg(reinterpret_cast<const uint4*>(a.vt + (plane ? a.vt_plane : 0) + (size_t)(h * HD + e) * a.ldv + key0 + 8 * j8));
+                    if (left < 8) {
+                        uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int q2 = 0; q2 < 4; ++q2) w4[q2] = 2 * q2 >= left ? 0u : (2 * q2 + 1 >= left ? (w4[q2] & 0xffffu) : w4[q2]);
+                        v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                    }
+                }
+                *reinterpret_cast<uint4*>(smem + OFF_VT + plane * VT_PLANE + (j8 >> 3) * VT_TILE + e * ROW_BYTES + (((j8 & 7) ^ (e & 7)) << 4)) = v;
+            }
+        } else {                                                // scenes whose first key is not 16-byte aligned (odd n): element by element
+            for (int i = tid; i < 2 * HD * MAXR; i += THREADS) {
+                const int plane = i >> 13, e = (i >> 8) & 31, j = i & 255;
+                unsigned short v = 0;
+                if (k0 + j < n) v = __ldg(reinterpret_cast<const unsigned short*>(a.vt + (plane ? a.vt_plane : 0) + (size_t)(h * HD + e) * a.ldv + key0 + j));
+                *reinterpret_cast<unsigned short*>(smem + OFF_VT + plane * VT_PLANE + (j >> 6) * VT_TILE + e * ROW_BYTES + ((((j >> 3) & 7) ^ (e & 7)) << 4) + (j & 7) * 2) = v;
+            }
+        }
+    };
+    for (int i = tid; i < MAXR * 8; i += THREADS) {             // Pt (all l <= 256 proxies stay resident)
+        const int r = i >> 3, ch = i & 7, half = ch >> 2, col = h * HD + 8 * (ch & 3);
+        uint4 pp = z4;
         if (r < l) pp = __ldg(reinterpret_cast<const uint4*>(a.pt + (half ? a.pt_plane : 0) + ((size_t)b * l + r) * c + col));
-        *reinterpret_cast<uint4*>(smem + OFF_K + dst) = kq;
-        *reinterpret_cast<uint4*>(smem + OFF_Q + dst) = qq;
-        *reinterpret_cast<uint4*>(smem + OFF_P + dst) = pp;
-    }
-    for (int i = tid; i < 2 * HD * 32; i += THREADS) {          // V^T: plane, row e, 8-key chunk j8
-        const int plane = i >> 10, e = (i >> 5) & 31, j8 = i & 31;
-        uint4 v = z4;
-        if (8 * j8 < n) v = __ldg(reinterpret_cast<const uint4*>(a.vt + (plane ? a.vt_plane : 0) + (size_t)(h * HD + e) * a.ldv + (size_t)b * n + 8 * j8));
-        *reinterpret_cast<uint4*>(smem + OFF_VT + plane * VT_PLANE + (j8 >> 3) * VT_TILE + e * ROW_BYTES + (((j8 & 7) ^ (e & 7)) << 4)) = v;
+        *reinterpret_cast<uint4*>(smem + OFF_P + r * ROW_BYTES + ((ch ^ (r & 7)) << 4)) = pp;
     }
     for (int i = tid; i < 2 * VT_PLANE / 16; i += THREADS) *reinterpret_cast<uint4*>(smem + OFF_PV + 16 * i) = z4;
-    for (int i = tid; i < 256; i += THREADS) keyflag[i] = (a.mask != nullptr && i < l && a.mask[(size_t)b * l + i] == 0) ? 1.f : 0.f;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int i = tid; i < 256; i += THREADS) {
+        keyflag[i] = (a.mask != nullptr && i < l && a.mask[(size_t)b * l + i] == 0) ? 1.f : 0.f;
+        runm[i] = -INFINITY;
+        runl[i] = 0.f;
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -261,7 +311,8 @@ __global__ void __launch_bounds__(at::THREADS, 1) proxy_attention_tc_kernel(cons
 
     // one (scores -> softmax -> values) pass over a 128-row tile
     //   sA: operand tile of the rows, sB: operand tile of the keys (nkeys_pad rows), sV: value planes (K-major over the keys)
-    auto pass = [&](uint32_t sA, uint32_t sB, int nkeys, int nkeys_pad, uint32_t sV, const float* flag) {
+    //   acc_col: accumulator columns; online >= 0: index of the tile's first row in runm / runl (stage 1, key tile `kt`)
+    auto pass = [&](uint32_t sA, uint32_t sB, int nkeys, int nkeys_pad, uint32_t sV, const float* flag, uint32_t acc_col, int online, int kt) {
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t idesc = at_idesc(nkeys_pad);
@@ -277,9 +328,24 @@ __global__ void __launch_bounds__(at::THREADS, 1) proxy_attention_tc_kernel(cons
         }
         at_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        at_softmax_tile(tmem_row, nkeys_pad, nkeys, flag, a.scale, hh, rowmax, rowsum, row);
+        const float m_old = online >= 0 ? runm[online + row] : -INFINITY;
+        const float m_new = at_softmax_tile(tmem_row, nkeys_pad, nkeys, flag, a.scale, hh, rowmax, rowsum, row, m_old);
+        float alpha = 0.f;
+        if (online >= 0 && kt > 0) {                            // earlier key tiles were accumulated relative to m_old: rescale
+            alpha = at_ex2((m_old - m_new) * 1.4426950408889634f);
+            uint32_t v[8];
+            at_ld8(v, tmem_row + acc_col + 8 * hh);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+            at_st8(tmem_row + acc_col + 8 * hh, v);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
+        if (online >= 0 && hh == 0) {
+            runl[online + row] = runl[online + row] * alpha + ((rowsum[row] + rowsum[128 + row]) + (rowsum[256 + row] + rowsum[384 + row]));
+            runm[online + row] = m_new;
+        }
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t idesc = at_idesc(HD);
@@ -287,9 +353,9 @@ __global__ void __launch_bounds__(at::THREADS, 1) proxy_attention_tc_kernel(cons
                 const uint32_t a_hi = tmem + 32 * (ks >> 1) + 8 * (ks & 1), a_lo = a_hi + 16;
                 const uint32_t voff = (uint32_t)((ks >> 2) * VT_TILE + (ks & 3) * 32);
                 const uint64_t dv_hi = at_desc_sw128(sV + voff), dv_lo = at_desc_sw128(sV + VT_PLANE + voff);
-                at_mma_ts(tmem + ACC_COL, a_hi, dv_hi, idesc, ks != 0 ? 1u : 0u);
-                at_mma_ts(tmem + ACC_COL, a_lo, dv_hi, idesc, 1u);
-                at_mma_ts(tmem + ACC_COL, a_hi, dv_lo, idesc, 1u);
+                at_mma_ts(tmem + acc_col, a_hi, dv_hi, idesc, (ks != 0 || kt > 0) ? 1u : 0u);
+                at_mma_ts(tmem + acc_col, a_lo, dv_hi, idesc, 1u);
+                at_mma_ts(tmem + acc_col, a_hi, dv_lo, idesc, 1u);
             }
             at_commit(bar);
         }
@@ -297,14 +363,32 @@ __global__ void __launch_bounds__(at::THREADS, 1) proxy_attention_tc_kernel(cons
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     };
 
-    // ---- stage 1: rows = proxies, keys = clusters, values = V  ->  Pv^T (normalised) as K-major operand planes
-    for (int mt = 0; mt * 128 < lpad; ++mt) {
-        pass(sP + mt * 128 * ROW_BYTES, sK, n, npad, sVT, nullptr);
+    // ---- stage 1: rows = proxies, keys = clusters in tiles of 256 (online softmax), values = V  ->  Pv^T (normalised) as K-major
+    // operand planes.  Accumulator of proxy row tile mt: columns ACC_COL + 32 mt.
+    const int nmt1 = (lpad + 127) >> 7;
+    uint4 kreg[4], qreg[4];
+    load_rows(kreg, c + h * HD, 0, MAXR, n);
+    for (int kt = 0; kt * MAXR < n; ++kt) {
+        const int k0 = kt * MAXR, nk = min(MAXR, n - k0), nkpad = (nk + 15) & ~15;
+        store_rows(kreg, OFF_K, MAXR);
+        stage_vt(k0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (k0 + MAXR < n) load_rows(kreg, c + h * HD, k0 + MAXR, MAXR, n);                  // next K tile in flight during the passes
+        else load_rows(qreg, h * HD, 128 * (int)blockIdx.z, 128, n);                          // ... or the first Q tile of stage 2
+        for (int mt = 0; mt < nmt1; ++mt) {
+            pass(sP + mt * 128 * ROW_BYTES, sK, nk, nkpad, sVT, nullptr, ACC_COL + 32 * mt, 128 * mt, kt);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();                                    // rowmax / rowsum reusable; (last mt) K / V^T tiles reusable
+        }
+    }
+    for (int mt = 0; mt < nmt1; ++mt) {
         uint32_t v[8];
-        at_ld8(v, tmem_row + ACC_COL + 8 * hh);
+        at_ld8(v, tmem_row + ACC_COL + 32 * mt + 8 * hh);
         const int i = mt * 128 + row;                           // proxy index
         if (i < l) {
-            const float inv = 1.0f / ((rowsum[row] + rowsum[128 + row]) + (rowsum[256 + row] + rowsum[384 + row]));
+            const float inv = 1.0f / runl[i];
             uint8_t* base = smem + OFF_PV + (i >> 6) * VT_TILE + (i & 7) * 2;
             const int ch = (i & 63) >> 3;
 #pragma unroll
@@ -317,14 +401,17 @@ __global__ void __launch_bounds__(at::THREADS, 1) proxy_attention_tc_kernel(cons
                 *reinterpret_cast<__nv_bfloat16*>(p + VT_PLANE) = yl;
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                                        // accumulator drained, Pv^T visible, rowmax / rowsum reusable
     }
 
-    // ---- stage 2: rows = clusters (Q), keys = proxies (masked), values = Pv
-    for (int mt = 0; mt * 128 < npad; ++mt) {
-        pass(sQ + mt * 128 * ROW_BYTES, sP, l, lpad, sPV, a.mask != nullptr ? keyflag : nullptr);
+    // ---- stage 2: rows = clusters (Q) in tiles of 128, keys = proxies (masked), values = Pv.  The row tiles are independent: with
+    // few (scene, head) pairs the launch spreads them over gridDim.z CTAs (each repeats stage 1).
+    for (int mt = blockIdx.z; mt * 128 < npad; mt += gridDim.z) {
+        store_rows(qreg, OFF_Q, 128);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                        // Q tile (and, first time, Pv^T) visible; accumulator drained
+        if ((mt + (int)gridDim.z) * 128 < npad) load_rows(qreg, h * HD, 128 * (mt + (int)gridDim.z), 128, n);
+        pass(sQ, sP, l, lpad, sPV, a.mask != nullptr ? keyflag : nullptr, ACC_COL, -1, 0);
         uint32_t v[8];
         at_ld8(v, tmem_row + ACC_COL + 8 * hh);
         const int r = mt * 128 + row;                           // cluster index
@@ -353,29 +440,35 @@ __global__ void __launch_bounds__(at::THREADS, 1) proxy_attention_tc_kernel(cons
 }
 
 bool proxy_attention_tc_supported(int n, int l, int c, int heads) {
-    return c % heads == 0 && c / heads == at::HD && c % 8 == 0 && n >= 1 && n <= at::MAXR && n % 8 == 0 && l >= 1 && l <= at::MAXR;
+    return c % heads == 0 && c / heads == at::HD && c % 8 == 0 && n >= 1 && n <= at::MAXN && l >= 1 && l <= at::MAXR;
 }
 
 // qk_split: [2][rows][ldq] bf16 (Q | K); vt_split: [2][c][ldv] bf16 (V^T, column = b*n + j); pt_split: [2][B*l][c] bf16.
-int launch_proxy_attention_tc(const void* qk_split, long long qk_plane, int ldq, const void* vt_split, long long vt_plane, long long ldv,
+int launch_proxy_attention_tc(const void* qk_split, long long qk_plane, int ldq, const void* vt_split, long long vt_plane, long long ldv, int vt_seg,
                               const void* pt_split, long long pt_plane, const uint8_t* mask, int B, int n, int l, int c, int heads,
                               float* o, void* o_split, long long o_plane, cudaStream_t s) {
     PT_REQUIRE(proxy_attention_tc_supported(n, l, c, heads), "attention(tcgen05): n=%d l=%d c=%d heads=%d unsupported", n, l, c, heads);
     PT_REQUIRE(qk_split && vt_split && pt_split && (o || o_split), "attention(tcgen05): null operand");
+    // (V^T: any pitch / plane offset — scenes whose columns are off the 16-byte grid are staged element by element)
     PT_REQUIRE(((uintptr_t)qk_split & 15) == 0 && ((uintptr_t)vt_split & 15) == 0 && ((uintptr_t)pt_split & 15) == 0 && ldq % 8 == 0 &&
-                   ldv % 8 == 0 && qk_plane % 8 == 0 && vt_plane % 8 == 0 && pt_plane % 8 == 0 && o_plane % 8 == 0,
+                   qk_plane % 8 == 0 && pt_plane % 8 == 0 && o_plane % 8 == 0,
                "attention(tcgen05): operand planes must be 16-byte aligned");
     static bool attr[PT_MAX_DEVICES] = {};
     if (first_use_on_current_device(attr))
         PT_CUDA_OK(cudaFuncSetAttribute(proxy_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, at::SMEM_BYTES));
     AtArgs a;
     a.qk = (const __nv_bfloat16*)qk_split; a.qk_plane = qk_plane; a.ldq = ldq;
-    a.vt = (const __nv_bfloat16*)vt_split; a.vt_plane = vt_plane; a.ldv = ldv;
+    PT_REQUIRE(vt_seg >= n && ldv >= (long long)B * vt_seg, "attention(tcgen05): vt_seg=%d ldv=%lld", vt_seg, ldv);
+    a.vt = (const __nv_bfloat16*)vt_split; a.vt_plane = vt_plane; a.ldv = ldv; a.vt_seg = vt_seg;
     a.pt = (const __nv_bfloat16*)pt_split; a.pt_plane = pt_plane;
     a.mask = mask; a.n = n; a.l = l; a.c = c;
     a.scale = (float)(1.0 / sqrt((double)at::HD));              // python float head_dim ** -0.5 (:186), rounded to fp32 once
     a.o = o; a.o_hi = (__nv_bfloat16*)o_split; a.o_plane = o_plane;
-    { ProfScope prof_(PROF_ATTENTION, s); proxy_attention_tc_kernel<<<dim3(heads, B), at::THREADS, at::SMEM_BYTES, s>>>(a); }
+    // few (scene, head) pairs (small batches): spread the independent cluster row tiles of stage 2 over the otherwise idle SMs
+    const int row_tiles = (n + 127) / 128;
+    int zsplit = 148 / (heads * B);                             // (one CTA per SM: stay within a single wave)
+    zsplit = zsplit < 1 ? 1 : (zsplit > row_tiles ? row_tiles : zsplit);
+    { ProfScope prof_(PROF_ATTENTION, s); proxy_attention_tc_kernel<<<dim3(heads, B, zsplit), at::THREADS, at::SMEM_BYTES, s>>>(a); }
     PT_LAUNCH_CHECK();
     return PT_OK;
 }
@@ -386,6 +479,7 @@ int launch_proxy_attention_tc(const void* qk_split, long long qk_plane, int ldq,
 extern "C" int pt_proxy_attention_tc(const void* qk_split, long long qk_plane, int ldq, const void* vt_split, long long vt_plane,
                                      long long ldv, const void* pt_split, long long pt_plane, const uint8_t* mask, int B, int n, int l,
                                      int c, int heads, float* o, void* o_split, long long o_plane, pt_stream_t stream) {
-    return pt::launch_proxy_attention_tc(qk_split, qk_plane, ldq, vt_split, vt_plane, ldv, pt_split, pt_plane, mask, B, n, l, c, heads, o,
+    // (V^T columns b*n + j: scenes back to back; the block driver pads every scene to a multiple of 8 columns instead)
+    return pt::launch_proxy_attention_tc(qk_split, qk_plane, ldq, vt_split, vt_plane, ldv, n, pt_split, pt_plane, mask, B, n, l, c, heads, o,
                                          o_split, o_plane, (cudaStream_t)stream);
 }

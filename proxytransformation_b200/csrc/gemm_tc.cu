@@ -103,6 +103,7 @@ struct TcKernelArgs {
     __nv_bfloat16* Cs; long long cs_plane; int ldcs; long long cs_off_z;     // optional bf16 hi/lo planes of the result
     int cs_fp16; float cs_scale;                                             // ... as IEEE half planes of cs_scale * result
     __nv_bfloat16* Ct; int ct_col0; long long ct_ld, ct_plane;               // optional transposed planes for columns >= ct_col0
+    int ct_seg, ct_seg_pad;                                                  // row segments (scenes) padded to ct_seg_pad columns
     int act;
     int tiles_m, tiles_n, stages;
 };
@@ -226,7 +227,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     const int row = row0 + lane;
                     if (row < g.M) {
-                        __nv_bfloat16* dst = g.Ct + (size_t)(n0 + cc * 32 - g.ct_col0) * g.ct_ld + row;
+                        const long long tcol = g.ct_seg > 0 ? (long long)(row / g.ct_seg) * g.ct_seg_pad + row % g.ct_seg : row;
+                        __nv_bfloat16* dst = g.Ct + (size_t)(n0 + cc * 32 - g.ct_col0) * g.ct_ld + tcol;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             if (n0 + cc * 32 + j < g.N) {
@@ -429,6 +431,8 @@ static int launch_bn(const CUtensorMap& mapA, const CUtensorMap& mapW, TcKernelA
 int launch_gemm_tc_ex(const GemmTc& p, cudaStream_t s) {
     PT_REQUIRE(gemm_tc_supported(p.M, p.N, p.K) && p.batch >= 1, "gemm_tc: M=%d N=%d K=%d batch=%d unsupported", p.M, p.N, p.K, p.batch);
     PT_REQUIRE(p.a_split && p.w_split && (p.C || p.c_split), "gemm_tc: null operand");
+    PT_REQUIRE(!p.ct_split || p.ct_seg == 0 || (p.ct_seg > 0 && p.ct_seg_pad >= p.ct_seg && p.ct_ld >= (long long)ceil_div(p.M, p.ct_seg) * p.ct_seg_pad),
+               "gemm_tc: transposed output segments: ct_seg=%d ct_seg_pad=%d ct_ld=%lld", p.ct_seg, p.ct_seg_pad, p.ct_ld);
     PT_REQUIRE(!p.ct_split || (p.ct_col0 % 32 == 0 && p.ct_col0 >= 0 && p.ct_ld >= p.M && p.batch == 1 && !p.act),
                "gemm_tc: transposed output needs ct_col0 %% 32 == 0, ct_ld >= M, batch 1, no activation");
     PT_REQUIRE(((uintptr_t)p.a_split & 15) == 0 && ((uintptr_t)p.w_split & 15) == 0 && (p.lda % 8) == 0 && (p.ldw % 8) == 0,
@@ -455,6 +459,7 @@ int launch_gemm_tc_ex(const GemmTc& p, cudaStream_t s) {
     k.cs_fp16 = p.cs_fp16 ? 1 : 0; k.cs_scale = p.cs_scale;
     k.act = p.act;
     k.Ct = (__nv_bfloat16*)p.ct_split; k.ct_col0 = p.ct_col0; k.ct_ld = p.ct_ld; k.ct_plane = p.ct_plane;
+    k.ct_seg = p.ct_seg; k.ct_seg_pad = p.ct_seg_pad;
     k.tiles_m = ceil_div(p.M, TC_BM);
     switch (bn) {
         case 32: return launch_bn<32>(mapA, mapW, k, s);

@@ -37,6 +37,9 @@ struct GemmTc {
     void* ct_split = nullptr;
     int ct_col0 = 0;
     long long ct_ld = 0, ct_plane = 0;
+    // rows come in segments of ct_seg (scenes) that start every ct_seg_pad columns of the transposed planes (0: no segments), so that
+    // every segment starts on a 16-byte boundary whatever its length
+    int ct_seg = 0, ct_seg_pad = 0;
     int bn = 0;                           // tile width override (32/64/128/256), 0 = auto
 };
 

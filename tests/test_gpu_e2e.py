@@ -208,7 +208,7 @@ def test_cuda_graph_replay_equals_eager_forward():
     (4, 0.5, 3000, 3, 5, 3, torch.bfloat16, 12.0),
     (5, 0.6, 4000, 7, 17, 2, torch.bfloat16, 20.0),
     (6, 0.55, 6000, 2, 77, 1, torch.float32, 30.0),
-    (7, 0.6, 9000, 5, 33, 2, torch.bfloat16, 40.0),          # n = 137 clusters: not a multiple of 8 -> mma.sync attention
+    (7, 0.6, 9000, 5, 33, 2, torch.bfloat16, 40.0),          # n = 137 clusters: not a multiple of 8 (element-wise V^T staging in the tcgen05 attention)
     (4, 0.5, 2000, 9, 8, 5, torch.bfloat16, 9.0),
     (5, 0.6, 4000, 7, 17, 2, torch.float16, 20.0),           # fp16 features (the reference's --amp backbone): tcgen05 pooling path
     (4, 0.5, 3000, 40, 5, 5, torch.float16, 12.0),           # 200 views: several views per CTA
@@ -307,3 +307,21 @@ def test_headline_config_full_forward_against_oracle():
     for o, w in zip(out, want):
         assert o.shape == w.shape
         np.testing.assert_allclose(np_(o), w.numpy(), rtol=0, atol=1e-4)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_module_on_second_gpu_while_the_current_device_is_the_first():
+    """ADVICE (round 1): the C side launches on the CURRENT device's stream; the module guards every call with the device of its
+    parameters, so a module on cuda:1 must give the results of the same module on cuda:0 while torch's current device stays 0
+    (DataParallel-style use, a second pipeline stage)."""
+    cfg = syn.C1.replace(n_views=3)
+    sd = syn.make_state_dict(cfg, 3, bf16_round=True)
+    pts, text_dict, img = syn.make_inputs(cfg, 2, first_scene=70, img_dtype=torch.bfloat16)
+    m0 = build_module(cfg, sd)
+    want = m0([p.to("cuda:0") for p in pts], {k: v.to("cuda:0") for k, v in text_dict.items()}, img.to("cuda:0"))
+    m1 = build_module(cfg, sd).to("cuda:1")
+    assert torch.cuda.current_device() == 0
+    got = m1([p.to("cuda:1") for p in pts], {k: v.to("cuda:1") for k, v in text_dict.items()}, img.to("cuda:1"))
+    assert torch.cuda.current_device() == 0
+    assert all(g.device == torch.device("cuda:1") for g in got)
+    assert all(torch.equal(g.cpu(), w.cpu()) for g, w in zip(got, want))
