@@ -159,6 +159,12 @@ class ProxyTransformationNormReverse(nn.Module):
         # geometric stages.  (The whole image stage on a side stream measured slower, 3.04 vs 2.86 ms/step: the persistent
         # pool kernel owns every SM's shared memory and the small kernels queue behind it.)
         self.overlap_mean_pass = os.environ.get("PT_OVERLAP_MEAN", "0") != "0"    # measured: 2.735 vs 2.765 ms/step at best, off by default
+        # the WHOLE image stage on a second stream next to the geometric stages + text branch (measured: 2.475 -> 2.410 ms per
+        # 64-scene step; shipped config at batch 4 as a CUDA graph 0.931 -> 0.888 ms, eager 1.018 -> 1.044 ms: the extra stream
+        # hand-offs cost host time that only matters when the forward is launch bound).  "auto": batches of at least
+        # `overlap_img_min_batch` scenes, or while a CUDA graph is being captured
+        self.overlap_img_stage = os.environ.get("PT_OVERLAP_IMG", "auto")
+        self.overlap_img_min_batch = 8
         self._streams: Dict[str, torch.cuda.Stream] = {}
         self.host_chunk_scenes = 8       # scenes per pipeline chunk when forward() is fed host tensors
         self.cuda_graphs = os.environ.get("PT_CUDA_GRAPHS", "0") != "0"     # replay small device-resident batches as one CUDA graph
@@ -498,7 +504,18 @@ class ProxyTransformationNormReverse(nn.Module):
         # ALU bound and barely touch HBM: the two run concurrently on two streams.  The second half (the persistent pooling
         # kernel, which owns every SM's shared memory) stays on the main stream.
         side = img_state = None
-        if img_proxy is None and self.overlap_mean_pass:
+        img_side = None
+        ov = self.overlap_img_stage
+        if img_proxy is None and not train and (ov == "1" or (ov == "auto" and (P.shape[0] >= self.overlap_img_min_batch or
+                                                                                  torch.cuda.is_current_stream_capturing()))):
+            cur = torch.cuda.current_stream(P.device)
+            img_side = self._side_stream(P.device)
+            img_side.wait_stream(cur)
+            with torch.cuda.stream(img_side):
+                img_proxy = ops.img_attnpool(img_feat, w["img"], self.num_heads, params=w["img_struct"])
+            img_feat.record_stream(img_side)
+            img_proxy.record_stream(cur)
+        elif img_proxy is None and self.overlap_mean_pass:
             cur = torch.cuda.current_stream(P.device)
             side = self._side_stream(P.device)
             side.wait_stream(cur)
@@ -531,7 +548,9 @@ class ProxyTransformationNormReverse(nn.Module):
                       else (th["bn_scale"], th["bn_shift"]))                                # :328 BatchNorm1d over (B, n)
         translate = ops.heads(tg, th["lin_w"], th["lin_b"], t_sc, t_sh)
         # S9 image proxies (:449) and image branch -> transform (:450-455)
-        if side is not None:
+        if img_side is not None:
+            torch.cuda.current_stream(P.device).wait_stream(img_side)
+        elif side is not None:
             torch.cuda.current_stream(P.device).wait_stream(side)
             img_proxy = ops.img_attnpool(img_feat, w["img"], self.num_heads, params=w["img_struct"], stages=ops.IMG_STAGE_BACK,
                                          out=img_state[0], ws=img_state[1])[0]
