@@ -29,12 +29,13 @@ def build(force: bool = False) -> str:
 # ---- oracle/_ref: the reference's own hot-path module, compiled where it lies ------------------------------------------
 # The reference is pure Python (setup.py:108 ext_modules=[]): "compiling" it means byte-compiling the UNMODIFIED file
 # /root/reference/embodiedscan/models/necks/preshape_norm_reverse_drop.py into oracle/_ref/ (git-ignored, not gpurun-ignored,
-# so the bytecode travels to the GPU box like a built .so; no reference source enters the repository).  oracle/ref_shim.py
+# so the bytecode travels to the GPU box like a built .so — under a neutral extension: snapshot tools drop *.pyc; no reference source
+# enters the repository).  oracle/ref_shim.py
 # loads it there under the same three import shims, which makes the CPU arm of bench.py the reference itself
 # (cpu_baseline.kind = "reference") instead of the restatement.
 REF_SRC = "/root/reference/embodiedscan/models/necks/preshape_norm_reverse_drop.py"
 REF_DIR = os.path.join(HERE, "_ref")
-REF_PYC = os.path.join(REF_DIR, "preshape_norm_reverse_drop.pyc")
+REF_PYC = os.path.join(REF_DIR, "preshape_norm_reverse_drop.bytecode")
 
 
 def build_ref(force: bool = False):

@@ -35,7 +35,7 @@ REF_ROOT = "/root/reference"
 REF_FILE = os.path.join(REF_ROOT, "embodiedscan/models/necks/preshape_norm_reverse_drop.py")
 
 
-REF_PYC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "preshape_norm_reverse_drop.pyc")
+REF_PYC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "preshape_norm_reverse_drop.bytecode")
 
 
 def available() -> bool:
