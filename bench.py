@@ -329,6 +329,11 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # set-up, not part of the contract's W warm-up steps: the first calls pack the weights, set function attributes and grow the
+    # caching allocator's pools of BOTH streams the forward uses (a cudaMalloc inside the timed region would stall the device)
+    for i in range(4):
+        step(i)
+    sync_all()
     for i in range(args.warmup):
         step(i)
     sync_all()
@@ -460,6 +465,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
     ms_max = allm[:, 3].max().item()
+    ms_ranks = [round(float(x) / args.steps, 4) for x in allm[:, 3].tolist()]
     scenes = allm[:, 0].sum().item() * args.steps
     value = scenes / (ms_max / 1e3)
 
@@ -549,7 +555,7 @@ def run_b200(args):
             "path_roofline": {"algorithmic_bytes_per_scene": path_bytes, "hbm_bound_scenes_per_s_per_gpu": path_bound,
                               "frac": value / world / path_bound},
             "image_stage_roofline": stage, "c4_strong": c4,
-            "core_region": core, "kernel_breakdown": breakdown, "profiled_pass_ms_per_step": prof_ms / args.steps,
+            "ms_per_step_by_rank": ms_ranks, "core_region": core, "kernel_breakdown": breakdown, "profiled_pass_ms_per_step": prof_ms / args.steps,
             "profiled_pass": "one stream, kernels back to back (the timed region overlaps the image stage with the geometric stages on two streams)",
             "cpu_baseline": cpu,
             "checks": checks}
