@@ -157,7 +157,8 @@ int pt_bn_batch_affine(const double* sums, long long count, const float* gamma, 
 /* ---- S9 image proxies — get_img_proxy (:335-342) + AttentionPool2d.forward (:154-177) -----------------
  * Only token 0 of the 226-token attention is kept (:177), so the stage is evaluated in single-query form:
  * one pass for the per-channel spatial mean, folded q/k projections, one pass for scores -> softmax ->
- * attention-weighted feature sum, folded v/c projections, LayerNorm.  img_feat (BV, C, HW) fp32 or bf16.
+ * attention-weighted feature sum, folded v/c projections, LayerNorm.  img_feat (BV, C, HW) fp32, bf16 or fp16 (PT_DTYPE_F16:
+ * tensor-core path of PT_POOL_VARIANT_UMMA only, i.e. the shipped geometry with the split weights below).
  * The folded weights are produced once per weight load by the host (see pt_img_pool_params). */
 typedef struct pt_img_pool_params {
     const float* w_qc;   /* (c,C)   = Wq @ Wc                                             */
@@ -169,7 +170,7 @@ typedef struct pt_img_pool_params {
     const float *cproj_w, *cproj_b; /* (c,c),(c) */
     const float *ln_w, *ln_b;       /* norm_img (c) */
     /* Optional bf16 hi/lo planes ([2][rows][cols], see pt_split_bf16) for the tensor-core fast path taken when img_feat
-     * is bf16 and (C, HW, c, heads) = (512, 225, 256, 8); all five or none:
+     * is bf16 / fp16 and (C, HW, c, heads) = (512, 225, 256, 8); all five or none:
      *   w_qc_split   (c, C)            W_qc
      *   wk_pad_split (heads*C, 64)     row h*C + j, col e < hd: (Wk Wc)[h*hd+e][score_order[j]]; cols >= hd zero
      *   gk_pad_split (heads*228, 64)   row h*228 + t, col e < hd: g_k[t][h*hd+e]; rows t >= T and cols >= hd zero
@@ -183,8 +184,8 @@ typedef struct pt_img_pool_params {
     const void *w_qc_split, *wk_pad_split, *gk_pad_split, *wv_cat_split, *cproj_split;
     /* Which pooling kernel the two channel orders above were folded for:
      *   PT_POOL_VARIANT_MMA  (0) img_pool_mma_kernel (mma.sync + ldmatrix on the raw rows), orders as stated above
-     *   PT_POOL_VARIANT_UMMA (1) img_pool_umma_kernel (tcgen05 / TMEM, TMA-fed; csrc/imgpool_umma.cu):
-     *                            score_order[64 s + r] = sum_order[64 s + r] = s + 8 r   (residue class s, row r of the class) */
+     *   PT_POOL_VARIANT_UMMA (1) img_pool_umma_kernel (tcgen05 / TMEM, TMA-fed; csrc/imgpool_umma.cu; what the Python module packs by
+     *                            default): score_order[64 s + r] = sum_order[64 s + r] = s + 8 r   (residue class s, row r of the class) */
     int variant;
 } pt_img_pool_params;
 #define PT_POOL_VARIANT_MMA 0

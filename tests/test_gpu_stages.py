@@ -211,6 +211,32 @@ def test_affine_scatter_compact_on_golden_inputs(name):
         np.testing.assert_allclose(o.astype(np.float64).sum(0), g["out_sum"][b], rtol=1e-7, atol=1e-2)
 
 
+@pytest.mark.parametrize("B,N,n,K,n_drop", [(3, 4099, 40, 30, 17), (2, 1001, 16, 7, 5), (1, 3, 2, 2, 1), (4, 20481, 64, 30, 33), (2, 1024, 8, 30, 3)])
+def test_scatter_compact_and_minmax_on_unaligned_sizes(B, N, n, K, n_drop):
+    """Point counts that are not multiples of 4 or of the 1024-point compaction blocks: the later scenes then start off the
+    16-byte grid, so the vector paths of the min/max pass and of the compaction must give way to the element paths, and the last
+    block is partial.  Against the oracle: grid prior bit-exact; duplicate destinations by the pinned last-writer rule, dropped
+    points (with repeats and -1 padding) removed, survivor order and counts exact, coordinates within 2e-5."""
+    g = torch.Generator().manual_seed(N + n)
+    P = torch.rand(B, N, 3, generator=g) * 20 - 3
+    c0, mn, mx = po.grid_prior(P, 3)
+    gmn, gmx, gc = ops.minmax_centres(cu(P), 3)
+    assert np.array_equal(np_(gmn), mn[:, 0].numpy()) and np.array_equal(np_(gmx), mx[:, 0].numpy()) and np.array_equal(np_(gc), c0.numpy())
+    kidx = torch.randint(-1, N, (B, n, K), generator=g)                    # -1 = padding; duplicates across clusters are likely
+    kidx[:, :, -1] = kidx[:, :, 0]                                          # and certain inside a cluster
+    drop = torch.randint(-1, N, (B, n_drop * K), generator=g)
+    drop[:, 1] = drop[:, 0]
+    kc = torch.rand(B, n, 3, generator=g) * 20 - 3
+    T = torch.randn(B, n, 3, 3, generator=g)
+    t = torch.randn(B, n, 3, generator=g)
+    cl = po.masked_gather(P, kidx)
+    want = po.remove_points(po.scatter_last_writer_wins(P, kidx, po.affine(T, t, kc, cl)), drop)
+    out, counts = ops.affine_scatter_compact(cu(P), cu(kidx, torch.int32), cu(drop, torch.int32), cu(kc), cu(T), cu(t))
+    assert np_(counts).tolist() == [len(w) for w in want]
+    for b, w in enumerate(want):
+        np.testing.assert_allclose(np_(out)[b, :len(w)], w.numpy(), rtol=0, atol=2e-5)
+
+
 @pytest.mark.parametrize("M,N,K,act", [(300, 768, 256, 0), (1000, 256, 1024, 0), (129, 130, 36, 1), (16384, 1024, 256, 1), (64, 3, 8, 0)])
 def test_gemm_fp32_cuda_cores(M, N, K, act):
     g = torch.Generator().manual_seed(M)
