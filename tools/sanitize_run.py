@@ -41,3 +41,21 @@ with torch.no_grad():
     outt = mt([p.cuda() for p in ptst], {k: v.cuda() for k, v in tdt.items()}, imgt.cuda())
 torch.cuda.synchronize()
 print("ok", [tuple(o.shape) for o in outt], int(mt.text_trans_norm.num_batches_tracked))
+# round 2: fp16 features (half instantiation of the tcgen05 pool kernel), the mma.sync pool kernel, the shipped config's cluster count
+# (691: streamed tcgen05 attention with per-scene padded V^T planes) and an odd point count (element paths of min/max / compaction)
+pts16, td16, img16 = syn.make_inputs(cfg, 2, first_scene=9, img_dtype=torch.float16)
+out16 = m([p.cuda() for p in pts16], {k: v.cuda() for k, v in td16.items()}, img16.cuda())
+os.environ["PT_POOL_KERNEL"] = "mma"
+m2 = ProxyTransformationNormReverse(**cfg.module_kwargs()).eval()
+m2.load_state_dict(syn.make_state_dict(cfg, 0, bf16_round=True))
+m2 = m2.cuda()
+outm = m2([p.cuda() for p in pts], {k: v.cuda() for k, v in text_dict.items()}, img.cuda())
+os.environ.pop("PT_POOL_KERNEL")
+cfg3 = syn.C3.replace(n_views=3, n_points=30001)
+m3 = ProxyTransformationNormReverse(**cfg3.module_kwargs()).eval()
+m3.load_state_dict(syn.make_state_dict(cfg3, 4, bf16_round=True))
+m3 = m3.cuda()
+pts3, td3, img3 = syn.make_inputs(cfg3, 3, first_scene=11, img_dtype=torch.bfloat16)
+out3 = m3([p.cuda() for p in pts3], {k: v.cuda() for k, v in td3.items()}, img3.cuda())
+torch.cuda.synchronize()
+print("ok", [tuple(o.shape) for o in out16], [tuple(o.shape) for o in outm], [tuple(o.shape) for o in out3])
