@@ -493,9 +493,13 @@ def run_b200(args):
     if dom in prof and dom in alg_bytes:
         t_ms, n = prof[dom]
         ach = alg_bytes[dom] / (t_ms / n / 1e3) / 1e9
+        traffic = measured_traffic(dom, B)
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": measured_traffic(dom, B), "peak_source": peak_src, "avg_launch_ms": t_ms / n,
+                "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": t_ms / n,
                 "algorithmic_bytes_per_launch": alg_bytes[dom]}
+        if traffic:     # what the kernel really moves (ncu dram bytes: features + per-view operand planes + outputs) over the same duration
+            roof["traffic_gbs"] = traffic / (t_ms / n / 1e3) / 1e9
+            roof["traffic_frac_of_peak"] = roof["traffic_gbs"] / hbm_peak
     elif dom in prof and dom in tensor_flops:
         t_ms, n = prof[dom]
         ach = tensor_flops[dom] / (t_ms / args.steps / 1e3) / 1e12
