@@ -123,10 +123,12 @@ int pt_proxy_block_fused(const float* x, const float* proxy, const uint8_t* mask
 int pt_position_bias(const float* pb, const float* pc, const float* pr, int n, int s, float* out, pt_stream_t stream);
 
 /* The two-stage proxy attention core (:225-252) alone, tcgen05 / TMEM form, on pre-split bf16 hi/lo operand planes
- * (heads of 32 channels, n <= 256, n % 8 == 0, l <= 256): qk_split [rows][ldq] holds Q at column 0 and K at column c,
- * vt_split [c][ldv] holds V^T (column = scene*n + cluster), pt_split [B*l][c] the projected proxies; every lo plane lies
- * *_plane elements behind its hi plane.  Writes o (fp32, optional) and / or o_split hi/lo planes, (B*n, c).
- * pt_proxy_block_fused uses it when the shape fits and the mma.sync kernel otherwise. */
+ * (heads of 32 channels, any n <= 1024 — the clusters are streamed in key tiles of 256 / row tiles of 128 — and l <= 256):
+ * qk_split [rows][ldq] holds Q at column 0 and K at column c, vt_split [c][ldv] holds V^T (column = scene*n + cluster; scenes whose
+ * first column is off the 16-byte grid are staged element by element — pt_proxy_block_fused pads every scene to a multiple of 8
+ * columns instead), pt_split [B*l][c] the projected proxies; every lo plane lies *_plane elements behind its hi plane.  Writes o
+ * (fp32, optional) and / or o_split hi/lo planes, (B*n, c).  pt_proxy_block_fused uses it when the shape fits and the mma.sync
+ * kernel otherwise (other head sizes, l > 256). */
 int pt_proxy_attention_tc(const void* qk_split, long long qk_plane, int ldq, const void* vt_split, long long vt_plane, long long ldv,
                           const void* pt_split, long long pt_plane, const uint8_t* mask, int B, int n, int l, int c, int heads,
                           float* o, void* o_split, long long o_plane, pt_stream_t stream);
