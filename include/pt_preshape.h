@@ -128,7 +128,8 @@ int pt_position_bias(const float* pb, const float* pc, const float* pr, int n, i
  * first column is off the 16-byte grid are staged element by element — pt_proxy_block_fused pads every scene to a multiple of 8
  * columns instead), pt_split [B*l][c] the projected proxies; every lo plane lies *_plane elements behind its hi plane.  Writes o
  * (fp32, optional) and / or o_split hi/lo planes, (B*n, c).  pt_proxy_block_fused uses it when the shape fits and the mma.sync
- * kernel otherwise (other head sizes, l > 256). */
+ * kernel otherwise (other head sizes, l > 256).  More than 148 (scene, head) pairs with l <= 224 run as two 8-warp CTAs per SM
+ * (key tiles of 128), anything else as one 16-warp CTA per SM (key tiles of 256); same results to rounding. */
 int pt_proxy_attention_tc(const void* qk_split, long long qk_plane, int ldq, const void* vt_split, long long vt_plane, long long ldv,
                           const void* pt_split, long long pt_plane, const uint8_t* mask, int B, int n, int l, int c, int heads,
                           float* o, void* o_split, long long o_plane, pt_stream_t stream);

@@ -2,9 +2,9 @@
 //   stage 1 (proxy as query, :232-238):  Pv = softmax_n((Pt*scale) K^T) V          (l x hd), unmasked
 //   stage 2 (proxy as key,   :241-250):  O  = softmax_l(mask((Q*scale) Pt^T)) Pv   (n x hd)
 // for heads of 32 channels, n <= 1024 point proxies (any n: the benchmark's 256, the shipped config's 691) and l <= 256 text / image
-// proxies.  The clusters are streamed: stage 1 walks the keys in tiles of 256 with an online softmax (running maximum / sum per
-// proxy row, accumulator rescaled in TMEM), stage 2 walks the cluster rows in tiles of 128; only one K / V^T tile and one Q tile
-// are resident at a time.  (Other head sizes / l > 256: the mma.sync kernel in attn_mma.cu.)
+// proxies.  The clusters are streamed: stage 1 walks the keys in tiles of 256 (128 in the 8-warp form, see the kernel) with an online
+// softmax (running maximum / sum per proxy row, accumulator rescaled in TMEM), stage 2 walks the cluster rows in tiles of 128; only
+// one K / V^T tile and one Q tile are resident at a time.  (Other head sizes / l > 256: the mma.sync kernel in attn_mma.cu.)
 //
 // Every contraction is a tcgen05.mma (cta_group::1, kind::f16, M = 128) with fp32 accumulation in TMEM and 3xBF16 operand
 // splitting (hi*hi + lo*hi + hi*lo), so scores and outputs keep ~2^-17 relative accuracy:
@@ -24,19 +24,20 @@
 namespace pt {
 
 namespace at {
-constexpr int THREADS = 512, HD = 32, MAXR = 256;   // 16 warps: 4 per TMEM lane quarter, each takes every 4th 32-column chunk
+constexpr int HD = 32, MAXR = 256;                    // MAXR: proxies (resident); NWQ warps per TMEM lane quarter take every NWQ-th 32-column chunk
 constexpr int MAXN = 1024;                            // clusters (streamed in key tiles of MAXR and row tiles of 128)
 constexpr int ROW_BYTES = 128;                        // [hi 32 | lo 32] bf16
 constexpr int TILE_BYTES = MAXR * ROW_BYTES;          // 32768: Q / K / Pt operand tiles (256 rows)
 constexpr int VT_TILE = HD * ROW_BYTES;               // 4096: one 64-key k-tile of V^T / Pv^T (32 rows)
 constexpr int VT_PLANE = 4 * VT_TILE;                 // 16384: 256 keys
-constexpr int OFF_K = 0, OFF_Q = OFF_K + TILE_BYTES, OFF_P = OFF_Q + TILE_BYTES;
+// K (stage 1) and Q (stage 2) share a tile, and so do V^T (stage 1) and Pv^T (written by the stage-1 epilogue, read by stage 2):
+// 104 KB per CTA, so two CTAs fit on an SM
+constexpr int OFF_K = 0, OFF_Q = OFF_K, OFF_P = OFF_K + TILE_BYTES;
 constexpr int OFF_VT = OFF_P + TILE_BYTES;            // hi plane, then lo plane
-constexpr int OFF_PV = OFF_VT + 2 * VT_PLANE;         // hi plane, then lo plane
-constexpr int OFF_MISC = OFF_PV + 2 * VT_PLANE;       // rowmax [4][128], rowsum [4][128], keyflag [256], runm [256], runl [256] floats
+constexpr int OFF_PV = OFF_VT;
+constexpr int OFF_MISC = OFF_VT + 2 * VT_PLANE;       // rowmax [4][128], rowsum [4][128], keyflag [256], runm [256], runl [256] floats
 constexpr int OFF_BAR = OFF_MISC + (8 * 128 + 3 * 256) * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 16 + 1024;       // + alignment slack
-constexpr int TMEM_COLS = 512, ACC_COL = 256;
 }  // namespace at
 
 __device__ __forceinline__ uint32_t at_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -104,6 +105,10 @@ __device__ __forceinline__ void at_ld8(uint32_t (&v)[8], uint32_t taddr) {
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void at_ldn(uint32_t (&v)[8], uint32_t taddr) { at_ld8(v, taddr); }
+__device__ __forceinline__ void at_ldn(uint32_t (&v)[16], uint32_t taddr) { at_ld16(v, taddr); }
+__device__ __forceinline__ void at_stn(uint32_t taddr, const uint32_t (&r)[8]) { at_st8(taddr, r); }
+__device__ __forceinline__ void at_stn(uint32_t taddr, const uint32_t (&r)[16]) { at_st16(taddr, r); }
 __device__ __forceinline__ float at_ex2(float x) {            // 2^x, ~2 ulp; x <= 0 here
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -146,6 +151,7 @@ struct AtArgs {
 // softmax(scale*s) is evaluated as 2^(s*c1 - max*c1) with c1 = scale*log2(e): one FFMA and one MUFU per element.
 // `m_old` (scaled running maximum of the row over the earlier key tiles, -inf for the first) makes it the step of an online softmax:
 // the probabilities are relative to max(m_old, tile maximum), which is returned for the caller's bookkeeping.
+template <int NWQ>
 __device__ __forceinline__ float at_softmax_tile(uint32_t tmem_row, int ncols, int nvalid, const float* __restrict__ flag, float scale,
                                                  int hh, float* __restrict__ rowmax, float* __restrict__ rowsum, int row,
                                                  float m_old = -INFINITY) {
@@ -153,7 +159,7 @@ __device__ __forceinline__ float at_softmax_tile(uint32_t tmem_row, int ncols, i
     const float c1 = scale * 1.4426950408889634f;
     float mx = -INFINITY;                                      // maximum of the UNSCALED scores of the real, unmasked keys
     bool any_masked = false;
-    for (int ch = hh; ch < nch; ch += 4) {
+    for (int ch = hh; ch < nch; ch += NWQ) {
         uint32_t v[32];
         at_ld32(v, tmem_row + 32 * ch);
         const int kv = nvalid - 32 * ch;                       // real keys in this chunk (>= 32: all)
@@ -175,12 +181,13 @@ __device__ __forceinline__ float at_softmax_tile(uint32_t tmem_row, int ncols, i
     if (any_masked) ms = fmaxf(ms, -1e9f);
     rowmax[hh * 128 + row] = ms;
     __syncthreads();
-    ms = fmaxf(fmaxf(rowmax[row], rowmax[128 + row]), fmaxf(rowmax[256 + row], rowmax[384 + row]));    // finite: key 0 is a real key
+    ms = fmaxf(rowmax[row], rowmax[128 + row]);                // finite: key 0 is a real key
+    if (NWQ == 4) ms = fmaxf(ms, fmaxf(rowmax[256 + row], rowmax[384 + row]));
     ms = fmaxf(ms, m_old);
     const float mc = ms * 1.4426950408889634f;
     const float pmask = at_ex2(-1e9f * 1.4426950408889634f - mc);      // probability weight of a masked key (1 if every key is masked)
     float sum = 0.f;
-    for (int ch = hh; ch < nch; ch += 4) {
+    for (int ch = hh; ch < nch; ch += NWQ) {
         uint32_t v[32];
         at_ld32(v, tmem_row + 32 * ch);
         uint32_t ph[16], pl[16];
@@ -214,8 +221,19 @@ __device__ __forceinline__ float at_softmax_tile(uint32_t tmem_row, int ncols, i
     return ms;
 }
 
-__global__ void __launch_bounds__(at::THREADS, 1) proxy_attention_tc_kernel(const AtArgs a) {
+// NWQ = 4, KT = 256: 16 warps, 256-key tiles, 512 TMEM columns (scores 256 | accumulators), one CTA per SM — any l <= 256.
+// NWQ = 2, KT = 128: 8 warps, 128-key tiles, 256 TMEM columns (stage 1: scores 128 | accumulators 2 x 32; stage 2: scores lpad <= 224 |
+// accumulator at 224), TWO CTAs per SM.  A CTA is one serial chain (stage tiles -> MMA -> softmax -> MMA -> epilogue, a block-wide
+// barrier between the links; ncu: 25 % of the warp slots active, long-scoreboard and barrier stalls on top): two independent chains
+// per SM hide each other's latencies.
+template <int NWQ, int KT>
+__global__ void __launch_bounds__(128 * NWQ, NWQ == 2 ? 2 : 1) proxy_attention_tc_kernel(const AtArgs a) {
     using namespace at;
+    constexpr int THREADS = 128 * NWQ;
+    constexpr int TMEM_COLS = NWQ == 2 ? 256 : 512;
+    constexpr int ACC1 = KT;                                    // stage-1 accumulators: columns ACC1 + 32 mt
+    constexpr int ACC2 = NWQ == 2 ? 224 : 256;                  // stage-2 accumulator
+    constexpr int AC = 32 / NWQ;                                // accumulator columns per thread in the epilogues
     extern __shared__ uint8_t at_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)at_smem_raw + 1023) & ~(uintptr_t)1023);
     float* rowmax = reinterpret_cast<float*>(smem + OFF_MISC);
@@ -259,11 +277,12 @@ __global__ void __launch_bounds__(at::THREADS, 1) proxy_attention_tc_kernel(cons
             if (i < nrows_tile * 8) *reinterpret_cast<uint4*>(smem + off + r * ROW_BYTES + ((ch ^ (r & 7)) << 4)) = reg[k];
         }
     };
-    auto stage_vt = [&](int k0) {                               // V^T planes of keys k0 .. k0 + 255 (zero past n)
+    auto stage_vt = [&](int k0) {                               // V^T planes of keys k0 .. k0 + KT - 1 (zero past n)
         const size_t key0 = (size_t)b * a.vt_seg + k0;
         if ((key0 & 7) == 0 && (a.vt_seg & 7) == 0 && (a.ldv & 7) == 0 && (a.vt_plane & 7) == 0) {  // 16-byte chunks of 8 keys
-            for (int i = tid; i < 2 * HD * 32; i += THREADS) {
-                const int plane = i >> 10, e = (i >> 5) & 31, j8 = i & 31;
+            constexpr int C8 = KT / 8;                          // 16-byte chunks per row
+            for (int i = tid; i < 2 * HD * C8; i += THREADS) {
+                const int plane = i / (HD * C8), e = (i / C8) & 31, j8 = i % C8;
                 uint4 v = z4;
                 const int left = n - (k0 + 8 * j8);             // real keys in this chunk (the rest of a scene's last chunk is padding)
                 if (left > 0) {
@@ -278,8 +297,8 @@ __global__ void __launch_bounds__(at::THREADS, 1) proxy_attention_tc_kernel(cons
                 *reinterpret_cast<uint4*>(smem + OFF_VT + plane * VT_PLANE + (j8 >> 3) * VT_TILE + e * ROW_BYTES + (((j8 & 7) ^ (e & 7)) << 4)) = v;
             }
         } else {                                                // scenes whose first key is not 16-byte aligned (odd n): element by element
-            for (int i = tid; i < 2 * HD * MAXR; i += THREADS) {
-                const int plane = i >> 13, e = (i >> 8) & 31, j = i & 255;
+            for (int i = tid; i < 2 * HD * KT; i += THREADS) {
+                const int plane = i / (HD * KT), e = (i / KT) & 31, j = i % KT;
                 unsigned short v = 0;
                 if (k0 + j < n) v = __ldg(reinterpret_cast<const unsigned short*>(a.vt + (plane ? a.vt_plane : 0) + (size_t)(h * HD + e) * a.ldv + key0 + j));
                 *reinterpret_cast<unsigned short*>(smem + OFF_VT + plane * VT_PLANE + (j >> 6) * VT_TILE + e * ROW_BYTES + ((((j >> 3) & 7) ^ (e & 7)) << 4) + (j & 7) * 2) = v;
@@ -292,7 +311,6 @@ __global__ void __launch_bounds__(at::THREADS, 1) proxy_attention_tc_kernel(cons
         if (r < l) pp = __ldg(reinterpret_cast<const uint4*>(a.pt + (half ? a.pt_plane : 0) + ((size_t)b * l + r) * c + col));
         *reinterpret_cast<uint4*>(smem + OFF_P + r * ROW_BYTES + ((ch ^ (r & 7)) << 4)) = pp;
     }
-    for (int i = tid; i < 2 * VT_PLANE / 16; i += THREADS) *reinterpret_cast<uint4*>(smem + OFF_PV + 16 * i) = z4;
     for (int i = tid; i < 256; i += THREADS) {
         keyflag[i] = (a.mask != nullptr && i < l && a.mask[(size_t)b * l + i] == 0) ? 1.f : 0.f;
         runm[i] = -INFINITY;
@@ -302,7 +320,7 @@ __global__ void __launch_bounds__(at::THREADS, 1) proxy_attention_tc_kernel(cons
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    const int q4 = warp & 3, hh = warp >> 2;                    // TMEM lane quarter, which of its 4 warps
+    const int q4 = warp & 3, hh = warp >> 2;                    // TMEM lane quarter, which of its NWQ warps
     const int row = 32 * q4 + lane;                             // row of the 128-row tile this thread owns
     const uint32_t tmem_row = tmem + ((uint32_t)(32 * q4) << 16);
     const uint32_t sK = at_smem_u32(smem + OFF_K), sQ = at_smem_u32(smem + OFF_Q), sP = at_smem_u32(smem + OFF_P);
@@ -329,21 +347,22 @@ __global__ void __launch_bounds__(at::THREADS, 1) proxy_attention_tc_kernel(cons
         at_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const float m_old = online >= 0 ? runm[online + row] : -INFINITY;
-        const float m_new = at_softmax_tile(tmem_row, nkeys_pad, nkeys, flag, a.scale, hh, rowmax, rowsum, row, m_old);
+        const float m_new = at_softmax_tile<NWQ>(tmem_row, nkeys_pad, nkeys, flag, a.scale, hh, rowmax, rowsum, row, m_old);
         float alpha = 0.f;
         if (online >= 0 && kt > 0) {                            // earlier key tiles were accumulated relative to m_old: rescale
             alpha = at_ex2((m_old - m_new) * 1.4426950408889634f);
-            uint32_t v[8];
-            at_ld8(v, tmem_row + acc_col + 8 * hh);
+            uint32_t v[AC];
+            at_ldn(v, tmem_row + acc_col + AC * hh);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
-            at_st8(tmem_row + acc_col + 8 * hh, v);
+            for (int e = 0; e < AC; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+            at_stn(tmem_row + acc_col + AC * hh, v);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (online >= 0 && hh == 0) {
-            runl[online + row] = runl[online + row] * alpha + ((rowsum[row] + rowsum[128 + row]) + (rowsum[256 + row] + rowsum[384 + row]));
+            runl[online + row] = runl[online + row] * alpha + (NWQ == 4 ? ((rowsum[row] + rowsum[128 + row]) + (rowsum[256 + row] + rowsum[384 + row]))
+                                                                         : (rowsum[row] + rowsum[128 + row]));
             runm[online + row] = m_new;
         }
         if (tid == 0) {
@@ -363,38 +382,40 @@ __global__ void __launch_bounds__(at::THREADS, 1) proxy_attention_tc_kernel(cons
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     };
 
-    // ---- stage 1: rows = proxies, keys = clusters in tiles of 256 (online softmax), values = V  ->  Pv^T (normalised) as K-major
-    // operand planes.  Accumulator of proxy row tile mt: columns ACC_COL + 32 mt.
+    // ---- stage 1: rows = proxies, keys = clusters in tiles of KT (online softmax), values = V  ->  Pv^T (normalised) as K-major
+    // operand planes.  Accumulator of proxy row tile mt: columns ACC1 + 32 mt.
     const int nmt1 = (lpad + 127) >> 7;
     uint4 kreg[4], qreg[4];
-    load_rows(kreg, c + h * HD, 0, MAXR, n);
-    for (int kt = 0; kt * MAXR < n; ++kt) {
-        const int k0 = kt * MAXR, nk = min(MAXR, n - k0), nkpad = (nk + 15) & ~15;
-        store_rows(kreg, OFF_K, MAXR);
+    load_rows(kreg, c + h * HD, 0, KT, n);
+    for (int kt = 0; kt * KT < n; ++kt) {
+        const int k0 = kt * KT, nk = min(KT, n - k0), nkpad = (nk + 15) & ~15;
+        store_rows(kreg, OFF_K, KT);
         stage_vt(k0);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (k0 + MAXR < n) load_rows(kreg, c + h * HD, k0 + MAXR, MAXR, n);                  // next K tile in flight during the passes
+        if (k0 + KT < n) load_rows(kreg, c + h * HD, k0 + KT, KT, n);                        // next K tile in flight during the passes
         else load_rows(qreg, h * HD, 128 * (int)blockIdx.z, 128, n);                          // ... or the first Q tile of stage 2
         for (int mt = 0; mt < nmt1; ++mt) {
-            pass(sP + mt * 128 * ROW_BYTES, sK, nk, nkpad, sVT, nullptr, ACC_COL + 32 * mt, 128 * mt, kt);
+            pass(sP + mt * 128 * ROW_BYTES, sK, nk, nkpad, sVT, nullptr, ACC1 + 32 * mt, 128 * mt, kt);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();                                    // rowmax / rowsum reusable; (last mt) K / V^T tiles reusable
         }
     }
+    // (Pv^T takes the place of the V^T tile: every MMA that read it has completed — the last pass waited for its commit.  Rows of
+    // proxies l .. lpad - 1 are written as zeros: stage 2 contracts over lpad proxies and the tile still holds V^T there.)
     for (int mt = 0; mt < nmt1; ++mt) {
-        uint32_t v[8];
-        at_ld8(v, tmem_row + ACC_COL + 32 * mt + 8 * hh);
+        uint32_t v[AC];
+        at_ldn(v, tmem_row + ACC1 + 32 * mt + AC * hh);
         const int i = mt * 128 + row;                           // proxy index
-        if (i < l) {
-            const float inv = 1.0f / runl[i];
+        if (i < lpad) {
+            const float inv = i < l ? 1.0f / runl[i] : 0.f;
             uint8_t* base = smem + OFF_PV + (i >> 6) * VT_TILE + (i & 7) * 2;
             const int ch = (i & 63) >> 3;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int ee = 8 * hh + e;
-                const float y = __uint_as_float(v[e]) * inv;
+            for (int e = 0; e < AC; ++e) {
+                const int ee = AC * hh + e;
+                const float y = i < l ? __uint_as_float(v[e]) * inv : 0.f;
                 const __nv_bfloat16 yh = __float2bfloat16_rn(y), yl = __float2bfloat16_rn(y - __bfloat162float(yh));
                 uint8_t* p = base + ee * ROW_BYTES + ((ch ^ (ee & 7)) << 4);
                 *reinterpret_cast<__nv_bfloat16*>(p) = yh;
@@ -411,26 +432,29 @@ __global__ void __launch_bounds__(at::THREADS, 1) proxy_attention_tc_kernel(cons
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();                                        // Q tile (and, first time, Pv^T) visible; accumulator drained
         if ((mt + (int)gridDim.z) * 128 < npad) load_rows(qreg, h * HD, 128 * (mt + (int)gridDim.z), 128, n);
-        pass(sQ, sP, l, lpad, sPV, a.mask != nullptr ? keyflag : nullptr, ACC_COL, -1, 0);
-        uint32_t v[8];
-        at_ld8(v, tmem_row + ACC_COL + 8 * hh);
+        pass(sQ, sP, l, lpad, sPV, a.mask != nullptr ? keyflag : nullptr, ACC2, -1, 0);
+        uint32_t v[AC];
+        at_ldn(v, tmem_row + ACC2 + AC * hh);
         const int r = mt * 128 + row;                           // cluster index
         if (r < n) {
-            const float inv = 1.0f / ((rowsum[row] + rowsum[128 + row]) + (rowsum[256 + row] + rowsum[384 + row]));
-            float y[8];
+            const float inv = 1.0f / (NWQ == 4 ? ((rowsum[row] + rowsum[128 + row]) + (rowsum[256 + row] + rowsum[384 + row])) : (rowsum[row] + rowsum[128 + row]));
+            float y[AC];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) y[e] = __uint_as_float(v[e]) * inv;
-            const size_t off = ((size_t)b * n + r) * c + h * HD + 8 * hh;
-            if (a.o != nullptr) {
-                *reinterpret_cast<float4*>(a.o + off) = make_float4(y[0], y[1], y[2], y[3]);
-                *reinterpret_cast<float4*>(a.o + off + 4) = make_float4(y[4], y[5], y[6], y[7]);
-            }
-            if (a.o_hi != nullptr) {
-                uint32_t wh[4], wl[4];
+            for (int e = 0; e < AC; ++e) y[e] = __uint_as_float(v[e]) * inv;
+            const size_t off = ((size_t)b * n + r) * c + h * HD + AC * hh;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) at_split2(y[2 * e], y[2 * e + 1], wh[e], wl[e]);
-                *reinterpret_cast<uint4*>(a.o_hi + off) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
-                *reinterpret_cast<uint4*>(a.o_hi + a.o_plane + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+            for (int e8 = 0; e8 < AC; e8 += 8) {
+                if (a.o != nullptr) {
+                    *reinterpret_cast<float4*>(a.o + off + e8) = make_float4(y[e8], y[e8 + 1], y[e8 + 2], y[e8 + 3]);
+                    *reinterpret_cast<float4*>(a.o + off + e8 + 4) = make_float4(y[e8 + 4], y[e8 + 5], y[e8 + 6], y[e8 + 7]);
+                }
+                if (a.o_hi != nullptr) {
+                    uint32_t wh[4], wl[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) at_split2(y[e8 + 2 * e], y[e8 + 2 * e + 1], wh[e], wl[e]);
+                    *reinterpret_cast<uint4*>(a.o_hi + off + e8) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                    *reinterpret_cast<uint4*>(a.o_hi + a.o_plane + off + e8) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+                }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -454,8 +478,10 @@ int launch_proxy_attention_tc(const void* qk_split, long long qk_plane, int ldq,
                    qk_plane % 8 == 0 && pt_plane % 8 == 0 && o_plane % 8 == 0,
                "attention(tcgen05): operand planes must be 16-byte aligned");
     static bool attr[PT_MAX_DEVICES] = {};
-    if (first_use_on_current_device(attr))
-        PT_CUDA_OK(cudaFuncSetAttribute(proxy_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, at::SMEM_BYTES));
+    if (first_use_on_current_device(attr)) {
+        PT_CUDA_OK(cudaFuncSetAttribute(proxy_attention_tc_kernel<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, at::SMEM_BYTES));
+        PT_CUDA_OK(cudaFuncSetAttribute(proxy_attention_tc_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, at::SMEM_BYTES));
+    }
     AtArgs a;
     a.qk = (const __nv_bfloat16*)qk_split; a.qk_plane = qk_plane; a.ldq = ldq;
     PT_REQUIRE(vt_seg >= n && ldv >= (long long)B * vt_seg, "attention(tcgen05): vt_seg=%d ldv=%lld", vt_seg, ldv);
@@ -464,11 +490,20 @@ int launch_proxy_attention_tc(const void* qk_split, long long qk_plane, int ldq,
     a.mask = mask; a.n = n; a.l = l; a.c = c;
     a.scale = (float)(1.0 / sqrt((double)at::HD));              // python float head_dim ** -0.5 (:186), rounded to fp32 once
     a.o = o; a.o_hi = (__nv_bfloat16*)o_split; a.o_plane = o_plane;
-    // few (scene, head) pairs (small batches): spread the independent cluster row tiles of stage 2 over the otherwise idle SMs
+    // Two co-resident 8-warp CTAs per SM when the proxies fit the 256-column layout (l <= 224) and there is more than one 16-warp CTA
+    // per SM to run; otherwise (few (scene, head) pairs: latency of ONE chain counts, and 256-key tiles halve its passes) the 16-warp form.
+    // Few pairs also spread the independent cluster row tiles of stage 2 over the otherwise idle SMs (each CTA repeats stage 1).
+    static const int force = getenv("PT_ATTN_FORM") ? atoi(getenv("PT_ATTN_FORM")) : 0;         // debug: 1 = 16-warp form, 2 = 8-warp form
+    const int lpad = (l + 15) & ~15;
+    const bool small = lpad <= 224 && (force == 2 || (force != 1 && heads * B > 148));
     const int row_tiles = (n + 127) / 128;
-    int zsplit = 148 / (heads * B);                             // (one CTA per SM: stay within a single wave)
+    int zsplit = (small ? 296 : 148) / (heads * B);             // stay within a single wave
     zsplit = zsplit < 1 ? 1 : (zsplit > row_tiles ? row_tiles : zsplit);
-    { ProfScope prof_(PROF_ATTENTION, s); proxy_attention_tc_kernel<<<dim3(heads, B, zsplit), at::THREADS, at::SMEM_BYTES, s>>>(a); }
+    {
+        ProfScope prof_(PROF_ATTENTION, s);
+        if (small) proxy_attention_tc_kernel<2, 128><<<dim3(heads, B, zsplit), 256, at::SMEM_BYTES, s>>>(a);
+        else proxy_attention_tc_kernel<4, 256><<<dim3(heads, B, zsplit), 512, at::SMEM_BYTES, s>>>(a);
+    }
     PT_LAUNCH_CHECK();
     return PT_OK;
 }
