@@ -51,6 +51,9 @@ int pt_profile_enable(int on);
 int pt_profile_num_tags(void);
 const char* pt_profile_tag_name(int tag);
 int pt_profile_read(int tag, double* total_ms, int64_t* launches);
+/* Every recorded launch in launch order: tag, start and end in milliseconds after the first record's start (event timestamps, so
+ * records of different streams share one time axis) — which kernels of the two streams of a forward actually ran side by side. */
+int pt_profile_timeline(int* tags, double* start_ms, double* end_ms, int max_records, int* n_records);
 
 /* ---- S1 grid prior — DeformablePointCluster.init_uniform_cluster_center (:33-51) --------------------
  * mn/mx (B,3) per-axis min/max over the scene; centres (B,M,3) = (mn + margin) + lin3[j] * ((mx - mn) - 2*margin),

@@ -51,6 +51,7 @@ _SIGNATURES = {
     "pt_profile_num_tags": (c_int, []),
     "pt_profile_tag_name": (c_char_p, [c_int]),
     "pt_profile_read": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(c_int64)]),
+    "pt_profile_timeline": (c_int, [POINTER(c_int), POINTER(ctypes.c_double), POINTER(ctypes.c_double), c_int, POINTER(c_int)]),
     "pt_minmax_ws_bytes": (c_size_t, [c_int, c_int]),
     "pt_minmax_centres": (c_int, [_P, c_int, c_int, c_int, _P, c_float, _P, _P, _P, _P, c_size_t, _P]),
     "pt_ball_query_firstk": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_float, _P, _P, _P]),
@@ -115,6 +116,17 @@ def launch_count() -> int:
 
 def profile_enable(on: bool):
     check(load().pt_profile_enable(1 if on else 0), "pt_profile_enable")
+
+
+def profile_timeline(max_records: int = 4096):
+    """-> [(kernel kind, start ms, end ms)] of every launch recorded since profile_enable(True), on one time axis."""
+    L = load()
+    tags = (c_int * max_records)()
+    t0 = (ctypes.c_double * max_records)()
+    t1 = (ctypes.c_double * max_records)()
+    n = c_int(0)
+    check(L.pt_profile_timeline(tags, t0, t1, max_records, ctypes.byref(n)), "pt_profile_timeline")
+    return [(L.pt_profile_tag_name(tags[i]).decode(), t0[i], t1[i]) for i in range(n.value)]
 
 
 def profile_read() -> dict:

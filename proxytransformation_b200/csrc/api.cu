@@ -139,6 +139,23 @@ extern "C" int pt_profile_read(int tag, double* total_ms, int64_t* launches) {
     return PT_OK;
 }
 
+extern "C" int pt_profile_timeline(int* tags, double* start_ms, double* end_ms, int max_records, int* n_records) {
+    PT_REQUIRE(tags && start_ms && end_ms && n_records && max_records >= 0, "pt_profile_timeline: bad argument");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    int n = 0;
+    for (auto& r : g_prof) {
+        if (n >= max_records) break;
+        PT_CUDA_OK(cudaEventSynchronize(r.b));
+        float t0 = 0.f, t1 = 0.f;
+        PT_CUDA_OK(cudaEventElapsedTime(&t0, g_prof.front().a, r.a));
+        PT_CUDA_OK(cudaEventElapsedTime(&t1, g_prof.front().a, r.b));
+        tags[n] = r.tag; start_ms[n] = t0; end_ms[n] = t1;
+        ++n;
+    }
+    *n_records = n;
+    return PT_OK;
+}
+
 extern "C" size_t pt_proxy_block_ws_bytes(int B, int n, int l, int c, int hidden) {
     return carve_block(nullptr, B, n, l, c, hidden).total;
 }
