@@ -135,13 +135,8 @@ __global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_kernel(const float* 
     int step = 0;
     if (vec_ok && nfull > 0) {
         const float4* P4 = reinterpret_cast<const float4*>(P) + 3 * lane;
-        float4 a = __ldg(P4), bq = __ldg(P4 + 1), c = __ldg(P4 + 2);
-        for (; step < nfull; ++step) {
-            float4 na = a, nb = bq, nc = c;
-            if (step + 1 < nfull) {                   // prefetch the next 128 points
-                const float4* q4 = P4 + (size_t)(step + 1) * 96;
-                na = __ldg(q4); nb = __ldg(q4 + 1); nc = __ldg(q4 + 2);
-            }
+        // one 128-point step on registers (a, bq, c); returns true when the centre has its K hits
+        auto test = [&](const float4& a, const float4& bq, const float4& c, int st) -> bool {
             float x[4], y[4], z[4];
             bq_unpack(a, bq, c, x, y, z);
             unsigned m[4];
@@ -153,7 +148,7 @@ __global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_kernel(const float* 
             }
             if ((m[0] | m[1] | m[2] | m[3]) != 0u) {
                 int slot = cnt + __popc(m[0] & lt) + __popc(m[1] & lt) + __popc(m[2] & lt) + __popc(m[3] & lt);
-                const int j0 = step * 128 + 4 * lane;
+                const int j0 = st * 128 + 4 * lane;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if (h[i]) {
@@ -162,11 +157,30 @@ __global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_kernel(const float* 
                     }
                 }
                 cnt += __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
-                if (cnt >= K) break;
+                if (cnt >= K) return true;
             }
-            a = na; bq = nb; c = nc;
+            return false;
+        };
+        // two steps per trip on two register sets, each reloaded (for the step after next) right after it has been tested: the
+        // single-set form spent 13 of its ~93 instructions per step copying the prefetched registers (the kernel is issue-bound:
+        // `not_selected` is its top stall)
+        float4 a0 = __ldg(P4), b0 = __ldg(P4 + 1), c0 = __ldg(P4 + 2);
+        float4 a1 = a0, b1 = b0, c1 = c0;
+        if (nfull > 1) { a1 = __ldg(P4 + 96); b1 = __ldg(P4 + 97); c1 = __ldg(P4 + 98); }
+        for (; step < nfull; step += 2) {
+            const bool done0 = test(a0, b0, c0, step);
+            if (done0 || step + 1 >= nfull) break;
+            if (step + 2 < nfull) {
+                const float4* q4 = P4 + (size_t)(step + 2) * 96;
+                a0 = __ldg(q4); b0 = __ldg(q4 + 1); c0 = __ldg(q4 + 2);
+            }
+            const bool done1 = test(a1, b1, c1, step + 1);
+            if (done1) break;
+            if (step + 3 < nfull) {
+                const float4* q4 = P4 + (size_t)(step + 3) * 96;
+                a1 = __ldg(q4); b1 = __ldg(q4 + 1); c1 = __ldg(q4 + 2);
+            }
         }
-        step = cnt >= K ? nfull : step;               // (unused after a break)
     }
     if (cnt < K) {                                     // scalar tail (and the unaligned / tiny-N case): 32 points per step
         for (int j0 = (vec_ok ? nfull * 128 : 0); j0 < N && cnt < K; j0 += 32) {
