@@ -59,3 +59,13 @@ pts3, td3, img3 = syn.make_inputs(cfg3, 3, first_scene=11, img_dtype=torch.bfloa
 out3 = m3([p.cuda() for p in pts3], {k: v.cuda() for k, v in td3.items()}, img3.cuda())
 torch.cuda.synchronize()
 print("ok", [tuple(o.shape) for o in out16], [tuple(o.shape) for o in outm], [tuple(o.shape) for o in out3])
+# round 2 (late): the 8-warp form of the tcgen05 attention (two CTAs per SM; taken with more than 148 (scene, head) pairs), the pipelined
+# GEMM epilogue with GELU / residual / transposed-V outputs (inside the blocks above) and the two-step ball-query loop (above)
+g = torch.Generator().manual_seed(3)
+q, k, v = (torch.randn(19, 200, 256, generator=g).cuda() for _ in range(3))
+pt_ = torch.randn(19, 50, 256, generator=g).cuda()
+mk = torch.ones(19, 50, dtype=torch.uint8)
+mk[:, 40:] = 0
+oa = ops.proxy_attention_tc(q, k, v, pt_, mk.cuda(), 8)
+torch.cuda.synchronize()
+print("ok", tuple(oa.shape))
