@@ -144,6 +144,11 @@ struct TcKernelArgs {
     int dbg;             // -DPT_GEMM_DBG builds only (PT_GEMM_DEBUG): 1 no MMAs, 2 epilogue only hands the accumulator back, 4 epilogue without global memory, 8 no W loads
 };
 #ifdef PT_GEMM_DBG
+#define TC_ZFAST (!(g.dbg & 16))
+#else
+#define TC_ZFAST true
+#endif
+#ifdef PT_GEMM_DBG
 #define TC_DBG(bit) (g.dbg & (bit))
 __device__ unsigned long long g_gemm_tl[160][8];      // per-CTA timeline (globaltimer ns), tools/gemm_timeline.py
 __device__ __forceinline__ void tc_mark(int slot) {
@@ -203,7 +208,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         if (lane == 0) {
             int it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int z = t / tiles_per_batch, r = t - z * tiles_per_batch;
+                const int z = TC_ZFAST ? t % g.batch : t / tiles_per_batch, r = TC_ZFAST ? t / g.batch : t - z * tiles_per_batch;
                 const int m0 = (r / g.tiles_n) * TC_BM, n0 = (r % g.tiles_n) * BN;
                 const int ak = z * g.a_koff_z, wr = z * g.w_row_z + n0;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         int tl = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
             const int as = tl & 1, aph = (tl >> 1) & 1;
-            const int z = t / tiles_per_batch, r = t - z * tiles_per_batch;
+            const int z = TC_ZFAST ? t % g.batch : t / tiles_per_batch, r = TC_ZFAST ? t / g.batch : t - z * tiles_per_batch;
             const int m0 = (r / g.tiles_n) * TC_BM, n0 = (r % g.tiles_n) * BN;
             mbar_wait(tmem_full + as, aph);
             tc_fence_after();
