@@ -510,11 +510,15 @@ class ProxyTransformationNormReverse(nn.Module):
                                                                                   torch.cuda.is_current_stream_capturing()))):
             cur = torch.cuda.current_stream(P.device)
             img_side = self._side_stream(P.device)
+            # The result is allocated from the CURRENT stream's pool and handed to the side stream: the current stream waits for
+            # the side stream before it reads the proxies, so every later reuse of the block (and of the caller's img_feat) is
+            # ordered after the side stream's work without record_stream().  A result allocated on the side stream and
+            # record_stream()-ed to the current one cannot be reused until its event has completed; with the host running
+            # several steps ahead that meant a fresh cudaMalloc per step in flight (seen as 8-11 ms steps at the start of a run).
+            img_proxy = torch.empty(img_feat.shape[0], img_feat.shape[1], self.embed_dim, dtype=torch.float32, device=P.device)
             img_side.wait_stream(cur)
             with torch.cuda.stream(img_side):
-                img_proxy = ops.img_attnpool(img_feat, w["img"], self.num_heads, params=w["img_struct"])
-            img_feat.record_stream(img_side)
-            img_proxy.record_stream(cur)
+                ops.img_attnpool(img_feat, w["img"], self.num_heads, params=w["img_struct"], out=img_proxy)
         elif img_proxy is None and self.overlap_mean_pass:
             cur = torch.cuda.current_stream(P.device)
             side = self._side_stream(P.device)
