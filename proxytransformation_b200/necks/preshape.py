@@ -4,9 +4,10 @@
 Same registry name, constructor signature, ``forward(points, text_dict, img_feat)`` contract and ``state_dict`` keys
 (released checkpoints load with ``strict=True``); the forward pass itself runs entirely in the sm_100a kernels behind
 ``include/pt_preshape.h`` — the sub-modules below are parameter containers that mirror the reference's key layout and
-are never called.  Eval / no-grad is the supported mode; train() mode runs as a forward-only batch-statistics pass
-(BatchNorm batch statistics + running-statistics update) when every drop rate is 0 and autograd is off, and raises
-otherwise (no Dropout / DropPath, no backward pass).
+are never called on that path.  Eval / no-grad is the measured mode.  train() mode: under no_grad with every drop rate at 0 a
+batch-statistics forward on the same kernels (BatchNorm batch statistics + running-statistics update); with autograd
+(or Dropout / DropPath) the differentiable path of necks/train_autograd.py — index work on the kernels, the arithmetic as
+torch ops on these sub-modules' parameters, torch autograd as the backward pass.
 
 Algorithmic differences from the reference, all output-preserving:
   * only the LAST block of ``textformer`` / ``imgformer`` is evaluated — every block is fed ``point_proxy`` and only the
@@ -302,29 +303,32 @@ class ProxyTransformationNormReverse(nn.Module):
         Host tensors are accepted (pinned memory makes the copies asynchronous); results then come back on the host.
         ``img_proxy`` (B,V,c) may replace ``img_feat`` (core region of the benchmark); ``trace`` collects intermediates.
 
-        train() mode is a FORWARD-ONLY mode: the four BatchNorm layers normalise with batch statistics and
-        update their running statistics as nn.BatchNorm does; it needs every drop rate at 0 (Dropout / DropPath are not
-        implemented) and a torch.no_grad() context (there is no backward pass) and raises otherwise."""
+        train() mode: under torch.no_grad() with every drop rate at 0 the forward runs on the sm_100a kernels
+        with BatchNorm batch statistics (the four layers update their running statistics as nn.BatchNorm does).  With autograd enabled,
+        or with Dropout / DropPath rates above 0, it runs as necks/train_autograd.py: index work on the same kernels, every
+        differentiable operation as torch ops on the module's parameters, so ``loss.backward()`` fills their ``.grad`` like the
+        reference's (pinned against the reference's gradients by tests/golden/c1_train.npz)."""
         self._check_mode()
+        if self.training and (torch.is_grad_enabled() or self.drop_rate or self.attn_drop_rate or self.drop_path_rate):
+            if img_proxy is not None or trace is not None:
+                raise NotImplementedError("ProxyTransformationNormReverse (B200): img_proxy= / trace= are eval-mode arguments")
+            from . import train_autograd
+            in_dev = points[0].device
+            out = train_autograd.forward_train(self, points, text_dict, img_feat)
+            self._packed_key = None                  # parameters / running statistics are about to change: re-fold for the next eval()
+            return out if in_dev.type == "cuda" else [o.to(in_dev) for o in out]
         with torch.no_grad():
             return self._forward_impl(points, text_dict, img_feat, img_proxy, trace)
 
     def _check_mode(self):
-        """train() mode is supported as a forward-only batch-statistics pass (see forward()); everything else raises."""
+        """eval() under autograd: one warning (the eval path carries no gradients)."""
         if not self.training and torch.is_grad_enabled() and not getattr(self, "_warned_no_grad", False) and \
                 any(p.requires_grad for p in self.parameters()):
             import warnings
             self._warned_no_grad = True
-            warnings.warn("ProxyTransformationNormReverse (B200) is inference-only: forward() runs under torch.no_grad() and its "
-                          "outputs carry no gradient into the parameters or the image / text backbones (the reference neck is "
-                          "differentiable); wrap the call in torch.no_grad() to silence this warning", stacklevel=3)
-        if self.training:
-            if self.drop_rate or self.attn_drop_rate or self.drop_path_rate:
-                raise NotImplementedError("ProxyTransformationNormReverse (B200): train() mode needs drop_rate = attn_drop_rate = "
-                                          "drop_path_rate = 0 (Dropout / DropPath are not implemented)")
-            if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-                raise NotImplementedError("ProxyTransformationNormReverse (B200): no backward pass — train() mode is a "
-                                          "batch-statistics forward only; call it under torch.no_grad()")
+            warnings.warn("ProxyTransformationNormReverse (B200): eval() mode runs under torch.no_grad() and its outputs carry no "
+                          "gradient into the parameters or the image / text backbones; use train() mode for a differentiable "
+                          "forward, or wrap the call in torch.no_grad() to silence this warning", stacklevel=3)
 
     def _forward_impl(self, points, text_dict, img_feat, img_proxy, trace) -> List[torch.Tensor]:
         dev = next(self.parameters()).device

@@ -331,7 +331,7 @@ def test_sparse_collate_handoff_bit_exact(reciprocal, floor):
                                           (1, 64, 33, True), (2, 200, 256, False),
                                           (4, 691, 32, True), (3, 691, 50, False), (2, 1024, 256, True), (3, 257, 129, True), (2, 137, 5, False),
                                           (20, 256, 64, True), (19, 256, 196, False), (19, 691, 50, True), (24, 137, 5, False),
-                                          (20, 300, 224, True), (19, 130, 225, False)])
+                                          (20, 300, 224, True), (19, 130, 225, False), (20, 16, 16, True), (19, 100, 33, False)])
 def test_proxy_attention_tcgen05_core(B, n, l, masked):
     """The tcgen05 / TMEM attention core (pt_proxy_attention_tc) against an fp64 evaluation of :225-252 on the same inputs:
     unmasked softmax over the clusters, masked (-1e9) softmax over the proxies, 8 heads of 32.  n > 256 streams the clusters
@@ -493,3 +493,21 @@ def test_standalone_proxy_block_dim64_config1(dim, n, l, B, masked):
     w = _block_weights(sd, "blk", "nrm", 0)
     got = ops.proxy_block(cu(x), cu(proxy), cu(mask) if mask is not None else None, w, heads)
     np.testing.assert_allclose(np_(got), want.numpy(), rtol=0, atol=3e-5)
+
+
+def test_profile_timeline_orders_the_kernels_of_a_call():
+    """pt_profile_timeline: every recorded launch with start / end on one time axis (tools/step_timeline.py)."""
+    from proxytransformation_b200 import _lib
+    x = torch.randn(64, 256, device=DEV)
+    w, b = torch.ones(256, device=DEV), torch.zeros(256, device=DEV)
+    _lib.profile_enable(True)
+    try:
+        ops.layernorm(x, w, b)
+        ops.split_bf16(x)
+        torch.cuda.synchronize()
+        tl = _lib.profile_timeline()
+    finally:
+        _lib.profile_enable(False)
+    assert [t[0] for t in tl] == ["layernorm", "split_bf16"]
+    assert tl[0][1] == 0.0 and all(e >= s for _, s, e in tl) and tl[1][1] >= tl[0][2] - 1e-3
+
