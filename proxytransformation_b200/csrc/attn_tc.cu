@@ -277,39 +277,63 @@ __global__ void __launch_bounds__(128 * NWQ, NWQ == 2 ? 2 : 1) proxy_attention_t
             if (i < nrows_tile * 8) *reinterpret_cast<uint4*>(smem + off + r * ROW_BYTES + ((ch ^ (r & 7)) << 4)) = reg[k];
         }
     };
-    auto stage_vt = [&](int k0) {                               // V^T planes of keys k0 .. k0 + KT - 1 (zero past n)
+    // V^T planes of keys k0 .. k0 + KT - 1 (zero past n).  Scenes whose first key is on the 16-byte grid (always, behind
+    // pt_proxy_block_fused) go through registers like the K / Q rows: the loads of the next tile are in flight during the passes.
+    const bool vt_vec = (((size_t)b * a.vt_seg) & 7) == 0 && (a.vt_seg & 7) == 0 && (a.ldv & 7) == 0 && (a.vt_plane & 7) == 0 && (KT & 7) == 0;
+    constexpr int C8 = KT / 8;                                  // 16-byte chunks (8 keys) per row of a tile
+    static_assert(2 * HD * C8 == 4 * THREADS, "V^T tile = 4 chunks per thread");
+    auto load_vt = [&](uint4 (&reg)[4], int k0) {
         const size_t key0 = (size_t)b * a.vt_seg + k0;
-        if ((key0 & 7) == 0 && (a.vt_seg & 7) == 0 && (a.ldv & 7) == 0 && (a.vt_plane & 7) == 0) {  // 16-byte chunks of 8 keys
-            constexpr int C8 = KT / 8;                          // 16-byte chunks per row
-            for (int i = tid; i < 2 * HD * C8; i += THREADS) {
-                const int plane = i / (HD * C8), e = (i / C8) & 31, j8 = i % C8;
-                uint4 v = z4;
-                const int left = n - (k0 + 8 * j8);             // real keys in this chunk (the rest of a scene's last chunk is padding)
-                if (left > 0) {
-                    v = __ldg(reinterpret_cast<const uint4*>(a.vt + (plane ? a.vt_plane : 0) + (size_t)(h * HD + e) * a.ldv + key0 + 8 * j8));
-                    if (left < 8) {
-                        uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                        for (int q2 = 0; q2 < 4; ++q2) w4[q2] = 2 * q2 >= left ? 0u : (2 * q2 + 1 >= left ? (w4[q2] & 0xffffu) : w4[q2]);
-                        v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-                    }
-                }
-                *reinterpret_cast<uint4*>(smem + OFF_VT + plane * VT_PLANE + (j8 >> 3) * VT_TILE + e * ROW_BYTES + (((j8 & 7) ^ (e & 7)) << 4)) = v;
-            }
-        } else {                                                // scenes whose first key is not 16-byte aligned (odd n): element by element
-            for (int i = tid; i < 2 * HD * KT; i += THREADS) {
-                const int plane = i / (HD * KT), e = (i / KT) & 31, j = i % KT;
-                unsigned short v = 0;
-                if (k0 + j < n) v = __ldg(reinterpret_cast<const unsigned short*>(a.vt + (plane ? a.vt_plane : 0) + (size_t)(h * HD + e) * a.ldv + key0 + j));
-                *reinterpret_cast<unsigned short*>(smem + OFF_VT + plane * VT_PLANE + (j >> 6) * VT_TILE + e * ROW_BYTES + ((((j >> 3) & 7) ^ (e & 7)) << 4) + (j & 7) * 2) = v;
-            }
+        for (int k = 0; k < 4; ++k) {
+            const int i = tid + k * THREADS, plane = i / (HD * C8), e = (i / C8) & 31, j8 = i % C8;
+            reg[k] = z4;
+            if (n - (k0 + 8 * j8) > 0)
+                reg[k] = __ldg(reinterpret_cast<const uint4*>(a.vt + (plane ? a.vt_plane : 0) + (size_t)(h * HD + e) * a.ldv + key0 + 8 * j8));
         }
     };
-    for (int i = tid; i < MAXR * 8; i += THREADS) {             // Pt (all l <= 256 proxies stay resident)
-        const int r = i >> 3, ch = i & 7, half = ch >> 2, col = h * HD + 8 * (ch & 3);
-        uint4 pp = z4;
-        if (r < l) pp = __ldg(reinterpret_cast<const uint4*>(a.pt + (half ? a.pt_plane : 0) + ((size_t)b * l + r) * c + col));
-        *reinterpret_cast<uint4*>(smem + OFF_P + r * ROW_BYTES + ((ch ^ (r & 7)) << 4)) = pp;
+    auto store_vt = [&](const uint4 (&reg)[4], int k0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = tid + k * THREADS, plane = i / (HD * C8), e = (i / C8) & 31, j8 = i % C8;
+            uint4 v = reg[k];
+            const int left = n - (k0 + 8 * j8);                 // real keys in this chunk (the rest of a scene's last chunk is padding)
+            if (left > 0 && left < 8) {
+                uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q2 = 0; q2 < 4; ++q2) w4[q2] = 2 * q2 >= left ? 0u : (2 * q2 + 1 >= left ? (w4[q2] & 0xffffu) : w4[q2]);
+                v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+            *reinterpret_cast<uint4*>(smem + OFF_VT + plane * VT_PLANE + (j8 >> 3) * VT_TILE + e * ROW_BYTES + (((j8 & 7) ^ (e & 7)) << 4)) = v;
+        }
+    };
+    auto stage_vt_elements = [&](int k0) {                      // scenes whose first key is not 16-byte aligned (odd n behind the stand-alone entry)
+        const size_t key0 = (size_t)b * a.vt_seg + k0;
+        for (int i = tid; i < 2 * HD * KT; i += THREADS) {
+            const int plane = i / (HD * KT), e = (i / KT) & 31, j = i % KT;
+            unsigned short v = 0;
+            if (k0 + j < n) v = __ldg(reinterpret_cast<const unsigned short*>(a.vt + (plane ? a.vt_plane : 0) + (size_t)(h * HD + e) * a.ldv + key0 + j));
+            *reinterpret_cast<unsigned short*>(smem + OFF_VT + plane * VT_PLANE + (j >> 6) * VT_TILE + e * ROW_BYTES + ((((j >> 3) & 7) ^ (e & 7)) << 4) + (j & 7) * 2) = v;
+        }
+    };
+    // first K and V^T tiles and the proxies: every load is issued before the first store, so the three latencies overlap
+    uint4 kreg[4], qreg[4], vreg[4];
+    load_rows(kreg, c + h * HD, 0, KT, n);
+    if (vt_vec) load_vt(vreg, 0);
+    {
+        constexpr int PPT = MAXR * 8 / THREADS;                 // Pt (all l <= 256 proxies stay resident): 16-byte chunks per thread
+        uint4 preg[PPT];
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const int i = tid + k * THREADS, r = i >> 3, ch = i & 7, half = ch >> 2, col = h * HD + 8 * (ch & 3);
+            preg[k] = z4;
+            if (r < l) preg[k] = __ldg(reinterpret_cast<const uint4*>(a.pt + (half ? a.pt_plane : 0) + ((size_t)b * l + r) * c + col));
+        }
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) {
+            const int i = tid + k * THREADS, r = i >> 3, ch = i & 7;
+            *reinterpret_cast<uint4*>(smem + OFF_P + r * ROW_BYTES + ((ch ^ (r & 7)) << 4)) = preg[k];
+        }
     }
     for (int i = tid; i < 256; i += THREADS) {
         keyflag[i] = (a.mask != nullptr && i < l && a.mask[(size_t)b * l + i] == 0) ? 1.f : 0.f;
@@ -385,17 +409,18 @@ __global__ void __launch_bounds__(128 * NWQ, NWQ == 2 ? 2 : 1) proxy_attention_t
     // ---- stage 1: rows = proxies, keys = clusters in tiles of KT (online softmax), values = V  ->  Pv^T (normalised) as K-major
     // operand planes.  Accumulator of proxy row tile mt: columns ACC1 + 32 mt.
     const int nmt1 = (lpad + 127) >> 7;
-    uint4 kreg[4], qreg[4];
-    load_rows(kreg, c + h * HD, 0, KT, n);
     for (int kt = 0; kt * KT < n; ++kt) {
         const int k0 = kt * KT, nk = min(KT, n - k0), nkpad = (nk + 15) & ~15;
         store_rows(kreg, OFF_K, KT);
-        stage_vt(k0);
+        if (vt_vec) store_vt(vreg, k0);
+        else stage_vt_elements(k0);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (k0 + KT < n) load_rows(kreg, c + h * HD, k0 + KT, KT, n);                        // next K tile in flight during the passes
-        else load_rows(qreg, h * HD, 128 * (int)blockIdx.z, 128, n);                          // ... or the first Q tile of stage 2
+        if (k0 + KT < n) {                                                                    // next K / V^T tiles in flight during the passes
+            load_rows(kreg, c + h * HD, k0 + KT, KT, n);
+            if (vt_vec) load_vt(vreg, k0 + KT);
+        } else load_rows(qreg, h * HD, 128 * (int)blockIdx.z, 128, n);                        // ... or the first Q tile of stage 2
         for (int mt = 0; mt < nmt1; ++mt) {
             pass(sP + mt * 128 * ROW_BYTES, sK, nk, nkpad, sVT, nullptr, ACC1 + 32 * mt, 128 * mt, kt);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
