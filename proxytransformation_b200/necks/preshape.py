@@ -166,6 +166,7 @@ class ProxyTransformationNormReverse(nn.Module):
         # `overlap_img_min_batch` scenes, or while a CUDA graph is being captured
         self.overlap_img_stage = os.environ.get("PT_OVERLAP_IMG", "auto")
         self.overlap_img_min_batch = 8
+        self.parallel_branch_max_rows = int(os.environ.get("PT_PARALLEL_BRANCH_ROWS", "8192"))     # B * n up to which the image branch runs beside the text branch
         self._streams: Dict[str, torch.cuda.Stream] = {}
         self.host_chunk_scenes = 8       # scenes per pipeline chunk when forward() is fed host tensors
         self.cuda_graphs = os.environ.get("PT_CUDA_GRAPHS", "0") != "0"     # replay small device-resident batches as one CUDA graph
@@ -549,6 +550,19 @@ class ProxyTransformationNormReverse(nn.Module):
             sc, sh = ops.bn_batch_affine_cluster_conv(P, kidx, kc, w_enc, self.simple_encoder.mlp[1])
             w_enc = dict(w_enc, bn_scale=sc, bn_shift=sh)
         pp = ops.point_encoder(P, kidx, kc, w_enc)
+        # The two branches (:440-446 text, :449-455 image) only share the point proxies.  While their GEMMs under-fill the GPU
+        # (B * n rows: fewer 128-row tiles than SMs — the shipped config at batch 4 has 22) the image branch follows the image
+        # stage on ITS stream and runs next to the text branch; the main stream joins before the scatter.
+        ig = transform = None
+        if img_side is not None and P.shape[0] * n <= self.parallel_branch_max_rows:
+            cur = torch.cuda.current_stream(P.device)
+            pp_ready = torch.cuda.Event()
+            pp_ready.record(cur)
+            with torch.cuda.stream(img_side):
+                img_side.wait_event(pp_ready)
+                ig = ops.proxy_block(pp, img_proxy, None, w["imgb"], self.num_heads, params=w["imgb_struct"])
+                ih = w["img_head"]
+                transform = ops.heads(ig, ih["lin_w"], ih["lin_b"], ih["bn_scale"], ih["bn_shift"])
         # S7/S8 text branch -> translate (:440-446)
         tg = ops.proxy_block(pp, text, mask, w["text"], self.num_heads, params=w["text_struct"])
         th = w["text_head"]
@@ -564,11 +578,12 @@ class ProxyTransformationNormReverse(nn.Module):
                                          out=img_state[0], ws=img_state[1])[0]
         elif img_proxy is None:
             img_proxy = ops.img_attnpool(img_feat, w["img"], self.num_heads, params=w["img_struct"])
-        ig = ops.proxy_block(pp, img_proxy, None, w["imgb"], self.num_heads, params=w["imgb_struct"])
-        ih = w["img_head"]
-        i_sc, i_sh = (ops.bn_batch_affine_linear(ig, ih["lin_w"], ih["lin_b"], self.img_trans_norm) if train
-                      else (ih["bn_scale"], ih["bn_shift"]))                                # :330 BatchNorm1d over (B, n)
-        transform = ops.heads(ig, ih["lin_w"], ih["lin_b"], i_sc, i_sh)
+        if transform is None:
+            ig = ops.proxy_block(pp, img_proxy, None, w["imgb"], self.num_heads, params=w["imgb_struct"])
+            ih = w["img_head"]
+            i_sc, i_sh = (ops.bn_batch_affine_linear(ig, ih["lin_w"], ih["lin_b"], self.img_trans_norm) if train
+                          else (ih["bn_scale"], ih["bn_shift"]))                            # :330 BatchNorm1d over (B, n)
+            transform = ops.heads(ig, ih["lin_w"], ih["lin_b"], i_sc, i_sh)
         if train:
             self._packed_key = None                  # running statistics changed behind torch's version counters: re-fold for eval
         # S10-S12 (:459-467)
