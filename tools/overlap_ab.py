@@ -28,4 +28,5 @@ for i in range(40):
     m.forward_packed(*sets[i % 2])
 e1.record()
 torch.cuda.synchronize()
-print(f"PT_MEAN_CTAS={os.environ.get('PT_MEAN_CTAS', '-')} PT_IMG_LAUNCH_AT={os.environ.get('PT_IMG_LAUNCH_AT', '0')} PT_POOL_GRID={os.environ.get('PT_POOL_GRID', '-')}: {e0.elapsed_time(e1) / 40:.4f} ms/step")
+knobs = " ".join(f"{k}={os.environ[k]}" for k in ("PT_MEAN_CTAS", "PT_POOL_GRID", "PT_PARALLEL_BRANCH_ROWS", "PT_OVERLAP_IMG", "PT_ATTN_FORM") if k in os.environ)
+print(f"{knobs or 'defaults'}: {e0.elapsed_time(e1) / 40:.4f} ms/step")
