@@ -232,6 +232,15 @@ int pt_affine_scatter_compact(const float* points, const int32_t* kept_idx, cons
                               const float* kept_centres, const float* transform, const float* translate, int B, int N,
                               int n, int K, int n_drop_entries, float* out, int32_t* counts, void* ws, size_t ws_bytes,
                               pt_stream_t stream);
+/* The same in two calls with the same ws: PT_SCATTER_STAGE_MARK is index work only (who writes each point, how many points of a block
+ * are dropped: needs kept_idx / drop_idx, the other pointers may be null) and can be issued as soon as the cluster dropout is done;
+ * PT_SCATTER_STAGE_COMPACT applies the affine maps and writes the survivors. */
+#define PT_SCATTER_STAGE_MARK 1
+#define PT_SCATTER_STAGE_COMPACT 2
+int pt_affine_scatter_compact_stage(const float* points, const int32_t* kept_idx, const int32_t* drop_idx,
+                                    const float* kept_centres, const float* transform, const float* translate, int B, int N,
+                                    int n, int K, int n_drop_entries, float* out, int32_t* counts, void* ws, size_t ws_bytes,
+                                    int stages, pt_stream_t stream);
 
 /* ---- N3 input side: AggregateMultiViewPoints (datasets/transforms/multiview.py:224-241) + the gather of PointSample
  * (datasets/transforms/points.py:411-417), fused so that only the sampled points are transformed.

@@ -73,6 +73,7 @@ _SIGNATURES = {
     "pt_debug_pool_events": (c_int, [POINTER(ctypes.c_longlong), c_int]),
     "pt_scatter_ws_bytes": (c_size_t, [c_int, c_int]),
     "pt_affine_scatter_compact": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "pt_affine_scatter_compact_stage": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, c_int, _P]),
     "pt_proxy_attention_tc": (c_int, [_P, ctypes.c_longlong, c_int, _P, ctypes.c_longlong, ctypes.c_longlong, _P, ctypes.c_longlong, _P,
                                       c_int, c_int, c_int, c_int, c_int, _P, _P, ctypes.c_longlong, _P]),
     "pt_aggregate_sample": (c_int, [_P, _P, c_int, _P, _P, ctypes.c_longlong, _P, _P]),

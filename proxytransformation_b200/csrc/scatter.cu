@@ -203,11 +203,13 @@ extern "C" size_t pt_scatter_ws_bytes(int B, int N) {
     return align_up((size_t)B * N * sizeof(int), 256) + align_up((size_t)B * ceil_div(N, SC_BLOCK) * sizeof(int), 256);
 }
 
-extern "C" int pt_affine_scatter_compact(const float* points, const int32_t* kept_idx, const int32_t* drop_idx,
-                                         const float* kept_centres, const float* transform, const float* translate, int B,
-                                         int N, int n, int K, int n_drop_entries, float* out, int32_t* counts, void* ws,
-                                         size_t ws_bytes, pt_stream_t stream) {
-    PT_REQUIRE(points && kept_idx && drop_idx && kept_centres && transform && translate && out && counts && ws,
+extern "C" int pt_affine_scatter_compact_stage(const float* points, const int32_t* kept_idx, const int32_t* drop_idx,
+                                               const float* kept_centres, const float* transform, const float* translate, int B,
+                                               int N, int n, int K, int n_drop_entries, float* out, int32_t* counts, void* ws,
+                                               size_t ws_bytes, int stages, pt_stream_t stream) {
+    PT_REQUIRE((stages & ~(PT_SCATTER_STAGE_MARK | PT_SCATTER_STAGE_COMPACT)) == 0 && stages != 0, "pt_affine_scatter_compact_stage: stages=%d", stages);
+    PT_REQUIRE(kept_idx && drop_idx && ws, "pt_affine_scatter_compact: null pointer");
+    PT_REQUIRE(!(stages & PT_SCATTER_STAGE_COMPACT) || (points && kept_centres && transform && translate && out && counts),
                "pt_affine_scatter_compact: null pointer");
     PT_REQUIRE(B > 0 && N > 0 && n > 0 && K > 0 && n_drop_entries >= 0 && (long long)n * K < SC_DROP,
                "pt_affine_scatter_compact: bad shape");
@@ -216,14 +218,26 @@ extern "C" int pt_affine_scatter_compact(const float* points, const int32_t* kep
     int* winner = (int*)ws;
     int* blockcnt = (int*)((char*)ws + align_up((size_t)B * N * sizeof(int), 256));
     const int nblk = ceil_div(N, SC_BLOCK);
-    PT_CUDA_OK(cudaMemsetAsync(winner, 0xff, (size_t)B * N * sizeof(int), s));   // -1 = untouched
-    PT_CUDA_OK(cudaMemsetAsync(blockcnt, 0, (size_t)B * nblk * sizeof(int), s));  // distinct dropped points per block
-    const long long total = (long long)B * ((long long)n * K + n_drop_entries);
-    int grid = (int)((total + 255) / 256);
-    if (grid > 148 * 16) grid = 148 * 16;
-    { ProfScope prof_(PROF_MARK, s); mark_kernel<<<grid, 256, 0, s>>>(kept_idx, drop_idx, B, N, n * K, n_drop_entries, nblk, winner, blockcnt); }
-    PT_LAUNCH_CHECK();
-    { ProfScope prof_(PROF_COMPACT, s); compact_kernel<<<dim3(nblk, B), SC_THREADS, 0, s>>>(points, winner, blockcnt, kept_centres, transform, translate, N, n, K, out, counts); }
-    PT_LAUNCH_CHECK();
+    if (stages & PT_SCATTER_STAGE_MARK) {       // index work only: who writes each point, how many points of a block are dropped
+        PT_CUDA_OK(cudaMemsetAsync(winner, 0xff, (size_t)B * N * sizeof(int), s));   // -1 = untouched
+        PT_CUDA_OK(cudaMemsetAsync(blockcnt, 0, (size_t)B * nblk * sizeof(int), s));  // distinct dropped points per block
+        const long long total = (long long)B * ((long long)n * K + n_drop_entries);
+        int grid = (int)((total + 255) / 256);
+        if (grid > 148 * 16) grid = 148 * 16;
+        { ProfScope prof_(PROF_MARK, s); mark_kernel<<<grid, 256, 0, s>>>(kept_idx, drop_idx, B, N, n * K, n_drop_entries, nblk, winner, blockcnt); }
+        PT_LAUNCH_CHECK();
+    }
+    if (stages & PT_SCATTER_STAGE_COMPACT) {
+        { ProfScope prof_(PROF_COMPACT, s); compact_kernel<<<dim3(nblk, B), SC_THREADS, 0, s>>>(points, winner, blockcnt, kept_centres, transform, translate, N, n, K, out, counts); }
+        PT_LAUNCH_CHECK();
+    }
     return PT_OK;
+}
+
+extern "C" int pt_affine_scatter_compact(const float* points, const int32_t* kept_idx, const int32_t* drop_idx,
+                                         const float* kept_centres, const float* transform, const float* translate, int B,
+                                         int N, int n, int K, int n_drop_entries, float* out, int32_t* counts, void* ws,
+                                         size_t ws_bytes, pt_stream_t stream) {
+    return pt_affine_scatter_compact_stage(points, kept_idx, drop_idx, kept_centres, transform, translate, B, N, n, K, n_drop_entries, out,
+                                           counts, ws, ws_bytes, PT_SCATTER_STAGE_MARK | PT_SCATTER_STAGE_COMPACT, stream);
 }

@@ -544,6 +544,8 @@ class ProxyTransformationNormReverse(nn.Module):
         idx2, _ = ops.ball_query(centres, P, K)
         # S5 dropout (:352-420)
         kept_src, kc, kidx, drop_idx, fps = ops.cluster_dropout(centres, idx2, self.keep1, n)
+        # index half of S10-S12 (who writes each point, dropped points per block) now, off the tail of the step
+        scatter_ws = ops.affine_scatter_mark(P, kidx, drop_idx)
         # S6 point proxies (:437)
         w_enc = w["encoder"]
         if train:                                    # :112 BatchNorm2d over (B, n, K)
@@ -588,7 +590,7 @@ class ProxyTransformationNormReverse(nn.Module):
         if train:
             self._packed_key = None                  # running statistics changed behind torch's version counters: re-fold for eval
         # S10-S12 (:459-467)
-        out, counts = ops.affine_scatter_compact(P, kidx, drop_idx, kc, transform, translate)
+        out, counts = ops.affine_scatter_compact(P, kidx, drop_idx, kc, transform, translate, ws=scatter_ws, marked=True)
         if trace is not None:
             trace.update(mn=mn, mx=mx, c0=c0, idx1=idx1, centres=centres, idx2=idx2, kept_src=kept_src, kept_centres=kc,
                          kept_idx=kidx, drop_idx=drop_idx, fps=fps, point_proxy=pp, text_guide=tg, translate=translate,

@@ -312,8 +312,25 @@ def img_attnpool(img_feat, w: Dict[str, torch.Tensor], heads: int, ws: Optional[
     return out, ws
 
 
-def affine_scatter_compact(points, kept_idx, drop_idx, kept_centres, transform, translate, ws: Optional[torch.Tensor] = None):
-    """S10-S12 (:459-525).  -> out (B,N,3) packed per scene, counts (B,) int32 (device)."""
+SCATTER_STAGE_MARK, SCATTER_STAGE_COMPACT = 1, 2
+
+
+def affine_scatter_mark(points, kept_idx, drop_idx):
+    """Index half of S10-S12 (needs the indices only): -> the workspace to hand to affine_scatter_compact(..., ws=, marked=True)."""
+    L = _lib.load()
+    B, N, _ = points.shape
+    n, K = kept_idx.shape[1], kept_idx.shape[2]
+    ws = _ws(L.pt_scatter_ws_bytes(B, N), points.device)
+    check(L.pt_affine_scatter_compact_stage(None, _chk(kept_idx, torch.int32, "kept_idx"), _chk(drop_idx, torch.int32, "drop_idx"), None, None,
+                                            None, B, N, n, K, drop_idx.shape[1], None, None, ws.data_ptr(), ws.numel(), SCATTER_STAGE_MARK,
+                                            _stream()), "pt_affine_scatter_compact_stage")
+    return ws
+
+
+def affine_scatter_compact(points, kept_idx, drop_idx, kept_centres, transform, translate, ws: Optional[torch.Tensor] = None,
+                           marked: bool = False):
+    """S10-S12 (:459-525).  -> out (B,N,3) packed per scene, counts (B,) int32 (device).  ``marked``: ``ws`` comes from
+    affine_scatter_mark on the same indices (only the affine + compaction half is left to do)."""
     L = _lib.load()
     B, N, _ = points.shape
     n, K = kept_idx.shape[1], kept_idx.shape[2]
@@ -323,13 +340,16 @@ def affine_scatter_compact(points, kept_idx, drop_idx, kept_centres, transform, 
     counts = torch.empty(B, dtype=torch.int32, device=dev)
     need = L.pt_scatter_ws_bytes(B, N)
     if ws is None or ws.numel() < need:
+        if marked:
+            raise ValueError("affine_scatter_compact(marked=True) needs the workspace returned by affine_scatter_mark")
         ws = _ws(need, dev)
     f = torch.float32
-    check(L.pt_affine_scatter_compact(_chk(points, f, "points"), _chk(kept_idx, torch.int32, "kept_idx"),
-                                      _chk(drop_idx, torch.int32, "drop_idx"), _chk(kept_centres, f, "kept_centres"),
-                                      _chk(transform, f, "transform"), _chk(translate, f, "translate"), B, N, n, K, nde,
-                                      out.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
-          "pt_affine_scatter_compact")
+    stages = SCATTER_STAGE_COMPACT if marked else SCATTER_STAGE_MARK | SCATTER_STAGE_COMPACT
+    check(L.pt_affine_scatter_compact_stage(_chk(points, f, "points"), _chk(kept_idx, torch.int32, "kept_idx"),
+                                            _chk(drop_idx, torch.int32, "drop_idx"), _chk(kept_centres, f, "kept_centres"),
+                                            _chk(transform, f, "transform"), _chk(translate, f, "translate"), B, N, n, K, nde,
+                                            out.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(), stages, _stream()),
+          "pt_affine_scatter_compact_stage")
     return out, counts
 
 
