@@ -195,6 +195,41 @@ __global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ g,
     }
 }
 
+// The shipped shapes (c = 256, o = 3 translate / 9 transform): the row is read once (two coalesced 16-byte loads per lane), the O
+// dot products are independent accumulators and their O warp reductions interleave — the generic kernel above re-reads the row
+// and runs one dependent load -> FMA -> 5-shuffle chain per output (26 us for 16 384 rows x 9 where 17 MB of input take 3 us).
+template <int O>
+__global__ void __launch_bounds__(256) heads256_kernel(const float* __restrict__ g, const float* __restrict__ lw,
+                                                       const float* __restrict__ lb, const float* __restrict__ sc,
+                                                       const float* __restrict__ sh, int rows, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float4* gr = reinterpret_cast<const float4*>(g + (size_t)row * 256);
+    const float4 x0 = gr[lane], x1 = gr[32 + lane];
+    float acc[O];
+#pragma unroll
+    for (int j = 0; j < O; ++j) {
+        const float4* wr = reinterpret_cast<const float4*>(lw + (size_t)j * 256);
+        const float4 w0 = __ldg(wr + lane), w1 = __ldg(wr + 32 + lane);
+        // same order of products inside a lane as the generic kernel's strided loop is NOT kept: the sum of 256 products is
+        // re-associated (|difference| ~1e-7 relative), well inside the path's 1e-4 coordinate bar
+        float a = x0.x * w0.x;
+        a = fmaf(x0.y, w0.y, a); a = fmaf(x0.z, w0.z, a); a = fmaf(x0.w, w0.w, a);
+        a = fmaf(x1.x, w1.x, a); a = fmaf(x1.y, w1.y, a); a = fmaf(x1.z, w1.z, a); a = fmaf(x1.w, w1.w, a);
+        acc[j] = a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < O; ++j) acc[j] += __shfl_xor_sync(FULL, acc[j], o);
+    }
+    float y = 0.f;
+#pragma unroll
+    for (int j = 0; j < O; ++j) y = lane == j ? acc[j] : y;
+    if (lane < O) out[(size_t)row * O + lane] = fmaf(y + __ldg(lb + lane), __ldg(sc + lane), __ldg(sh + lane));
+}
+
 int launch_layernorm_split(const float* x, const float* w, const float* b, const float* add, int add_rows, int rows, int c,
                            float* out, __nv_bfloat16* out_hi, long long out_plane, cudaStream_t s);
 int launch_layernorm(const float* x, const float* w, const float* b, const float* add, int add_rows, int rows, int c,
@@ -265,7 +300,13 @@ extern "C" int pt_heads(const float* guide, const float* lin_w, const float* lin
                         const float* bn_shift, int rows, int c, int o, float* out, pt_stream_t stream) {
     PT_REQUIRE(guide && lin_w && lin_b && bn_scale && bn_shift && out && rows > 0 && c > 0 && o > 0 && o <= 16,
                "pt_heads: bad argument");
-    { ProfScope prof_(PROF_HEADS, (cudaStream_t)stream); heads_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(guide, lin_w, lin_b, bn_scale, bn_shift, rows, c, o, out); }
+    {
+        ProfScope prof_(PROF_HEADS, (cudaStream_t)stream);
+        const bool vec = c == 256 && (((uintptr_t)guide | (uintptr_t)lin_w) & 15) == 0;
+        if (vec && o == 3) heads256_kernel<3><<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(guide, lin_w, lin_b, bn_scale, bn_shift, rows, out);
+        else if (vec && o == 9) heads256_kernel<9><<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(guide, lin_w, lin_b, bn_scale, bn_shift, rows, out);
+        else heads_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(guide, lin_w, lin_b, bn_scale, bn_shift, rows, c, o, out);
+    }
     PT_LAUNCH_CHECK();
     return PT_OK;
 }
