@@ -379,7 +379,10 @@ __device__ __forceinline__ void fps_rounds(const float* ux, const float* uy, con
     }
 }
 
-__global__ void cluster_dropout_kernel(const float* __restrict__ centres, const int32_t* __restrict__ idx, int M, int K,
+// MAXT = 256: launches of 256 threads (keep1 <= 2048) get the register budget for up to 10 slots per thread, so that up to 1 280
+// candidates (the shipped config keeps 1 210) run their rounds on 4 warps instead of 8 (cheaper cross-warp step).
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) cluster_dropout_kernel(const float* __restrict__ centres, const int32_t* __restrict__ idx, int M, int K,
                                        int keep1, int n_keep, int32_t* __restrict__ kept_src,
                                        float* __restrict__ kept_centres, int32_t* __restrict__ kept_idx,
                                        int32_t* __restrict__ drop_idx, int32_t* __restrict__ fps_sel) {
@@ -434,9 +437,12 @@ __global__ void cluster_dropout_kernel(const float* __restrict__ centres, const 
     // chain (distances -> arg-max -> next centre), so its latency is what counts: only the first TF threads take part
     // (TF = 128 / 256 / T by keep1: fewer warps make the cross-warp step cheaper, nper slots per thread actually used) and
     // they meet at a named barrier of their own.
-    const int TF = keep1 <= 128 * FPS_PER ? 128 : (keep1 <= 256 * FPS_PER ? 256 : T);
+    constexpr int PER128 = MAXT <= 256 ? 10 : FPS_PER;     // slots per thread up to which 4 warps take the rounds
+    const int TF = keep1 <= 128 * PER128 ? 128 : (keep1 <= 256 * FPS_PER ? 256 : T);
     if (tid < TF) {
         switch ((keep1 + TF - 1) / TF) {               // slots per thread, compile-time inside the rounds
+            case 9: if (MAXT <= 256) { fps_rounds<9>(ux, uy, uz, keep1, n_drop, TF, red, sel); break; }
+            case 10: if (MAXT <= 256) { fps_rounds<10>(ux, uy, uz, keep1, n_drop, TF, red, sel); break; }
             case 1: fps_rounds<1>(ux, uy, uz, keep1, n_drop, TF, red, sel); break;
             case 2: fps_rounds<2>(ux, uy, uz, keep1, n_drop, TF, red, sel); break;
             case 3: fps_rounds<3>(ux, uy, uz, keep1, n_drop, TF, red, sel); break;
@@ -563,8 +569,12 @@ extern "C" int pt_cluster_dropout(const float* centres, const int32_t* idx, int 
                   ((size_t)M + (K + 2) + n_drop + n_keep) * sizeof(int) + (size_t)M * sizeof(unsigned short) + keep1;
     smem = align_up(smem, 16);
     PT_REQUIRE(smem <= 227 * 1024, "pt_cluster_dropout: M=%d needs %zu B shared memory", M, smem);
-    if (smem > 48 * 1024) PT_CUDA_OK(cudaFuncSetAttribute(cluster_dropout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { ProfScope prof_(PROF_DROPOUT, (cudaStream_t)stream); cluster_dropout_kernel<<<B, T, smem, (cudaStream_t)stream>>>(centres, idx, M, K, keep1, n_keep, kept_src, kept_centres,
+    if (smem > 48 * 1024) {
+        PT_CUDA_OK(cudaFuncSetAttribute(cluster_dropout_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PT_CUDA_OK(cudaFuncSetAttribute(cluster_dropout_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    auto kern = T == 256 ? cluster_dropout_kernel<256> : cluster_dropout_kernel<1024>;
+    { ProfScope prof_(PROF_DROPOUT, (cudaStream_t)stream); kern<<<B, T, smem, (cudaStream_t)stream>>>(centres, idx, M, K, keep1, n_keep, kept_src, kept_centres,
                                                                  kept_idx, drop_idx, fps_sel); }
     PT_LAUNCH_CHECK();
     return PT_OK;
